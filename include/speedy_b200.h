@@ -1,0 +1,160 @@
+/* speedy_b200.h — C ABI of the B200-native (sm_100a) replacement for the hot path of
+ * samhatfield/speedy.f90: spectral transforms, spectral operators, grid-point dynamics,
+ * column physics, semi-implicit spectral time step and the per-step surface slabs.
+ *
+ * Every entry point replaces a Fortran module procedure of the reference; the comment
+ * above each one names it (file:line relative to the reference's source/).  The
+ * reference-side iso_c_binding interface block is in fortran/speedy_b200_c.f90 and the
+ * integration recipe in INTEGRATION.md.
+ *
+ * Conventions
+ *  - All arrays are Fortran (column-major) order, exactly as the reference declares them:
+ *    complex(mx,nx) spectral fields are interleaved (re,im) doubles, m fastest;
+ *    real(ix,il) grid fields have longitude fastest, latitude j=1 southernmost.
+ *  - Batched calls take `nbatch` fields stored back to back.
+ *  - Host-pointer entry points copy in/out (synchronously, on the ctx stream);
+ *    `_dev` entry points take device pointers and only enqueue work on the ctx stream.
+ *  - Every function returns 0 on success, <0 on argument/CUDA errors (text via
+ *    speedy_last_error()), >0 for model range errors (check_diagnostics).
+ *  - One ctx per (GPU, member batch); calls on one ctx are serialised on its stream and
+ *    a ctx is not re-entrant (like the reference's module state).
+ *  - There is no CPU fallback: if no CUDA device is usable speedy_create fails.
+ */
+#ifndef SPEEDY_B200_H
+#define SPEEDY_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct speedy_ctx speedy_ctx;
+
+typedef struct speedy_cfg {
+    int trunc;     /* params.f90:19  30 (T30: ix=96, iy=24) or 47 (ix=144, iy=36) */
+    int kx;        /* params.f90:23  must be 8 */
+    int ntr;       /* params.f90:26  must be 1 */
+    int nmembers;  /* ensemble members batched in this ctx (outermost batch dim), >=1 */
+    int device;    /* CUDA device ordinal */
+    int sppt_on;   /* params.f90:42 */
+    unsigned long long seed; /* SPPT counter-RNG seed (sppt.f90:119-132 uses system_clock) */
+} speedy_cfg;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+/* initialize_geometry/spectral/geopotential/horizontal_diffusion/physics
+ * (initialization.f90:47-59): builds every table on the host and uploads it. */
+int speedy_create(const speedy_cfg* cfg, speedy_ctx** out);
+int speedy_destroy(speedy_ctx* ctx);
+const char* speedy_last_error(void);
+int speedy_synchronize(speedy_ctx* ctx);
+/* dims[8] = trunc, ix, iy, il, kx, nx, mx, ntr */
+int speedy_dims(const speedy_ctx* ctx, int* dims);
+/* Copy a named host table (e.g. "wt","cpol","epsi","el2","dmp","xj","fband", ...) */
+int speedy_get_table(const speedy_ctx* ctx, const char* name, double* out, size_t n);
+/* Replace a named table with the caller's own (a Fortran host passes the arrays its own
+ * initialize_* computed so that table arithmetic is shared bit for bit). */
+int speedy_set_table(speedy_ctx* ctx, const char* name, const double* in, size_t n);
+
+/* Host-only access to the start-up tables for a truncation (no GPU needed; the CPU test
+ * suite checks them against the oracle). */
+int speedy_host_table(int trunc, const char* name, double* out, size_t n);
+long long speedy_host_table_len(int trunc, const char* name);
+
+/* ---- transforms: legendre.f90 / fourier.f90 / spectral.f90 -------------------------- */
+/* spec_to_grid  spectral.f90:98-110 ; kcos[b]==1 -> no scaling, else * cosgr(j)
+ * (fourier.f90:47-51). spec: nbatch*complex(mx,nx); grid: nbatch*real(ix,il) */
+int speedy_spec_to_grid(speedy_ctx* ctx, const double* spec, int nbatch, const int* kcos, double* grid);
+/* grid_to_spec  spectral.f90:112-122 */
+int speedy_grid_to_spec(speedy_ctx* ctx, const double* grid, int nbatch, double* spec);
+/* legendre_inv  legendre.f90:74-111: real(2*mx,nx) -> real(2*mx,il) */
+int speedy_legendre_inv(speedy_ctx* ctx, const double* in, int nbatch, double* out);
+/* legendre_dir  legendre.f90:114-155: real(2*mx,il) -> real(2*mx,nx) */
+int speedy_legendre_dir(speedy_ctx* ctx, const double* in, int nbatch, double* out);
+/* fourier_inv   fourier.f90:23-53: real(2*mx,il) -> real(ix,il) */
+int speedy_fourier_inv(speedy_ctx* ctx, const double* in, int nbatch, const int* kcos, double* out);
+/* fourier_dir   fourier.f90:56-82: real(ix,il) -> real(2*mx,il) */
+int speedy_fourier_dir(speedy_ctx* ctx, const double* in, int nbatch, double* out);
+/* device-pointer variants (enqueue only; kcos stays a HOST array, NULL = all 1) */
+int speedy_spec_to_grid_dev(speedy_ctx* ctx, const double* d_spec, int nbatch, const int* kcos, double* d_grid);
+int speedy_grid_to_spec_dev(speedy_ctx* ctx, const double* d_grid, int nbatch, double* d_spec);
+
+/* ---- spectral operators: spectral.f90:84-96,124-233 --------------------------------- */
+int speedy_laplacian(speedy_ctx* ctx, const double* in, int nbatch, double* out);
+int speedy_inverse_laplacian(speedy_ctx* ctx, const double* in, int nbatch, double* out);
+int speedy_grad(speedy_ctx* ctx, const double* psi, int nbatch, double* psdx, double* psdy);
+int speedy_vds(speedy_ctx* ctx, const double* ucosm, const double* vcosm, int nbatch, double* vorm, double* divm);
+int speedy_uvspec(speedy_ctx* ctx, const double* vorm, const double* divm, int nbatch, double* ucosm, double* vcosm);
+int speedy_vdspec(speedy_ctx* ctx, const double* ug, const double* vg, int nbatch, int kcos, double* vorm, double* divm);
+int speedy_trunct(speedy_ctx* ctx, double* vor, int nbatch);
+
+/* ---- model state (prognostics.f90:16-24, module state of physics/slabs) --------------
+ * Named fields, each nmembers copies back to back.  Spectral prognostics:
+ *   "vor","div","t" complex(mx,nx,kx,2); "tr" complex(mx,nx,kx,2,ntr); "ps" complex(mx,nx,2);
+ *   "phi" complex(mx,nx,kx); "phis" complex(mx,nx);
+ * grid/surface/forcing fields: see speedy_field_names(). */
+int speedy_set_field(speedy_ctx* ctx, const char* name, const double* host, size_t n);
+int speedy_get_field(speedy_ctx* ctx, const char* name, double* host, size_t n);
+int speedy_get_ifield(speedy_ctx* ctx, const char* name, int* host, size_t n);
+const char* speedy_field_names(void);
+
+/* initialize_implicit(dt)  implicit.f90:36-165 (host LU, uploads xj,xc,xd,elz,dmp1*,tref*) */
+int speedy_initialize_implicit(speedy_ctx* ctx, double dt);
+/* get_geopotential  geopotential.f90:33-57 on the resident state: phi <- T(time level j) */
+int speedy_get_geopotential(speedy_ctx* ctx, int j);
+/* get_tendencies    tendencies.f90:11-37 (grid-point + spectral + implicit) into the
+ * resident tendency arrays ("vordt","divdt","tdt","trdt","psdt") */
+int speedy_get_tendencies(speedy_ctx* ctx, int j2, int compute_shortwave);
+/* get_physical_tendencies physics.f90:43-223 on host arrays (testing/drop-in form):
+ * spectral inputs complex(mx,nx,kx) [psl complex(mx,nx)], grid tendencies real(ix,il,kx) in/out */
+int speedy_get_physical_tendencies(speedy_ctx* ctx, const double* vor, const double* div, const double* t,
+                                   const double* q, const double* phi, const double* psl,
+                                   double* utend, double* vtend, double* ttend, double* qtend,
+                                   int compute_shortwave);
+/* step(j1,j2,dt)    time_stepping.f90:35-122 on the resident state */
+int speedy_step(speedy_ctx* ctx, int j1, int j2, double dt, int compute_shortwave);
+/* first_step        time_stepping.f90:12-24 */
+int speedy_first_step(speedy_ctx* ctx);
+/* couple_sea_land per-step slab update (land_model.f90:184-239, sea_model.f90:253-444);
+ * daily climatological inputs must have been set with speedy_set_field */
+int speedy_couple_sea_land(speedy_ctx* ctx, int day);
+/* set_forcing daily part that depends on resident state (forcing.f90:55-99):
+ * albedos, snow cover, tcorh/qcorh */
+int speedy_set_forcing(speedy_ctx* ctx, int imode);
+/* check_diagnostics diagnostics.f90:16-75: diag[kx*3] (reke, deke, temp per level), member 0..;
+ * returns 1 if out of range like the reference's `stop` */
+int speedy_check_diagnostics(speedy_ctx* ctx, int time_level, double* diag);
+/* main-loop body speedy.f90:27-54 repeated nsteps times with the state resident;
+ * `model_step` is the 1-based step counter of the reference (speedy.f90:21).
+ * Daily host-side inputs are pulled through the callback-free "env" below. */
+int speedy_run_steps(speedy_ctx* ctx, int nsteps);
+
+/* ---- model environment: boundaries.f90, forcing.f90, date.f90, land/sea init -------- */
+/* initialize (initialization.f90:12-82) from a boundary-condition source:
+ * `bc_path` is either a directory holding the reference's data/bc/t30 tree or a packed
+ * .bin produced by tools/pack_boundary.py.  Start date as in namelist.nml. */
+int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month, int day, int hour, int minute);
+/* current model date (date.f90:20) and step counter */
+int speedy_model_date(const speedy_ctx* ctx, int* ymdhm, long long* model_step);
+/* output() conversions input_output.f90:184-214: float32 u,v,t,q,phi (ix,il,kx) and ps (ix,il) */
+int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float* t, float* q, float* phi, float* ps);
+/* ensemble sums for the mean/spread diagnostic: writes sum and sum of squares of the 41
+ * output levels over this ctx's members into device buffers (for NCCL all-reduce) */
+int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq);
+size_t speedy_output_len(const speedy_ctx* ctx); /* (5*kx+1)*ix*il */
+
+/* host-resident drop-in step: uploads the prognostic state from host arrays, runs
+ * step(j1,j2,dt), downloads it (the literal replacement of `call step` with the Fortran
+ * module arrays left on the host).  state layout: vor,div,t,tr,ps concatenated. */
+int speedy_step_host(speedy_ctx* ctx, double* state, size_t n, int j1, int j2, double dt, int compute_shortwave);
+size_t speedy_state_len(const speedy_ctx* ctx);
+
+/* number of kernel launches issued by this ctx so far (bench.py's gpu_launches) */
+long long speedy_launch_count(const speedy_ctx* ctx);
+/* raw CUDA stream handle (cudaStream_t) for event timing from the host language */
+void* speedy_stream(const speedy_ctx* ctx);
+/* use CUDA graphs for speedy_run_steps (1, default) or plain launches (0) */
+int speedy_set_graphs(speedy_ctx* ctx, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

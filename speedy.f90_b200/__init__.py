@@ -1,0 +1,217 @@
+"""speedy.f90_b200 — host-side Python mirror of the reference's module interfaces
+(`spectral`, `legendre`, `fourier`, `tendencies`, `time_stepping`, `physics`) on top of the
+C ABI in include/speedy_b200.h.  The compute path is libspeedy_b200.so (hand-written CUDA
+for sm_100a); there is no CPU fallback: if the library or a GPU is missing, calls raise.
+
+Arrays follow the reference's Fortran layout.  In numpy (C order) that means spectral
+fields are complex128 arrays of shape (..., nx, mx) and grid fields float64 (..., il, ix).
+"""
+import ctypes
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIBPATH = os.path.join(_HERE, "libspeedy_b200.so")
+_lib = None
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+
+
+class SpeedyError(RuntimeError):
+    pass
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [("trunc", ctypes.c_int), ("kx", ctypes.c_int), ("ntr", ctypes.c_int),
+                ("nmembers", ctypes.c_int), ("device", ctypes.c_int), ("sppt_on", ctypes.c_int),
+                ("seed", ctypes.c_ulonglong)]
+
+
+def lib():
+    """Load libspeedy_b200.so (built in-tree by `make -C speedy.f90_b200`)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIBPATH):
+            raise SpeedyError(f"{_LIBPATH} not built: run __graft_entry__.build() / make -C speedy.f90_b200")
+        _lib = ctypes.CDLL(_LIBPATH)
+        for name, rt in (("speedy_last_error", ctypes.c_char_p), ("speedy_launch_count", ctypes.c_longlong),
+                         ("speedy_stream", ctypes.c_void_p), ("speedy_host_table_len", ctypes.c_longlong),
+                         ("speedy_output_len", ctypes.c_size_t), ("speedy_state_len", ctypes.c_size_t),
+                         ("speedy_field_names", ctypes.c_char_p)):
+            getattr(_lib, name).restype = rt
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _chk(rc):
+    if rc < 0:
+        raise SpeedyError(lib().speedy_last_error().decode())
+    return rc
+
+
+def host_table(trunc, name):
+    """Start-up table `name` for truncation `trunc`, built on the host (no GPU needed)."""
+    L = lib()
+    n = L.speedy_host_table_len(trunc, name.encode())
+    if n < 0:
+        raise SpeedyError(f"unknown table {name}")
+    out = np.zeros(n)
+    _chk(L.speedy_host_table(trunc, name.encode(), _p(out), ctypes.c_size_t(n)))
+    return out
+
+
+def _c(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Speedy:
+    """One context = one GPU + one batch of ensemble members (speedy_ctx)."""
+
+    def __init__(self, trunc=30, nmembers=1, device=0, sppt_on=0, seed=0):
+        L = lib()
+        cfg = Cfg(trunc, 8, 1, nmembers, device, sppt_on, seed)
+        h = ctypes.c_void_p()
+        _chk(L.speedy_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.h = h
+        self.L = L
+        d = (ctypes.c_int * 8)()
+        _chk(L.speedy_dims(h, d))
+        self.trunc, self.ix, self.iy, self.il, self.kx, self.nx, self.mx, self.ntr = list(d)
+        self.nmembers = nmembers
+
+    def close(self):
+        if self.h:
+            self.L.speedy_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables -------------------------------------------------------------------
+    def table(self, name, n):
+        out = np.zeros(n)
+        _chk(self.L.speedy_get_table(self.h, name.encode(), _p(out), ctypes.c_size_t(n)))
+        return out
+
+    def set_table(self, name, arr):
+        a = _c(arr, np.float64).ravel()
+        _chk(self.L.speedy_set_table(self.h, name.encode(), _p(a), ctypes.c_size_t(a.size)))
+
+    # ---- module spectral / legendre / fourier ----------------------------------------
+    def _batch(self, a, tail):
+        a = np.asarray(a)
+        if a.shape[-len(tail):] != tuple(tail):
+            raise ValueError(f"expected trailing shape {tail}, got {a.shape}")
+        lead = a.shape[:-len(tail)]
+        return lead, int(np.prod(lead)) if lead else 1
+
+    def spec_to_grid(self, vorm, kcos=1):
+        """spectral.f90:98 — vorm complex (..., nx, mx) -> grid (..., il, ix)."""
+        lead, nb = self._batch(vorm, (self.nx, self.mx))
+        a = _c(vorm, np.complex128)
+        k = np.broadcast_to(np.asarray(kcos, dtype=np.int32), lead).astype(np.int32).ravel() if lead else np.array([kcos], np.int32)
+        k = _c(k, np.int32)
+        out = np.empty(lead + (self.il, self.ix))
+        _chk(self.L.speedy_spec_to_grid(self.h, _p(a), nb, _p(k), _p(out)))
+        return out
+
+    def grid_to_spec(self, vorg):
+        """spectral.f90:112 — grid (..., il, ix) -> complex (..., nx, mx)."""
+        lead, nb = self._batch(vorg, (self.il, self.ix))
+        a = _c(vorg, np.float64)
+        out = np.empty(lead + (self.nx, self.mx), dtype=np.complex128)
+        _chk(self.L.speedy_grid_to_spec(self.h, _p(a), nb, _p(out)))
+        return out
+
+    def legendre_inv(self, x):
+        """legendre.f90:74 — real (..., nx, 2mx) -> (..., il, 2mx)."""
+        lead, nb = self._batch(x, (self.nx, 2 * self.mx))
+        a = _c(x, np.float64)
+        out = np.empty(lead + (self.il, 2 * self.mx))
+        _chk(self.L.speedy_legendre_inv(self.h, _p(a), nb, _p(out)))
+        return out
+
+    def legendre_dir(self, x):
+        """legendre.f90:114 — real (..., il, 2mx) -> (..., nx, 2mx)."""
+        lead, nb = self._batch(x, (self.il, 2 * self.mx))
+        a = _c(x, np.float64)
+        out = np.empty(lead + (self.nx, 2 * self.mx))
+        _chk(self.L.speedy_legendre_dir(self.h, _p(a), nb, _p(out)))
+        return out
+
+    def fourier_inv(self, x, kcos=1):
+        """fourier.f90:23 — real (..., il, 2mx) -> (..., il, ix)."""
+        lead, nb = self._batch(x, (self.il, 2 * self.mx))
+        a = _c(x, np.float64)
+        k = np.full(nb, kcos, dtype=np.int32)
+        out = np.empty(lead + (self.il, self.ix))
+        _chk(self.L.speedy_fourier_inv(self.h, _p(a), nb, _p(k), _p(out)))
+        return out
+
+    def fourier_dir(self, x):
+        """fourier.f90:56 — real (..., il, ix) -> (..., il, 2mx)."""
+        lead, nb = self._batch(x, (self.il, self.ix))
+        a = _c(x, np.float64)
+        out = np.empty(lead + (self.il, 2 * self.mx))
+        _chk(self.L.speedy_fourier_dir(self.h, _p(a), nb, _p(out)))
+        return out
+
+    def _op2(self, fn, a, b, two_out=True):
+        lead, nb = self._batch(a, (self.nx, self.mx))
+        a = _c(a, np.complex128)
+        o1 = np.empty_like(a)
+        o2 = np.empty_like(a)
+        if b is None:
+            _chk(fn(self.h, _p(a), nb, _p(o1), _p(o2)) if two_out else fn(self.h, _p(a), nb, _p(o1)))
+        else:
+            b = _c(b, np.complex128)
+            _chk(fn(self.h, _p(a), _p(b), nb, _p(o1), _p(o2)))
+        return (o1, o2) if two_out else o1
+
+    def laplacian(self, x):
+        return self._op2(self.L.speedy_laplacian, x, None, two_out=False)
+
+    def inverse_laplacian(self, x):
+        return self._op2(self.L.speedy_inverse_laplacian, x, None, two_out=False)
+
+    def grad(self, psi):
+        return self._op2(self.L.speedy_grad, psi, None)
+
+    def vds(self, ucosm, vcosm):
+        return self._op2(self.L.speedy_vds, ucosm, vcosm)
+
+    def uvspec(self, vorm, divm):
+        return self._op2(self.L.speedy_uvspec, vorm, divm)
+
+    def trunct(self, x):
+        lead, nb = self._batch(x, (self.nx, self.mx))
+        a = _c(x, np.complex128).copy()
+        _chk(self.L.speedy_trunct(self.h, _p(a), nb))
+        return a
+
+    def vdspec(self, ug, vg, kcos=2):
+        lead, nb = self._batch(ug, (self.il, self.ix))
+        a = _c(ug, np.float64)
+        b = _c(vg, np.float64)
+        o1 = np.empty(lead + (self.nx, self.mx), dtype=np.complex128)
+        o2 = np.empty_like(o1)
+        _chk(self.L.speedy_vdspec(self.h, _p(a), _p(b), nb, kcos, _p(o1), _p(o2)))
+        return o1, o2
+
+    # ---- misc -----------------------------------------------------------------------
+    def synchronize(self):
+        _chk(self.L.speedy_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return self.L.speedy_launch_count(self.h)
+
+    @property
+    def stream(self):
+        return self.L.speedy_stream(self.h)

@@ -1,0 +1,104 @@
+// Internal context of the speedy_b200 library (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <stdexcept>
+#include "host/tables.h"
+
+namespace spd {
+
+// Device-side view of the constant tables (passed to kernels by value; < 1 KB)
+struct DevTables {
+    int trunc, ix, iy, il, kx, nx, mx;
+    const double* poly;     // [iy][nx][mx]
+    const double* finv;     // [ix][k2pad]
+    const double* ffwd;     // [k2pad][ix]
+    const double* wt;       // iy
+    const double* cosgr;    // il
+    const double* cosgr2;   // il
+    const double* coriol;   // il
+    const double* cosg;     // il
+    const double* sia;      // il
+    const double* coa;      // il
+    // spectral operator tables (mx,nx) m fastest
+    const double *el2, *elm2, *trfilt, *gradx, *gradym, *gradyp, *uvdx, *uvdym, *uvdyp, *vddym, *vddyp;
+    // dynamics
+    const double *dmp, *dmpd, *dmps, *dmp1, *dmp1d, *dmp1s, *elz;
+    const double *xj, *xc, *xd;          // Fortran order (kx,kx[,l])
+    const double* fband;                 // (301,4)
+};
+
+// small per-level constants go to __constant__ memory (see consts.cuh)
+struct LevelConsts {
+    double hsg[9], dhs[8], fsg[8], dhsr[8], fsgr[8];
+    double tref[8], tref1[8], tref2[8], tref3[8], dhsx[8];
+    double xgeop1[8], xgeop2[8], geop_corf[8];
+    double tcorv[8], qcorv[8];
+    double sigl[8], sigh[9], grdsig[8], grdscp[8], wvi[16];
+    double rgas, akap, cp, p0, grav, alhc, alhs, sbc, rearth, refrh1;
+    double rob, wil, sdrag;
+};
+
+// descriptor of one transform in a batch
+struct XDesc {
+    long long off;   // element (double) offset of the field relative to the member base pointer
+    int flags;       // K1: bit0 scale by cosgr(j), bit1 add coriol(j);  K2: bit0 scale by cosgr, bit1 scale by cosgr2
+    int pad;
+};
+
+#define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    void alloc(size_t cnt) { free(); n = cnt; if (cnt) { CUDA_CHECK(cudaMalloc(&p, cnt * sizeof(T))); CUDA_CHECK(cudaMemset(p, 0, cnt * sizeof(T))); } }
+    void upload(const std::vector<T>& v) { if (v.size() != n) alloc(v.size()); if (n) CUDA_CHECK(cudaMemcpy(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice)); }
+    void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free(); }
+};
+
+struct Model;   // model.h
+
+}  // namespace spd
+
+struct speedy_ctx {
+    spd::Tables tab;
+    spd::Dims d;
+    int nmembers = 1;
+    int device = 0;
+    int sppt_on = 0;
+    unsigned long long seed = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    bool use_graphs = true;
+    // device tables
+    std::map<std::string, spd::DevBuf<double>> dtab;
+    spd::DevTables dv;
+    // scratch for host-pointer API calls
+    spd::DevBuf<double> scratch_a, scratch_b, scratch_c, scratch_d;
+    std::map<unsigned long long, spd::DevBuf<spd::XDesc>> desc_cache;
+    spd::Model* model = nullptr;
+    void ensure_scratch(spd::DevBuf<double>& b, size_t n) { if (b.n < n) b.alloc(n); }
+};
+
+namespace spd {
+void upload_tables(speedy_ctx* ctx);            // abi.cu
+void upload_implicit(speedy_ctx* ctx);          // abi.cu
+void upload_level_consts(speedy_ctx* ctx);      // consts in dynamics.cu
+
+// transforms.cu ----------------------------------------------------------------------
+// mode: 0 full spec->grid, 1 legendre_inv only (out = (2mx,il)), 2 fourier_inv only (in = (2mx,il))
+void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
+                         const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
+                         int nmembers, int mode);
+// mode: 0 full grid->spec, 1 fourier_dir only (out = (2mx,il)), 2 legendre_dir only (in = (2mx,il))
+void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
+                         const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
+                         int nmembers, int mode);
+void setup_transform_kernels();
+// spectral_ops.cu ---------------------------------------------------------------------
+void launch_spectral_op(speedy_ctx* ctx, int op, const double* a, const double* b, double* o1, double* o2, int nbatch);
+enum { OP_LAPLACIAN = 0, OP_INVLAPLACIAN, OP_GRAD, OP_VDS, OP_UVSPEC, OP_TRUNCT };
+}  // namespace spd

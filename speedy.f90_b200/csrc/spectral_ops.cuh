@@ -1,0 +1,69 @@
+// Device inline forms of the reference's spectral operators (spectral.f90:84-96,124-233).
+// Fields are complex(mx,nx), interleaved (re,im), m fastest.  All operators are
+// 3-point stencils in n at fixed m; `f(m,n)` style accessors read global memory.
+#pragma once
+#include "ctx.h"
+
+namespace spd {
+
+struct cd { double re, im; };
+__device__ __forceinline__ cd ld(const double* f, int mx, int m, int n) {
+    const double2 v = *reinterpret_cast<const double2*>(f + 2 * (m + (size_t)mx * n));
+    return cd{v.x, v.y};
+}
+__device__ __forceinline__ void st(double* f, int mx, int m, int n, cd v) {
+    *reinterpret_cast<double2*>(f + 2 * (m + (size_t)mx * n)) = make_double2(v.re, v.im);
+}
+__device__ __forceinline__ cd operator*(double a, cd b) { return cd{a * b.re, a * b.im}; }
+__device__ __forceinline__ cd operator+(cd a, cd b) { return cd{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cd operator-(cd a, cd b) { return cd{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ cd neg(cd a) { return cd{-a.re, -a.im}; }
+__device__ __forceinline__ cd times_i(cd a) { return cd{-a.im, a.re}; }
+
+// uvspec  spectral.f90:173-196
+__device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vor, const double* div, int m, int n, cd& uc, cd& vc) {
+    const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
+    const size_t q = m + (size_t)mx * n;
+    const cd zp = times_i(tv.uvdx[q] * ld(vor, mx, m, n));
+    const cd zc = times_i(tv.uvdx[q] * ld(div, mx, m, n));
+    if (n == 0) {
+        uc = zc - tv.uvdyp[q] * ld(vor, mx, m, 1);
+        vc = zp + tv.uvdyp[q] * ld(div, mx, m, 1);
+    } else if (n == nx - 1) {
+        uc = tv.uvdym[q] * ld(vor, mx, m, tr);
+        vc = neg(tv.uvdym[q] * ld(div, mx, m, tr));
+    } else {
+        vc = (neg(tv.uvdym[q] * ld(div, mx, m, n - 1)) + tv.uvdyp[q] * ld(div, mx, m, n + 1)) + zp;
+        uc = (tv.uvdym[q] * ld(vor, mx, m, n - 1) - tv.uvdyp[q] * ld(vor, mx, m, n + 1)) + zc;
+    }
+}
+
+// grad  spectral.f90:124-144
+__device__ __forceinline__ void dev_grad(const DevTables& tv, const double* psi, int m, int n, cd& dx, cd& dy) {
+    const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
+    const size_t q = m + (size_t)mx * n;
+    dx = times_i(tv.gradx[m] * ld(psi, mx, m, n));
+    if (n == 0) dy = tv.gradyp[q] * ld(psi, mx, m, 1);
+    else if (n == nx - 1) dy = neg(tv.gradym[q] * ld(psi, mx, m, tr));
+    else dy = neg(tv.gradym[q] * ld(psi, mx, m, n - 1)) + tv.gradyp[q] * ld(psi, mx, m, n + 1);
+}
+
+// vds  spectral.f90:146-171
+__device__ __forceinline__ void dev_vds(const DevTables& tv, const double* uc, const double* vc, int m, int n, cd& vor, cd& div) {
+    const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
+    const size_t q = m + (size_t)mx * n;
+    const cd zp = times_i(tv.gradx[m] * ld(uc, mx, m, n));
+    const cd zc = times_i(tv.gradx[m] * ld(vc, mx, m, n));
+    if (n == 0) {
+        vor = zc - tv.vddyp[q] * ld(uc, mx, m, 1);
+        div = zp + tv.vddyp[q] * ld(vc, mx, m, 1);
+    } else if (n == nx - 1) {
+        vor = tv.vddym[q] * ld(uc, mx, m, tr);
+        div = neg(tv.vddym[q] * ld(vc, mx, m, tr));
+    } else {
+        vor = (tv.vddym[q] * ld(uc, mx, m, n - 1) - tv.vddyp[q] * ld(uc, mx, m, n + 1)) + zc;
+        div = (neg(tv.vddym[q] * ld(vc, mx, m, n - 1)) + tv.vddyp[q] * ld(vc, mx, m, n + 1)) + zp;
+    }
+}
+
+}  // namespace spd
