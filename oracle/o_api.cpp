@@ -1,6 +1,12 @@
 /* ORACLE (test infrastructure) — extern "C" surface used by tests/ via ctypes. */
 #include "oracle.h"
 #include <string>
+#include <map>
+namespace orc {
+extern FA<int, ix, il> dbg_iptop, dbg_icnv;
+extern FA<int, ix, il, 2> dbg_icltop;
+extern Grid3 dbg_tt_rsw;
+}
 using namespace orc;
 
 extern "C" {
@@ -82,5 +88,137 @@ int orc_vdspec(const double* ug, const double* vg, double* vorm, double* divm, i
 int orc_laplacian(const double* in, double* out) { laplacian((const cplx*)in, (cplx*)out); return 0; }
 int orc_inverse_laplacian(const double* in, double* out) { inverse_laplacian((const cplx*)in, (cplx*)out); return 0; }
 int orc_trunct(double* x) { trunct((cplx*)x); return 0; }
+
+
+/* ======================= model-level surface ======================= */
+struct FieldRef { double* p; size_t n; };
+static std::map<std::string, FieldRef>& registry() {
+    static std::map<std::string, FieldRef> r;
+    if (r.empty()) {
+#define REG(name, obj) r[name] = FieldRef{reinterpret_cast<double*>((obj).p()), (obj).size() * sizeof(*(obj).p()) / sizeof(double)}
+        REG("vor", vor); REG("div", div_); REG("t", t); REG("tr", tr); REG("ps", ps); REG("phi", phi); REG("phis", phis);
+        REG("tcorh", tcorh); REG("qcorh", qcorh);
+        REG("precnv", precnv); REG("precls", precls); REG("cbmf", cbmf); REG("tsr", tsr); REG("ssrd", ssrd); REG("ssr", ssr);
+        REG("slrd", slrd); REG("slr", slr); REG("olr", olr); REG("slru", slru); REG("ustr", ustr); REG("vstr", vstr);
+        REG("shf", shf); REG("evap", evap); REG("hfluxn", hfluxn);
+        REG("alb_l", alb_l); REG("alb_s", alb_s); REG("albsfc", albsfc); REG("snowc", snowc);
+        REG("tau2", tau2); REG("st4a", st4a); REG("stratc", stratc); REG("flux", flux);
+        REG("fsol", fsol); REG("ozone", ozone); REG("ozupp", ozupp); REG("zenit", zenit); REG("stratz", stratz); REG("qcloud", qcloud);
+        REG("forog", forog); REG("fmask", fmask); REG("phi0", phi0); REG("phis0", phis0); REG("alb0", alb0);
+        REG("stl_am", stl_am); REG("snowd_am", snowd_am); REG("soilw_am", soilw_am); REG("fmask_l", fmask_l); REG("stl_lm", stl_lm);
+        REG("fmask_s", fmask_s); REG("sstcl_ob", sstcl_ob); REG("sst_am", sst_am); REG("sice_am", sice_am); REG("tice_am", tice_am);
+        REG("ssti_om", ssti_om); REG("sst_om", sst_om); REG("tice_om", tice_om); REG("sice_om", sice_om);
+        REG("tt_rsw", dbg_tt_rsw); REG("fband", fband); REG("sppt_eta", sppt_eta);
+        REG("dmp", dmp); REG("dmpd", dmpd); REG("dmps", dmps); REG("dmp1", dmp1); REG("dmp1d", dmp1d); REG("dmp1s", dmp1s);
+        REG("xj", xj); REG("xc", xc); REG("xd", xd); REG("elz", elz);
+#undef REG
+    }
+    return r;
+}
+
+int orc_get_field(const char* name, double* out, long long n) {
+    auto& r = registry();
+    auto it = r.find(name);
+    if (it == r.end()) return -1;
+    if ((long long)it->second.n != n) return -2;
+    memcpy(out, it->second.p, sizeof(double) * n);
+    return 0;
+}
+int orc_set_field(const char* name, const double* in, long long n) {
+    auto& r = registry();
+    auto it = r.find(name);
+    if (it == r.end()) return -1;
+    if ((long long)it->second.n != n) return -2;
+    memcpy(it->second.p, in, sizeof(double) * n);
+    return 0;
+}
+long long orc_field_len(const char* name) {
+    auto& r = registry();
+    auto it = r.find(name);
+    return it == r.end() ? -1 : (long long)it->second.n;
+}
+int orc_get_ifield(const char* name, int* out, long long n) {
+    std::string s(name);
+    const int* src = nullptr; size_t cnt = 0;
+    if (s == "iptop") { src = dbg_iptop.p(); cnt = dbg_iptop.size(); }
+    else if (s == "icnv") { src = dbg_icnv.p(); cnt = dbg_icnv.size(); }
+    else if (s == "icltop") { src = dbg_icltop.p(); cnt = (size_t)ix * il; }
+    else return -1;
+    if ((long long)cnt != n) return -2;
+    memcpy(out, src, sizeof(int) * cnt);
+    return 0;
+}
+/* kx-vectors and scalars of the implicit scheme / physics constants */
+int orc_get_vec(const char* name, double* out, int n) {
+    std::string s(name);
+    const double* src = nullptr; int cnt = kx;
+    if (s == "tref") src = tref + 1; else if (s == "tref1") src = tref1 + 1; else if (s == "tref2") src = tref2 + 1;
+    else if (s == "tref3") src = tref3 + 1; else if (s == "dhsx") src = dhsx + 1; else if (s == "tcorv") src = tcorv + 1;
+    else if (s == "qcorv") src = qcorv + 1; else if (s == "xgeop1") src = xgeop1 + 1; else if (s == "xgeop2") src = xgeop2 + 1;
+    else if (s == "sigl") src = sigl + 1; else if (s == "grdsig") src = grdsig + 1; else if (s == "grdscp") src = grdscp + 1;
+    else if (s == "sigh") { src = sigh; cnt = kx + 1; }
+    else if (s == "wvi") { src = wvi.p(); cnt = 2 * kx; }
+    else return -1;
+    if (cnt != n) return -2;
+    memcpy(out, src, sizeof(double) * cnt);
+    return 0;
+}
+
+int orc_model_init(const char* bc_file, int y, int m, int d, int h, int mi) {
+    g_init_transforms = true;
+    return model_initialize(bc_file, y, m, d, h, mi);
+}
+int orc_model_run(int nsteps_to_run) { return model_run_steps(nsteps_to_run); }
+int orc_model_date(int* ymdhm, long long* step) {
+    ymdhm[0] = model_datetime.year; ymdhm[1] = model_datetime.month; ymdhm[2] = model_datetime.day;
+    ymdhm[3] = model_datetime.hour; ymdhm[4] = model_datetime.minute; *step = model_step;
+    return 0;
+}
+int orc_set_date_fractions(double tmonth_, double tyear_, int imont1_) { tmonth = tmonth_; tyear = tyear_; imont1 = imont1_; return 0; }
+int orc_initialize_implicit(double dt) { initialize_implicit(dt); return 0; }
+int orc_step(int j1, int j2, double dt, int csw) { compute_shortwave = csw != 0; step(j1, j2, dt); return 0; }
+int orc_set_sppt(int on) { sppt_on = on != 0; if (on) sppt_reset(); return 0; }
+int orc_get_geopotential(const double* tt, const double* phis_, double* phi_) {
+    get_geopotential((const cplx*)tt, (const cplx*)phis_, (cplx*)phi_); return 0; }
+/* get_tendencies on the resident state */
+int orc_get_tendencies(int j2, int csw, double* vordt, double* divdt, double* tdt, double* psdt, double* trdt) {
+    static Spec3 a, b, c; static Spec2 d; static FA<cplx, mx, nx, kx, ntr> e;
+    compute_shortwave = csw != 0;
+    get_tendencies(a, b, c, d, e, j2);
+    memcpy(vordt, a.p(), sizeof(cplx) * a.size()); memcpy(divdt, b.p(), sizeof(cplx) * b.size());
+    memcpy(tdt, c.p(), sizeof(cplx) * c.size()); memcpy(psdt, d.p(), sizeof(cplx) * d.size());
+    memcpy(trdt, e.p(), sizeof(cplx) * e.size());
+    return 0;
+}
+/* physics.f90:43 on caller-supplied spectral inputs and grid tendencies (in/out) */
+int orc_get_physical_tendencies(const double* vor_, const double* divv, const double* tt, const double* q, const double* phi_, const double* psl,
+                                double* utend, double* vtend, double* ttend, double* qtend, int csw) {
+    static Grid3 u, v, w, x;
+    compute_shortwave = csw != 0;
+    memcpy(u.p(), utend, sizeof(double) * u.size()); memcpy(v.p(), vtend, sizeof(double) * u.size());
+    memcpy(w.p(), ttend, sizeof(double) * u.size()); memcpy(x.p(), qtend, sizeof(double) * u.size());
+    get_physical_tendencies((const cplx*)vor_, (const cplx*)divv, (const cplx*)tt, (const cplx*)q, (const cplx*)phi_, (const cplx*)psl, u, v, w, x);
+    memcpy(utend, u.p(), sizeof(double) * u.size()); memcpy(vtend, v.p(), sizeof(double) * u.size());
+    memcpy(ttend, w.p(), sizeof(double) * u.size()); memcpy(qtend, x.p(), sizeof(double) * u.size());
+    return 0;
+}
+int orc_check_diagnostics(int level, double* diag) {
+    return check_diagnostics(vor.p(1, 1, 1, level), div_.p(1, 1, 1, level), t.p(1, 1, 1, level), model_step, diag, false);
+}
+/* input_output.f90:184-206: float32 u,v,t,q,phi (ix,il,kx), ps (ix,il) from time level 1 */
+int orc_output_fields(float* u, float* v, float* tt, float* q, float* ph, float* pso) {
+    static Spec2 ucos, vcos; static Grid2 g;
+    const size_t N = (size_t)ix * il;
+    for (int k = 1; k <= kx; k++) {
+        uvspec(vor.p(1, 1, k, 1), div_.p(1, 1, k, 1), ucos.p(), vcos.p());
+        spec_to_grid(ucos.p(), 2, g.p()); for (size_t i = 0; i < N; i++) u[N * (k - 1) + i] = (float)g.d[i];
+        spec_to_grid(vcos.p(), 2, g.p()); for (size_t i = 0; i < N; i++) v[N * (k - 1) + i] = (float)g.d[i];
+        spec_to_grid(t.p(1, 1, k, 1), 1, g.p()); for (size_t i = 0; i < N; i++) tt[N * (k - 1) + i] = (float)g.d[i];
+        spec_to_grid(tr.p(1, 1, k, 1, 1), 1, g.p()); for (size_t i = 0; i < N; i++) q[N * (k - 1) + i] = (float)(g.d[i] * (double)1.0e-3f);
+        spec_to_grid(phi.p(1, 1, k), 1, g.p()); for (size_t i = 0; i < N; i++) ph[N * (k - 1) + i] = (float)(g.d[i] / grav);
+    }
+    spec_to_grid(ps.p(1, 1, 1), 1, g.p()); for (size_t i = 0; i < N; i++) pso[i] = (float)(p0 * exp(g.d[i]));
+    return 0;
+}
 
 }  // extern "C"

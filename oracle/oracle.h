@@ -140,4 +140,101 @@ void uvspec(const cplx* vorm, const cplx* divm, cplx* ucosm, cplx* vcosm);
 void vdspec(const double* ug, const double* vg, cplx* vorm, cplx* divm, int kcos);
 void trunct(cplx* vor);
 
+
+/* ======================= model state and procedures (o_dynamics / o_physics / o_env) ======================= */
+typedef FA<cplx, mx, nx, kx, 2> Spec4;
+
+/* prognostics.f90:16-24 */
+extern Spec4 vor, div_, t;
+extern FA<cplx, mx, nx, 2> ps;
+extern FA<cplx, mx, nx, kx, 2, ntr> tr;
+extern Spec3 phi;
+extern Spec2 phis;
+void initialize_prognostics();
+
+/* geopotential.f90 */
+extern double xgeop1[kx + 1], xgeop2[kx + 1];
+void initialize_geopotential();
+void get_geopotential(const cplx* t /*(mx,nx,kx)*/, const cplx* phis /*(mx,nx)*/, cplx* phi /*(mx,nx,kx)*/);
+
+/* horizontal_diffusion.f90 */
+extern FA<double, mx, nx> dmp, dmpd, dmps, dmp1, dmp1d, dmp1s;
+extern double tcorv[kx + 1], qcorv[kx + 1];
+extern Spec2 tcorh, qcorh;
+void initialize_horizontal_diffusion();
+
+/* implicit.f90 */
+extern double tref[kx + 1], tref1[kx + 1], tref2[kx + 1], tref3[kx + 1], dhsx[kx + 1];
+extern FA<double, kx, kx> xa, xb, xc, xd, xe;
+extern FA<double, kx, kx, mx + nx + 1> xf, xj;
+extern FA<double, mx, nx> elz;
+void initialize_implicit(double dt);
+void implicit_terms(Spec3& divdt, Spec3& tdt, Spec2& psdt);
+
+/* tendencies.f90 / time_stepping.f90 */
+void get_tendencies(Spec3& vordt, Spec3& divdt, Spec3& tdt, Spec2& psdt, FA<cplx, mx, nx, kx, ntr>& trdt, int j2);
+void step(int j1, int j2, double dt);
+void first_step();
+
+/* diagnostics.f90: returns 1 when the reference would `stop` */
+int check_diagnostics(const cplx* vor, const cplx* div, const cplx* t, int istep, double* diag /*(kx,3)*/, bool print);
+
+/* physical_constants.f90:31-37 / physics.f90 */
+extern double sigl[kx + 1], sigh[kx + 1] /*0..kx*/, grdsig[kx + 1], grdscp[kx + 1];
+extern FA<double, kx, 2> wvi;
+void initialize_physics();
+void get_physical_tendencies(const cplx* vor, const cplx* div, const cplx* t, const cplx* q, const cplx* phi, const cplx* psl,
+                             Grid3& utend, Grid3& vtend, Grid3& ttend, Grid3& qtend);
+
+/* auxiliaries.f90 */
+extern Grid2 precnv, precls, snowcv, snowls, cbmf, tsr, ssrd, ssr, slrd, slr, olr;
+extern FA<double, ix, il, 3> slru, ustr, vstr, shf, evap, hfluxn;
+
+/* mod_radcon.f90 */
+extern double albsea, albice, albsn, epslw, emisfc, ablco2_ref;
+extern FA<double, 301, 4> fband; /* fband(100:400,4): first index = T-99 */
+extern Grid2 alb_l, alb_s, albsfc, snowc;
+extern FA<double, ix, il, kx, 4> tau2;
+extern FA<double, ix, il, kx, 2> st4a;
+extern FA<double, ix, il, 2> stratc;
+extern FA<double, ix, il, 4> flux;
+
+/* shortwave_radiation.f90 */
+extern double ablco2;
+extern Grid2 fsol, ozone, ozupp, zenit, stratz, qcloud;
+extern bool compute_shortwave;
+void get_zonal_average_fields(double tyear);
+void radset();
+
+/* surface_fluxes.f90 */
+extern Grid2 forog;
+void set_orog_land_sfc_drag(const Grid2& phi0);
+
+/* humidity.f90 */
+void get_qsat(const double* ta, const double* ps, double sig, double* qsat); /* (ix,il) */
+
+/* boundaries.f90 */
+extern Grid2 fmask, phi0, phis0, alb0;
+/* land_model.f90 / sea_model.f90 public state */
+extern Grid2 stl_am, snowd_am, soilw_am, fmask_l, stl_lm;
+extern Grid2 fmask_s, sstcl_ob, sst_am, sice_am, tice_am, ssti_om, sst_om, tice_om, sice_om;
+extern int sea_coupling_flag;
+
+/* date.f90 */
+struct DateTime { int year, month, day, hour, minute; };
+extern DateTime model_datetime, start_datetime, end_datetime;
+extern int imont1, isst0;
+extern double tmonth, tyear;
+
+/* sppt.f90 */
+extern bool sppt_on;
+extern Spec3 sppt_eta;   /* test hook: the Gaussian noise eta(m,n,k) is supplied by the caller (the reference seeds from system_clock) */
+void gen_sppt(Grid3& sppt_grid);
+void sppt_reset();
+
+/* initialization.f90 / speedy.f90 driver (o_env.cpp) */
+int model_initialize(const char* bc_file, int y, int m, int d, int h, int mi);
+int model_run_steps(int nsteps_to_run);   /* main-loop body speedy.f90:27-54; returns 1 on diagnostics stop */
+extern int model_step;
+
 }  // namespace orc
