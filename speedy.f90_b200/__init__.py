@@ -13,6 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIBPATH = os.path.join(_HERE, "libspeedy_b200.so")
 _lib = None
+BC_T30 = os.path.join(os.path.dirname(_HERE), "data", "bc_t30.bin")   # packed reference boundary files (tools/pack_boundary.py)
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 
@@ -39,6 +40,13 @@ def lib():
                          ("speedy_output_len", ctypes.c_size_t), ("speedy_state_len", ctypes.c_size_t),
                          ("speedy_field_names", ctypes.c_char_p)):
             getattr(_lib, name).restype = rt
+        _lib.speedy_set_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        _lib.speedy_get_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        _lib.speedy_get_ifield.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
+        _lib.speedy_get_physical_tendencies.argtypes = [ctypes.c_void_p] * 11 + [ctypes.c_int]
+        _lib.speedy_output_fields.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        _lib.speedy_step_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        _lib.speedy_model_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.c_int] * 5
     return _lib
 
 
@@ -203,6 +211,113 @@ class Speedy:
         o2 = np.empty_like(o1)
         _chk(self.L.speedy_vdspec(self.h, _p(a), _p(b), nb, kcos, _p(o1), _p(o2)))
         return o1, o2
+
+
+    # ---- model state (prognostics.f90 / physics / slab module state) -------------------
+    def field_len(self, name):
+        shapes = self.field_shapes()
+        return int(np.prod(shapes[name][0]))
+
+    def field_shapes(self):
+        """name -> (numpy shape, dtype) per member, C order (= reversed Fortran shape)."""
+        nx, mx, kx, il, ix = self.nx, self.mx, self.kx, self.il, self.ix
+        c, f = np.complex128, np.float64
+        sh = {"vor": ((2, kx, nx, mx), c), "div": ((2, kx, nx, mx), c), "t": ((2, kx, nx, mx), c), "tr": ((2, kx, nx, mx), c),
+              "ps": ((2, nx, mx), c), "phi": ((kx, nx, mx), c), "phis": ((nx, mx), c), "tcorh": ((nx, mx), c), "qcorh": ((nx, mx), c),
+              "vordt": ((kx, nx, mx), c), "divdt": ((kx, nx, mx), c), "tdt": ((kx, nx, mx), c), "trdt": ((kx, nx, mx), c), "psdt": ((nx, mx), c),
+              "sppt_spec": ((kx, nx, mx), c), "sppt_eta": ((kx, nx, mx), c), "sprep": ((34, nx, mx), c), "sout": ((73, nx, mx), c),
+              "gin": ((99, il, ix), f), "gout": ((73, il, ix), f), "sstan3": ((3, il, ix), f), "tau2": ((4, kx, il, ix), f),
+              "stratc": ((2, il, ix), f), "tt_rsw": ((kx, il, ix), f)}
+        for n in ("slru", "ustr", "vstr", "shf", "evap", "hfluxn"):
+            sh[n] = ((3, il, ix), f)
+        for n in ("phis0 fmask_l fmask_s forog alb0 fsol ozone ozupp zenit stratz alb_l alb_s albsfc snowc stl_am stl_lm snowd_am "
+                  "soilw_am sst_am sice_am tice_am ssti_om sst_om tice_om sice_om sstcl_ob sicecl_ob ticecl_ob stlcl_ob ssrd ssr tsr "
+                  "precnv precls cbmf slrd slr olr ts tskin u0 v0 t0 qcloud cloudc clstr qcorh_g").split():
+            sh[n] = ((il, ix), f)
+        for n in ("iptop", "icltop", "icnv"):
+            sh[n] = ((il, ix), np.int32)
+        return sh
+
+    def get_field(self, name, all_members=False):
+        shape, dt = self.field_shapes()[name]
+        lead = (self.nmembers,) if all_members else ()
+        out = np.empty(lead + shape, dtype=dt)
+        if dt == np.int32:
+            _chk(self.L.speedy_get_ifield(self.h, name.encode(), _p(out), ctypes.c_size_t(out.size)))
+        else:
+            _chk(self.L.speedy_get_field(self.h, name.encode(), _p(out), ctypes.c_size_t(out.size * (2 if dt == np.complex128 else 1))))
+        return out
+
+    def set_field(self, name, arr):
+        """arr has the per-member shape (broadcast to all members) or a leading nmembers axis."""
+        shape, dt = self.field_shapes()[name]
+        a = _c(arr, dt)
+        if a.shape != shape and a.shape != (self.nmembers,) + shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
+        _chk(self.L.speedy_set_field(self.h, name.encode(), _p(a), ctypes.c_size_t(a.size * (2 if dt == np.complex128 else 1))))
+
+    # ---- module time_stepping / tendencies / physics / coupler -------------------------------
+    def model_init(self, bc_path, year=1982, month=1, day=1, hour=0, minute=0):
+        """initialization.f90:12 — boundary data, rest state, coupler, forcing, first_step."""
+        _chk(self.L.speedy_model_init(self.h, str(bc_path).encode(), year, month, day, hour, minute))
+
+    def initialize_implicit(self, dt):
+        _chk(self.L.speedy_initialize_implicit(self.h, ctypes.c_double(dt)))
+
+    def step(self, j1, j2, dt, compute_shortwave=True):
+        """time_stepping.f90:35 on the resident state."""
+        _chk(self.L.speedy_step(self.h, j1, j2, ctypes.c_double(dt), int(compute_shortwave)))
+
+    def first_step(self):
+        _chk(self.L.speedy_first_step(self.h))
+
+    def get_tendencies(self, j2, compute_shortwave=True):
+        """tendencies.f90:11 — returns (vordt, divdt, tdt, psdt, trdt) of member 0."""
+        _chk(self.L.speedy_get_tendencies(self.h, j2, int(compute_shortwave)))
+        return tuple(self.get_field(n) for n in ("vordt", "divdt", "tdt", "psdt", "trdt"))
+
+    def get_physical_tendencies(self, vor, div, t, q, phi, psl, utend, vtend, ttend, qtend, compute_shortwave=True):
+        """physics.f90:43 — spectral inputs (kx,nx,mx) [psl (nx,mx)], grid tendencies (kx,il,ix) returned updated."""
+        a = [_c(x, np.complex128) for x in (vor, div, t, q, phi, psl)]
+        g = [_c(x, np.float64).copy() for x in (utend, vtend, ttend, qtend)]
+        _chk(self.L.speedy_get_physical_tendencies(self.h, *[_p(x) for x in a], *[_p(x) for x in g], int(compute_shortwave)))
+        return tuple(g)
+
+    def run_steps(self, nsteps):
+        """speedy.f90:27-54 main-loop body, nsteps times; returns 1 if check_diagnostics tripped."""
+        return _chk(self.L.speedy_run_steps(self.h, int(nsteps)))
+
+    def couple_sea_land(self, day):
+        _chk(self.L.speedy_couple_sea_land(self.h, int(day)))
+
+    def set_forcing(self, imode=1):
+        _chk(self.L.speedy_set_forcing(self.h, int(imode)))
+
+    def check_diagnostics(self, time_level=2):
+        d = np.zeros(3 * self.kx)
+        rc = _chk(self.L.speedy_check_diagnostics(self.h, time_level, _p(d)))
+        return rc, d.reshape(3, self.kx)
+
+    def model_date(self):
+        d = (ctypes.c_int * 5)()
+        s = ctypes.c_longlong()
+        _chk(self.L.speedy_model_date(self.h, d, ctypes.byref(s)))
+        return tuple(d), s.value
+
+    def output_fields(self, member=0):
+        """input_output.f90:184-206 — float32 u,v,t,q,phi (kx,il,ix) and ps (il,ix)."""
+        k, il, ix = self.kx, self.il, self.ix
+        o = [np.empty((k, il, ix), np.float32) for _ in range(5)] + [np.empty((il, ix), np.float32)]
+        _chk(self.L.speedy_output_fields(self.h, member, *[_p(x) for x in o]))
+        return dict(zip(("u", "v", "t", "q", "phi", "ps"), o))
+
+    def step_host(self, state, j1, j2, dt, compute_shortwave=True):
+        a = _c(state, np.float64).copy()
+        _chk(self.L.speedy_step_host(self.h, _p(a), ctypes.c_size_t(a.size), j1, j2, ctypes.c_double(dt), int(compute_shortwave)))
+        return a
+
+    def set_graphs(self, on):
+        _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))
 
     # ---- misc -----------------------------------------------------------------------
     def synchronize(self):

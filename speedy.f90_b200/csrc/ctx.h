@@ -37,7 +37,7 @@ struct LevelConsts {
     double xgeop1[8], xgeop2[8], geop_corf[8];
     double tcorv[8], qcorv[8];
     double sigl[8], sigh[9], grdsig[8], grdscp[8], wvi[16];
-    double rgas, akap, cp, p0, grav, alhc, alhs, sbc, rearth, refrh1;
+    double rgas, akap, cp, p0, grav, alhc, alhs, sbc, rearth, refrh1, gamma;
     double rob, wil, sdrag;
 };
 
@@ -96,7 +96,7 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_membe
 // mode: 0 full grid->spec, 1 fourier_dir only (out = (2mx,il)), 2 legendre_dir only (in = (2mx,il))
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
-                         int nmembers, int mode);
+                         int nmembers, int mode, const int* gate = nullptr);
 void setup_transform_kernels();
 // spectral_ops.cu ---------------------------------------------------------------------
 void launch_spectral_op(speedy_ctx* ctx, int op, const double* a, const double* b, double* o1, double* o2, int nbatch);

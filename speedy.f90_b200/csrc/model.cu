@@ -1,14 +1,605 @@
-// placeholder: model-level entry points are added next
+// Model-level entry points of the C ABI: device-resident state, start-up
+// (initialization.f90:12-82), the time step (time_stepping.f90:12-122), the main-loop body
+// (speedy.f90:27-54) replayed as a CUDA graph, the surface slabs, diagnostics and output.
 #include "../../include/speedy_b200.h"
-#include "ctx.h"
+#include "model.h"
+#include "calendar.h"
 #include "abi_util.h"
+#include <cmath>
+#include <cstring>
+
+using namespace spd;
+
 namespace spd {
-void model_create(speedy_ctx*) {}
-void model_destroy(speedy_ctx*) {}
-void upload_level_consts(speedy_ctx*) {}
+
+static const int KXc = 8;
+
+void calendar_init(DevClock& c, int y, int m, int d, int h, int mi, int nssta) {
+    memset(&c, 0, sizeof(c));
+    c.year = y; c.month = m; c.day = d; c.hour = h; c.minute = mi;
+    c.start_year = y;
+    c.model_step = 1;
+    c.nssta = nssta;
+    cal_fractions(c);
+    cal_step_flags(c);
 }
+void calendar_advance(DevClock& c) { cal_advance(c); }
+
+void upload_level_consts(speedy_ctx* ctx) {
+    if (!ctx->model) return;
+    const Tables& t = ctx->tab;
+    LevelConsts h;
+    memset(&h, 0, sizeof(h));
+    for (int k = 0; k < 9; k++) { h.hsg[k] = t.hsg[k]; h.sigh[k] = t.sigh[k]; }
+    for (int k = 0; k < 8; k++) {
+        h.dhs[k] = t.dhs[k]; h.fsg[k] = t.fsg[k]; h.dhsr[k] = t.dhsr[k]; h.fsgr[k] = t.fsgr[k];
+        h.tref[k] = t.imp.tref[k]; h.tref1[k] = t.imp.tref1[k]; h.tref2[k] = t.imp.tref2[k]; h.tref3[k] = t.imp.tref3[k];
+        h.dhsx[k] = t.imp.dhsx[k];
+        h.xgeop1[k] = t.xgeop1[k]; h.xgeop2[k] = t.xgeop2[k]; h.geop_corf[k] = t.geop_corf[k];
+        h.tcorv[k] = t.tcorv[k]; h.qcorv[k] = t.qcorv[k];
+        h.sigl[k] = t.sigl[k]; h.grdsig[k] = t.grdsig[k]; h.grdscp[k] = t.grdscp[k];
+    }
+    for (int k = 0; k < 16; k++) h.wvi[k] = t.wvi[k];
+    const Consts& c = t.c;
+    h.rgas = c.rgas; h.akap = c.akap; h.cp = c.cp; h.p0 = c.p0; h.grav = c.grav; h.alhc = c.alhc; h.alhs = c.alhs;
+    h.sbc = c.sbc; h.rearth = c.rearth; h.refrh1 = c.refrh1; h.gamma = c.gamma;
+    h.rob = c.rob; h.wil = c.wil;
+    h.sdrag = 1.0 / (c.tdrs * 3600.0);   // time_stepping.f90:77
+    Model& M = *ctx->model;
+    if (!M.lc.p) M.lc.alloc(1);
+    CUDA_CHECK(cudaMemcpyAsync(M.lc.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+static void push_clock(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    CUDA_CHECK(cudaMemcpyAsync(M.clock.p, &M.hclock, sizeof(DevClock), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+static void pull_clock(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    CUDA_CHECK(cudaMemcpyAsync(&M.hclock, M.clock.p, sizeof(DevClock), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+static void drop_graph(Model& M) {
+    if (M.day_graph) { cudaGraphExecDestroy(M.day_graph); M.day_graph = nullptr; M.day_graph_steps = 0; }
+}
+
+void model_create(speedy_ctx* ctx) {
+    Model* Mp = new Model();
+    ctx->model = Mp;
+    Model& M = *Mp;
+    const Dims& d = ctx->d;
+    const long long NS2 = 2LL * d.nspec(), NG = d.ngrid();
+    Layout& L = M.L;
+    long long off = 0;
+    auto reg = [&](const char* name, long long& slot, long long len) {
+        slot = off;
+        M.fields[name] = FieldInfo{off, (size_t)len, false};
+        off += len;
+    };
+    // spectral state, Fortran layouts (prognostics.f90:16-24)
+    reg("vor", L.vor, 2 * KXc * NS2); reg("div", L.div, 2 * KXc * NS2); reg("t", L.t, 2 * KXc * NS2); reg("tr", L.tr, 2 * KXc * NS2);
+    reg("ps", L.ps, 2 * NS2); reg("phi", L.phi, KXc * NS2); reg("phis", L.phis, NS2);
+    reg("tcorh", L.tcorh, NS2); reg("qcorh", L.qcorh, NS2);
+    reg("sprep", L.sprep, SP_N * NS2); reg("sout", L.sout, GO_N * NS2);
+    reg("sppt_spec", L.sppt_spec, KXc * NS2); reg("sppt_eta", L.sppt_eta, KXc * NS2);
+    reg("vordt", L.vordt, KXc * NS2); reg("divdt", L.divdt, KXc * NS2); reg("tdt", L.tdt, KXc * NS2); reg("trdt", L.trdt, KXc * NS2);
+    reg("psdt", L.psdt, NS2);
+    reg("gin", L.gin, GI_N * NG); reg("gout", L.gout, GO_N * NG);
+    reg("phis0", L.phis0, NG); reg("fmask_l", L.fmask_l, NG); reg("fmask_s", L.fmask_s, NG); reg("forog", L.forog, NG); reg("alb0", L.alb0, NG);
+    reg("fsol", L.fsol, NG); reg("ozone", L.ozone, NG); reg("ozupp", L.ozupp, NG); reg("zenit", L.zenit, NG); reg("stratz", L.stratz, NG);
+    reg("alb_l", L.alb_l, NG); reg("alb_s", L.alb_s, NG); reg("albsfc", L.albsfc, NG); reg("snowc", L.snowc, NG);
+    reg("stl_am", L.stl_am, NG); reg("stl_lm", L.stl_lm, NG); reg("snowd_am", L.snowd_am, NG); reg("soilw_am", L.soilw_am, NG);
+    reg("sst_am", L.sst_am, NG); reg("sice_am", L.sice_am, NG); reg("tice_am", L.tice_am, NG); reg("ssti_om", L.ssti_om, NG);
+    reg("sst_om", L.sst_om, NG); reg("tice_om", L.tice_om, NG); reg("sice_om", L.sice_om, NG);
+    reg("sstcl_ob", L.sstcl_ob, NG); reg("sicecl_ob", L.sicecl_ob, NG); reg("ticecl_ob", L.ticecl_ob, NG); reg("stlcl_ob", L.stlcl_ob, NG);
+    reg("sstan3", L.sstan3, 3 * NG);
+    reg("tau2", L.tau2, 4 * KXc * NG); reg("stratc", L.stratc, 2 * NG); reg("tt_rsw", L.tt_rsw, KXc * NG);
+    reg("ssrd", L.ssrd, NG); reg("ssr", L.ssr, NG); reg("tsr", L.tsr, NG);
+    reg("precnv", L.precnv, NG); reg("precls", L.precls, NG); reg("cbmf", L.cbmf, NG); reg("slrd", L.slrd, NG); reg("slr", L.slr, NG); reg("olr", L.olr, NG);
+    reg("slru", L.slru, 3 * NG); reg("ustr", L.ustr, 3 * NG); reg("vstr", L.vstr, 3 * NG); reg("shf", L.shf, 3 * NG); reg("evap", L.evap, 3 * NG);
+    reg("hfluxn", L.hfluxn, 3 * NG);
+    reg("ts", L.ts, NG); reg("tskin", L.tskin, NG); reg("u0", L.u0, NG); reg("v0", L.v0, NG); reg("t0", L.t0, NG);
+    reg("qcloud", L.qcloud, NG); reg("cloudc", L.cloudc, NG); reg("clstr", L.clstr, NG); reg("qcorh_g", L.qcorh_g, NG);
+    L.stride = (off + 15) / 16 * 16;
+    long long ioff = 0;
+    auto ireg = [&](const char* name, long long& slot, long long len) {
+        slot = ioff;
+        M.fields[name] = FieldInfo{ioff, (size_t)len, true};
+        ioff += len;
+    };
+    ireg("iptop", L.iptop, NG); ireg("icltop", L.icltop, NG); ireg("icnv", L.icnv, NG);
+    L.istride = ioff;
+    M.mem.alloc((size_t)L.stride * ctx->nmembers);
+    M.imem.alloc((size_t)L.istride * ctx->nmembers);
+    M.clock.alloc(1);
+    calendar_init(M.hclock, 1982, 1, 1, 0, 0, 0);
+    CUDA_CHECK(cudaMemcpy(M.clock.p, &M.hclock, sizeof(DevClock), cudaMemcpyHostToDevice));
+    upload_level_consts(ctx);
+
+    // transform descriptors --------------------------------------------------------------
+    {
+        std::vector<XDesc> h(2 * GI_N);
+        for (int j2 = 1; j2 <= 2; j2++) {
+            XDesc* D = h.data() + (size_t)(j2 - 1) * GI_N;
+            const long long lev = (long long)(j2 - 1) * KXc * NS2;
+            for (int k = 0; k < KXc; k++) {
+                D[GI_VOR + k] = XDesc{L.vor + lev + k * NS2, 0, 0};
+                D[GI_DIV + k] = XDesc{L.div + lev + k * NS2, 0, 0};
+                D[GI_T + k] = XDesc{L.t + lev + k * NS2, 0, 0};
+                D[GI_TR + k] = XDesc{L.tr + lev + k * NS2, 0, 0};
+                D[GI_U + k] = XDesc{L.sprep + (SP_U2 + k) * NS2, 1, 0};     // spec_to_grid(., 2): * cosgr
+                D[GI_V + k] = XDesc{L.sprep + (SP_V2 + k) * NS2, 1, 0};
+                D[GI_U1 + k] = XDesc{L.sprep + (SP_U1 + k) * NS2, 1, 0};
+                D[GI_V1 + k] = XDesc{L.sprep + (SP_V1 + k) * NS2, 1, 0};
+                D[GI_T1 + k] = XDesc{L.t + k * NS2, 0, 0};
+                D[GI_Q1 + k] = XDesc{L.tr + k * NS2, 0, 0};
+                D[GI_PHI + k] = XDesc{L.phi + k * NS2, 0, 0};
+                D[GI_SPPT + k] = XDesc{L.sppt_spec + k * NS2, 0, 0};
+            }
+            D[GI_PX] = XDesc{L.sprep + SP_PX * NS2, 1, 0};
+            D[GI_PY] = XDesc{L.sprep + SP_PY * NS2, 1, 0};
+            D[GI_PSL] = XDesc{L.ps, 0, 0};
+        }
+        M.desc_inv.upload(h);
+        std::vector<XDesc> g(GO_N);
+        for (int f = 0; f < GO_N; f++) {
+            const int r = f % GO_PER;
+            const bool cosgr = f < GO_PSDT && (r == 0 || r == 1 || r == 3 || r == 4 || r == 6 || r == 7);   // vdspec(.,.,2): spectral.f90:208-213
+            g[f] = XDesc{L.gout + f * NG, cosgr ? 1 : 0, 0};
+        }
+        M.desc_dir.upload(g);
+        std::vector<XDesc> one(1, XDesc{L.qcorh_g, 0, 0});
+        M.desc_one_dir.upload(one);
+    }
+}
+
+void model_destroy(speedy_ctx* ctx) {
+    if (!ctx->model) return;
+    drop_graph(*ctx->model);
+    delete ctx->model;
+    ctx->model = nullptr;
+}
+
+// ---- launch sequences -------------------------------------------------------------------
+static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
+    Model& M = *ctx->model;
+    const long long NG = ctx->d.ngrid();
+    launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_inv.p + (size_t)(j2 - 1) * GI_N + first, count,
+                        M.mem.p + M.L.gin + first * NG, M.L.stride, ctx->nmembers, 0);
+}
+static void xform_direct(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_dir.p, GO_N, M.mem.p + M.L.sout, M.L.stride, ctx->nmembers, 0);
+}
+static void xform_qcorh(speedy_ctx* ctx, bool gated) {
+    Model& M = *ctx->model;
+    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0,
+                        gated ? &M.clock.p->do_forcing : nullptr);
+}
+
+// get_tendencies up to (and including) the direct transforms
+static void enqueue_tendency_front(speedy_ctx* ctx, int j2, int csw_override) {
+    launch_spec_prologue(ctx, j2, 1);
+    if (ctx->sppt_on) launch_sppt_update(ctx);
+    xform_inverse(ctx, j2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
+    launch_grid_columns(ctx, 0, csw_override);
+    xform_direct(ctx);
+}
+// step(j1,j2,dt)  time_stepping.f90:35-122
+static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_override) {
+    enqueue_tendency_front(ctx, j2, csw_override);
+    launch_spec_step(ctx, j1, j2, dt, 0);
+}
+// main-loop body speedy.f90:27-54
+static void enqueue_main_loop_step(speedy_ctx* ctx) {
+    const double delt = ctx->tab.c.delt;
+    launch_daily_forcing(ctx, 0);          // set_forcing(1), gated on the device clock
+    xform_qcorh(ctx, true);
+    enqueue_step(ctx, 2, 2, 2 * delt, -1);
+    launch_diagnostics(ctx, 2);
+    launch_clock_advance(ctx);
+    launch_slab(ctx, 0);                   // couple_sea_land
+}
+
+static void set_implicit(speedy_ctx* ctx, double dt) {
+    Model& M = *ctx->model;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    build_implicit(ctx->tab, dt);
+    upload_implicit(ctx);      // also refreshes the level constants
+    M.implicit_dt = dt;
+}
+
+static void check_ready(speedy_ctx* ctx) {
+    if (!ctx || !ctx->model) throw std::runtime_error("null context");
+    CUDA_CHECK(cudaSetDevice(ctx->device));
+}
+
+static void set_all_members(speedy_ctx* ctx, long long off, const double* host, size_t len) {
+    Model& M = *ctx->model;
+    for (int e = 0; e < ctx->nmembers; e++)
+        CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + off, host, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+
+}  // namespace spd
+
 extern "C" {
+
 size_t speedy_output_len(const speedy_ctx* ctx) { return (size_t)(5 * ctx->d.kx + 1) * ctx->d.ngrid(); }
-size_t speedy_state_len(const speedy_ctx* ctx) { return 0; }
-const char* speedy_field_names(void) { return ""; }
+size_t speedy_state_len(const speedy_ctx* ctx) { return (size_t)2 * ctx->d.nspec() * (4 * 2 * ctx->d.kx + 2); }
+
+const char* speedy_field_names(void) {
+    return "vor div t tr ps phi phis tcorh qcorh vordt divdt tdt trdt psdt gin gout sprep sout sppt_spec sppt_eta "
+           "phis0 fmask_l fmask_s forog alb0 fsol ozone ozupp zenit stratz alb_l alb_s albsfc snowc "
+           "stl_am stl_lm snowd_am soilw_am sst_am sice_am tice_am ssti_om sst_om tice_om sice_om "
+           "sstcl_ob sicecl_ob ticecl_ob stlcl_ob sstan3 tau2 stratc tt_rsw ssrd ssr tsr precnv precls cbmf slrd slr olr "
+           "slru ustr vstr shf evap hfluxn ts tskin u0 v0 t0 qcloud cloudc clstr qcorh_g iptop icltop icnv";
 }
+
+static const FieldInfo& find_field(speedy_ctx* ctx, const char* name, bool want_int) {
+    auto it = ctx->model->fields.find(name);
+    if (it == ctx->model->fields.end()) throw std::runtime_error(std::string("unknown field ") + name);
+    if (it->second.is_int != want_int) throw std::runtime_error(std::string("field ") + name + (want_int ? " is not an integer field" : " is an integer field"));
+    return it->second;
+}
+
+// n == len: broadcast to every member; n == nmembers*len: one copy per member
+int speedy_set_field(speedy_ctx* ctx, const char* name, const double* host, size_t n) {
+    API_BEGIN
+    check_ready(ctx);
+    const FieldInfo& f = find_field(ctx, name, false);
+    Model& M = *ctx->model;
+    if (n == f.len) set_all_members(ctx, f.off, host, f.len);
+    else if (n == f.len * (size_t)ctx->nmembers) {
+        for (int e = 0; e < ctx->nmembers; e++)
+            CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + f.off, host + (size_t)e * f.len, f.len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    } else throw std::runtime_error(std::string("field ") + name + ": expected " + std::to_string(f.len) + " (or nmembers x that) values");
+    API_END
+}
+// n == len: member 0; n == nmembers*len: every member
+int speedy_get_field(speedy_ctx* ctx, const char* name, double* host, size_t n) {
+    API_BEGIN
+    check_ready(ctx);
+    const FieldInfo& f = find_field(ctx, name, false);
+    Model& M = *ctx->model;
+    if (n != f.len && n != f.len * (size_t)ctx->nmembers)
+        throw std::runtime_error(std::string("field ") + name + ": expected " + std::to_string(f.len) + " (or nmembers x that) values");
+    const int ne = (int)(n / f.len);
+    for (int e = 0; e < ne; e++)
+        CUDA_CHECK(cudaMemcpyAsync(host + (size_t)e * f.len, M.mem.p + (size_t)e * M.L.stride + f.off, f.len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+int speedy_get_ifield(speedy_ctx* ctx, const char* name, int* host, size_t n) {
+    API_BEGIN
+    check_ready(ctx);
+    const FieldInfo& f = find_field(ctx, name, true);
+    Model& M = *ctx->model;
+    if (n != f.len && n != f.len * (size_t)ctx->nmembers) throw std::runtime_error(std::string("field ") + name + ": size mismatch");
+    const int ne = (int)(n / f.len);
+    for (int e = 0; e < ne; e++)
+        CUDA_CHECK(cudaMemcpyAsync(host + (size_t)e * f.len, M.imem.p + (size_t)e * M.L.istride + f.off, f.len * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+
+int speedy_initialize_implicit(speedy_ctx* ctx, double dt) {
+    API_BEGIN
+    check_ready(ctx);
+    set_implicit(ctx, dt);
+    API_END
+}
+
+int speedy_get_geopotential(speedy_ctx* ctx, int j) {
+    API_BEGIN
+    check_ready(ctx);
+    if (j != 1) throw std::runtime_error("get_geopotential: the resident phi is tied to time level 1 (tendencies.f90:203,288)");
+    launch_spec_prologue(ctx, 1, 1);
+    API_END
+}
+
+int speedy_get_tendencies(speedy_ctx* ctx, int j2, int compute_shortwave) {
+    API_BEGIN
+    check_ready(ctx);
+    if (j2 != 1 && j2 != 2) throw std::runtime_error("j2 must be 1 or 2");
+    enqueue_tendency_front(ctx, j2, compute_shortwave ? 1 : 0);
+    launch_spec_step(ctx, 1, j2, 0.0, 1);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+
+int speedy_get_physical_tendencies(speedy_ctx* ctx, const double* vor, const double* div, const double* t, const double* q,
+                                   const double* phi, const double* psl, double* utend, double* vtend, double* ttend, double* qtend,
+                                   int compute_shortwave) {
+    API_BEGIN
+    check_ready(ctx);
+    if (ctx->nmembers != 1) throw std::runtime_error("host-array physics entry point needs a single-member context");
+    Model& M = *ctx->model;
+    const Layout& L = M.L;
+    const size_t NS2 = (size_t)2 * ctx->d.nspec(), NG = ctx->d.ngrid();
+    auto up = [&](long long off, const double* h, size_t n) { CUDA_CHECK(cudaMemcpyAsync(M.mem.p + off, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); };
+    // the arguments are the caller's time-level-1 arrays (tendencies.f90:205): they become the resident level 1
+    up(L.vor, vor, KXc * NS2); up(L.div, div, KXc * NS2); up(L.t, t, KXc * NS2); up(L.tr, q, KXc * NS2); up(L.phi, phi, KXc * NS2); up(L.ps, psl, NS2);
+    std::vector<double> g((size_t)GO_N * NG, 0.0);
+    for (int k = 0; k < KXc; k++) {
+        memcpy(&g[(size_t)(GO_PER * k + 0) * NG], utend + k * NG, NG * sizeof(double));
+        memcpy(&g[(size_t)(GO_PER * k + 1) * NG], vtend + k * NG, NG * sizeof(double));
+        memcpy(&g[(size_t)(GO_PER * k + 5) * NG], ttend + k * NG, NG * sizeof(double));
+        memcpy(&g[(size_t)(GO_PER * k + 8) * NG], qtend + k * NG, NG * sizeof(double));
+    }
+    up(L.gout, g.data(), g.size());
+    launch_spec_prologue(ctx, 1, 0);
+    if (ctx->sppt_on) { launch_sppt_update(ctx); xform_inverse(ctx, 1, GI_SPPT, 8); }
+    xform_inverse(ctx, 1, GI_U1, 41);
+    launch_grid_columns(ctx, 1, compute_shortwave ? 1 : 0);
+    CUDA_CHECK(cudaMemcpyAsync(g.data(), M.mem.p + L.gout, g.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < KXc; k++) {
+        memcpy(utend + k * NG, &g[(size_t)(GO_PER * k + 0) * NG], NG * sizeof(double));
+        memcpy(vtend + k * NG, &g[(size_t)(GO_PER * k + 1) * NG], NG * sizeof(double));
+        memcpy(ttend + k * NG, &g[(size_t)(GO_PER * k + 5) * NG], NG * sizeof(double));
+        memcpy(qtend + k * NG, &g[(size_t)(GO_PER * k + 8) * NG], NG * sizeof(double));
+    }
+    API_END
+}
+
+int speedy_step(speedy_ctx* ctx, int j1, int j2, double dt, int compute_shortwave) {
+    API_BEGIN
+    check_ready(ctx);
+    if ((j1 != 1 && j1 != 2) || (j2 != 1 && j2 != 2)) throw std::runtime_error("j1, j2 must be 1 or 2");
+    enqueue_step(ctx, j1, j2, dt, compute_shortwave < 0 ? -1 : (compute_shortwave ? 1 : 0));
+    API_END
+}
+
+int speedy_first_step(speedy_ctx* ctx) {   // time_stepping.f90:12-24; compute_shortwave = .true. (shortwave_radiation.f90:67)
+    API_BEGIN
+    check_ready(ctx);
+    const double delt = ctx->tab.c.delt;
+    set_implicit(ctx, 0.5 * delt);
+    enqueue_step(ctx, 1, 1, 0.5 * delt, 1);
+    set_implicit(ctx, delt);
+    enqueue_step(ctx, 1, 2, delt, 1);
+    set_implicit(ctx, 2 * delt);
+    API_END
+}
+
+int speedy_step_host(speedy_ctx* ctx, double* state, size_t n, int j1, int j2, double dt, int compute_shortwave) {
+    API_BEGIN
+    check_ready(ctx);
+    if (ctx->nmembers != 1) throw std::runtime_error("host-array step needs a single-member context");
+    if (n != speedy_state_len(ctx)) throw std::runtime_error("state length mismatch (see speedy_state_len)");
+    Model& M = *ctx->model;
+    const Layout& L = M.L;
+    const size_t NS2 = (size_t)2 * ctx->d.nspec(), n4 = 2 * KXc * NS2;
+    const long long offs[5] = {L.vor, L.div, L.t, L.tr, L.ps};
+    const size_t lens[5] = {n4, n4, n4, n4, 2 * NS2};
+    size_t p = 0;
+    for (int i = 0; i < 5; i++) { CUDA_CHECK(cudaMemcpyAsync(M.mem.p + offs[i], state + p, lens[i] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); p += lens[i]; }
+    enqueue_step(ctx, j1, j2, dt, compute_shortwave ? 1 : 0);
+    p = 0;
+    for (int i = 0; i < 5; i++) { CUDA_CHECK(cudaMemcpyAsync(state + p, M.mem.p + offs[i], lens[i] * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream)); p += lens[i]; }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+
+int speedy_couple_sea_land(speedy_ctx* ctx, int day) {
+    API_BEGIN
+    check_ready(ctx);
+    launch_slab(ctx, day == 0 ? 1 : 0);
+    API_END
+}
+
+int speedy_set_forcing(speedy_ctx* ctx, int imode) {
+    API_BEGIN
+    check_ready(ctx);
+    (void)imode;   // the time-independent part of imode 0 (radset, forog, tcorh) is done by speedy_model_init
+    launch_daily_forcing(ctx, 1);
+    xform_qcorh(ctx, false);
+    API_END
+}
+
+int speedy_check_diagnostics(speedy_ctx* ctx, int time_level, double* diag) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    launch_diagnostics(ctx, time_level);
+    pull_clock(ctx);
+    if (diag) memcpy(diag, M.hclock.diag, sizeof(double) * 24);
+    if (M.hclock.diag_fail) return 1;
+    API_END
+}
+
+int speedy_model_date(const speedy_ctx* cctx, int* ymdhm, long long* model_step) {
+    API_BEGIN
+    speedy_ctx* ctx = const_cast<speedy_ctx*>(cctx);
+    check_ready(ctx);
+    pull_clock(ctx);
+    const DevClock& c = ctx->model->hclock;
+    if (ymdhm) { ymdhm[0] = c.year; ymdhm[1] = c.month; ymdhm[2] = c.day; ymdhm[3] = c.hour; ymdhm[4] = c.minute; }
+    if (model_step) *model_step = c.model_step;
+    API_END
+}
+
+// initialization.f90:12-82
+int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month, int day, int hour, int minute) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    drop_graph(M);
+    const Dims& d = ctx->d;
+    const Consts& c = ctx->tab.c;
+    const int NG = d.ngrid(), NS = d.nspec();
+    HostEnv env;
+    load_host_env(bc_path, ctx->tab, env);
+    // shared device tables
+    {
+        std::vector<double> sh;
+        auto put = [&](const std::vector<double>& v) { size_t o = sh.size(); sh.insert(sh.end(), v.begin(), v.end()); return o; };
+        const size_t o_stl = put(env.stl12), o_snd = put(env.snowd12), o_sw = put(env.soilw12), o_sst = put(env.sst12), o_sic = put(env.sice12);
+        const size_t o_rl = put(env.rhcapl), o_cl = put(env.cdland), o_rs = put(env.rhcaps), o_ri = put(env.rhcapi), o_cs = put(env.cdsea), o_ci = put(env.cdice);
+        const size_t o_bm = put(env.bmask_s), o_sol = put(env.solar);
+        M.shared.upload(sh);
+        M.ssta.upload(env.ssta);
+        const double* b = M.shared.p;
+        M.sh = SharedDev{b + o_stl, b + o_snd, b + o_sw, b + o_sst, b + o_sic, b + o_rl, b + o_cl, b + o_rs, b + o_ri, b + o_cs, b + o_ci, b + o_bm, M.ssta.p, b + o_sol};
+    }
+    CUDA_CHECK(cudaMemsetAsync(M.mem.p, 0, M.mem.n * sizeof(double), ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(M.imem.p, 0, M.imem.n * sizeof(int), ctx->stream));
+    // date.f90:53-105, initialization.f90:37
+    calendar_init(M.hclock, year, month, day, hour, minute, env.nssta);
+    const int isst0 = (year - 1979) * 12 + month;
+    if (isst0 - 1 < 1 || isst0 + 1 > env.nssta) throw std::runtime_error("start date outside the resident SST-anomaly window of the boundary file");
+    push_clock(ctx);
+    // boundaries.f90:28-43: spectrally truncated surface geopotential (through the transform kernels)
+    std::vector<double> phis0(NG), spec((size_t)2 * NS), tmp(NG);
+    if (speedy_grid_to_spec(ctx, env.phi0.data(), 1, spec.data())) throw std::runtime_error(speedy_last_error());
+    for (int n = 0; n < d.nx; n++)
+        for (int m = 0; m < d.mx; m++)
+            if (m + n > d.trunc) { spec[2 * (m + (size_t)d.mx * n)] = 0.0; spec[2 * (m + (size_t)d.mx * n) + 1] = 0.0; }
+    int kcos1 = 1;
+    if (speedy_spec_to_grid(ctx, spec.data(), 1, &kcos1, phis0.data())) throw std::runtime_error(speedy_last_error());
+    M.h_phis0 = phis0;
+    set_all_members(ctx, M.L.phis0, phis0.data(), NG);
+    set_all_members(ctx, M.L.fmask_l, env.fmask_l.data(), NG);
+    set_all_members(ctx, M.L.fmask_s, env.fmask_s.data(), NG);
+    set_all_members(ctx, M.L.alb0, env.alb0.data(), NG);
+    {   // set_orog_land_sfc_drag  surface_fluxes.f90:300-309
+        const double rhdrag = 1.0 / (c.grav * 2000.0);
+        for (int q = 0; q < NG; q++) tmp[q] = 1.0 + rhdrag * (1.0 - exp(-std::max(phis0[q], 0.0) * rhdrag));
+        set_all_members(ctx, M.L.forog, tmp.data(), NG);
+    }
+    // ---- prognostics.f90:34-127 rest state (time level 1; level 2 stays zero until the first step writes it)
+    {
+        const size_t NS2 = (size_t)2 * NS;
+        std::vector<double> phis(NS2), surfs(NS2), st((size_t)2 * KXc * NS2, 0.0), ps2(2 * NS2, 0.0), trs((size_t)2 * KXc * NS2, 0.0);
+        if (speedy_grid_to_spec(ctx, phis0.data(), 1, phis.data())) throw std::runtime_error(speedy_last_error());
+        set_all_members(ctx, M.L.phis, phis.data(), NS2);
+        const double gam1 = c.gamma / (1000.0 * c.grav);
+        const double tref = 288.0, ttop = 216.0, gam2 = gam1 / tref, rgam = c.rgas * gam1, rgamr = 1.0 / rgam;
+        for (size_t i = 0; i < NS2; i++) surfs[i] = -gam1 * phis[i];
+        const double sq2 = (double)sqrtf(2.0f);
+        st[0] = sq2 * ttop; st[1] = 0.0 * ttop;
+        st[NS2 + 0] = sq2 * ttop; st[NS2 + 1] = 0.0 * ttop;
+        surfs[0] = sq2 * tref - gam1 * phis[0];
+        surfs[1] = 0.0 - gam1 * phis[1];
+        for (int k = 2; k < KXc; k++) {
+            const double f = pow(ctx->tab.fsg[k], rgam);
+            for (size_t i = 0; i < NS2; i++) st[(size_t)k * NS2 + i] = surfs[i] * f;
+        }
+        set_all_members(ctx, M.L.t, st.data(), st.size());
+        const double rlog0 = (double)logf(1.013f);
+        std::vector<double> surfg(NG);
+        for (int q = 0; q < NG; q++) surfg[q] = rlog0 + rgamr * log(1.0 - gam2 * phis0[q]);
+        if (speedy_grid_to_spec(ctx, surfg.data(), 1, ps2.data())) throw std::runtime_error(speedy_last_error());
+        for (int n = 0; n < d.nx; n++)
+            for (int m = 0; m < d.mx; m++)
+                if (m + n > d.trunc) { ps2[2 * (m + (size_t)d.mx * n)] = 0.0; ps2[2 * (m + (size_t)d.mx * n) + 1] = 0.0; }
+        set_all_members(ctx, M.L.ps, ps2.data(), ps2.size());
+        const double esref = 17.0, qref = c.refrh1 * (double)0.622f * esref, qexp = c.hscale / c.hshum;
+        for (int q = 0; q < NG; q++) surfg[q] = qref * exp(qexp * surfg[q]);
+        if (speedy_grid_to_spec(ctx, surfg.data(), 1, surfs.data())) throw std::runtime_error(speedy_last_error());
+        for (int n = 0; n < d.nx; n++)
+            for (int m = 0; m < d.mx; m++)
+                if (m + n > d.trunc) { surfs[2 * (m + (size_t)d.mx * n)] = 0.0; surfs[2 * (m + (size_t)d.mx * n) + 1] = 0.0; }
+        for (int k = 2; k < KXc; k++) {
+            const double f = pow(ctx->tab.fsg[k], qexp);
+            for (size_t i = 0; i < NS2; i++) trs[(size_t)k * NS2 + i] = surfs[i] * f;
+        }
+        set_all_members(ctx, M.L.tr, trs.data(), trs.size());
+        // tcorh = grid_to_spec(gamlat*phis0) (forcing.f90:77-82) does not depend on the date
+        for (int q = 0; q < NG; q++) tmp[q] = gam1 * phis0[q];
+        if (speedy_grid_to_spec(ctx, tmp.data(), 1, surfs.data())) throw std::runtime_error(speedy_last_error());
+        set_all_members(ctx, M.L.tcorh, surfs.data(), NS2);
+    }
+    // ---- initialize_coupler (coupler.f90:15-30): sstan3 months isst0-1..isst0+1, then the day-0 coupling
+    {
+        std::vector<double> an((size_t)3 * NG);
+        for (int s = 0; s < 3; s++)
+            for (int q = 0; q < NG; q++) an[(size_t)s * NG + q] = (double)env.ssta[(size_t)(isst0 - 2 + s) * NG + q];
+        set_all_members(ctx, M.L.sstan3, an.data(), an.size());
+    }
+    launch_slab(ctx, 1);
+    // ---- set_forcing(0) (forcing.f90:15-100); fband/forog/tcorh are already resident
+    launch_daily_forcing(ctx, 1);
+    xform_qcorh(ctx, false);
+    // geopotential of the rest state (prognostics.f90:123) so that an immediate output sees it
+    launch_spec_prologue(ctx, 1, 1);
+    M.sppt_first = true; M.sppt_counter = 0;
+    // ---- first_step (time_stepping.f90:12-24)
+    if (speedy_first_step(ctx)) throw std::runtime_error(speedy_last_error());
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    M.initialized = true;
+    API_END
+}
+
+// speedy.f90:27-54 repeated nsteps times; whole days are replayed from a CUDA graph
+int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
+    if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
+    int left = nsteps;
+    const int G = 36;
+    if (ctx->use_graphs && left >= G) {
+        if (!M.day_graph) {
+            cudaGraph_t graph;
+            const long long before = ctx->launches;
+            CUDA_CHECK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+            try {
+                for (int s = 0; s < G; s++) enqueue_main_loop_step(ctx);
+            } catch (...) { cudaGraph_t g2; cudaStreamEndCapture(ctx->stream, &g2); throw; }
+            CUDA_CHECK(cudaStreamEndCapture(ctx->stream, &graph));
+            ctx->launches = before;
+            CUDA_CHECK(cudaGraphInstantiate(&M.day_graph, graph, 0));
+            CUDA_CHECK(cudaGraphDestroy(graph));
+            M.day_graph_steps = G;
+        }
+        while (left >= G) {
+            CUDA_CHECK(cudaGraphLaunch(M.day_graph, ctx->stream));
+            ctx->launches += (long long)G * (ctx->sppt_on ? 11 : 10);
+            left -= G;
+        }
+    }
+    for (int s = 0; s < left; s++) enqueue_main_loop_step(ctx);
+    pull_clock(ctx);
+    if (M.hclock.ssta_missing) throw std::runtime_error("run left the SST-anomaly window resident in the boundary file (pack more months)");
+    if (M.hclock.diag_fail) return 1;   // 'Model variables out of accepted range' (diagnostics.f90:68)
+    API_END
+}
+
+int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float* t, float* q, float* phi, float* ps) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    if (member < 0 || member >= ctx->nmembers) throw std::runtime_error("bad member index");
+    const size_t NG = ctx->d.ngrid(), n = speedy_output_len(ctx);
+    launch_spec_prologue(ctx, 1, 0);           // uvspec of level 1; phi stays the one of the last step (input_output.f90:184-192)
+    xform_inverse(ctx, 1, GI_U1, 41);
+    DevBuf<float> out;
+    out.alloc(n);
+    launch_output_convert(ctx, member, out.p);
+    std::vector<float> h(n);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    float* dst[5] = {u, v, t, q, phi};
+    for (int f = 0; f < 5; f++)
+        if (dst[f]) memcpy(dst[f], h.data() + (size_t)f * KXc * NG, KXc * NG * sizeof(float));
+    if (ps) memcpy(ps, h.data() + (size_t)5 * KXc * NG, NG * sizeof(float));
+    API_END
+}
+
+int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
+    API_BEGIN
+    check_ready(ctx);
+    launch_spec_prologue(ctx, 1, 0);
+    xform_inverse(ctx, 1, GI_U1, 41);
+    launch_ensemble_sums(ctx, d_sum, d_sumsq);
+    API_END
+}
+
+}  // extern "C"

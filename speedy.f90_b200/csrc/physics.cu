@@ -1,0 +1,919 @@
+// K4 + K5 — the grid-point column kernel: non-linear dynamics tendencies
+// (tendencies.f90:109-197) and the whole physics sweep (physics.f90:110-205 dispatching
+// convection.f90, large_scale_condensation.f90, shortwave_radiation.f90,
+// longwave_radiation.f90, surface_fluxes.f90, vertical_diffusion.f90) fused into ONE pass
+// over the (ix,il) columns: every parameterisation is column-local, so a thread owns a
+// column, keeps its 8 levels on chip and touches HBM once per input field and once per
+// output field.  Longitude is the fastest thread index = unit stride in every array.
+// Also here: the per-step land/sea slab update (land_model.f90:184-239,
+// sea_model.f90:253-444), the daily forcing (forcing.f90:55-99) and the device calendar.
+//
+// Compiled with --fmad=false so that the arithmetic is the reference's operation by
+// operation (the checker is built with -ffp-contract=off).
+#include "model.h"
+#include "calendar.h"
+
+namespace spd {
+
+#define KX 8
+#define F32(x) ((double)(x##f))
+
+__device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }   // Fortran min/max on non-NaN data
+__device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
+
+// humidity.f90:44-78 for one point; p = sig*ps (or ps(1,1) for sig <= 0)
+__device__ __forceinline__ double qsat_pt(double ta, double p) {
+    const double e0 = 6.108e-3, c1 = F32(17.269), c2 = F32(21.875), t0 = F32(273.16), t1 = F32(35.86), t2 = F32(7.66);
+    double q;
+    if (ta >= t0) q = e0 * exp(c1 * (ta - t0) / (ta - t1));
+    else q = e0 * exp(c2 * (ta - t0) / (ta - t2));
+    return 622.0 * q / (p - F32(0.378) * q);
+}
+
+struct ColumnArgs {
+    double* base; long long stride;
+    int* ibase;
+    Layout L;
+    const LevelConsts* lc;
+    const DevClock* clk;
+    const double* fband;     // (301,4) Fortran order
+    const double* coriol;    // il
+    const double* coa;       // il
+    int ix, il;
+    int mode;                // 0: dynamics + physics -> K2 inputs; 1: physics only, tendencies in/out in gout slots
+    int csw_override;        // -1: take compute_shortwave from the device clock
+    int sppt_on;
+};
+
+__global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
+    const int ix = a.ix, il = a.il, N = ix * il;
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= N) return;
+    const int e = blockIdx.y;
+    const int j = col / ix;
+    double* mb = a.base + (size_t)e * a.stride;
+    int* ib = a.ibase + (size_t)e * a.L.istride;
+    const LevelConsts& lc = *a.lc;
+    const double* gin = mb + a.L.gin;
+    double* gout = mb + a.L.gout;
+#define GIN(f) gin[(size_t)(f) * N + col]
+#define GOUT(f) gout[(size_t)(f) * N + col]
+#define G2(off) mb[(off) + col]
+#define G3(off, k) mb[(off) + (size_t)((k)-1) * N + col]
+
+    double utend[KX + 1], vtend[KX + 1], ttend[KX + 1], qtend[KX + 1];
+
+    if (a.mode == 0) {
+        // ============================ tendencies.f90:109-197 ============================
+        double ug[KX + 1], vg[KX + 1], tg[KX + 1], vorg[KX + 1], divg[KX + 1], trg[KX + 1], tgg[KX + 1], puv[KX + 1];
+        double sigdt[KX + 2], sigm[KX + 2], temp[KX + 2];
+        const double cor = a.coriol[j];
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            vorg[k] = GIN(GI_VOR + k - 1) + cor;   // :103-107
+            divg[k] = GIN(GI_DIV + k - 1);
+            tg[k] = GIN(GI_T + k - 1);
+            trg[k] = GIN(GI_TR + k - 1);
+            ug[k] = GIN(GI_U + k - 1);
+            vg[k] = GIN(GI_V + k - 1);
+        }
+        const double px = GIN(GI_PX), py = GIN(GI_PY);
+        double umean = 0.0, vmean = 0.0, dmean = 0.0;
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            umean = umean + ug[k] * lc.dhs[k - 1];
+            vmean = vmean + vg[k] * lc.dhs[k - 1];
+            dmean = dmean + divg[k] * lc.dhs[k - 1];
+        }
+        GOUT(GO_PSDT) = -umean * px - vmean * py;   // :125
+        sigdt[1] = 0.0; sigm[1] = 0.0;
+#pragma unroll
+        for (int k = 1; k <= KX; k++) puv[k] = (ug[k] - umean) * px + (vg[k] - vmean) * py;
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {   // :140-143 (the loop also overwrites level kx+1)
+            sigdt[k + 1] = sigdt[k] - lc.dhs[k - 1] * (puv[k] + divg[k] - dmean);
+            sigm[k + 1] = sigm[k] - lc.dhs[k - 1] * puv[k];
+        }
+#pragma unroll
+        for (int k = 1; k <= KX; k++) tgg[k] = tg[k] - lc.tref[k - 1];
+        temp[1] = 0.0; temp[KX + 1] = 0.0;
+#pragma unroll
+        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (ug[k] - ug[k - 1]);
+#pragma unroll
+        for (int k = 1; k <= KX; k++) utend[k] = vg[k] * vorg[k] - tgg[k] * lc.rgas * px - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
+#pragma unroll
+        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (vg[k] - vg[k - 1]);
+#pragma unroll
+        for (int k = 1; k <= KX; k++) vtend[k] = -ug[k] * vorg[k] - tgg[k] * lc.rgas * py - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
+#pragma unroll
+        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (tgg[k] - tgg[k - 1]) + sigm[k] * (lc.tref[k - 1] - lc.tref[k - 2]);
+#pragma unroll
+        for (int k = 1; k <= KX; k++)
+            ttend[k] = tgg[k] * divg[k] - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1] + lc.fsgr[k - 1] * tgg[k] * (sigdt[k + 1] + sigdt[k]) +
+                       lc.tref3[k - 1] * (sigm[k + 1] + sigm[k]) + lc.akap * (tg[k] * puv[k] - tgg[k] * dmean);
+#pragma unroll
+        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (trg[k] - trg[k - 1]);
+        temp[2] = 0.0; temp[3] = 0.0;   // :192
+#pragma unroll
+        for (int k = 1; k <= KX; k++) qtend[k] = trg[k] * divg[k] - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
+        // products for the direct transforms (tendencies.f90:219-232)
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            const int f = GO_PER * (k - 1);
+            GOUT(f + 2) = 0.5 * (ug[k] * ug[k] + vg[k] * vg[k]);
+            GOUT(f + 3) = -ug[k] * tgg[k];
+            GOUT(f + 4) = -vg[k] * tgg[k];
+            GOUT(f + 6) = -ug[k] * trg[k];
+            GOUT(f + 7) = -vg[k] * trg[k];
+        }
+    } else {
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            const int f = GO_PER * (k - 1);
+            utend[k] = GOUT(f + 0); vtend[k] = GOUT(f + 1); ttend[k] = GOUT(f + 5); qtend[k] = GOUT(f + 8);
+        }
+    }
+
+    // ================================ physics.f90:110-205 ================================
+    {
+        double ug[KX + 1], vg[KX + 1], tg[KX + 1], qg[KX + 1], phig[KX + 1], se[KX + 1], rh[KX + 1], qsat[KX + 1];
+        double ut_dyn[KX + 1], vt_dyn[KX + 1], tt_dyn[KX + 1], qt_dyn[KX + 1];
+        const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
+        if (a.sppt_on) {
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { ut_dyn[k] = utend[k]; vt_dyn[k] = vtend[k]; tt_dyn[k] = ttend[k]; qt_dyn[k] = qtend[k]; }
+        }
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            ug[k] = GIN(GI_U1 + k - 1); vg[k] = GIN(GI_V1 + k - 1); tg[k] = GIN(GI_T1 + k - 1);
+            qg[k] = GIN(GI_Q1 + k - 1); phig[k] = GIN(GI_PHI + k - 1);
+        }
+        const double psg = exp(GIN(GI_PSL));
+        const double rps = 1.0 / psg;
+#pragma unroll
+        for (int k = 1; k <= KX; k++) {
+            qg[k] = dmax(qg[k], 0.0);
+            se[k] = lc.cp * tg[k] + phig[k];
+            qsat[k] = qsat_pt(tg[k], lc.fsg[k - 1] * psg);
+            rh[k] = qg[k] / qsat[k];
+        }
+        const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
+
+        // ---------------------------- convection.f90:27-245 ----------------------------
+        int iptop;
+        double cbmf = 0.0, precnv = 0.0;
+        {
+            const double psmin = F32(0.8), trcnv = 6.0, rhbl = F32(0.9), rhil = F32(0.7), entmax = 0.5, smf = F32(0.8);
+            const int nl1 = KX - 1, nlp = KX + 1;
+            double dfse[KX + 1], dfqa[KX + 1];
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { dfse[k] = 0.0; dfqa[k] = 0.0; }
+            // diagnose_convection :170-245
+            int itop = nlp;
+            double qdif = 0.0;
+            if (psg > psmin) {
+                const double mse0 = se[KX] + lc.alhc * qg[KX];
+                double mse1 = se[nl1] + lc.alhc * qg[nl1];
+                mse1 = dmin(mse0, mse1);
+                const double mss0 = dmax(mse0, se[KX] + lc.alhc * qsat[KX]);
+                int ktop1 = KX, ktop2 = KX;
+                double msthr = 0.0;
+                for (int k = KX - 3; k >= 3; k--) {
+                    const double mssk = se[k] + lc.alhc * qsat[k], mssk1 = se[k + 1] + lc.alhc * qsat[k + 1];
+                    const double mss2 = mssk + wvi2[k] * (mssk1 - mssk);
+                    if (mss0 > mss2) ktop1 = k;
+                    if (mse1 > mss2) { ktop2 = k; msthr = mss2; }
+                }
+                if (ktop1 < KX) {
+                    const double qthr0 = rhbl * qsat[KX], qthr1 = rhbl * qsat[nl1];
+                    const bool lqthr = (qg[KX] > qthr0 && qg[nl1] > qthr1);
+                    if (ktop2 < KX) {
+                        itop = ktop1;
+                        qdif = dmax(qg[KX] - qthr0, (mse0 - msthr) * (1.0 / lc.alhc));
+                    } else if (lqthr) {
+                        itop = ktop1;
+                        qdif = qg[KX] - qthr0;
+                    }
+                }
+            }
+            if (itop != nlp) {
+                const double fqmax = 5.0;
+                const double fm0 = lc.p0 * lc.dhs[KX - 1] / (lc.grav * trcnv * 3600.0);
+                const double rdps = 2.0 / (1.0 - psmin);
+                double entr[KX + 1];
+                double sentr = 0.0;
+                for (int k = 2; k <= nl1; k++) {
+                    const double ee = dmax(0.0, lc.fsg[k - 1] - 0.5);
+                    entr[k] = ee * ee;
+                    sentr = sentr + entr[k];
+                }
+                sentr = entmax / sentr;
+                for (int k = 2; k <= nl1; k++) entr[k] = entr[k] * sentr;
+                int k = KX, k1 = k - 1;
+                const double qmax = dmax(F32(1.01) * qg[k], qsat[k]);
+                double sb = se[k1] + wvi2[k1] * (se[k] - se[k1]);
+                double qb = qg[k1] + wvi2[k1] * (qg[k] - qg[k1]);
+                qb = dmin(qb, qg[k]);
+                const double fpsa = psg * dmin(1.0, (psg - psmin) * rdps);
+                double fmass = fm0 * fpsa * dmin(fqmax, qdif / (qmax - qb));
+                cbmf = fmass;
+                double fus = fmass * se[k], fuq = fmass * qmax;
+                double fds = fmass * sb, fdq = fmass * qb;
+                dfse[k] = fds - fus;
+                dfqa[k] = fdq - fuq;
+                for (k = KX - 1; k >= itop + 1; k--) {
+                    k1 = k - 1;
+                    dfse[k] = fus - fds;
+                    dfqa[k] = fuq - fdq;
+                    const double enmass = entr[k] * psg * cbmf;
+                    fmass = fmass + enmass;
+                    fus = fus + enmass * se[k];
+                    fuq = fuq + enmass * qg[k];
+                    sb = se[k1] + wvi2[k1] * (se[k] - se[k1]);
+                    qb = qg[k1] + wvi2[k1] * (qg[k] - qg[k1]);
+                    fds = fmass * sb;
+                    fdq = fmass * qb;
+                    dfse[k] = dfse[k] + fds - fus;
+                    dfqa[k] = dfqa[k] + fdq - fuq;
+                    const double delq = rhil * qsat[k] - qg[k];
+                    if (delq > 0.0) {
+                        const double fsq = smf * cbmf * delq;
+                        dfqa[k] = dfqa[k] + fsq;
+                        dfqa[KX] = dfqa[KX] - fsq;
+                    }
+                }
+                k = itop;
+                const double qsatb = qsat[k] + wvi2[k] * (qsat[k + 1] - qsat[k]);
+                precnv = dmax(fuq - fmass * qsatb, 0.0);
+                dfse[k] = fus - fds + lc.alhc * precnv;
+                dfqa[k] = fuq - fdq - precnv;
+            }
+            iptop = itop;
+            // physics.f90:127-138 (level 1 is not rescaled)
+#pragma unroll
+            for (int k = 2; k <= KX; k++) {
+                dfse[k] = dfse[k] * rps * lc.grdscp[k - 1];
+                dfqa[k] = dfqa[k] * rps * lc.grdsig[k - 1];
+            }
+            // ---------------------- large_scale_condensation.f90:33-95 ----------------------
+            const double trlsc = 4.0, rhlsc = F32(0.9), drhlsc = F32(0.1), rhblsc = F32(0.95), qsmax = 10.0;
+            const double rtlsc = 1.0 / (trlsc * 3600.0), tfact = lc.alhc / lc.cp, prg = lc.p0 / lc.grav;
+            const double psa2 = psg * psg;
+            double dtlsc[KX + 1], dqlsc[KX + 1];
+            dtlsc[1] = 0.0; dqlsc[1] = 0.0;
+            const int icnv_ = KX - iptop;   // physics.f90:132, before LSC lowers iptop
+            ib[a.L.icnv + col] = icnv_;
+#pragma unroll
+            for (int k = 2; k <= KX; k++) {
+                const double sig2 = lc.fsg[k - 1] * lc.fsg[k - 1];
+                double rhref = rhlsc + drhlsc * (sig2 - 1.0);
+                if (k == KX) rhref = dmax(rhref, rhblsc);
+                const double dqmax = qsmax * sig2 * rtlsc;
+                const double dqa = rhref * qsat[k] - qg[k];
+                if (dqa < 0.0) {
+                    iptop = min(k, iptop);
+                    dqlsc[k] = dqa * rtlsc;
+                    dtlsc[k] = tfact * dmin(-dqlsc[k], dqmax * psa2);
+                } else {
+                    dqlsc[k] = 0.0;
+                    dtlsc[k] = 0.0;
+                }
+            }
+            double precls = 0.0;
+#pragma unroll
+            for (int k = 2; k <= KX; k++) {
+                const double pfact = lc.dhs[k - 1] * prg;
+                precls = precls - pfact * dqlsc[k];
+            }
+            precls = precls * psg;
+#pragma unroll
+            for (int k = 1; k <= KX; k++) {   // physics.f90:137-138
+                ttend[k] = ttend[k] + dfse[k] + dtlsc[k];
+                qtend[k] = qtend[k] + dfqa[k] + dqlsc[k];
+            }
+            G2(a.L.precnv) = precnv; G2(a.L.precls) = precls; G2(a.L.cbmf) = cbmf;
+            ib[a.L.iptop + col] = iptop;
+
+            // ------------------------- shortwave (every nstrad-th step) -------------------------
+            if (csw) {
+                const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
+                const double clsmax = F32(0.60), clsminl = F32(0.15), gse_s0 = 0.25, gse_s1 = F32(0.40);
+                const double albcl = F32(0.43), albcls = 0.50;
+                const double absdry = F32(0.033), absaer = F32(0.033), abswv1 = F32(0.022), abswv2 = 15.000, abscl1 = F32(0.015), abscl2 = F32(0.15);
+                const double ablwin = F32(0.3), ablco2 = 6.0, ablwv1 = F32(0.7), ablwv2 = 50.0, ablcl1 = 12.0, ablcl2 = F32(0.6);
+                const double epslw = F32(0.05);
+                const double gse = (se[KX - 1] - se[KX]) / (phig[KX - 1] - phig[KX]);   // physics.f90:147
+                // clouds  shortwave_radiation.f90:332-410
+                double cloudc, clstr;
+                int icltop;
+                const double rrcl = 1. / (rhcl2 - rhcl1);
+                if (rh[nl1] > rhcl1) { cloudc = rh[nl1] - rhcl1; icltop = nl1; }
+                else { cloudc = 0.0; icltop = nlp; }
+                for (int k = 3; k <= KX - 2; k++) {
+                    const double drh = rh[k] - rhcl1;
+                    if (drh > cloudc && qg[k] > qacl) { cloudc = drh; icltop = k; }
+                }
+                {
+                    const double pr1 = dmin(pmaxcl, F32(86.4) * (precnv + precls));
+                    const double cc = dmin(1.0, cloudc * rrcl);
+                    cloudc = dmin(1.0, wpcl * sqrt(pr1) + cc * cc);
+                    icltop = min(iptop, icltop);
+                }
+                const double qcloud = qg[nl1];
+                {
+                    const double clfact = F32(1.2), rgse = 1.0 / (gse_s1 - gse_s0);
+                    const double fstab = dmax(0.0, dmin(1.0, rgse * (gse - gse_s0)));
+                    clstr = fstab * dmax(clsmax - clfact * cloudc, 0.0);
+                    const double clstrl = dmax(clstr, clsminl) * rh[KX];
+                    const double fm = G2(a.L.fmask_l);
+                    clstr = clstr + fm * (clstrl - clstr);
+                }
+                ib[a.L.icltop + col] = icltop;
+                G2(a.L.qcloud) = qcloud; G2(a.L.cloudc) = cloudc; G2(a.L.clstr) = clstr;
+                // get_shortwave_rad_fluxes  shortwave_radiation.f90:74-234
+                const double fsol = G2(a.L.fsol), ozone = G2(a.L.ozone), ozupp = G2(a.L.ozupp), zenit = G2(a.L.zenit), stratz = G2(a.L.stratz);
+                const double albsfc = G2(a.L.albsfc);
+                const double fband2 = F32(0.05), fband1 = 1.0 - fband2;
+                double tau1[KX + 1], tau2_[KX + 1], tau3[KX + 1], dfabs[KX + 1];
+#pragma unroll
+                for (int k = 1; k <= KX; k++) tau3[k] = 0.0;
+                if (icltop <= KX) tau3[icltop] = albcl * cloudc;
+                tau3[KX] = albcls * clstr;
+                const double psaz = psg * zenit;
+                double acloud = cloudc * dmin(abscl1 * qcloud, abscl2);
+                tau1[1] = exp(-psaz * lc.dhs[0] * absdry);
+                for (int k = 2; k <= nl1; k++) {
+                    const double abs1 = absdry + absaer * (lc.fsg[k - 1] * lc.fsg[k - 1]);
+                    if (k >= icltop) tau1[k] = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qg[k] + acloud));
+                    else tau1[k] = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qg[k]));
+                }
+                {
+                    const double abs1 = absdry + absaer * (lc.fsg[KX - 1] * lc.fsg[KX - 1]);
+                    tau1[KX] = exp(-psaz * lc.dhs[KX - 1] * (abs1 + abswv1 * qg[KX]));
+                }
+                tau2_[1] = 0.0;
+                for (int k = 2; k <= KX; k++) tau2_[k] = exp(-psaz * lc.dhs[k - 1] * abswv2 * qg[k]);
+                double ftop = fsol;
+                double flux1 = fsol * fband1, flux2 = fsol * fband2;
+                dfabs[1] = flux1;
+                flux1 = tau1[1] * (flux1 - ozupp * psg);
+                dfabs[1] = dfabs[1] - flux1;
+                dfabs[2] = flux1;
+                flux1 = tau1[2] * (flux1 - ozone * psg);
+                dfabs[2] = dfabs[2] - flux1;
+                for (int k = 3; k <= KX; k++) {
+                    tau3[k] = flux1 * tau3[k];
+                    flux1 = flux1 - tau3[k];
+                    dfabs[k] = flux1;
+                    flux1 = tau1[k] * flux1;
+                    dfabs[k] = dfabs[k] - flux1;
+                }
+                for (int k = 2; k <= KX; k++) {
+                    dfabs[k] = dfabs[k] + flux2;
+                    flux2 = tau2_[k] * flux2;
+                    dfabs[k] = dfabs[k] - flux2;
+                }
+                const double fsfcd = flux1 + flux2;
+                flux1 = flux1 * albsfc;
+                const double fsfc = fsfcd - flux1;
+                for (int k = KX; k >= 1; k--) {
+                    dfabs[k] = dfabs[k] + flux1;
+                    flux1 = tau1[k] * flux1;
+                    dfabs[k] = dfabs[k] - flux1;
+                    flux1 = flux1 + tau3[k];
+                }
+                ftop = ftop - flux1;
+                G2(a.L.ssrd) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
+#pragma unroll
+                for (int k = 1; k <= KX; k++) G3(a.L.tt_rsw, k) = dfabs[k] * rps * lc.grdscp[k - 1];   // physics.f90:160-162
+                // longwave transmissivities :190-233 -> persistent tau2(ix,il,kx,4)
+#define TAU2(k, b) mb[a.L.tau2 + ((size_t)((b)-1) * KX + ((k)-1)) * N + col]
+                TAU2(1, 1) = exp(-psg * lc.dhs[0] * ablwin);
+                TAU2(1, 2) = exp(-psg * lc.dhs[0] * ablco2);
+                TAU2(1, 3) = 1.0;
+                TAU2(1, 4) = 1.0;
+                for (int k = 2; k <= KX; k += KX - 2) {
+                    TAU2(k, 1) = exp(-psg * lc.dhs[k - 1] * ablwin);
+                    TAU2(k, 2) = exp(-psg * lc.dhs[k - 1] * ablco2);
+                    TAU2(k, 3) = exp(-psg * lc.dhs[k - 1] * ablwv1 * qg[k]);
+                    TAU2(k, 4) = exp(-psg * lc.dhs[k - 1] * ablwv2 * qg[k]);
+                }
+                acloud = cloudc * ablcl2;
+                for (int k = 3; k <= nl1; k++) {
+                    const double deltap = psg * lc.dhs[k - 1];
+                    double acloud1;
+                    if (k < icltop) acloud1 = acloud;
+                    else acloud1 = ablcl1 * cloudc;
+                    TAU2(k, 1) = exp(-deltap * (ablwin + acloud1));
+                    TAU2(k, 2) = exp(-deltap * ablco2);
+                    TAU2(k, 3) = exp(-deltap * dmax(ablwv1 * qg[k], acloud));
+                    TAU2(k, 4) = exp(-deltap * dmax(ablwv2 * qg[k], acloud));
+                }
+                const double eps1 = epslw / (lc.dhs[0] + lc.dhs[1]);
+                mb[a.L.stratc + col] = stratz * psg;
+                mb[a.L.stratc + N + col] = eps1 * psg;
+            }
+        }
+
+        // ------------------- downward longwave  longwave_radiation.f90:16-117 -------------------
+        const double emisfc = F32(0.98), epslw = F32(0.05);
+        double st4a1[KX + 1], st4a2[KX + 1], tt_rlw[KX + 1], flux[5];
+        double slrd;
+        {
+            const int nl1 = KX - 1;
+#pragma unroll
+            for (int k = 1; k <= nl1; k++) st4a1[k] = tg[k] + wvi2[k] * (tg[k + 1] - tg[k]);
+            st4a2[1] = 0.75 * tg[1] + 0.25 * st4a1[1];
+            st4a2[2] = 0.50 * tg[2] + 0.25 * (st4a1[1] + st4a1[2]);
+            const double anis = 1.0;
+#pragma unroll
+            for (int k = 3; k <= nl1; k++) st4a2[k] = 0.5 * anis * dmax(st4a1[k] - st4a1[k - 1], 0.0);
+            st4a2[KX] = anis * dmax(tg[KX] - st4a1[nl1], 0.0);
+#pragma unroll
+            for (int k = 1; k <= 2; k++) {
+                const double x = st4a2[k];
+                st4a1[k] = lc.sbc * ((x * x) * (x * x));
+                st4a2[k] = 0.0;
+            }
+#pragma unroll
+            for (int k = 3; k <= KX; k++) {
+                const double x = tg[k];
+                const double st3a = lc.sbc * ((x * x) * x);
+                st4a1[k] = st3a * tg[k];
+                st4a2[k] = 4.0 * st3a * st4a2[k];
+            }
+            double fsfcd = 0.0;
+#pragma unroll
+            for (int k = 1; k <= KX; k++) tt_rlw[k] = 0.0;
+            int nt[KX + 1];
+#pragma unroll
+            for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;   // nint(T) -> row of fband(100:400,:)
+            for (int jb = 1; jb <= 2; jb++) {
+                const double emis = 1.0 - TAU2(1, jb);
+                const double brad = a.fband[nt[1] + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
+                flux[jb] = emis * brad;
+                tt_rlw[1] = tt_rlw[1] - flux[jb];
+            }
+            flux[3] = 0.0; flux[4] = 0.0;
+            for (int jb = 1; jb <= 4; jb++)
+                for (int k = 2; k <= KX; k++) {
+                    const double tau = TAU2(k, jb);
+                    const double emis = 1.0 - tau;
+                    const double brad = a.fband[nt[k] + 301 * (jb - 1)] * (st4a1[k] + emis * st4a2[k]);
+                    tt_rlw[k] = tt_rlw[k] + flux[jb];
+                    flux[jb] = tau * flux[jb] + emis * brad;
+                    tt_rlw[k] = tt_rlw[k] - flux[jb];
+                }
+            for (int jb = 1; jb <= 4; jb++) fsfcd = fsfcd + emisfc * flux[jb];
+            const double corlw = epslw * emisfc * st4a1[KX];
+            tt_rlw[KX] = tt_rlw[KX] - corlw;
+            fsfcd = fsfcd + corlw;
+            slrd = fsfcd;
+            G2(a.L.slrd) = slrd;
+        }
+
+        // ------------------------- surface_fluxes.f90:42-296 (lfluxland = .true.) -------------------------
+        double ts, shf3, evap3, ustr3, vstr3, slru3;
+        {
+            const double fwind0 = F32(0.95), ftemp0 = 1.0, cdl = F32(2.4e-3), cds = F32(1.0e-3), chl = F32(1.2e-3), chs = F32(0.9e-3);
+            const double vgust = 5.0, ctday = F32(1.0e-2), dtheta = 3.0, fstab = F32(0.67), clambda = 7.0, clambsn = 7.0;
+            const double esbc = emisfc * lc.sbc;
+            const int nl1 = KX - 1;
+            const double phi0 = G2(a.L.phis0), fmask = G2(a.L.fmask_l), tsea = G2(a.L.sst_am), stl_am = G2(a.L.stl_am);
+            const double soilw_am = G2(a.L.soilw_am), alb_l = G2(a.L.alb_l), alb_s = G2(a.L.alb_s), snowc = G2(a.L.snowc), forog = G2(a.L.forog);
+            const double ssrd = G2(a.L.ssrd);
+            const double u0 = fwind0 * ug[KX], v0 = fwind0 * vg[KX];
+            const double gtemp0 = 1.0 - ftemp0, rcp = 1.0 / lc.cp;
+            const double dt1 = wvi2[KX] * (tg[KX] - tg[nl1]);
+            double t1_1 = tg[KX] + dt1;
+            double t1_2 = t1_1 - phi0 * dt1 / (lc.rgas * 288.0 * lc.sigl[KX - 1]);
+            const double t2_2 = tg[KX] + rcp * phig[KX];
+            const double t2_1 = t2_2 - rcp * phi0;
+            if (tg[KX] > tg[nl1]) {
+                t1_1 = ftemp0 * t1_1 + gtemp0 * t2_1;
+                t1_2 = ftemp0 * t1_2 + gtemp0 * t2_2;
+            } else {
+                t1_1 = tg[KX];
+                t1_2 = tg[KX];
+            }
+            double t0 = t1_2 + fmask * (t1_1 - t1_2);
+            const double denvvs0 = (lc.p0 * psg / (lc.rgas * t0)) * sqrt(u0 * u0 + v0 * v0 + vgust * vgust);
+            double tskin = stl_am + ctday * sqrt(a.coa[j]) * ssrd * (1.0 - alb_l) * psg;
+            const double rdth = fstab / dtheta, astab = 0.5;
+            double dthl;
+            if (tskin > t2_1) dthl = dmin(dtheta, tskin - t2_1);
+            else dthl = dmax(-dtheta, astab * (tskin - t2_1));
+            const double denvvs1 = denvvs0 * (1.0 + dthl * rdth);
+            const double cdldv = cdl * denvvs0 * forog;
+            const double ustr1 = -cdldv * ug[KX], vstr1 = -cdldv * vg[KX];
+            const double chlcp = chl * lc.cp;
+            double shf1 = chlcp * denvvs1 * (tskin - t1_1);
+            const double q1_1 = qg[KX];
+            const double qsat0_1 = qsat_pt(tskin, psg);
+            double evap1 = chl * denvvs1 * dmax(0.0, soilw_am * qsat0_1 - q1_1);
+            const double tsk3 = (tskin * tskin) * tskin;
+            const double dslr = 4.0 * esbc * tsk3;
+            double slru1 = esbc * tsk3 * tskin;
+            double hfluxn1 = ssrd * (1.0 - alb_l) + slrd - (slru1 + shf1 + lc.alhc * evap1);
+            {   // lskineb
+                const double clamb = clambda + snowc * (clambsn - clambda);
+                hfluxn1 = hfluxn1 - clamb * (tskin - stl_am);
+                double dtskin = tskin + 1.0;
+                double qsat0_2 = qsat_pt(dtskin, psg);
+                if (evap1 > 0.0) qsat0_2 = soilw_am * (qsat0_2 - qsat0_1);
+                else qsat0_2 = 0.0;
+                dtskin = hfluxn1 / (clamb + dslr + chl * denvvs1 * (lc.cp + lc.alhc * qsat0_2));
+                tskin = tskin + dtskin;
+                shf1 = shf1 + chlcp * denvvs1 * dtskin;
+                evap1 = evap1 + chl * denvvs1 * qsat0_2 * dtskin;
+                slru1 = slru1 + dslr * dtskin;
+                hfluxn1 = clamb * (tskin - stl_am);
+            }
+            double dths;
+            if (tsea > t2_2) dths = dmin(dtheta, tsea - t2_2);
+            else dths = dmax(-dtheta, astab * (tsea - t2_2));
+            const double denvvs2 = denvvs0 * (1.0 + dths * rdth);
+            const double q1_2 = qg[KX];
+            const double cdsdv = cds * denvvs2;
+            const double ustr2 = -cdsdv * ug[KX], vstr2 = -cdsdv * vg[KX];
+            const double shf2 = chs * lc.cp * denvvs2 * (tsea - t1_2);
+            const double qsat0_s = qsat_pt(tsea, psg);
+            const double evap2 = chs * denvvs2 * (qsat0_s - q1_2);
+            const double slru2 = esbc * ((tsea * tsea) * (tsea * tsea));
+            const double hfluxn2 = ssrd * (1.0 - alb_s) + slrd - slru2 + shf2 + lc.alhc * evap2;
+            ustr3 = ustr2 + fmask * (ustr1 - ustr2);
+            vstr3 = vstr2 + fmask * (vstr1 - vstr2);
+            shf3 = shf2 + fmask * (shf1 - shf2);
+            evap3 = evap2 + fmask * (evap1 - evap2);
+            slru3 = slru2 + fmask * (slru1 - slru2);
+            ts = tsea + fmask * (stl_am - tsea);
+            tskin = tsea + fmask * (tskin - tsea);
+            t0 = t1_2 + fmask * (t1_1 - t1_2);
+            mb[a.L.ustr + col] = ustr1; mb[a.L.ustr + N + col] = ustr2; mb[a.L.ustr + 2 * N + col] = ustr3;
+            mb[a.L.vstr + col] = vstr1; mb[a.L.vstr + N + col] = vstr2; mb[a.L.vstr + 2 * N + col] = vstr3;
+            mb[a.L.shf + col] = shf1; mb[a.L.shf + N + col] = shf2; mb[a.L.shf + 2 * N + col] = shf3;
+            mb[a.L.evap + col] = evap1; mb[a.L.evap + N + col] = evap2; mb[a.L.evap + 2 * N + col] = evap3;
+            mb[a.L.slru + col] = slru1; mb[a.L.slru + N + col] = slru2; mb[a.L.slru + 2 * N + col] = slru3;
+            mb[a.L.hfluxn + col] = hfluxn1; mb[a.L.hfluxn + N + col] = hfluxn2;
+            G2(a.L.ts) = ts; G2(a.L.tskin) = tskin; G2(a.L.u0) = u0; G2(a.L.v0) = v0; G2(a.L.t0) = t0;
+        }
+
+        // ------------------- upward longwave  longwave_radiation.f90:120-194 -------------------
+        {
+            const double refsfc = 1.0 - emisfc;
+            const double fsfcu = slru3;
+            G2(a.L.slr) = fsfcu - slrd;
+            const int nts = (int)round(ts) - 100;
+            for (int jb = 1; jb <= 4; jb++) flux[jb] = a.fband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
+            tt_rlw[KX] = tt_rlw[KX] + epslw * fsfcu;
+            int nt[KX + 1];
+#pragma unroll
+            for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;
+            for (int jb = 1; jb <= 4; jb++)
+                for (int k = KX; k >= 2; k--) {
+                    const double tau = TAU2(k, jb);
+                    const double emis = 1.0 - tau;
+                    const double brad = a.fband[nt[k] + 301 * (jb - 1)] * (st4a1[k] - emis * st4a2[k]);
+                    tt_rlw[k] = tt_rlw[k] + flux[jb];
+                    flux[jb] = tau * flux[jb] + emis * brad;
+                    tt_rlw[k] = tt_rlw[k] - flux[jb];
+                }
+            for (int jb = 1; jb <= 2; jb++) {
+                const double tau = TAU2(1, jb);
+                const double emis = 1.0 - tau;
+                const double brad = a.fband[nt[1] + 301 * (jb - 1)] * (st4a1[1] - emis * st4a2[1]);
+                tt_rlw[1] = tt_rlw[1] + flux[jb];
+                flux[jb] = tau * flux[jb] + emis * brad;
+                tt_rlw[1] = tt_rlw[1] - flux[jb];
+            }
+            const double stratc1 = mb[a.L.stratc + col], stratc2 = mb[a.L.stratc + N + col];
+            const double corlw1 = lc.dhs[0] * stratc2 * st4a1[1] + stratc1;
+            const double corlw2 = lc.dhs[1] * stratc2 * st4a1[2];
+            tt_rlw[1] = tt_rlw[1] - corlw1;
+            tt_rlw[2] = tt_rlw[2] - corlw2;
+            double ftop = corlw1 + corlw2;
+            for (int jb = 1; jb <= 4; jb++) ftop = ftop + flux[jb];
+            G2(a.L.olr) = ftop;
+#pragma unroll
+            for (int k = 1; k <= KX; k++) {   // physics.f90:182-186
+                tt_rlw[k] = tt_rlw[k] * rps * lc.grdscp[k - 1];
+                ttend[k] = ttend[k] + G3(a.L.tt_rsw, k) + tt_rlw[k];
+            }
+        }
+
+        // ------------------- vertical_diffusion.f90:30-143 -------------------
+        {
+            const double trshc = 6.0, trvdi = 24.0, trvds = 6.0, redshc = 0.5, rhgrad = 0.5, segrad = F32(0.1);
+            const int nl1 = KX - 1;
+            double rsig[KX + 1], rsig1[KX + 1], ttenvd[KX + 1], qtenvd[KX + 1];
+            const double cshc = lc.dhs[KX - 1] / 3600.0;
+            const double cvdi = (lc.sigh[nl1] - lc.sigh[1]) / ((nl1 - 1) * 3600.0);
+            const double fshcq = cshc / trshc, fshcse = cshc / (trshc * lc.cp);
+            const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * lc.cp);
+#pragma unroll
+            for (int k = 1; k <= nl1; k++) { rsig[k] = 1.0 / lc.dhs[k - 1]; rsig1[k] = 1.0 / (1.0 - lc.sigh[k]); }
+            rsig[KX] = 1.0 / lc.dhs[KX - 1];
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { ttenvd[k] = 0.0; qtenvd[k] = 0.0; }
+            double drh0 = rhgrad * (lc.fsg[KX - 1] - lc.fsg[nl1 - 1]);
+            double fvdiq2 = fvdiq * lc.sigh[nl1];
+            {
+                const double dmse = se[KX] - se[nl1] + lc.alhc * (qg[KX] - qsat[nl1]);
+                const double drh = rh[KX] - rh[nl1];
+                double fcnv = 1.0;
+                if (dmse >= 0.0) {
+                    if (ib[a.L.icnv + col] > 0) fcnv = redshc;
+                    const double fluxse = fcnv * fshcse * dmse;
+                    ttenvd[nl1] = fluxse * rsig[nl1];
+                    ttenvd[KX] = -fluxse * rsig[KX];
+                    if (drh >= 0.0) {
+                        const double fluxq = fcnv * fshcq * qsat[KX] * drh;
+                        qtenvd[nl1] = fluxq * rsig[nl1];
+                        qtenvd[KX] = -fluxq * rsig[KX];
+                    }
+                } else if (drh > drh0) {
+                    const double fluxq = fvdiq2 * qsat[nl1] * drh;
+                    qtenvd[nl1] = fluxq * rsig[nl1];
+                    qtenvd[KX] = -fluxq * rsig[KX];
+                }
+            }
+            for (int k = 3; k <= KX - 2; k++) {
+                if (lc.sigh[k] > 0.5) {
+                    drh0 = rhgrad * (lc.fsg[k] - lc.fsg[k - 1]);
+                    fvdiq2 = fvdiq * lc.sigh[k];
+                    const double drh = rh[k + 1] - rh[k];
+                    if (drh >= drh0) {
+                        const double fluxq = fvdiq2 * qsat[k] * drh;
+                        qtenvd[k] = qtenvd[k] + fluxq * rsig[k];
+                        qtenvd[k + 1] = qtenvd[k + 1] - fluxq * rsig[k + 1];
+                    }
+                }
+            }
+            for (int k = 1; k <= nl1; k++) {
+                const double se0 = se[k + 1] + segrad * (phig[k] - phig[k + 1]);
+                if (se[k] < se0) {
+                    const double fluxse = fvdise * (se0 - se[k]);
+                    ttenvd[k] = ttenvd[k] + fluxse * rsig[k];
+                    for (int k1 = k + 1; k1 <= KX; k1++) ttenvd[k1] = ttenvd[k1] - fluxse * rsig1[k];
+                }
+            }
+            // physics.f90:197-205 (ut_pbl, vt_pbl are zero above the lowest level)
+            const double ut8 = 0.0 + ustr3 * rps * lc.grdsig[KX - 1];
+            const double vt8 = 0.0 + vstr3 * rps * lc.grdsig[KX - 1];
+            ttenvd[KX] = ttenvd[KX] + shf3 * rps * lc.grdscp[KX - 1];
+            qtenvd[KX] = qtenvd[KX] + evap3 * rps * lc.grdsig[KX - 1];
+#pragma unroll
+            for (int k = 1; k <= KX - 1; k++) { utend[k] = utend[k] + 0.0; vtend[k] = vtend[k] + 0.0; }
+            utend[KX] = utend[KX] + ut8;
+            vtend[KX] = vtend[KX] + vt8;
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { ttend[k] = ttend[k] + ttenvd[k]; qtend[k] = qtend[k] + qtenvd[k]; }
+        }
+
+        // ------------------- SPPT blend  physics.f90:208-222 (mu(k) = 1) -------------------
+        if (a.sppt_on) {
+#pragma unroll
+            for (int k = 1; k <= KX; k++) {
+                double p = GIN(GI_SPPT + k - 1);
+                p = dmin(1.0, fabs(p)) * copysign(1.0, p);   // sppt.f90:98
+                const double f = (1 + p * 1.0);
+                utend[k] = f * (utend[k] - ut_dyn[k]) + ut_dyn[k];
+                vtend[k] = f * (vtend[k] - vt_dyn[k]) + vt_dyn[k];
+                ttend[k] = f * (ttend[k] - tt_dyn[k]) + tt_dyn[k];
+                qtend[k] = f * (qtend[k] - qt_dyn[k]) + qt_dyn[k];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 1; k <= KX; k++) {
+        const int f = GO_PER * (k - 1);
+        GOUT(f + 0) = utend[k]; GOUT(f + 1) = vtend[k]; GOUT(f + 5) = ttend[k]; GOUT(f + 8) = qtend[k];
+    }
+#undef TAU2
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-step surface slabs: couple_land_atm + couple_sea_atm (land_model.f90:184-239,
+// sea_model.f90:253-444, interpolation.f90:16-69) for one grid point per thread.
+// ------------------------------------------------------------------------------------------
+struct SlabArgs {
+    double* base; long long stride;
+    Layout L;
+    SharedDev sh;
+    DevClock* clk;
+    const LevelConsts* lc;
+    int N;
+    int day0;    // 1: the `day == 0` initialisation call of initialize_coupler
+};
+
+__device__ __forceinline__ double forint_pt(const double* f12, int N, int q, int imon, double tmonth) {   // interpolation.f90:16-35
+    int imon2;
+    double wmon;
+    if (tmonth <= 0.5) { imon2 = imon - 1; if (imon == 1) imon2 = 12; wmon = 0.5 - tmonth; }
+    else { imon2 = imon + 1; if (imon == 12) imon2 = 1; wmon = tmonth - 0.5; }
+    const double a0 = f12[(size_t)(imon - 1) * N + q], b0 = f12[(size_t)(imon2 - 1) * N + q];
+    return a0 + wmon * (b0 - a0);
+}
+__device__ __forceinline__ double forin5_pt(const double* f12, int N, int q, int imon, double tmonth) {   // interpolation.f90:38-69
+    int im2 = imon - 2, im1 = imon - 1, ip1 = imon + 1, ip2 = imon + 2;
+    if (im2 < 1) im2 += 12;
+    if (im1 < 1) im1 += 12;
+    if (ip1 > 12) ip1 -= 12;
+    if (ip2 > 12) ip2 -= 12;
+    const double c0 = (double)(1.0f / 12.0f);
+    const double t0 = c0 * tmonth, t1 = c0 * (1.0 - tmonth), t2 = 0.25 * tmonth * (1 - tmonth);
+    const double wm2 = -t1 + t2, wm1 = -c0 + 8 * t1 - 6 * t2, w0 = 7 * c0 + 10 * t2, wp1 = -c0 + 8 * t0 - 6 * t2, wp2 = -t0 + t2;
+    return wm2 * f12[(size_t)(im2 - 1) * N + q] + wm1 * f12[(size_t)(im1 - 1) * N + q] + w0 * f12[(size_t)(imon - 1) * N + q] +
+           wp1 * f12[(size_t)(ip1 - 1) * N + q] + wp2 * f12[(size_t)(ip2 - 1) * N + q];
+}
+
+__global__ void k_slab(SlabArgs a) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.N) return;
+    const int N = a.N;
+    double* mb = a.base + (size_t)blockIdx.y * a.stride;
+    const DevClock& c = *a.clk;
+    const LevelConsts& lc = *a.lc;
+    const int imont1 = c.imont1;
+    const double tmonth = c.tmonth;
+#define S2(off) mb[(off) + q]
+    // ---- land (land_model.f90:184-239)
+    const double stlcl = forin5_pt(a.sh.stl12, N, q, imont1, tmonth);
+    const double snowdcl = forint_pt(a.sh.snowd12, N, q, imont1, tmonth);
+    const double soilwcl = forint_pt(a.sh.soilw12, N, q, imont1, tmonth);
+    if (a.day0) {
+        S2(a.L.stl_lm) = stlcl;
+        S2(a.L.stl_am) = stlcl;
+    } else {
+        double tanom = S2(a.L.stl_lm) - stlcl;
+        tanom = a.sh.cdland[q] * (tanom + a.sh.rhcapl[q] * mb[a.L.hfluxn + q]);
+        const double v = tanom + stlcl;
+        S2(a.L.stl_lm) = v;
+        S2(a.L.stl_am) = v;
+    }
+    S2(a.L.stlcl_ob) = stlcl;
+    S2(a.L.snowd_am) = snowdcl;
+    S2(a.L.soilw_am) = soilwcl;
+    // ---- sea (sea_model.f90:253-363)
+    double sstcl = forin5_pt(a.sh.sst12, N, q, imont1, tmonth);
+    double sicecl = forint_pt(a.sh.sice12, N, q, imont1, tmonth);
+    double* an = mb + a.L.sstan3;
+    if (!a.day0 && c.obs_ssta) {   // obs_ssta :366-385
+        an[q] = an[N + q];
+        an[N + q] = an[2 * N + q];
+        const int rec = c.next_month;
+        an[2 * N + q] = (rec >= 1 && rec <= c.nssta) ? (double)a.sh.ssta[(size_t)(rec - 1) * N + q] : 0.0;
+    }
+    double sstan_ob;
+    {   // forint(2, sstan3, sstan_ob)
+        int imon2;
+        double wmon;
+        if (tmonth <= 0.5) { imon2 = 1; wmon = 0.5 - tmonth; }
+        else { imon2 = 3; wmon = tmonth - 0.5; }
+        const double a0 = an[N + q], b0 = an[(size_t)(imon2 - 1) * N + q];
+        sstan_ob = a0 + wmon * (b0 - a0);
+    }
+    const double sstfr = (double)(273.2f - 1.8f);   // :285 real32 subtraction
+    double ticecl;
+    if (sstcl > sstfr) {
+        sicecl = dmin(0.5, sicecl);
+        ticecl = sstfr;
+        if (sicecl > 0.0) sstcl = sstfr + (sstcl - sstfr) / (1.0 - sicecl);
+    } else {
+        sicecl = dmax(0.5, sicecl);
+        ticecl = sstfr + (sstcl - sstfr) / sicecl;
+        sstcl = sstfr;
+    }
+    double sst_om, tice_om, sice_om;
+    if (a.day0) {
+        sst_om = 0.0;   // sea_coupling_flag <= 0
+        tice_om = ticecl;
+        sice_om = sicecl;
+    } else {   // run_sea_model :387-444 (uses the pre-update sstcl_ob/sicecl_ob just computed, tice_am/sice_am of the last coupling)
+        const double albsea = F32(0.07), albice = F32(0.60), emisfc = F32(0.98), beta = 1.0;
+        const double tice_am = S2(a.L.tice_am), sice_am = S2(a.L.sice_am);
+        const double ssrd = S2(a.L.ssrd), shf2 = mb[a.L.shf + N + q], evap2 = mb[a.L.evap + N + q], hfluxn2 = mb[a.L.hfluxn + N + q];
+        sst_om = S2(a.L.sst_om); tice_om = S2(a.L.tice_om);
+        const double sstfr4 = (sstfr * sstfr) * (sstfr * sstfr);
+        const double difice = (albsea - albice) * ssrd + emisfc * lc.sbc * (sstfr4 - (tice_am * tice_am) * (tice_am * tice_am)) + shf2 + evap2 * lc.alhc;
+        const double hflux_i = hfluxn2 + difice * (1.0 - sice_am);
+        double hflux = hfluxn2 - 0.0 - sicecl * (hflux_i + beta * (sstfr - tice_om));
+        double tanom = sst_om - sstcl;
+        tanom = a.sh.cdsea[q] * (tanom + a.sh.rhcaps[q] * hflux);
+        sst_om = tanom + sstcl;
+        hflux = hflux_i + beta * (sstfr - tice_om);
+        tanom = tice_om - ticecl;
+        const double anom0 = 20.;
+        const double cdis = a.sh.cdice[q] * (anom0 / (anom0 + fabs(tanom)));
+        tanom = cdis * (tanom + a.sh.rhcapi[q] * hflux);
+        tice_om = tanom + ticecl;
+        sice_om = sicecl;
+    }
+    S2(a.L.sst_om) = sst_om; S2(a.L.tice_om) = tice_om; S2(a.L.sice_om) = sice_om;
+    S2(a.L.sstcl_ob) = sstcl; S2(a.L.sicecl_ob) = sicecl; S2(a.L.ticecl_ob) = ticecl;
+    double sst_am = sstcl + sstan_ob;
+    const double sice_am = sice_om, tice_am = tice_om;
+    sst_am = sst_am + sice_am * (tice_am - sst_am);
+    S2(a.L.sst_am) = sst_am; S2(a.L.sice_am) = sice_am; S2(a.L.tice_am) = tice_am;
+    S2(a.L.ssti_om) = sst_om + sice_am * (tice_am - sst_om);
+#undef S2
+}
+
+// ------------------------------------------------------------------------------------------
+// Daily forcing (forcing.f90:44-99): solar fields from the per-day table, albedos, snow
+// cover and the grid-point humidity correction (its transform follows in K2).
+// Runs every step inside the graph but returns at once unless the clock says it is due.
+// ------------------------------------------------------------------------------------------
+struct ForcingArgs {
+    double* base; long long stride;
+    Layout L;
+    SharedDev sh;
+    const DevClock* clk;
+    const LevelConsts* lc;
+    int ix, il;
+    int force;
+};
+
+__global__ void k_daily_forcing(ForcingArgs a) {
+    if (!a.force && !a.clk->do_forcing) return;
+    const int N = a.ix * a.il;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    const int j = q / a.ix;
+    double* mb = a.base + (size_t)blockIdx.y * a.stride;
+    const LevelConsts& lc = *a.lc;
+    const double* S = a.sh.solar + (size_t)a.clk->doy * 5 * a.il;
+    mb[a.L.fsol + q] = S[0 * a.il + j];
+    mb[a.L.ozone + q] = S[1 * a.il + j];
+    mb[a.L.ozupp + q] = S[2 * a.il + j];
+    mb[a.L.zenit + q] = S[3 * a.il + j];
+    mb[a.L.stratz + q] = S[4 * a.il + j];
+    const double albsea = F32(0.07), albice = F32(0.60), albsn = F32(0.60), sd2sc = 60.0;
+    const double alb0 = mb[a.L.alb0 + q], fmask_l = mb[a.L.fmask_l + q], fmask_s = mb[a.L.fmask_s + q];
+    const double snowc = dmin(1.0, mb[a.L.snowd_am + q] / sd2sc);
+    const double alb_l = alb0 + snowc * (albsn - alb0);
+    const double alb_s = albsea + mb[a.L.sice_am + q] * (albice - albsea);
+    mb[a.L.snowc + q] = snowc;
+    mb[a.L.alb_l + q] = alb_l;
+    mb[a.L.alb_s + q] = alb_s;
+    mb[a.L.albsfc + q] = alb_s + fmask_l * (alb_l - alb_s);
+    // forcing.f90:77-99
+    const double gamlat = lc.gamma / (1000. * lc.grav);
+    const double corh = gamlat * mb[a.L.phis0 + q];
+    const double pexp = 1. / (lc.rgas * gamlat);
+    const double tsfc = fmask_l * mb[a.L.stl_am + q] + fmask_s * mb[a.L.sst_am + q];
+    const double tref = tsfc + corh;
+    const double psfc = pow(tsfc / tref, pexp);
+    const double qref = qsat_pt(tref, psfc / psfc);   // get_qsat(tref, psfc/psfc, -1): ps(1,1) = 1 wherever psfc is finite
+    const double qsfc = qsat_pt(tsfc, psfc);
+    mb[a.L.qcorh_g + q] = lc.refrh1 * (qref - qsfc);
+}
+
+// device calendar: the end-of-step bookkeeping of speedy.f90:44-47
+__global__ void k_clock_advance(DevClock* c) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) cal_advance(*c);
+}
+
+// ---- launchers ------------------------------------------------------------------------------
+void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override) {
+    Model& M = *ctx->model;
+    ColumnArgs a;
+    a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
+    a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
+    a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on;
+    const int N = ctx->d.ngrid();
+    dim3 grid((N + 63) / 64, ctx->nmembers);
+    k_grid_columns<<<grid, 64, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_slab(speedy_ctx* ctx, int day0) {
+    Model& M = *ctx->model;
+    SlabArgs a;
+    a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.sh = M.sh; a.clk = M.clock.p; a.lc = M.lc.p; a.N = ctx->d.ngrid(); a.day0 = day0;
+    dim3 grid((a.N + 127) / 128, ctx->nmembers);
+    k_slab<<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_daily_forcing(speedy_ctx* ctx, int force) {
+    Model& M = *ctx->model;
+    ForcingArgs a;
+    a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.sh = M.sh; a.clk = M.clock.p; a.lc = M.lc.p;
+    a.ix = ctx->d.ix; a.il = ctx->d.il; a.force = force;
+    const int N = ctx->d.ngrid();
+    dim3 grid((N + 127) / 128, ctx->nmembers);
+    k_daily_forcing<<<grid, 128, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_clock_advance(speedy_ctx* ctx) {
+    k_clock_advance<<<1, 32, 0, ctx->stream>>>(ctx->model->clock.p);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace spd

@@ -111,9 +111,10 @@ k_spec_to_grid(const double* __restrict__ in_base, long long in_ms, const XDesc*
 template <int TRUNC>
 __global__ void __launch_bounds__(TCfg<TRUNC>::K2_THREADS)
 k_grid_to_spec(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc,
-               double* __restrict__ out_base, long long out_ms, DevTables tv, int mode) {
+               double* __restrict__ out_base, long long out_ms, DevTables tv, int mode, const int* __restrict__ gate) {
     using C = TCfg<TRUNC>;
     extern __shared__ double smem[];
+    if (gate && !*gate) return;     // in-graph conditional work (daily forcing transform)
     double* sG = smem;
     double* sY = smem + C::IL * C::GS;
     const int b = blockIdx.x, e = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
@@ -208,13 +209,13 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, c
 }
 
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                         double* d_out, long long out_ms, int nmembers, int mode) {
+                         double* d_out, long long out_ms, int nmembers, int mode, const int* gate) {
     if (nbatch <= 0) return;
     dim3 grid(nbatch, nmembers);
     if (ctx->d.trunc == 30)
-        k_grid_to_spec<30><<<grid, TCfg<30>::K2_THREADS, TCfg<30>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode);
+        k_grid_to_spec<30><<<grid, TCfg<30>::K2_THREADS, TCfg<30>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode, gate);
     else
-        k_grid_to_spec<47><<<grid, TCfg<47>::K2_THREADS, TCfg<47>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode);
+        k_grid_to_spec<47><<<grid, TCfg<47>::K2_THREADS, TCfg<47>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode, gate);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

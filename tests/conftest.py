@@ -113,6 +113,84 @@ class Oracle:
             fn(*args)
         return (o1, o2) if nout == 2 else o1
 
+    # ---- model-level surface (o_api.cpp) ------------------------------------------------
+    def model_init(self, bc=None, y=1982, m=1, d=1, h=0, mi=0):
+        bc = bc or os.path.join(ROOT, "data", "bc_t30.bin")
+        rc = self.L.orc_model_init(bc.encode(), y, m, d, h, mi)
+        assert rc == 0, rc
+
+    def run(self, nsteps):
+        return self.L.orc_model_run(nsteps)
+
+    def field(self, name, shape=None, dtype=np.float64):
+        self.L.orc_field_len.restype = ctypes.c_longlong
+        n = self.L.orc_field_len(name.encode())
+        assert n > 0, name
+        a = np.zeros(n)
+        assert self.L.orc_get_field(name.encode(), self.p(a), ctypes.c_longlong(n)) == 0
+        if dtype == np.complex128:
+            a = a.view(np.complex128)
+        return a.reshape(shape) if shape is not None else a
+
+    def set_field(self, name, arr):
+        a = np.ascontiguousarray(arr)
+        a = a.view(np.float64).ravel() if a.dtype == np.complex128 else np.ascontiguousarray(a, dtype=np.float64).ravel()
+        rc = self.L.orc_set_field(name.encode(), self.p(a), ctypes.c_longlong(a.size))
+        assert rc == 0, (name, rc)
+
+    def ifield(self, name):
+        a = np.zeros(self.ix * self.il, dtype=np.int32)
+        assert self.L.orc_get_ifield(name.encode(), self.p(a), ctypes.c_longlong(a.size)) == 0
+        return a.reshape(self.il, self.ix)
+
+    def vec(self, name, n):
+        a = np.zeros(n)
+        assert self.L.orc_get_vec(name.encode(), self.p(a), n) == 0, name
+        return a
+
+    def state(self):
+        k, nx, mx = self.kx, self.nx, self.mx
+        c = np.complex128
+        return {"vor": self.field("vor", (2, k, nx, mx), c), "div": self.field("div", (2, k, nx, mx), c),
+                "t": self.field("t", (2, k, nx, mx), c), "tr": self.field("tr", (2, k, nx, mx), c),
+                "ps": self.field("ps", (2, nx, mx), c), "phi": self.field("phi", (k, nx, mx), c)}
+
+    def step(self, j1, j2, dt, csw=True):
+        self.L.orc_step(j1, j2, ctypes.c_double(dt), int(csw))
+
+    def initialize_implicit(self, dt):
+        self.L.orc_initialize_implicit(ctypes.c_double(dt))
+
+    def get_tendencies(self, j2, csw=True):
+        k, nx, mx = self.kx, self.nx, self.mx
+        o = [np.zeros((k, nx, mx), np.complex128), np.zeros((k, nx, mx), np.complex128), np.zeros((k, nx, mx), np.complex128),
+             np.zeros((nx, mx), np.complex128), np.zeros((k, nx, mx), np.complex128)]
+        self.L.orc_get_tendencies(j2, int(csw), *[self.p(x) for x in o])
+        return tuple(o)
+
+    def physics(self, vor, div, t, q, phi, psl, ut, vt, tt, qt, csw=True):
+        a = [np.ascontiguousarray(x, dtype=np.complex128) for x in (vor, div, t, q, phi, psl)]
+        g = [np.ascontiguousarray(x, dtype=np.float64).copy() for x in (ut, vt, tt, qt)]
+        self.L.orc_get_physical_tendencies(*[self.p(x) for x in a], *[self.p(x) for x in g], int(csw))
+        return tuple(g)
+
+    def check_diagnostics(self, level=2):
+        d = np.zeros(24)
+        rc = self.L.orc_check_diagnostics(level, self.p(d))
+        return rc, d.reshape(3, 8)
+
+    def output_fields(self):
+        k, il, ix = self.kx, self.il, self.ix
+        o = [np.empty((k, il, ix), np.float32) for _ in range(5)] + [np.empty((il, ix), np.float32)]
+        self.L.orc_output_fields(*[self.p(x) for x in o])
+        return dict(zip(("u", "v", "t", "q", "phi", "ps"), o))
+
+    def date(self):
+        d = (ctypes.c_int * 5)()
+        s = ctypes.c_longlong()
+        self.L.orc_model_date(d, ctypes.byref(s))
+        return tuple(d), s.value
+
 
 @pytest.fixture(scope="session")
 def pkg():
