@@ -154,6 +154,14 @@ void* speedy_stream(const speedy_ctx* ctx);
 /* use CUDA graphs for speedy_run_steps (1, default) or plain launches (0) */
 int speedy_set_graphs(speedy_ctx* ctx, int on);
 
+
+/* bench/profiling: mean CUDA-event duration (ms) of each kernel of the main-loop body over
+ * nsteps plain-launch steps; ms[10] in the order of speedy_kernel_names() */
+int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms);
+const char* speedy_kernel_names(void);
+/* host-only: date.f90:109-157 newdate applied nsteps times to ymdhm[5] (no GPU needed) */
+int speedy_host_calendar(int* ymdhm, int nsteps, double* tmonth, double* tyear, int* imont1);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,6 +316,13 @@ class Speedy:
         _chk(self.L.speedy_step_host(self.h, _p(a), ctypes.c_size_t(a.size), j1, j2, ctypes.c_double(dt), int(compute_shortwave)))
         return a
 
+    def time_kernels(self, nsteps=36, flush_l2=False):
+        """mean CUDA-event ms per kernel of the main-loop body -> dict name -> ms"""
+        ms = np.zeros(10)
+        _chk(self.L.speedy_time_kernels(self.h, int(nsteps), int(flush_l2), _p(ms)))
+        self.L.speedy_kernel_names.restype = ctypes.c_char_p
+        return dict(zip(self.L.speedy_kernel_names().decode().split(), ms.tolist()))
+
     def set_graphs(self, on):
         _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))
 

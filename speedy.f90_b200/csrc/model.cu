@@ -602,4 +602,71 @@ int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
     API_END
 }
 
+
+// ---- per-kernel timing of the main-loop body (bench.py's roofline leg) -------------------
+static const char* const kKernelNames[] = {"daily_forcing", "grid_to_spec_qcorh", "spec_prologue", "spec_to_grid", "grid_columns",
+                                           "grid_to_spec", "spec_step", "diagnostics", "clock_advance", "slab"};
+const char* speedy_kernel_names(void) {
+    return "daily_forcing grid_to_spec_qcorh spec_prologue spec_to_grid grid_columns grid_to_spec spec_step diagnostics clock_advance slab";
+}
+// Runs nsteps main-loop steps with plain launches, a CUDA-event pair around every launch on
+// the context's stream; ms[10] receives the mean duration of each kernel (names above).
+// flush_l2 != 0 overwrites a 256 MiB buffer before every launch (cold-cache timing).
+int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
+    if (ctx->sppt_on) throw std::runtime_error("speedy_time_kernels: SPPT contexts are not supported");
+    if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
+    const int NK = 10;
+    cudaEvent_t ev[NK + 1][2];
+    for (int i = 0; i < NK; i++) { CUDA_CHECK(cudaEventCreate(&ev[i][0])); CUDA_CHECK(cudaEventCreate(&ev[i][1])); }
+    DevBuf<double> flush;
+    if (flush_l2) flush.alloc((size_t)32 << 20);
+    for (int i = 0; i < NK; i++) ms[i] = 0.0;
+    const double delt = ctx->tab.c.delt;
+    for (int s = 0; s < nsteps; s++) {
+        for (int i = 0; i < NK; i++) {
+            if (flush_l2) CUDA_CHECK(cudaMemsetAsync(flush.p, s & 1, flush.n * sizeof(double), ctx->stream));
+            CUDA_CHECK(cudaEventRecord(ev[i][0], ctx->stream));
+            switch (i) {
+                case 0: launch_daily_forcing(ctx, 0); break;
+                case 1: xform_qcorh(ctx, true); break;
+                case 2: launch_spec_prologue(ctx, 2, 1); break;
+                case 3: xform_inverse(ctx, 2, 0, GI_NBASE); break;
+                case 4: launch_grid_columns(ctx, 0, -1); break;
+                case 5: xform_direct(ctx); break;
+                case 6: launch_spec_step(ctx, 2, 2, 2 * delt, 0); break;
+                case 7: launch_diagnostics(ctx, 2); break;
+                case 8: launch_clock_advance(ctx); break;
+                case 9: launch_slab(ctx, 0); break;
+            }
+            CUDA_CHECK(cudaEventRecord(ev[i][1], ctx->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < NK; i++) {
+            float t = 0.f;
+            CUDA_CHECK(cudaEventElapsedTime(&t, ev[i][0], ev[i][1]));
+            ms[i] += t / nsteps;
+        }
+    }
+    for (int i = 0; i < NK; i++) { cudaEventDestroy(ev[i][0]); cudaEventDestroy(ev[i][1]); }
+    (void)kKernelNames;
+    API_END
+}
+
+// host-only calendar check (no GPU): advance a date by nsteps time steps as newdate does
+int speedy_host_calendar(int* ymdhm, int nsteps, double* tmonth, double* tyear, int* imont1) {
+    API_BEGIN
+    DevClock c;
+    calendar_init(c, ymdhm[0], ymdhm[1], ymdhm[2], ymdhm[3], ymdhm[4], 1 << 30);
+    for (int s = 0; s < nsteps; s++) cal_advance(c);
+    ymdhm[0] = c.year; ymdhm[1] = c.month; ymdhm[2] = c.day; ymdhm[3] = c.hour; ymdhm[4] = c.minute;
+    if (tmonth) *tmonth = c.tmonth;
+    if (tyear) *tyear = c.tyear;
+    if (imont1) *imont1 = c.imont1;
+    API_END
+}
+
 }  // extern "C"
