@@ -238,10 +238,9 @@ def run_b200(args):
     alg = {  # algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)
         "spec_to_grid": M * 91 * (8 * nact + 8 * NG),
         "grid_to_spec": M * 73 * (8 * NG + 8 * (nact - 2)),
-        "grid_columns": M * NG * 8 * (91 + 73 + 25 + 8 + 32 + 2),       # 91 fields in, 73 out, ~25 2-D state, tt_rsw, tau2, stratc
+        "grid_columns": M * NG * 8 * (91 + 73 + 45 + 8 + 32 + 2),       # 91 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
         "spec_step": M * c.mx * c.nx * 16 * 165,
-        "spec_prologue": M * c.mx * c.nx * 16 * (32 + 1 + 8 + 1 + 34 + 8),
-        "slab": M * NG * 8 * 45,
+        "spec_prologue": M * c.mx * c.nx * 16 * (32 + 1 + 34),
     }
     tot = sum(kt_warm.values())
     dom = max(alg, key=lambda k: kt_warm[k])

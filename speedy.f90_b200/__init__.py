@@ -318,10 +318,11 @@ class Speedy:
 
     def time_kernels(self, nsteps=36, flush_l2=False):
         """mean CUDA-event ms per kernel of the main-loop body -> dict name -> ms"""
-        ms = np.zeros(10)
-        _chk(self.L.speedy_time_kernels(self.h, int(nsteps), int(flush_l2), _p(ms)))
         self.L.speedy_kernel_names.restype = ctypes.c_char_p
-        return dict(zip(self.L.speedy_kernel_names().decode().split(), ms.tolist()))
+        names = self.L.speedy_kernel_names().decode().split()
+        ms = np.zeros(len(names))
+        _chk(self.L.speedy_time_kernels(self.h, int(nsteps), int(flush_l2), _p(ms)))
+        return dict(zip(names, ms.tolist()))
 
     def set_graphs(self, on):
         _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))

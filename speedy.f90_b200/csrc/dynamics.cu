@@ -11,6 +11,7 @@
 // Compiled with --fmad=false (operation-by-operation agreement with the checker).
 #include "model.h"
 #include "spectral_ops.cuh"
+#include "calendar.h"
 
 namespace spd {
 
@@ -25,6 +26,7 @@ struct SpecArgs {
     int j1, j2;
     double dt;
     int flag;
+    double* partial;
 };
 
 __device__ __forceinline__ const double* sfield(const double* mb, long long off, int nsp, int f) { return mb + off + (size_t)f * nsp * 2; }
@@ -71,160 +73,221 @@ __global__ void k_spec_prologue(SpecArgs a) {
     }
 }
 
+// k_spec_step — block = 32 coefficients x 8 levels (threadIdx.y = level, one warp per level).
+// Everything that couples the levels of one coefficient (vertical sums, sigma-dot prefix,
+// hydrostatic integration, the three 8x8 mat-vecs of the semi-implicit solve) goes through
+// shared memory in the reference's summation order; everything else is one thread per (m,n,k).
 // flag bit0: stop after implicit_terms and store the tendencies (get_tendencies drop-in)
-__global__ void __launch_bounds__(64) k_spec_step(SpecArgs a) {
+// flag bit1: main-loop step: take qcorh from the day's transform when due, add the
+//            check_diagnostics partial sums, and let the LAST block to arrive close the step
+//            (final diagnostics reduction in fixed order, range guard, calendar advance).
+#define SC 32
+__global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nsp) return;
-    const int n = r / mx, m = r - n * mx;
+    const int c = threadIdx.x, k = threadIdx.y;
+    const int r = blockIdx.x * SC + c;
+    const bool valid = r < nsp;
+    const int rr = valid ? r : nsp - 1;
+    const int n = rr / mx, m = rr - n * mx;
     double* mb = a.base + (size_t)blockIdx.y * a.stride;
     const LevelConsts& lc = *a.lc;
     const DevTables& tv = a.tv;
-    const size_t q = r;
+    const size_t q = rr;
     const double el2 = tv.el2[q];
     const cd zero{0.0, 0.0};
+    __shared__ cd s_a[KX][SC], s_b[KX][SC], s_phi[KX][SC], s_sig[KX + 1][SC];
+    __shared__ cd s_dmeanc[SC], s_psdt[SC];
 
-    cd vordt[KX], divdt[KX], tdt[KX], trdt[KX], psdt;
     // ---- tendencies.f90:212-234: spectral assembly of the transformed grid-point tendencies
-#pragma unroll
-    for (int k = 0; k < KX; k++) {
+    cd vordt, divdt, tdt, trdt, psdt = zero;
+    {
         const int f = GO_PER * k;
         cd vo, di, dum;
         dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 0), sfield(mb, a.L.sout, nsp, f + 1), m, n, vo, di);
-        vordt[k] = vo;
+        vordt = vo;
         const cd ke = ld(sfield(mb, a.L.sout, nsp, f + 2), mx, m, n);
-        divdt[k] = di - neg(el2 * ke);                                   // - laplacian(KE)
+        divdt = di - neg(el2 * ke);                                      // - laplacian(KE)
         dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 3), sfield(mb, a.L.sout, nsp, f + 4), m, n, dum, di);
-        tdt[k] = di + ld(sfield(mb, a.L.sout, nsp, f + 5), mx, m, n);
+        tdt = di + ld(sfield(mb, a.L.sout, nsp, f + 5), mx, m, n);
         dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 6), sfield(mb, a.L.sout, nsp, f + 7), m, n, dum, di);
-        trdt[k] = di + ld(sfield(mb, a.L.sout, nsp, f + 8), mx, m, n);
+        trdt = di + ld(sfield(mb, a.L.sout, nsp, f + 8), mx, m, n);
     }
-    psdt = ld(sfield(mb, a.L.sout, nsp, GO_PSDT), mx, m, n);
-    if (r == 0) psdt = zero;                                             // tendencies.f90:126
-
     // time level 1 of the prognostics (all linear terms use it, alph = 0.5: tendencies.f90:32)
-    cd vor1[KX], div1[KX], t1[KX], tr1[KX];
-#pragma unroll
-    for (int k = 0; k < KX; k++) {
-        vor1[k] = ld(sfield(mb, a.L.vor, nsp, k), mx, m, n);
-        div1[k] = ld(sfield(mb, a.L.div, nsp, k), mx, m, n);
-        t1[k] = ld(sfield(mb, a.L.t, nsp, k), mx, m, n);
-        tr1[k] = ld(sfield(mb, a.L.tr, nsp, k), mx, m, n);
-    }
+    const cd vor1 = ld(sfield(mb, a.L.vor, nsp, k), mx, m, n);
+    const cd div1 = ld(sfield(mb, a.L.div, nsp, k), mx, m, n);
+    const cd t1 = ld(sfield(mb, a.L.t, nsp, k), mx, m, n);
+    const cd tr1 = ld(sfield(mb, a.L.tr, nsp, k), mx, m, n);
     const cd ps1 = ld(sfield(mb, a.L.ps, nsp, 0), mx, m, n);
-
-    // ---- get_spectral_tendencies  tendencies.f90:242-293
-    {
+    s_a[k][c] = div1;
+    s_b[k][c] = t1;
+    __syncthreads();
+    // ---- get_spectral_tendencies  tendencies.f90:242-293 (level-coupled parts: one warp each)
+    if (k == 0) {
+        psdt = ld(sfield(mb, a.L.sout, nsp, GO_PSDT), mx, m, n);
+        if (rr == 0) psdt = zero;                                        // tendencies.f90:126
         cd dmeanc = zero;
 #pragma unroll
-        for (int k = 0; k < KX; k++) dmeanc = dmeanc + lc.dhs[k] * div1[k];
+        for (int kk = 0; kk < KX; kk++) dmeanc = dmeanc + lc.dhs[kk] * s_a[kk][c];
         psdt = psdt - dmeanc;
-        if (r == 0) psdt = zero;
-        cd sigdtc[KX + 1], dumk[KX + 1];
-        sigdtc[0] = zero; sigdtc[KX] = zero;
+        if (rr == 0) psdt = zero;
+        s_dmeanc[c] = dmeanc;
+        s_psdt[c] = psdt;
+        cd sg = zero;
+        s_sig[0][c] = zero;
 #pragma unroll
-        for (int k = 0; k < KX - 1; k++) sigdtc[k + 1] = sigdtc[k] - lc.dhs[k] * (div1[k] - dmeanc);
-        dumk[0] = zero; dumk[KX] = zero;
+        for (int kk = 0; kk < KX - 1; kk++) { sg = sg - lc.dhs[kk] * (s_a[kk][c] - dmeanc); s_sig[kk + 1][c] = sg; }
+        s_sig[KX][c] = zero;
+    } else if (k == 1) {
+        // get_geopotential(t(:,:,:,1), phis)  geopotential.f90:33-57 (tendencies.f90:288)
+        cd ph = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
+        s_phi[KX - 1][c] = ph;
 #pragma unroll
-        for (int k = 1; k < KX; k++) dumk[k] = (lc.tref[k] - lc.tref[k - 1]) * sigdtc[k];
+        for (int kk = KX - 2; kk >= 0; kk--) { ph = (ph + lc.xgeop2[kk + 1] * s_b[kk + 1][c]) + lc.xgeop1[kk] * s_b[kk][c]; s_phi[kk][c] = ph; }
+        if (m == 0) {
 #pragma unroll
-        for (int k = 0; k < KX; k++)
-            tdt[k] = ((tdt[k] - lc.dhsr[k] * (dumk[k + 1] + dumk[k])) + lc.tref3[k] * (sigdtc[k + 1] + sigdtc[k])) - lc.tref2[k] * dmeanc;
-        // phi was refreshed from t(:,:,:,1) by the prologue of this step (same values as :288)
-#pragma unroll
-        for (int k = 0; k < KX; k++) {
-            const cd x = ld(sfield(mb, a.L.phi, nsp, k), mx, m, n) + (lc.rgas * lc.tref[k]) * ps1;
-            divdt[k] = divdt[k] - neg(el2 * x);
+            for (int kk = 1; kk < KX - 1; kk++) s_phi[kk][c] = s_phi[kk][c] + lc.geop_corf[kk] * (s_b[kk + 1][c] - s_b[kk - 1][c]);
         }
     }
-    // ---- implicit_terms  implicit.f90:168-217
+    __syncthreads();
     {
-        cd ye[KX], yf[KX];
-#pragma unroll
-        for (int k = 0; k < KX; k++) {
-            cd s = zero;
-#pragma unroll
-            for (int k1 = 0; k1 < KX; k1++) s = s + tv.xd[k + KX * k1] * tdt[k1];
-            ye[k] = s + lc.tref1[k] * psdt;
-        }
-        const double elz = tv.elz[q];
-#pragma unroll
-        for (int k = 0; k < KX; k++) yf[k] = divdt[k] + elz * ye[k];
-#pragma unroll
-        for (int k = 0; k < KX; k++) divdt[k] = zero;
-        if (m + n != 0) {
-            const double* xj = tv.xj + (size_t)KX * KX * (m + n - 1);   // xj(:,:,l), l = total wavenumber
-            for (int k1 = 0; k1 < KX; k1++) {
-#pragma unroll
-                for (int k = 0; k < KX; k++) divdt[k] = divdt[k] + xj[k + KX * k1] * yf[k1];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < KX; k++) psdt = psdt - lc.dhsx[k] * divdt[k];
-#pragma unroll
-        for (int k = 0; k < KX; k++) {
-#pragma unroll
-            for (int k1 = 0; k1 < KX; k1++) tdt[k] = tdt[k] + tv.xc[k + KX * k1] * divdt[k1];
-        }
+        const cd dmeanc = s_dmeanc[c];
+        const cd sg0 = s_sig[k][c], sg1 = s_sig[k + 1][c];
+        const cd dk0 = (k >= 1) ? (lc.tref[k] - lc.tref[k - 1]) * sg0 : zero;
+        const cd dk1 = (k + 1 <= KX - 1) ? (lc.tref[k + 1] - lc.tref[k]) * sg1 : zero;
+        tdt = ((tdt - lc.dhsr[k] * (dk1 + dk0)) + lc.tref3[k] * (sg1 + sg0)) - lc.tref2[k] * dmeanc;
+        const cd x = s_phi[k][c] + (lc.rgas * lc.tref[k]) * ps1;
+        divdt = divdt - neg(el2 * x);
+        if (valid) st(sfield(mb, a.L.phi, nsp, k), mx, m, n, s_phi[k][c]);   // module phi (tendencies.f90:288), read by output()
     }
-    if (a.flag & 1) {
+    __syncthreads();          // s_a (div1) and s_b (t1) are free again
+    // ---- implicit_terms  implicit.f90:168-217
+    s_a[k][c] = tdt;
+    __syncthreads();
+    {
+        cd s = zero;
 #pragma unroll
-        for (int k = 0; k < KX; k++) {
-            st(sfield(mb, a.L.vordt, nsp, k), mx, m, n, vordt[k]);
-            st(sfield(mb, a.L.divdt, nsp, k), mx, m, n, divdt[k]);
-            st(sfield(mb, a.L.tdt, nsp, k), mx, m, n, tdt[k]);
-            st(sfield(mb, a.L.trdt, nsp, k), mx, m, n, trdt[k]);
+        for (int k1 = 0; k1 < KX; k1++) s = s + tv.xd[k + KX * k1] * s_a[k1][c];
+        const cd ye = s + lc.tref1[k] * s_psdt[c];
+        s_b[k][c] = divdt + tv.elz[q] * ye;       // yf
+    }
+    __syncthreads();
+    divdt = zero;
+    if (m + n != 0) {
+        const double* xj = tv.xj + (size_t)KX * KX * (m + n - 1);   // xj(:,:,l), l = total wavenumber
+#pragma unroll
+        for (int k1 = 0; k1 < KX; k1++) divdt = divdt + xj[k + KX * k1] * s_b[k1][c];
+    }
+    __syncthreads();          // all reads of tdt (s_a) done
+    s_a[k][c] = divdt;
+    __syncthreads();
+    if (k == 0) {
+#pragma unroll
+        for (int kk = 0; kk < KX; kk++) psdt = psdt - lc.dhsx[kk] * s_a[kk][c];
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < KX; k1++) tdt = tdt + tv.xc[k + KX * k1] * s_a[k1][c];
+
+    if (a.flag & 1) {
+        if (valid) {
+            st(sfield(mb, a.L.vordt, nsp, k), mx, m, n, vordt);
+            st(sfield(mb, a.L.divdt, nsp, k), mx, m, n, divdt);
+            st(sfield(mb, a.L.tdt, nsp, k), mx, m, n, tdt);
+            st(sfield(mb, a.L.trdt, nsp, k), mx, m, n, trdt);
+            if (k == 0) st(mb + a.L.psdt, mx, m, n, psdt);
         }
-        st(mb + a.L.psdt, mx, m, n, psdt);
         return;
     }
     // ---- horizontal diffusion + drag  time_stepping.f90:63-96
     {
         const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
-        const cd tcorh = ld(mb + a.L.tcorh, mx, m, n), qcorh = ld(mb + a.L.qcorh, mx, m, n);
-#pragma unroll
-        for (int k = 0; k < KX; k++) {
-            vordt[k] = dmp1 * (vordt[k] - dmp * vor1[k]);
-            divdt[k] = dmp1d * (divdt[k] - dmpd * div1[k]);
-            const cd ctmp = t1[k] + lc.tcorv[k] * tcorh;
-            tdt[k] = dmp1 * (tdt[k] - dmp * ctmp);
-            if (k == 0 && m == 0) {
-                vordt[0] = vordt[0] - lc.sdrag * vor1[0];
-                divdt[0] = divdt[0] - lc.sdrag * div1[0];
-            }
-            vordt[k] = dmp1s * (vordt[k] - dmps * vor1[k]);
-            divdt[k] = dmp1s * (divdt[k] - dmps * div1[k]);
-            tdt[k] = dmp1s * (tdt[k] - dmps * ctmp);
-            const cd qtmp = tr1[k] + lc.qcorv[k] * qcorh;
-            trdt[k] = dmp1d * (trdt[k] - dmpd * qtmp);
+        const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
+        cd qcorh;
+        if ((a.flag & 2) && a.clk->do_forcing) {       // qcorh = grid_to_spec(corh) of today's set_forcing (forcing.f90:99)
+            qcorh = ld(sfield(mb, a.L.sout, nsp, GO_QCORH), mx, m, n);
+            if (k == 0 && valid) st(mb + a.L.qcorh, mx, m, n, qcorh);
+        } else {
+            qcorh = ld(mb + a.L.qcorh, mx, m, n);
         }
+        vordt = dmp1 * (vordt - dmp * vor1);
+        divdt = dmp1d * (divdt - dmpd * div1);
+        const cd ctmp = t1 + lc.tcorv[k] * tcorh;
+        tdt = dmp1 * (tdt - dmp * ctmp);
+        if (k == 0 && m == 0) {
+            vordt = vordt - lc.sdrag * vor1;
+            divdt = divdt - lc.sdrag * div1;
+        }
+        vordt = dmp1s * (vordt - dmps * vor1);
+        divdt = dmp1s * (divdt - dmps * div1);
+        tdt = dmp1s * (tdt - dmps * ctmp);
+        const cd qtmp = tr1 + lc.qcorv[k] * qcorh;
+        trdt = dmp1d * (trdt - dmpd * qtmp);
     }
     // ---- step_field_2d  time_stepping.f90:141-167
+    cd vor2n = zero, div2n = zero, t2n = zero;
     {
         const double eps = (a.j1 == 1) ? 0.0 : lc.rob;
         const double trf = tv.trfilt[q];
         const double c1 = lc.wil * eps, c2 = (1.0 - lc.wil) * eps;
-        auto stepf = [&](long long off, int nlev_fields, int k, cd fdt) {
-            double* p1 = sfield(mb, off, nsp, k);
-            double* p2 = sfield(mb, off, nsp, nlev_fields + k);
+        auto stepf = [&](long long off, int nlev_fields, int kk, cd fdt, cd f1) -> cd {
+            double* p1 = sfield(mb, off, nsp, kk);
+            double* p2 = sfield(mb, off, nsp, nlev_fields + kk);
             fdt = trf * fdt;
-            const cd f1 = ld(p1, mx, m, n);
             const cd fj = (a.j1 == 1) ? f1 : ld(p2, mx, m, n);
             const cd fnew = f1 + a.dt * fdt;
             const cd f1n = fj + c1 * ((f1 - 2.0 * fj) + fnew);
             const cd fj2 = (a.j1 == 1) ? f1n : fj;     // :166 re-reads output(:,:,j1) after :163 overwrote level 1
             const cd f2n = fnew - c2 * ((f1n - 2.0 * fj2) + fnew);
-            st(p1, mx, m, n, f1n);
-            st(p2, mx, m, n, f2n);
+            if (valid) { st(p1, mx, m, n, f1n); st(p2, mx, m, n, f2n); }
+            return f2n;
         };
-        stepf(a.L.ps, 1, 0, psdt);
-#pragma unroll
-        for (int k = 0; k < KX; k++) {
-            stepf(a.L.vor, KX, k, vordt[k]);
-            stepf(a.L.div, KX, k, divdt[k]);
-            stepf(a.L.t, KX, k, tdt[k]);
-            stepf(a.L.tr, KX, k, trdt[k]);
+        if (k == 0) stepf(a.L.ps, 1, 0, psdt, ps1);
+        vor2n = stepf(a.L.vor, KX, k, vordt, vor1);
+        div2n = stepf(a.L.div, KX, k, divdt, div1);
+        t2n = stepf(a.L.t, KX, k, tdt, t1);
+        stepf(a.L.tr, KX, k, trdt, tr1);
+    }
+    if (!(a.flag & 2)) return;
+    // ---- check_diagnostics on the new time level 2 (diagnostics.f90:16-75): per-block partial sums
+    {
+        double s1 = 0.0, s2 = 0.0;
+        if (valid && m >= 1) {
+            const double e = tv.elm2[q];
+            const cd tv_ = neg(e * vor2n), td = neg(e * div2n);
+            s1 = -(tv_.re * vor2n.re - tv_.im * (-vor2n.im));
+            s2 = -(td.re * div2n.re - td.im * (-div2n.im));
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+        double* part = a.partial + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * (2 * KX);
+        if (c == 0) { part[k] = s1; part[KX + k] = s2; }
+        if (valid && rr == 0) a.partial[(size_t)gridDim.y * gridDim.x * 2 * KX + (size_t)blockIdx.y * KX + k] = t2n.re;
+    }
+    // ---- the last block to arrive closes the step
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (c == 0 && k == 0) s_last = (atomicAdd(&a.clk->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nb = gridDim.x, ne = gridDim.y;
+    for (int idx = k * SC + c; idx < ne * KX; idx += SC * KX) {
+        const int e = idx / KX, kk = idx - e * KX;
+        double d1 = 0.0, d2 = 0.0;
+        for (int b = 0; b < nb; b++) {
+            const double* part = a.partial + ((size_t)e * nb + b) * (2 * KX);
+            d1 += __ldcg(part + kk); d2 += __ldcg(part + KX + kk);
+        }
+        const double d3 = (double)sqrtf(0.5f) * __ldcg(a.partial + (size_t)ne * nb * 2 * KX + (size_t)e * KX + kk);
+        if (e == 0) { a.clk->diag[kk] = d1; a.clk->diag[KX + kk] = d2; a.clk->diag[2 * KX + kk] = d3; }
+        const bool bad = !(d1 <= 500.0) || !(d2 <= 500.0) || !(d3 >= 180.0) || !(d3 <= 320.0);
+        if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
+    }
+    __syncthreads();
+    if (c == 0 && k == 0) {
+        a.clk->ticket = 0;
+        cal_advance(*a.clk);          // speedy.f90:44-47
+        a.clk->slab_pending = 1;      // couple_sea_land of this step rides in the next column kernel
     }
 }
 
@@ -352,7 +415,7 @@ static SpecArgs spec_args(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpecArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv; a.lc = M.lc.p; a.clk = M.clock.p;
-    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0;
+    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p;
     return a;
 }
 
@@ -366,11 +429,14 @@ void launch_spec_prologue(speedy_ctx* ctx, int j2, int refresh_phi) {
     CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only) {
+void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step) {
+    Model& M = *ctx->model;
     SpecArgs a = spec_args(ctx);
-    a.j1 = j1; a.j2 = j2; a.dt = dt; a.flag = store_tend_only ? 1 : 0;
-    dim3 grid((ctx->d.nspec() + 63) / 64, ctx->nmembers);
-    k_spec_step<<<grid, 64, 0, ctx->stream>>>(a);
+    a.j1 = j1; a.j2 = j2; a.dt = dt; a.flag = (store_tend_only ? 1 : 0) | (close_step ? 2 : 0);
+    dim3 grid((ctx->d.nspec() + SC - 1) / SC, ctx->nmembers);
+    const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
+    if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }
+    k_spec_step<<<grid, dim3(SC, KX), 0, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

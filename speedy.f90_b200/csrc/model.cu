@@ -102,7 +102,9 @@ void model_create(speedy_ctx* ctx) {
     reg("slru", L.slru, 3 * NG); reg("ustr", L.ustr, 3 * NG); reg("vstr", L.vstr, 3 * NG); reg("shf", L.shf, 3 * NG); reg("evap", L.evap, 3 * NG);
     reg("hfluxn", L.hfluxn, 3 * NG);
     reg("ts", L.ts, NG); reg("tskin", L.tskin, NG); reg("u0", L.u0, NG); reg("v0", L.v0, NG); reg("t0", L.t0, NG);
-    reg("qcloud", L.qcloud, NG); reg("cloudc", L.cloudc, NG); reg("clstr", L.clstr, NG); reg("qcorh_g", L.qcorh_g, NG);
+    reg("qcloud", L.qcloud, NG); reg("cloudc", L.cloudc, NG); reg("clstr", L.clstr, NG);
+    L.qcorh_g = L.gout + (long long)GO_QCORH * NG;     // the daily humidity-correction field is the 74th K2 input
+    M.fields["qcorh_g"] = FieldInfo{L.qcorh_g, (size_t)NG, false};
     L.stride = (off + 15) / 16 * 16;
     long long ioff = 0;
     auto ireg = [&](const char* name, long long& slot, long long len) {
@@ -118,6 +120,10 @@ void model_create(speedy_ctx* ctx) {
     calendar_init(M.hclock, 1982, 1, 1, 0, 0, 0);
     CUDA_CHECK(cudaMemcpy(M.clock.p, &M.hclock, sizeof(DevClock), cudaMemcpyHostToDevice));
     upload_level_consts(ctx);
+    {
+        const size_t nb = (d.nspec() + 31) / 32;
+        M.diag_partial.alloc(nb * ctx->nmembers * 2 * KXc + (size_t)ctx->nmembers * KXc);
+    }
 
     // transform descriptors --------------------------------------------------------------
     {
@@ -150,6 +156,7 @@ void model_create(speedy_ctx* ctx) {
             const bool cosgr = f < GO_PSDT && (r == 0 || r == 1 || r == 3 || r == 4 || r == 6 || r == 7);   // vdspec(.,.,2): spectral.f90:208-213
             g[f] = XDesc{L.gout + f * NG, cosgr ? 1 : 0, 0};
         }
+        g[GO_QCORH].flags = 4;      // gated on the device clock's do_forcing
         M.desc_dir.upload(g);
         std::vector<XDesc> one(1, XDesc{L.qcorh_g, 0, 0});
         M.desc_one_dir.upload(one);
@@ -170,14 +177,15 @@ static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_inv.p + (size_t)(j2 - 1) * GI_N + first, count,
                         M.mem.p + M.L.gin + first * NG, M.L.stride, ctx->nmembers, 0);
 }
-static void xform_direct(speedy_ctx* ctx) {
+static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
-    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_dir.p, GO_N, M.mem.p + M.L.sout, M.L.stride, ctx->nmembers, 0);
+    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
+                        ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
 }
 static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     Model& M = *ctx->model;
-    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0,
-                        gated ? &M.clock.p->do_forcing : nullptr);
+    (void)gated;
+    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0, nullptr);
 }
 
 // get_tendencies up to (and including) the direct transforms
@@ -193,15 +201,24 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
     enqueue_tendency_front(ctx, j2, csw_override);
     launch_spec_step(ctx, j1, j2, dt, 0);
 }
-// main-loop body speedy.f90:27-54
+// main-loop body speedy.f90:27-54 in 5 launches.  The column kernel first applies the pending
+// couple_sea_land of the previous step and, when due, set_forcing(1); the spectral-step kernel
+// ends with check_diagnostics and the calendar advance (last block to arrive).
+static const int kLaunchesPerStep = 5;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
-    launch_daily_forcing(ctx, 0);          // set_forcing(1), gated on the device clock
-    xform_qcorh(ctx, true);
-    enqueue_step(ctx, 2, 2, 2 * delt, -1);
-    launch_diagnostics(ctx, 2);
-    launch_clock_advance(ctx);
-    launch_slab(ctx, 0);                   // couple_sea_land
+    launch_spec_prologue(ctx, 2, 1);
+    if (ctx->sppt_on) launch_sppt_update(ctx);
+    xform_inverse(ctx, 2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
+    launch_grid_columns(ctx, 0, -1, 1);
+    xform_direct(ctx, true);
+    launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1);
+}
+// the coupler call of the last step (speedy.f90:53) when no further step follows in this call
+static void flush_pending_slab(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    launch_slab(ctx, 0);
+    CUDA_CHECK(cudaMemsetAsync(&M.clock.p->slab_pending, 0, sizeof(int), ctx->stream));
 }
 
 static void set_implicit(speedy_ctx* ctx, double dt) {
@@ -561,11 +578,12 @@ int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
         }
         while (left >= G) {
             CUDA_CHECK(cudaGraphLaunch(M.day_graph, ctx->stream));
-            ctx->launches += (long long)G * (ctx->sppt_on ? 11 : 10);
+            ctx->launches += (long long)G * (kLaunchesPerStep + (ctx->sppt_on ? 1 : 0));
             left -= G;
         }
     }
     for (int s = 0; s < left; s++) enqueue_main_loop_step(ctx);
+    if (nsteps > 0) flush_pending_slab(ctx);
     pull_clock(ctx);
     if (M.hclock.ssta_missing) throw std::runtime_error("run left the SST-anomaly window resident in the boundary file (pack more months)");
     if (M.hclock.diag_fail) return 1;   // 'Model variables out of accepted range' (diagnostics.f90:68)
@@ -604,13 +622,9 @@ int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
 
 
 // ---- per-kernel timing of the main-loop body (bench.py's roofline leg) -------------------
-static const char* const kKernelNames[] = {"daily_forcing", "grid_to_spec_qcorh", "spec_prologue", "spec_to_grid", "grid_columns",
-                                           "grid_to_spec", "spec_step", "diagnostics", "clock_advance", "slab"};
-const char* speedy_kernel_names(void) {
-    return "daily_forcing grid_to_spec_qcorh spec_prologue spec_to_grid grid_columns grid_to_spec spec_step diagnostics clock_advance slab";
-}
+const char* speedy_kernel_names(void) { return "spec_prologue spec_to_grid grid_columns grid_to_spec spec_step"; }
 // Runs nsteps main-loop steps with plain launches, a CUDA-event pair around every launch on
-// the context's stream; ms[10] receives the mean duration of each kernel (names above).
+// the context's stream; ms[] receives the mean duration of each kernel (names above).
 // flush_l2 != 0 overwrites a 256 MiB buffer before every launch (cold-cache timing).
 int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
     API_BEGIN
@@ -619,8 +633,8 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
     if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
     if (ctx->sppt_on) throw std::runtime_error("speedy_time_kernels: SPPT contexts are not supported");
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
-    const int NK = 10;
-    cudaEvent_t ev[NK + 1][2];
+    const int NK = 5;
+    cudaEvent_t ev[NK][2];
     for (int i = 0; i < NK; i++) { CUDA_CHECK(cudaEventCreate(&ev[i][0])); CUDA_CHECK(cudaEventCreate(&ev[i][1])); }
     DevBuf<double> flush;
     if (flush_l2) flush.alloc((size_t)32 << 20);
@@ -631,16 +645,11 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
             if (flush_l2) CUDA_CHECK(cudaMemsetAsync(flush.p, s & 1, flush.n * sizeof(double), ctx->stream));
             CUDA_CHECK(cudaEventRecord(ev[i][0], ctx->stream));
             switch (i) {
-                case 0: launch_daily_forcing(ctx, 0); break;
-                case 1: xform_qcorh(ctx, true); break;
-                case 2: launch_spec_prologue(ctx, 2, 1); break;
-                case 3: xform_inverse(ctx, 2, 0, GI_NBASE); break;
-                case 4: launch_grid_columns(ctx, 0, -1); break;
-                case 5: xform_direct(ctx); break;
-                case 6: launch_spec_step(ctx, 2, 2, 2 * delt, 0); break;
-                case 7: launch_diagnostics(ctx, 2); break;
-                case 8: launch_clock_advance(ctx); break;
-                case 9: launch_slab(ctx, 0); break;
+                case 0: launch_spec_prologue(ctx, 2, 1); break;
+                case 1: xform_inverse(ctx, 2, 0, GI_NBASE); break;
+                case 2: launch_grid_columns(ctx, 0, -1, 1); break;
+                case 3: xform_direct(ctx, true); break;
+                case 4: launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1); break;
             }
             CUDA_CHECK(cudaEventRecord(ev[i][1], ctx->stream));
         }
@@ -651,8 +660,9 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
             ms[i] += t / nsteps;
         }
     }
+    if (nsteps > 0) flush_pending_slab(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < NK; i++) { cudaEventDestroy(ev[i][0]); cudaEventDestroy(ev[i][1]); }
-    (void)kKernelNames;
     API_END
 }
 

@@ -24,6 +24,8 @@ struct DevClock {
     int ssta_missing;    // sticky: a record outside the resident ssta window was requested
     int diag_fail;       // sticky: check_diagnostics range violation (diagnostics.f90:60-70); holds the failing step
     int nssta;           // records in the resident ssta window
+    int slab_pending;    // the coupler call of the last completed step has not run yet (it rides in the next column kernel)
+    int ticket;          // arrival counter of the spectral-step blocks (last block closes the step)
     double tmonth, tyear;
     double diag[24];     // (kx,3) of the last check_diagnostics
 };
@@ -35,7 +37,7 @@ enum {
     GI_SPPT = 91, GI_N = 99, GI_NBASE = 91
 };
 // K2 input fields: per level 9 (utend, vtend, KE, -uT', -vT', ttend, -uq, -vq, qtend) + psdt
-enum { GO_PER = 9, GO_PSDT = 72, GO_N = 73 };
+enum { GO_PER = 9, GO_PSDT = 72, GO_QCORH = 73, GO_N = 74 };   // slot 73: daily humidity-correction field (forcing.f90:98)
 // derived spectral fields written by the spectral prologue kernel
 enum { SP_U2 = 0, SP_V2 = 8, SP_U1 = 16, SP_V1 = 24, SP_PX = 32, SP_PY = 33, SP_N = 34 };
 
@@ -79,6 +81,7 @@ struct Model {
     SharedDev sh;
     DevBuf<DevClock> clock;   // one clock (members share the calendar)
     DevBuf<LevelConsts> lc;
+    DevBuf<double> diag_partial;   // [member][block][kx][2] + [member][kx] partial sums of check_diagnostics
     DevBuf<XDesc> desc_inv, desc_dir, desc_out, desc_one_dir, desc_sppt;
     std::map<std::string, FieldInfo> fields;
     // host-side calendar mirror
@@ -97,8 +100,8 @@ struct Model {
 
 // ---- kernels (dynamics.cu / physics.cu) ------------------------------------------------
 void launch_spec_prologue(speedy_ctx* ctx, int j2, int refresh_phi);
-void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override);   // mode 0 dyn+phys, 1 physics only on resident tendencies
-void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only);
+void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged = 0);   // mode 0 dyn+phys, 1 physics only on resident tendencies
+void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step = 0);
 void launch_diagnostics(speedy_ctx* ctx, int level);
 void launch_slab(speedy_ctx* ctx, int day0);
 void launch_daily_forcing(speedy_ctx* ctx, int force);

@@ -30,10 +30,15 @@ __device__ __forceinline__ double qsat_pt(double ta, double p) {
     return 622.0 * q / (p - F32(0.378) * q);
 }
 
+__device__ __forceinline__ void slab_point(double* mb, const Layout& L_, const SharedDev& sh_, const DevClock& c, const LevelConsts& lc, int N, int q, int day0);
+__device__ __forceinline__ void forcing_point(double* mb, const Layout& L_, const SharedDev& sh_, const DevClock& clk, const LevelConsts& lc, int ix, int il, int q);
+
 struct ColumnArgs {
     double* base; long long stride;
     int* ibase;
     Layout L;
+    SharedDev sh;
+    int merged;              // 1 (main loop): the pending slab update of the previous step and the daily forcing run here first
     const LevelConsts* lc;
     const DevClock* clk;
     const double* fband;     // (301,4) Fortran order
@@ -132,6 +137,13 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             const int f = GO_PER * (k - 1);
             utend[k] = GOUT(f + 0); vtend[k] = GOUT(f + 1); ttend[k] = GOUT(f + 5); qtend[k] = GOUT(f + 8);
         }
+    }
+
+    // ===== main loop only: couple_sea_land of the previous step (speedy.f90:53) and set_forcing(1) (speedy.f90:29-32),
+    // both column-local, ride in front of the physics that consumes them
+    if (a.merged) {
+        if (a.clk->slab_pending) slab_point(mb, a.L, a.sh, *a.clk, lc, N, col, 0);
+        if (a.clk->do_forcing) forcing_point(mb, a.L, a.sh, *a.clk, lc, ix, il, col);
     }
 
     // ================================ physics.f90:110-205 ================================
@@ -727,13 +739,9 @@ __device__ __forceinline__ double forin5_pt(const double* f12, int N, int q, int
            wp1 * f12[(size_t)(ip1 - 1) * N + q] + wp2 * f12[(size_t)(ip2 - 1) * N + q];
 }
 
-__global__ void k_slab(SlabArgs a) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.N) return;
-    const int N = a.N;
-    double* mb = a.base + (size_t)blockIdx.y * a.stride;
-    const DevClock& c = *a.clk;
-    const LevelConsts& lc = *a.lc;
+// one grid point of couple_land_atm + couple_sea_atm
+__device__ __forceinline__ void slab_point(double* mb, const Layout& L_, const SharedDev& sh_, const DevClock& c, const LevelConsts& lc, int N, int q, int day0) {
+    struct { const Layout& L; const SharedDev& sh; int day0; } a{L_, sh_, day0};
     const int imont1 = c.imont1;
     const double tmonth = c.tmonth;
 #define S2(off) mb[(off) + q]
@@ -819,6 +827,13 @@ __global__ void k_slab(SlabArgs a) {
 #undef S2
 }
 
+
+__global__ void k_slab(SlabArgs a) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= a.N) return;
+    slab_point(a.base + (size_t)blockIdx.y * a.stride, a.L, a.sh, *a.clk, *a.lc, a.N, q, a.day0);
+}
+
 // ------------------------------------------------------------------------------------------
 // Daily forcing (forcing.f90:44-99): solar fields from the per-day table, albedos, snow
 // cover and the grid-point humidity correction (its transform follows in K2).
@@ -834,15 +849,11 @@ struct ForcingArgs {
     int force;
 };
 
-__global__ void k_daily_forcing(ForcingArgs a) {
-    if (!a.force && !a.clk->do_forcing) return;
-    const int N = a.ix * a.il;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= N) return;
-    const int j = q / a.ix;
-    double* mb = a.base + (size_t)blockIdx.y * a.stride;
-    const LevelConsts& lc = *a.lc;
-    const double* S = a.sh.solar + (size_t)a.clk->doy * 5 * a.il;
+// one grid point of set_forcing's daily part
+__device__ __forceinline__ void forcing_point(double* mb, const Layout& L_, const SharedDev& sh_, const DevClock& clk, const LevelConsts& lc, int ix, int il, int q) {
+    struct { const Layout& L; const SharedDev& sh; int il; } a{L_, sh_, il};
+    const int j = q / ix;
+    const double* S = a.sh.solar + (size_t)clk.doy * 5 * a.il;
     mb[a.L.fsol + q] = S[0 * a.il + j];
     mb[a.L.ozone + q] = S[1 * a.il + j];
     mb[a.L.ozupp + q] = S[2 * a.il + j];
@@ -869,15 +880,25 @@ __global__ void k_daily_forcing(ForcingArgs a) {
     mb[a.L.qcorh_g + q] = lc.refrh1 * (qref - qsfc);
 }
 
+
+__global__ void k_daily_forcing(ForcingArgs a) {
+    if (!a.force && !a.clk->do_forcing) return;
+    const int N = a.ix * a.il;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N) return;
+    forcing_point(a.base + (size_t)blockIdx.y * a.stride, a.L, a.sh, *a.clk, *a.lc, a.ix, a.il, q);
+}
+
 // device calendar: the end-of-step bookkeeping of speedy.f90:44-47
 __global__ void k_clock_advance(DevClock* c) {
     if (threadIdx.x == 0 && blockIdx.x == 0) cal_advance(*c);
 }
 
 // ---- launchers ------------------------------------------------------------------------------
-void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override) {
+void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged) {
     Model& M = *ctx->model;
     ColumnArgs a;
+    a.sh = M.sh; a.merged = merged;
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on;

@@ -114,11 +114,11 @@ k_grid_to_spec(const double* __restrict__ in_base, long long in_ms, const XDesc*
                double* __restrict__ out_base, long long out_ms, DevTables tv, int mode, const int* __restrict__ gate) {
     using C = TCfg<TRUNC>;
     extern __shared__ double smem[];
-    if (gate && !*gate) return;     // in-graph conditional work (daily forcing transform)
     double* sG = smem;
     double* sY = smem + C::IL * C::GS;
     const int b = blockIdx.x, e = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     const XDesc dsc = desc[b];
+    if (gate && (dsc.flags & 4) && !*gate) return;     // in-graph conditional work (the daily forcing transform)
     const double* in = in_base + (size_t)e * in_ms + dsc.off;
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
 
