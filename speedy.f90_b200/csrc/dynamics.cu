@@ -271,17 +271,22 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     if (!s_last) return;
     __threadfence();
     const int nb = gridDim.x, ne = gridDim.y;
-    for (int idx = k * SC + c; idx < ne * KX; idx += SC * KX) {
+    // warp k reduces the (member, level) pairs k, k+8, ...: lanes take blocks in a fixed order, then a fixed shuffle tree
+    for (int idx = k; idx < ne * KX; idx += KX) {
         const int e = idx / KX, kk = idx - e * KX;
         double d1 = 0.0, d2 = 0.0;
-        for (int b = 0; b < nb; b++) {
+        for (int b = c; b < nb; b += SC) {
             const double* part = a.partial + ((size_t)e * nb + b) * (2 * KX);
             d1 += __ldcg(part + kk); d2 += __ldcg(part + KX + kk);
         }
-        const double d3 = (double)sqrtf(0.5f) * __ldcg(a.partial + (size_t)ne * nb * 2 * KX + (size_t)e * KX + kk);
-        if (e == 0) { a.clk->diag[kk] = d1; a.clk->diag[KX + kk] = d2; a.clk->diag[2 * KX + kk] = d3; }
-        const bool bad = !(d1 <= 500.0) || !(d2 <= 500.0) || !(d3 >= 180.0) || !(d3 <= 320.0);
-        if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+        if (c == 0) {
+            const double d3 = (double)sqrtf(0.5f) * __ldcg(a.partial + (size_t)ne * nb * 2 * KX + (size_t)e * KX + kk);
+            if (e == 0) { a.clk->diag[kk] = d1; a.clk->diag[KX + kk] = d2; a.clk->diag[2 * KX + kk] = d3; }
+            const bool bad = !(d1 <= 500.0) || !(d2 <= 500.0) || !(d3 >= 180.0) || !(d3 <= 320.0);
+            if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
+        }
     }
     __syncthreads();
     if (c == 0 && k == 0) {

@@ -51,18 +51,25 @@ k_spec_to_grid(const double* __restrict__ in_base, long long in_ms, const XDesc*
 
     for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
     if (mode != 2) {
-        for (int t = tid; t < C::NX * C::K2; t += nthr) sIn[t] = in[t];
+        // coefficients outside the triangle m+n <= trunc+1 are never read by the reference
+        // (legendre.f90:38 nsh2); they are zeroed here so that the sums below have a fixed trip
+        // count and every P load of a sum is in flight at once
+        for (int t = tid; t < C::NX * C::K2; t += nthr) {
+            const int n = t / C::K2, c = t - n * C::K2;
+            sIn[t] = ((c >> 1) + n <= C::MX) ? in[t] : 0.0;
+        }
         __syncthreads();
         // inverse Legendre: even/odd split in n, hemispheric symmetry
         for (int t = tid; t < C::IY * C::KP; t += nthr) {
             const int jh = t / C::KP, c = t - jh * C::KP;
             if (c < C::K2) {
                 const int m = c >> 1;
-                const int nmax = C::MX - m;                 // total wavenumber m+n <= trunc+1
                 const double* P = tv.poly + (size_t)jh * C::NX * C::MX + m;
                 double ev = 0.0, od = 0.0;
-                for (int n = 0; n <= nmax; n += 2) ev += sIn[n * C::K2 + c] * P[n * C::MX];
-                for (int n = 1; n <= nmax; n += 2) od += sIn[n * C::K2 + c] * P[n * C::MX];
+#pragma unroll
+                for (int n = 0; n < C::NX; n += 2) ev += sIn[n * C::K2 + c] * P[n * C::MX];
+#pragma unroll
+                for (int n = 1; n < C::NX; n += 2) od += sIn[n * C::K2 + c] * P[n * C::MX];
                 sX[c * C::XS + jh] = ev - od;                  // j = jh (southern row)
                 sX[c * C::XS + (C::IL - 1 - jh)] = ev + od;    // j = il+1-j (northern row)
             }
@@ -182,7 +189,7 @@ k_grid_to_spec(const double* __restrict__ in_base, long long in_ms, const XDesc*
         if (n <= TRUNC && m + n <= C::MX) {
             const double* P = tv.poly + (size_t)n * C::MX + m;
             const double* F = ((n & 1) ? sO : sE) + c * C::ES;
-#pragma unroll 4
+#pragma unroll
             for (int jh = 0; jh < C::IY; jh++) s += P[(size_t)jh * C::NX * C::MX] * F[jh];
         }
         out[n * C::K2 + c] = s;
