@@ -240,7 +240,6 @@ def run_b200(args):
         "grid_to_spec": M * 73 * (8 * NG + 8 * (nact - 2)),
         "grid_columns": M * NG * 8 * (91 + 73 + 45 + 8 + 32 + 2),       # 91 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
         "spec_step": M * c.mx * c.nx * 16 * 165,
-        "spec_prologue": M * c.mx * c.nx * 16 * (32 + 1 + 34),
     }
     tot = sum(kt_warm.values())
     dom = max(alg, key=lambda k: kt_warm[k])

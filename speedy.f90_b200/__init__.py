@@ -225,8 +225,8 @@ class Speedy:
         sh = {"vor": ((2, kx, nx, mx), c), "div": ((2, kx, nx, mx), c), "t": ((2, kx, nx, mx), c), "tr": ((2, kx, nx, mx), c),
               "ps": ((2, nx, mx), c), "phi": ((kx, nx, mx), c), "phis": ((nx, mx), c), "tcorh": ((nx, mx), c), "qcorh": ((nx, mx), c),
               "vordt": ((kx, nx, mx), c), "divdt": ((kx, nx, mx), c), "tdt": ((kx, nx, mx), c), "trdt": ((kx, nx, mx), c), "psdt": ((nx, mx), c),
-              "sppt_spec": ((kx, nx, mx), c), "sppt_eta": ((kx, nx, mx), c), "sprep": ((34, nx, mx), c), "sout": ((73, nx, mx), c),
-              "gin": ((99, il, ix), f), "gout": ((73, il, ix), f), "sstan3": ((3, il, ix), f), "tau2": ((4, kx, il, ix), f),
+              "sppt_spec": ((kx, nx, mx), c), "sppt_eta": ((kx, nx, mx), c), "phi_next": ((kx, nx, mx), c), "sout": ((74, nx, mx), c),
+              "gin": ((99, il, ix), f), "gout": ((74, il, ix), f), "sstan3": ((3, il, ix), f), "tau2": ((4, kx, il, ix), f),
               "stratc": ((2, il, ix), f), "tt_rsw": ((kx, il, ix), f)}
         for n in ("slru", "ustr", "vstr", "shf", "evap", "hfluxn"):
             sh[n] = ((3, il, ix), f)

@@ -72,7 +72,8 @@ static const XDesc* make_desc(speedy_ctx* ctx, int nbatch, size_t stride, const 
         if (flags_host) f = kcos_semantics ? ((flags_host[b] != 1) ? 1 : 0) : flags_host[b];
         else f = flag_if_set;
         h[b].flags = f;
-        h[b].pad = 0;
+        h[b].op = 0;
+        h[b].off2 = 0;
         mix((unsigned long long)f + 7);
     }
     auto it = ctx->desc_cache.find(key);

@@ -44,8 +44,9 @@ struct LevelConsts {
 // descriptor of one transform in a batch
 struct XDesc {
     long long off;   // element (double) offset of the field relative to the member base pointer
-    int flags;       // K1: bit0 scale by cosgr(j), bit1 add coriol(j);  K2: bit0 scale by cosgr, bit1 scale by cosgr2
-    int pad;
+    int flags;       // K1: bit0 scale by cosgr(j), bit1 add coriol(j);  K2: bit0 scale by cosgr, bit1 scale by cosgr2, bit2 gated
+    int op;          // K1 input: 0 the field at `off`; 1 ucos, 2 vcos of uvspec(vor@off, div@off2); 3 d/dx, 4 d/dy of grad(ps@off)
+    long long off2;
 };
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)

@@ -1,5 +1,5 @@
 // K3 / K6 — spectral-space kernels of the time step.
-//   k_spec_prologue : uvspec (both time levels), grad(ps), get_geopotential        (spectral.f90:124-196, geopotential.f90:33-57)
+//   k_geopotential  : get_geopotential (geopotential.f90:33-57) outside the fused main loop (uvspec/grad live in K1's input stage)
 //   k_spec_step     : vds/laplacian assembly of the transformed tendencies          (tendencies.f90:212-234)
 //                     + get_spectral_tendencies (:242-293) + implicit_terms (implicit.f90:168-217)
 //                     + 7 horizontal-diffusion passes, stratospheric drag (time_stepping.f90:63-96)
@@ -32,44 +32,29 @@ struct SpecArgs {
 __device__ __forceinline__ const double* sfield(const double* mb, long long off, int nsp, int f) { return mb + off + (size_t)f * nsp * 2; }
 __device__ __forceinline__ double* sfield(double* mb, long long off, int nsp, int f) { return mb + off + (size_t)f * nsp * 2; }
 
-// flag bit0: also refresh phi <- get_geopotential(t(:,:,:,1))
-__global__ void k_spec_prologue(SpecArgs a) {
+// get_geopotential(t(:,:,:,1), phis)  geopotential.f90:33-57 for the paths outside the fused main loop.
+// flag bit0: write the module variable phi; bit1: write phi_next (the field K1 transforms for the physics)
+__global__ void k_geopotential(SpecArgs a) {
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= KX * nsp) return;
-    const int k = t / nsp, r = t - k * nsp;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nsp) return;
     const int n = r / mx, m = r - n * mx;
     double* mb = a.base + (size_t)blockIdx.y * a.stride;
     const LevelConsts& lc = *a.lc;
-    cd uc, vc;
-    // dynamics set: time level j2 (tendencies.f90:99-101)
-    dev_uvspec(a.tv, sfield(mb, a.L.vor, nsp, (a.j2 - 1) * KX + k), sfield(mb, a.L.div, nsp, (a.j2 - 1) * KX + k), m, n, uc, vc);
-    st(sfield(mb, a.L.sprep, nsp, SP_U2 + k), mx, m, n, uc);
-    st(sfield(mb, a.L.sprep, nsp, SP_V2 + k), mx, m, n, vc);
-    // physics set: time level 1 (physics.f90:96-98)
-    dev_uvspec(a.tv, sfield(mb, a.L.vor, nsp, k), sfield(mb, a.L.div, nsp, k), m, n, uc, vc);
-    st(sfield(mb, a.L.sprep, nsp, SP_U1 + k), mx, m, n, uc);
-    st(sfield(mb, a.L.sprep, nsp, SP_V1 + k), mx, m, n, vc);
-    if (k == 0) {
-        cd dx, dy;
-        dev_grad(a.tv, sfield(mb, a.L.ps, nsp, a.j2 - 1), m, n, dx, dy);   // tendencies.f90:121
-        st(sfield(mb, a.L.sprep, nsp, SP_PX), mx, m, n, dx);
-        st(sfield(mb, a.L.sprep, nsp, SP_PY), mx, m, n, dy);
-        if (a.flag & 1) {
-            // get_geopotential(t(:,:,:,1), phis)  geopotential.f90:33-57
-            cd tt[KX], ph[KX];
+    cd tt[KX], ph[KX];
 #pragma unroll
-            for (int kk = 0; kk < KX; kk++) tt[kk] = ld(sfield(mb, a.L.t, nsp, kk), mx, m, n);
-            ph[KX - 1] = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * tt[KX - 1];
+    for (int kk = 0; kk < KX; kk++) tt[kk] = ld(sfield(mb, a.L.t, nsp, kk), mx, m, n);
+    ph[KX - 1] = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * tt[KX - 1];
 #pragma unroll
-            for (int kk = KX - 2; kk >= 0; kk--) ph[kk] = (ph[kk + 1] + lc.xgeop2[kk + 1] * tt[kk + 1]) + lc.xgeop1[kk] * tt[kk];
-            if (m == 0) {
+    for (int kk = KX - 2; kk >= 0; kk--) ph[kk] = (ph[kk + 1] + lc.xgeop2[kk + 1] * tt[kk + 1]) + lc.xgeop1[kk] * tt[kk];
+    if (m == 0) {
 #pragma unroll
-                for (int kk = 1; kk < KX - 1; kk++) ph[kk] = ph[kk] + lc.geop_corf[kk] * (tt[kk + 1] - tt[kk - 1]);
-            }
+        for (int kk = 1; kk < KX - 1; kk++) ph[kk] = ph[kk] + lc.geop_corf[kk] * (tt[kk + 1] - tt[kk - 1]);
+    }
 #pragma unroll
-            for (int kk = 0; kk < KX; kk++) st(sfield(mb, a.L.phi, nsp, kk), mx, m, n, ph[kk]);
-        }
+    for (int kk = 0; kk < KX; kk++) {
+        if (a.flag & 1) st(sfield(mb, a.L.phi, nsp, kk), mx, m, n, ph[kk]);
+        if (a.flag & 2) st(sfield(mb, a.L.phi_next, nsp, kk), mx, m, n, ph[kk]);
     }
 }
 
@@ -223,12 +208,12 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
         trdt = dmp1d * (trdt - dmpd * qtmp);
     }
     // ---- step_field_2d  time_stepping.f90:141-167
-    cd vor2n = zero, div2n = zero, t2n = zero;
+    cd vor2n = zero, div2n = zero, t2n = zero, t1n = zero;
     {
         const double eps = (a.j1 == 1) ? 0.0 : lc.rob;
         const double trf = tv.trfilt[q];
         const double c1 = lc.wil * eps, c2 = (1.0 - lc.wil) * eps;
-        auto stepf = [&](long long off, int nlev_fields, int kk, cd fdt, cd f1) -> cd {
+        auto stepf = [&](long long off, int nlev_fields, int kk, cd fdt, cd f1, cd* new_level1 = nullptr) -> cd {
             double* p1 = sfield(mb, off, nsp, kk);
             double* p2 = sfield(mb, off, nsp, nlev_fields + kk);
             fdt = trf * fdt;
@@ -238,15 +223,33 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
             const cd fj2 = (a.j1 == 1) ? f1n : fj;     // :166 re-reads output(:,:,j1) after :163 overwrote level 1
             const cd f2n = fnew - c2 * ((f1n - 2.0 * fj2) + fnew);
             if (valid) { st(p1, mx, m, n, f1n); st(p2, mx, m, n, f2n); }
+            if (new_level1) *new_level1 = f1n;
             return f2n;
         };
         if (k == 0) stepf(a.L.ps, 1, 0, psdt, ps1);
         vor2n = stepf(a.L.vor, KX, k, vordt, vor1);
         div2n = stepf(a.L.div, KX, k, divdt, div1);
-        t2n = stepf(a.L.t, KX, k, tdt, t1);
+        t2n = stepf(a.L.t, KX, k, tdt, t1, &t1n);
         stepf(a.L.tr, KX, k, trdt, tr1);
     }
     if (!(a.flag & 2)) return;
+    // ---- geopotential of the NEW time level 1: the field the next step's physics transforms (physics.f90:103,
+    // tendencies.f90:203); the module variable phi above keeps the reference's one-step-old value for output()
+    __syncthreads();
+    s_b[k][c] = t1n;
+    __syncthreads();
+    if (k == 1) {
+        cd ph = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
+        s_phi[KX - 1][c] = ph;
+#pragma unroll
+        for (int kk = KX - 2; kk >= 0; kk--) { ph = (ph + lc.xgeop2[kk + 1] * s_b[kk + 1][c]) + lc.xgeop1[kk] * s_b[kk][c]; s_phi[kk][c] = ph; }
+        if (m == 0) {
+#pragma unroll
+            for (int kk = 1; kk < KX - 1; kk++) s_phi[kk][c] = s_phi[kk][c] + lc.geop_corf[kk] * (s_b[kk + 1][c] - s_b[kk - 1][c]);
+        }
+    }
+    __syncthreads();
+    if (valid) st(sfield(mb, a.L.phi_next, nsp, k), mx, m, n, s_phi[k][c]);
     // ---- check_diagnostics on the new time level 2 (diagnostics.f90:16-75): per-block partial sums
     {
         double s1 = 0.0, s2 = 0.0;
@@ -424,12 +427,11 @@ static SpecArgs spec_args(speedy_ctx* ctx) {
     return a;
 }
 
-void launch_spec_prologue(speedy_ctx* ctx, int j2, int refresh_phi) {
+void launch_geopotential(speedy_ctx* ctx, int which) {
     SpecArgs a = spec_args(ctx);
-    a.j2 = j2; a.flag = refresh_phi ? 1 : 0;
-    const int total = KX * ctx->d.nspec();
-    dim3 grid((total + 127) / 128, ctx->nmembers);
-    k_spec_prologue<<<grid, 128, 0, ctx->stream>>>(a);
+    a.flag = which;
+    dim3 grid((ctx->d.nspec() + 63) / 64, ctx->nmembers);
+    k_geopotential<<<grid, 64, 0, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

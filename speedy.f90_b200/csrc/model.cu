@@ -81,9 +81,9 @@ void model_create(speedy_ctx* ctx) {
     };
     // spectral state, Fortran layouts (prognostics.f90:16-24)
     reg("vor", L.vor, 2 * KXc * NS2); reg("div", L.div, 2 * KXc * NS2); reg("t", L.t, 2 * KXc * NS2); reg("tr", L.tr, 2 * KXc * NS2);
-    reg("ps", L.ps, 2 * NS2); reg("phi", L.phi, KXc * NS2); reg("phis", L.phis, NS2);
+    reg("ps", L.ps, 2 * NS2); reg("phi", L.phi, KXc * NS2); reg("phi_next", L.phi_next, KXc * NS2); reg("phis", L.phis, NS2);
     reg("tcorh", L.tcorh, NS2); reg("qcorh", L.qcorh, NS2);
-    reg("sprep", L.sprep, SP_N * NS2); reg("sout", L.sout, GO_N * NS2);
+    reg("sout", L.sout, GO_N * NS2);
     reg("sppt_spec", L.sppt_spec, KXc * NS2); reg("sppt_eta", L.sppt_eta, KXc * NS2);
     reg("vordt", L.vordt, KXc * NS2); reg("divdt", L.divdt, KXc * NS2); reg("tdt", L.tdt, KXc * NS2); reg("trdt", L.trdt, KXc * NS2);
     reg("psdt", L.psdt, NS2);
@@ -136,20 +136,25 @@ void model_create(speedy_ctx* ctx) {
                 D[GI_DIV + k] = XDesc{L.div + lev + k * NS2, 0, 0};
                 D[GI_T + k] = XDesc{L.t + lev + k * NS2, 0, 0};
                 D[GI_TR + k] = XDesc{L.tr + lev + k * NS2, 0, 0};
-                D[GI_U + k] = XDesc{L.sprep + (SP_U2 + k) * NS2, 1, 0};     // spec_to_grid(., 2): * cosgr
-                D[GI_V + k] = XDesc{L.sprep + (SP_V2 + k) * NS2, 1, 0};
-                D[GI_U1 + k] = XDesc{L.sprep + (SP_U1 + k) * NS2, 1, 0};
-                D[GI_V1 + k] = XDesc{L.sprep + (SP_V1 + k) * NS2, 1, 0};
-                D[GI_T1 + k] = XDesc{L.t + k * NS2, 0, 0};
-                D[GI_Q1 + k] = XDesc{L.tr + k * NS2, 0, 0};
-                D[GI_PHI + k] = XDesc{L.phi + k * NS2, 0, 0};
-                D[GI_SPPT + k] = XDesc{L.sppt_spec + k * NS2, 0, 0};
+                // winds: K1 builds ucos/vcos from (vor, div) in its input stage (uvspec) and scales by cosgr (spec_to_grid(., 2))
+                D[GI_U + k] = XDesc{L.vor + lev + k * NS2, 1, 1, L.div + lev + k * NS2};
+                D[GI_V + k] = XDesc{L.vor + lev + k * NS2, 1, 2, L.div + lev + k * NS2};
+                D[GI_U1 + k] = XDesc{L.vor + k * NS2, 1, 1, L.div + k * NS2};
+                D[GI_V1 + k] = XDesc{L.vor + k * NS2, 1, 2, L.div + k * NS2};
+                D[GI_T1 + k] = XDesc{L.t + k * NS2, 0, 0, 0};
+                D[GI_Q1 + k] = XDesc{L.tr + k * NS2, 0, 0, 0};
+                D[GI_PHI + k] = XDesc{L.phi_next + k * NS2, 0, 0, 0};
+                D[GI_SPPT + k] = XDesc{L.sppt_spec + k * NS2, 0, 0, 0};
             }
-            D[GI_PX] = XDesc{L.sprep + SP_PX * NS2, 1, 0};
-            D[GI_PY] = XDesc{L.sprep + SP_PY * NS2, 1, 0};
-            D[GI_PSL] = XDesc{L.ps, 0, 0};
+            D[GI_PX] = XDesc{L.ps + (long long)(j2 - 1) * NS2, 1, 3, 0};     // grad(ps(:,:,j2)) tendencies.f90:121-123
+            D[GI_PY] = XDesc{L.ps + (long long)(j2 - 1) * NS2, 1, 4, 0};
+            D[GI_PSL] = XDesc{L.ps, 0, 0, 0};
         }
         M.desc_inv.upload(h);
+        // output(): the 41 level-1 fields with the module variable phi (input_output.f90:184-192)
+        std::vector<XDesc> o(h.begin() + GI_U1, h.begin() + GI_U1 + 41);
+        for (int k = 0; k < KXc; k++) o[GI_PHI - GI_U1 + k].off = L.phi + k * NS2;
+        M.desc_out.upload(o);
         std::vector<XDesc> g(GO_N);
         for (int f = 0; f < GO_N; f++) {
             const int r = f % GO_PER;
@@ -177,6 +182,10 @@ static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_inv.p + (size_t)(j2 - 1) * GI_N + first, count,
                         M.mem.p + M.L.gin + first * NG, M.L.stride, ctx->nmembers, 0);
 }
+static void xform_output(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_out.p, 41, M.mem.p + M.L.gin + (long long)GI_U1 * ctx->d.ngrid(), M.L.stride, ctx->nmembers, 0);
+}
 static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
     launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
@@ -190,7 +199,7 @@ static void xform_qcorh(speedy_ctx* ctx, bool gated) {
 
 // get_tendencies up to (and including) the direct transforms
 static void enqueue_tendency_front(speedy_ctx* ctx, int j2, int csw_override) {
-    launch_spec_prologue(ctx, j2, 1);
+    launch_geopotential(ctx, 3);
     if (ctx->sppt_on) launch_sppt_update(ctx);
     xform_inverse(ctx, j2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
     launch_grid_columns(ctx, 0, csw_override);
@@ -201,13 +210,12 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
     enqueue_tendency_front(ctx, j2, csw_override);
     launch_spec_step(ctx, j1, j2, dt, 0);
 }
-// main-loop body speedy.f90:27-54 in 5 launches.  The column kernel first applies the pending
+// main-loop body speedy.f90:27-54 in 4 launches.  The column kernel first applies the pending
 // couple_sea_land of the previous step and, when due, set_forcing(1); the spectral-step kernel
 // ends with check_diagnostics and the calendar advance (last block to arrive).
-static const int kLaunchesPerStep = 5;
+static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
-    launch_spec_prologue(ctx, 2, 1);
     if (ctx->sppt_on) launch_sppt_update(ctx);
     xform_inverse(ctx, 2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
     launch_grid_columns(ctx, 0, -1, 1);
@@ -249,7 +257,7 @@ size_t speedy_output_len(const speedy_ctx* ctx) { return (size_t)(5 * ctx->d.kx 
 size_t speedy_state_len(const speedy_ctx* ctx) { return (size_t)2 * ctx->d.nspec() * (4 * 2 * ctx->d.kx + 2); }
 
 const char* speedy_field_names(void) {
-    return "vor div t tr ps phi phis tcorh qcorh vordt divdt tdt trdt psdt gin gout sprep sout sppt_spec sppt_eta "
+    return "vor div t tr ps phi phi_next phis tcorh qcorh vordt divdt tdt trdt psdt gin gout sout sppt_spec sppt_eta "
            "phis0 fmask_l fmask_s forog alb0 fsol ozone ozupp zenit stratz alb_l alb_s albsfc snowc "
            "stl_am stl_lm snowd_am soilw_am sst_am sice_am tice_am ssti_om sst_om tice_om sice_om "
            "sstcl_ob sicecl_ob ticecl_ob stlcl_ob sstan3 tau2 stratc tt_rsw ssrd ssr tsr precnv precls cbmf slrd slr olr "
@@ -315,7 +323,7 @@ int speedy_get_geopotential(speedy_ctx* ctx, int j) {
     API_BEGIN
     check_ready(ctx);
     if (j != 1) throw std::runtime_error("get_geopotential: the resident phi is tied to time level 1 (tendencies.f90:203,288)");
-    launch_spec_prologue(ctx, 1, 1);
+    launch_geopotential(ctx, 3);
     API_END
 }
 
@@ -341,6 +349,7 @@ int speedy_get_physical_tendencies(speedy_ctx* ctx, const double* vor, const dou
     auto up = [&](long long off, const double* h, size_t n) { CUDA_CHECK(cudaMemcpyAsync(M.mem.p + off, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream)); };
     // the arguments are the caller's time-level-1 arrays (tendencies.f90:205): they become the resident level 1
     up(L.vor, vor, KXc * NS2); up(L.div, div, KXc * NS2); up(L.t, t, KXc * NS2); up(L.tr, q, KXc * NS2); up(L.phi, phi, KXc * NS2); up(L.ps, psl, NS2);
+    up(L.phi_next, phi, KXc * NS2);
     std::vector<double> g((size_t)GO_N * NG, 0.0);
     for (int k = 0; k < KXc; k++) {
         memcpy(&g[(size_t)(GO_PER * k + 0) * NG], utend + k * NG, NG * sizeof(double));
@@ -349,7 +358,6 @@ int speedy_get_physical_tendencies(speedy_ctx* ctx, const double* vor, const dou
         memcpy(&g[(size_t)(GO_PER * k + 8) * NG], qtend + k * NG, NG * sizeof(double));
     }
     up(L.gout, g.data(), g.size());
-    launch_spec_prologue(ctx, 1, 0);
     if (ctx->sppt_on) { launch_sppt_update(ctx); xform_inverse(ctx, 1, GI_SPPT, 8); }
     xform_inverse(ctx, 1, GI_U1, 41);
     launch_grid_columns(ctx, 1, compute_shortwave ? 1 : 0);
@@ -544,7 +552,7 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
     launch_daily_forcing(ctx, 1);
     xform_qcorh(ctx, false);
     // geopotential of the rest state (prognostics.f90:123) so that an immediate output sees it
-    launch_spec_prologue(ctx, 1, 1);
+    launch_geopotential(ctx, 3);
     M.sppt_first = true; M.sppt_counter = 0;
     // ---- first_step (time_stepping.f90:12-24)
     if (speedy_first_step(ctx)) throw std::runtime_error(speedy_last_error());
@@ -562,6 +570,7 @@ int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
     int left = nsteps;
     const int G = 36;
+    if (nsteps > 0) launch_geopotential(ctx, 2);   // phi_next of the current level-1 T (the state may have been set from the host)
     if (ctx->use_graphs && left >= G) {
         if (!M.day_graph) {
             cudaGraph_t graph;
@@ -596,8 +605,7 @@ int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float*
     Model& M = *ctx->model;
     if (member < 0 || member >= ctx->nmembers) throw std::runtime_error("bad member index");
     const size_t NG = ctx->d.ngrid(), n = speedy_output_len(ctx);
-    launch_spec_prologue(ctx, 1, 0);           // uvspec of level 1; phi stays the one of the last step (input_output.f90:184-192)
-    xform_inverse(ctx, 1, GI_U1, 41);
+    xform_output(ctx);                         // phi stays the one of the last step (input_output.f90:184-192)
     DevBuf<float> out;
     out.alloc(n);
     launch_output_convert(ctx, member, out.p);
@@ -614,15 +622,14 @@ int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float*
 int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
     API_BEGIN
     check_ready(ctx);
-    launch_spec_prologue(ctx, 1, 0);
-    xform_inverse(ctx, 1, GI_U1, 41);
+    xform_output(ctx);
     launch_ensemble_sums(ctx, d_sum, d_sumsq);
     API_END
 }
 
 
 // ---- per-kernel timing of the main-loop body (bench.py's roofline leg) -------------------
-const char* speedy_kernel_names(void) { return "spec_prologue spec_to_grid grid_columns grid_to_spec spec_step"; }
+const char* speedy_kernel_names(void) { return "spec_to_grid grid_columns grid_to_spec spec_step"; }
 // Runs nsteps main-loop steps with plain launches, a CUDA-event pair around every launch on
 // the context's stream; ms[] receives the mean duration of each kernel (names above).
 // flush_l2 != 0 overwrites a 256 MiB buffer before every launch (cold-cache timing).
@@ -633,23 +640,23 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
     if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
     if (ctx->sppt_on) throw std::runtime_error("speedy_time_kernels: SPPT contexts are not supported");
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
-    const int NK = 5;
+    const int NK = 4;
     cudaEvent_t ev[NK][2];
     for (int i = 0; i < NK; i++) { CUDA_CHECK(cudaEventCreate(&ev[i][0])); CUDA_CHECK(cudaEventCreate(&ev[i][1])); }
     DevBuf<double> flush;
     if (flush_l2) flush.alloc((size_t)32 << 20);
     for (int i = 0; i < NK; i++) ms[i] = 0.0;
     const double delt = ctx->tab.c.delt;
+    if (nsteps > 0) launch_geopotential(ctx, 2);
     for (int s = 0; s < nsteps; s++) {
         for (int i = 0; i < NK; i++) {
             if (flush_l2) CUDA_CHECK(cudaMemsetAsync(flush.p, s & 1, flush.n * sizeof(double), ctx->stream));
             CUDA_CHECK(cudaEventRecord(ev[i][0], ctx->stream));
             switch (i) {
-                case 0: launch_spec_prologue(ctx, 2, 1); break;
-                case 1: xform_inverse(ctx, 2, 0, GI_NBASE); break;
-                case 2: launch_grid_columns(ctx, 0, -1, 1); break;
-                case 3: xform_direct(ctx, true); break;
-                case 4: launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1); break;
+                case 0: xform_inverse(ctx, 2, 0, GI_NBASE); break;
+                case 1: launch_grid_columns(ctx, 0, -1, 1); break;
+                case 2: xform_direct(ctx, true); break;
+                case 3: launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1); break;
             }
             CUDA_CHECK(cudaEventRecord(ev[i][1], ctx->stream));
         }

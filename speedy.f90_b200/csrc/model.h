@@ -38,14 +38,12 @@ enum {
 };
 // K2 input fields: per level 9 (utend, vtend, KE, -uT', -vT', ttend, -uq, -vq, qtend) + psdt
 enum { GO_PER = 9, GO_PSDT = 72, GO_QCORH = 73, GO_N = 74 };   // slot 73: daily humidity-correction field (forcing.f90:98)
-// derived spectral fields written by the spectral prologue kernel
-enum { SP_U2 = 0, SP_V2 = 8, SP_U1 = 16, SP_V1 = 24, SP_PX = 32, SP_PY = 33, SP_N = 34 };
 
 // offsets (in doubles) inside a member region
 struct Layout {
     long long stride;
     // spectral (complex interleaved)
-    long long vor, div, t, tr, ps, phi, phis, tcorh, qcorh, sprep, sout, sppt_spec, sppt_eta;
+    long long vor, div, t, tr, ps, phi, phi_next, phis, tcorh, qcorh, sout, sppt_spec, sppt_eta;
     long long vordt, divdt, tdt, trdt, psdt;
     // grid work
     long long gin, gout;
@@ -99,7 +97,7 @@ struct Model {
 };
 
 // ---- kernels (dynamics.cu / physics.cu) ------------------------------------------------
-void launch_spec_prologue(speedy_ctx* ctx, int j2, int refresh_phi);
+void launch_geopotential(speedy_ctx* ctx, int which);   // which: bit0 module phi, bit1 phi_next (K1's physics input)
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged = 0);   // mode 0 dyn+phys, 1 physics only on resident tendencies
 void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step = 0);
 void launch_diagnostics(speedy_ctx* ctx, int level);
