@@ -194,22 +194,22 @@ def run_b200(args):
     value = total_days / dev_s
 
     # ---------------- end-to-end through the C ABI with host buffers (`e2e`) ----------------
-    # every step: prognostic state host(pinned) -> device, one simulated day, state + the 41 output levels device -> host
+    # every step: prognostic state host(pinned) -> device, one simulated day, state + the 41 output levels device -> host,
+    # all inside ONE reference-facing call: speedy_run_steps_host (the main loop with the module arrays left on the host)
     names = ("vor", "div", "t", "tr", "ps")
-    host = {n: torch.from_numpy(c.get_field(n, all_members=True)).pin_memory() for n in names}
-    h2d = sum(v.numel() * 16 for v in host.values())
-    d2h = h2d + args.members * (5 * c.kx + 1) * c.il * c.ix * 4
-    e2e_days = max(3, min(args.steps, 20))
+    st = np.concatenate([np.concatenate([c.get_field(n, all_members=True)[e].view(np.float64).ravel() for n in names]) for e in range(args.members)])
+    state = torch.from_numpy(st).pin_memory()
+    outb = torch.empty((5 * c.kx + 1) * c.il * c.ix, dtype=torch.float32).pin_memory()
+    assert state.numel() == c.state_len() * args.members
+    h2d = state.numel() * 8
+    d2h = state.numel() * 8 + outb.numel() * 4
+    e2e_days = max(3, min(args.steps, 30))
+    s_np, o_np = state.numpy(), outb.numpy()
+    assert c.run_steps_host(s_np, NSTEPS_PER_DAY, o_np) == 0      # warm-up of the host path
     barrier()
     t0 = time.perf_counter()
     for k in range(e2e_days):
-        for n in names:
-            c.set_field(n, host[n].numpy())
-        assert c.run_steps(NSTEPS_PER_DAY) == 0
-        for n in names:
-            host[n].numpy()[...] = c.get_field(n, all_members=True)
-        for e in range(args.members):
-            out = c.output_fields(e)
+        assert c.run_steps_host(s_np, NSTEPS_PER_DAY, o_np) == 0
     barrier()
     e2e_s = time.perf_counter() - t0
     t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
@@ -258,7 +258,7 @@ def run_b200(args):
             "dtype": "f64", "data": "reference T30 boundary files (packed), rest-state initial condition",
             "config": _config(args), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "speedy_set_field x5 (pinned host -> device) + speedy_run_steps(36) + speedy_get_field x5 + speedy_output_fields per simulated day",
+                    "api": "speedy_run_steps_host(ctx, state, n, 36, out): pinned host state -> device, 36 steps, state + output() fields -> host, per simulated day; wall clock",
                     "days": e2e_days},
             "gpu_launches": int(launches), "us_per_model_step": 1e6 * dev_s / (args.steps * NSTEPS_PER_DAY),
             "wall_s_timed_region": t_wall, "roofline": roofline}

@@ -146,6 +146,10 @@ size_t speedy_output_len(const speedy_ctx* ctx); /* (5*kx+1)*ix*il */
  * module arrays left on the host).  state layout: vor,div,t,tr,ps concatenated. */
 int speedy_step_host(speedy_ctx* ctx, double* state, size_t n, int j1, int j2, double dt, int compute_shortwave);
 size_t speedy_state_len(const speedy_ctx* ctx);
+/* host-resident drop-in of the main loop (speedy.f90:27-54 x nsteps): state = nmembers x
+ * [vor,div,t,tr,ps] in HOST memory is uploaded, advanced and downloaded; out (nullable,
+ * speedy_output_len floats: u,v,t,q,phi (ix,il,kx) then ps) gets member 0's output() fields */
+int speedy_run_steps_host(speedy_ctx* ctx, double* state, size_t n, int nsteps, float* out);
 
 /* number of kernel launches issued by this ctx so far (bench.py's gpu_launches) */
 long long speedy_launch_count(const speedy_ctx* ctx);

@@ -221,4 +221,14 @@ int orc_output_fields(float* u, float* v, float* tt, float* q, float* ph, float*
     return 0;
 }
 
+
+/* calendar-only hooks for the CPU tests (date.f90) */
+int orc_calendar_init(int y, int m, int d, int h, int mi) { test_calendar_init(y, m, d, h, mi); return 0; }
+int orc_newdate() { test_newdate(); return 0; }
+int orc_get_date(int* ymdhm, double* tm, double* ty, int* im) {
+    ymdhm[0] = model_datetime.year; ymdhm[1] = model_datetime.month; ymdhm[2] = model_datetime.day;
+    ymdhm[3] = model_datetime.hour; ymdhm[4] = model_datetime.minute; *tm = tmonth; *ty = tyear; *im = imont1;
+    return 0;
+}
+
 }  // extern "C"

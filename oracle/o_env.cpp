@@ -155,6 +155,9 @@ static void newdate() {
     set_time_fractions();
 }
 
+void test_calendar_init(int y, int m, int d, int h, int mi) { initialize_date(y, m, d, h, mi); }
+void test_newdate() { newdate(); }
+
 /* ---------------------------------------------------------------- interpolation.f90 */
 /* :16-35 for12(ix*il,*) */
 static void forint(int imon, const double* for12, double* for1) {

@@ -236,5 +236,7 @@ void sppt_reset();
 int model_initialize(const char* bc_file, int y, int m, int d, int h, int mi);
 int model_run_steps(int nsteps_to_run);   /* main-loop body speedy.f90:27-54; returns 1 on diagnostics stop */
 extern int model_step;
+void test_calendar_init(int y, int m, int d, int h, int mi);   /* date.f90 hooks for the CPU tests */
+void test_newdate();
 
 }  // namespace orc

@@ -46,6 +46,7 @@ def lib():
         _lib.speedy_get_physical_tendencies.argtypes = [ctypes.c_void_p] * 11 + [ctypes.c_int]
         _lib.speedy_output_fields.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
         _lib.speedy_step_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int]
+        _lib.speedy_run_steps_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
         _lib.speedy_model_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.c_int] * 5
     return _lib
 
@@ -323,6 +324,20 @@ class Speedy:
         ms = np.zeros(len(names))
         _chk(self.L.speedy_time_kernels(self.h, int(nsteps), int(flush_l2), _p(ms)))
         return dict(zip(names, ms.tolist()))
+
+    def state_len(self):
+        return int(self.L.speedy_state_len(self.h))
+
+    def run_steps_host(self, state, nsteps, out=None):
+        """Main loop with the prognostic state resident in HOST memory: `state` (float64, nmembers*state_len,
+        [vor,div,t,tr,ps] per member) is uploaded, advanced nsteps steps and downloaded IN PLACE;
+        `out` (float32, output_len) receives member 0's output() fields.  Pinned arrays copy asynchronously."""
+        assert state.dtype == np.float64 and state.flags.c_contiguous
+        po = None
+        if out is not None:
+            assert out.dtype == np.float32 and out.flags.c_contiguous
+            po = _p(out)
+        return _chk(self.L.speedy_run_steps_host(self.h, _p(state), ctypes.c_size_t(state.size), int(nsteps), po))
 
     def set_graphs(self, on):
         _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))

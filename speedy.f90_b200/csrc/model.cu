@@ -561,10 +561,8 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
     API_END
 }
 
-// speedy.f90:27-54 repeated nsteps times; whole days are replayed from a CUDA graph
-int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
-    API_BEGIN
-    check_ready(ctx);
+// speedy.f90:27-54 repeated nsteps times; whole days are replayed from a CUDA graph.  Enqueue only.
+static void run_steps_core(speedy_ctx* ctx, int nsteps) {
     Model& M = *ctx->model;
     if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
@@ -593,24 +591,63 @@ int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
     }
     for (int s = 0; s < left; s++) enqueue_main_loop_step(ctx);
     if (nsteps > 0) flush_pending_slab(ctx);
+}
+static int finish_run(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
     pull_clock(ctx);
     if (M.hclock.ssta_missing) throw std::runtime_error("run left the SST-anomaly window resident in the boundary file (pack more months)");
-    if (M.hclock.diag_fail) return 1;   // 'Model variables out of accepted range' (diagnostics.f90:68)
+    return M.hclock.diag_fail ? 1 : 0;   // 1: 'Model variables out of accepted range' (diagnostics.f90:68)
+}
+
+int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
+    API_BEGIN
+    check_ready(ctx);
+    run_steps_core(ctx, nsteps);
+    if (finish_run(ctx)) return 1;
+    API_END
+}
+
+// enqueue the output() conversions of one member into the context's device buffer
+static float* enqueue_output(speedy_ctx* ctx, int member) {
+    Model& M = *ctx->model;
+    const size_t n = speedy_output_len(ctx);
+    if (M.outbuf.n < n) M.outbuf.alloc(n);
+    xform_output(ctx);                         // phi stays the one of the last step (input_output.f90:184-192)
+    launch_output_convert(ctx, member, M.outbuf.p);
+    return M.outbuf.p;
+}
+
+// Host-resident drop-in of the main loop: the caller keeps the prognostic arrays (vor, div, t, tr,
+// ps as in prognostics.f90:16-20, concatenated, nmembers copies) in HOST memory; they are uploaded,
+// advanced nsteps time steps and downloaded, and `out` (optional, speedy_output_len floats) receives
+// member 0's output() fields.  One stream synchronisation at the end.
+int speedy_run_steps_host(speedy_ctx* ctx, double* state, size_t n, int nsteps, float* out) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    const size_t len = speedy_state_len(ctx);
+    if (n != len * (size_t)ctx->nmembers) throw std::runtime_error("state length mismatch (nmembers x speedy_state_len)");
+    for (int e = 0; e < ctx->nmembers; e++)
+        CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + M.L.vor, state + (size_t)e * len, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    run_steps_core(ctx, nsteps);
+    for (int e = 0; e < ctx->nmembers; e++)
+        CUDA_CHECK(cudaMemcpyAsync(state + (size_t)e * len, M.mem.p + (size_t)e * M.L.stride + M.L.vor, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out) {
+        float* d = enqueue_output(ctx, 0);
+        CUDA_CHECK(cudaMemcpyAsync(out, d, speedy_output_len(ctx) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (finish_run(ctx)) return 1;
     API_END
 }
 
 int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float* t, float* q, float* phi, float* ps) {
     API_BEGIN
     check_ready(ctx);
-    Model& M = *ctx->model;
     if (member < 0 || member >= ctx->nmembers) throw std::runtime_error("bad member index");
     const size_t NG = ctx->d.ngrid(), n = speedy_output_len(ctx);
-    xform_output(ctx);                         // phi stays the one of the last step (input_output.f90:184-192)
-    DevBuf<float> out;
-    out.alloc(n);
-    launch_output_convert(ctx, member, out.p);
+    float* d = enqueue_output(ctx, member);
     std::vector<float> h(n);
-    CUDA_CHECK(cudaMemcpyAsync(h.data(), out.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     float* dst[5] = {u, v, t, q, phi};
     for (int f = 0; f < 5; f++)

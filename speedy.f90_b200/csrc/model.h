@@ -79,6 +79,7 @@ struct Model {
     SharedDev sh;
     DevBuf<DevClock> clock;   // one clock (members share the calendar)
     DevBuf<LevelConsts> lc;
+    DevBuf<float> outbuf;          // output() staging (input_output.f90:201-206)
     DevBuf<double> diag_partial;   // [member][block][kx][2] + [member][kx] partial sums of check_diagnostics
     DevBuf<XDesc> desc_inv, desc_dir, desc_out, desc_one_dir, desc_sppt;
     std::map<std::string, FieldInfo> fields;

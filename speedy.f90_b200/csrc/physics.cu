@@ -21,12 +21,17 @@ namespace spd {
 __device__ __forceinline__ double dmin(double a, double b) { return a < b ? a : b; }   // Fortran min/max on non-NaN data
 __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : b; }
 
+// The column kernel evaluates exp ~60 times per column; inlined, those copies are most of its
+// 12k-instruction body and it stalls on instruction fetch (ncu: 40 % "no instruction").  One
+// shared out-of-line copy keeps the body inside the instruction cache.  Same libdevice routine.
+__device__ __noinline__ double exp_ol(double x) { return exp(x); }
+#define exp(x) exp_ol(x)
+
 // humidity.f90:44-78 for one point; p = sig*ps (or ps(1,1) for sig <= 0)
 __device__ __forceinline__ double qsat_pt(double ta, double p) {
     const double e0 = 6.108e-3, c1 = F32(17.269), c2 = F32(21.875), t0 = F32(273.16), t1 = F32(35.86), t2 = F32(7.66);
-    double q;
-    if (ta >= t0) q = e0 * exp(c1 * (ta - t0) / (ta - t1));
-    else q = e0 * exp(c2 * (ta - t0) / (ta - t2));
+    const bool warm = ta >= t0;
+    const double q = e0 * exp((warm ? c1 : c2) * (ta - t0) / (ta - (warm ? t1 : t2)));
     return 622.0 * q / (p - F32(0.378) * q);
 }
 

@@ -122,3 +122,22 @@ def test_ensemble_members_identical(pkg):
     v = c.get_field("vor", all_members=True)
     assert np.array_equal(v[0], v[1]) and np.array_equal(v[0], v[2])
     c.close()
+
+
+def test_host_resident_main_loop(pkg):
+    """speedy_run_steps_host (module arrays left on the host) == the device-resident run, bit for bit"""
+    a = pkg.Speedy(trunc=30)
+    a.model_init(BC)
+    b = pkg.Speedy(trunc=30)
+    b.model_init(BC)
+    st = np.concatenate([b.get_field(n).view(np.float64).ravel() for n in PROG])
+    assert st.size == b.state_len()
+    out = np.empty((5 * b.kx + 1) * b.il * b.ix, np.float32)
+    assert b.run_steps_host(st, 40, out) == 0
+    assert a.run_steps(40) == 0
+    ref = np.concatenate([a.get_field(n).view(np.float64).ravel() for n in PROG])
+    assert np.array_equal(st, ref)
+    o = a.output_fields()
+    ref_out = np.concatenate([o[n].ravel() for n in ("u", "v", "t", "q", "phi", "ps")])
+    assert np.array_equal(out, ref_out)
+    a.close(); b.close()
