@@ -139,6 +139,21 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def _ncu_traffic(kernel, members):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the newest committed
+    `ncu --set full` summary under profiles/ (captured at 1 member; None for other batch sizes)"""
+    import glob
+    if members != 1:
+        return None, "no ncu capture at this member count"
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_full_summary.json")), reverse=True):
+        try:
+            k = json.load(open(path))["kernels"][kernel]
+            return k["traffic_bytes"], os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, "no ncu summary committed"
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -244,7 +259,9 @@ def run_b200(args):
     tot = sum(kt_warm.values())
     dom = max(alg, key=lambda k: kt_warm[k])
     ach = alg[dom] / (kt_cold[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None,
+    traffic, traffic_src = _ncu_traffic(dom, M)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg[dom],
                 "peak_source": peak_src, "timing": "CUDA events on the library stream around each launch, L2 flushed before each launch, mean of 36 steps",
                 "achieved_warm_l2": alg[dom] / (kt_warm[dom] * 1e-3) / 1e9,
                 "share_of_step": kt_warm[dom] / tot,
