@@ -37,6 +37,9 @@ typedef struct speedy_cfg {
     int device;    /* CUDA device ordinal */
     int sppt_on;   /* params.f90:42 */
     unsigned long long seed; /* SPPT counter-RNG seed (sppt.f90:119-132 uses system_clock) */
+    int member_offset; /* global index of this context's member 0 in a sharded ensemble: the SPPT noise of
+                        * member e is keyed by (seed, step, member_offset + e, coefficient), so a member's
+                        * trajectory does not depend on how the ensemble is spread over GPUs */
 } speedy_cfg;
 
 /* ---- life cycle -------------------------------------------------------------------- */
@@ -138,6 +141,9 @@ int speedy_model_date(const speedy_ctx* ctx, int* ymdhm, long long* model_step);
 int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float* t, float* q, float* phi, float* ps);
 /* ensemble sums for the mean/spread diagnostic: writes sum and sum of squares of the 41
  * output levels over this ctx's members into device buffers (for NCCL all-reduce) */
+/* sppt.f90:45-99 noise source: on != 0 (default) draws eta on the device; 0 reads it from the
+ * `sppt_eta` field set by the caller */
+int speedy_set_sppt_draw(speedy_ctx* ctx, int on);
 int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq);
 size_t speedy_output_len(const speedy_ctx* ctx); /* (5*kx+1)*ix*il */
 

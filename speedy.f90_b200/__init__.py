@@ -25,7 +25,7 @@ class SpeedyError(RuntimeError):
 class Cfg(ctypes.Structure):
     _fields_ = [("trunc", ctypes.c_int), ("kx", ctypes.c_int), ("ntr", ctypes.c_int),
                 ("nmembers", ctypes.c_int), ("device", ctypes.c_int), ("sppt_on", ctypes.c_int),
-                ("seed", ctypes.c_ulonglong)]
+                ("seed", ctypes.c_ulonglong), ("member_offset", ctypes.c_int)]
 
 
 def lib():
@@ -79,9 +79,9 @@ def _c(a, dtype):
 class Speedy:
     """One context = one GPU + one batch of ensemble members (speedy_ctx)."""
 
-    def __init__(self, trunc=30, nmembers=1, device=0, sppt_on=0, seed=0):
+    def __init__(self, trunc=30, nmembers=1, device=0, sppt_on=0, seed=0, member_offset=0):
         L = lib()
-        cfg = Cfg(trunc, 8, 1, nmembers, device, sppt_on, seed)
+        cfg = Cfg(trunc, 8, 1, nmembers, device, sppt_on, seed, member_offset)
         h = ctypes.c_void_p()
         _chk(L.speedy_create(ctypes.byref(cfg), ctypes.byref(h)))
         self.h = h
@@ -338,6 +338,10 @@ class Speedy:
             assert out.dtype == np.float32 and out.flags.c_contiguous
             po = _p(out)
         return _chk(self.L.speedy_run_steps_host(self.h, _p(state), ctypes.c_size_t(state.size), int(nsteps), po))
+
+    def set_sppt_draw(self, on):
+        """sppt.f90:45-99 — draw eta on the device (default) or read it from the `sppt_eta` field"""
+        _chk(self.L.speedy_set_sppt_draw(self.h, int(bool(on))))
 
     def set_graphs(self, on):
         _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))

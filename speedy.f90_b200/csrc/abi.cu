@@ -117,6 +117,8 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->device = cfg->device;
         ctx->sppt_on = cfg->sppt_on;
         ctx->seed = cfg->seed;
+        ctx->member_offset = cfg->member_offset;
+        if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         setup_transform_kernels();
         upload_tables(ctx);

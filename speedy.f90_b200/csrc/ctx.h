@@ -71,6 +71,7 @@ struct speedy_ctx {
     int device = 0;
     int sppt_on = 0;
     unsigned long long seed = 0;
+    int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
     cudaStream_t stream = nullptr;
     long long launches = 0;
     bool use_graphs = true;

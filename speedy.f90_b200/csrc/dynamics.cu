@@ -351,14 +351,20 @@ __global__ void k_output(const double* __restrict__ gin, int N, double grav, dou
     out[(size_t)(5 * KX) * N + q] = (float)(p0 * exp(gin[(size_t)GI_PSL * N + q]));
 }
 
-// sum and sum of squares over this context's members of the 41 level-1 grid fields
-__global__ void k_ensemble_sums(const double* __restrict__ base, long long stride, long long gin_off, int nmembers, int nvals,
-                                double* __restrict__ sum, double* __restrict__ sumsq) {
+// sum and sum of squares over this context's members of the 41 output levels, in the units of
+// output() (input_output.f90:201-206: u, v, t, q*1e-3, phi/grav, p0*exp(ps)) but kept in fp64;
+// members are added in index order so that the partial sums are reproducible
+__global__ void k_ensemble_sums(const double* __restrict__ base, long long stride, long long gin_off, int nmembers, int nvals, int N,
+                                double grav, double p0, double* __restrict__ sum, double* __restrict__ sumsq) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nvals) return;
+    const int f = q / N;   // 0..7 u, 8..15 v, 16..23 t, 24..31 q, 32..39 phi, 40 ps
     double s = 0.0, s2 = 0.0;
     for (int e = 0; e < nmembers; e++) {
-        const double v = base[(size_t)e * stride + gin_off + q];
+        double v = base[(size_t)e * stride + gin_off + q];
+        if (f >= 40) v = p0 * exp(v);
+        else if (f >= 32) v = v / grav;
+        else if (f >= 24) v = v * (double)1.0e-3f;
         s += v; s2 += v * v;
     }
     sum[q] = s; sumsq[q] = s2;
@@ -368,7 +374,7 @@ __global__ void k_ensemble_sums(const double* __restrict__ base, long long strid
 // drawn with a counter-based generator: flag bit0 = first step, bit1 = draw eta on device
 struct SpptArgs {
     double* base; long long stride; Layout L; DevTables tv;
-    unsigned long long seed; long long counter; int first; int draw; double rearth;
+    unsigned long long seed; int* state; int member0; int draw; double rearth;   // state[0] = updates done so far, state[1] = block ticket
 };
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -380,10 +386,14 @@ __device__ __forceinline__ double u01(unsigned long long h) { return ((double)(h
 __global__ void k_sppt_update(SpptArgs a) {
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= KX * nsp) return;
-    const int k = t / nsp, r = t - k * nsp;
+    const bool live = t < KX * nsp;
+    const int k = live ? t / nsp : 0, r = live ? t - k * nsp : 0;
     const int n = r / mx, m = r - n * mx;
     const int e = blockIdx.y;
+    // the update counter lives on the device so that a replayed CUDA graph draws fresh noise every
+    // step; the last block to finish advances it (every block has read it by then)
+    const int counter = a.state[0];
+    const bool first = counter == 0;
     double* mb = a.base + (size_t)e * a.stride;
     const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
     const double phi = exp(-(24 / 36.0) / time_decorr);
@@ -395,7 +405,7 @@ __global__ void k_sppt_update(SpptArgs a) {
     cd eta;
     if (a.draw) {
         // counter-based Box-Muller (sppt.f90:103-117 shape: u = sqrt(-2 ln r1), v = 2*2pi*r2, sin only), clipped to +-10
-        const unsigned long long id = ((unsigned long long)a.counter * 64ull + (unsigned long long)e) * (unsigned long long)(KX * nsp) + (unsigned long long)t;
+        const unsigned long long id = ((unsigned long long)counter * 65536ull + (unsigned long long)(a.member0 + e)) * (unsigned long long)(KX * nsp) + (unsigned long long)t;
         const unsigned long long h = splitmix64(a.seed ^ splitmix64(id));
         const double r1 = u01(splitmix64(h + 1)), r2 = u01(splitmix64(h + 2)), r3 = u01(splitmix64(h + 3)), r4 = u01(splitmix64(h + 4));
         const double c = (double)(2.0f * 6.28318530718f);
@@ -403,19 +413,25 @@ __global__ void k_sppt_update(SpptArgs a) {
         gr = fmin(10.0, fabs(gr)) * copysign(1.0, gr);
         gi = fmin(10.0, fabs(gi)) * copysign(1.0, gi);
         eta = cd{gr, gi};
-        st(sfield(mb, a.L.sppt_eta, nsp, k), mx, m, n, eta);
+        if (live) st(sfield(mb, a.L.sppt_eta, nsp, k), mx, m, n, eta);
     } else {
         eta = ld(sfield(mb, a.L.sppt_eta, nsp, k), mx, m, n);
     }
     double* sp = sfield(mb, a.L.sppt_spec, nsp, k);
     cd v;
-    if (a.first) {
+    if (first) {
         const double c = pow(1 - phi * phi, -0.5);
         v = (c * sigma) * eta;
     } else {
         v = phi * ld(sp, mx, m, n) + sigma * eta;
     }
-    st(sp, mx, m, n, v);
+    if (live) st(sp, mx, m, n, v);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int nblk = gridDim.x * gridDim.y;
+        if (atomicAdd(&a.state[1], 1) == nblk - 1) { a.state[0] = counter + 1; a.state[1] = 0; __threadfence(); }
+    }
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -469,12 +485,10 @@ void launch_sppt_update(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpptArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv;
-    a.seed = ctx->seed; a.counter = M.sppt_counter; a.first = M.sppt_first ? 1 : 0; a.draw = M.sppt_draw ? 1 : 0; a.rearth = ctx->tab.c.rearth;
+    a.seed = ctx->seed; a.state = M.sppt_state.p; a.member0 = ctx->member_offset; a.draw = M.sppt_draw ? 1 : 0; a.rearth = ctx->tab.c.rearth;
     const int total = KX * ctx->d.nspec();
     dim3 grid((total + 127) / 128, ctx->nmembers);
     k_sppt_update<<<grid, 128, 0, ctx->stream>>>(a);
-    M.sppt_first = false;
-    M.sppt_counter++;
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }
@@ -482,7 +496,7 @@ void launch_sppt_update(speedy_ctx* ctx) {
 void launch_ensemble_sums(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
     Model& M = *ctx->model;
     const int nvals = 41 * ctx->d.ngrid();
-    k_ensemble_sums<<<(nvals + 255) / 256, 256, 0, ctx->stream>>>(M.mem.p, M.L.stride, M.L.gin + (long long)GI_U1 * ctx->d.ngrid(), ctx->nmembers, nvals, d_sum, d_sumsq);
+    k_ensemble_sums<<<(nvals + 255) / 256, 256, 0, ctx->stream>>>(M.mem.p, M.L.stride, M.L.gin + (long long)GI_U1 * ctx->d.ngrid(), ctx->nmembers, nvals, (int)ctx->d.ngrid(), ctx->tab.c.grav, ctx->tab.c.p0, d_sum, d_sumsq);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

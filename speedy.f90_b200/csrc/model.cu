@@ -472,8 +472,20 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
         const double* b = M.shared.p;
         M.sh = SharedDev{b + o_stl, b + o_snd, b + o_sw, b + o_sst, b + o_sic, b + o_rl, b + o_cl, b + o_rs, b + o_ri, b + o_cs, b + o_ci, b + o_bm, M.ssta.p, b + o_sol};
     }
+    // caller-supplied SPPT noise (speedy_set_sppt_draw(ctx, 0) + set_field("sppt_eta")) survives the reset
+    std::vector<double> keep_eta;
+    const size_t eta_len = (size_t)KXc * 2 * NS;
+    if (!M.sppt_draw) {
+        keep_eta.resize(eta_len * ctx->nmembers);
+        for (int e = 0; e < ctx->nmembers; e++)
+            CUDA_CHECK(cudaMemcpyAsync(keep_eta.data() + e * eta_len, M.mem.p + (size_t)e * M.L.stride + M.L.sppt_eta, eta_len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     CUDA_CHECK(cudaMemsetAsync(M.mem.p, 0, M.mem.n * sizeof(double), ctx->stream));
     CUDA_CHECK(cudaMemsetAsync(M.imem.p, 0, M.imem.n * sizeof(int), ctx->stream));
+    for (int e = 0; e < ctx->nmembers && !keep_eta.empty(); e++)
+        CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + M.L.sppt_eta, keep_eta.data() + e * eta_len, eta_len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     // date.f90:53-105, initialization.f90:37
     calendar_init(M.hclock, year, month, day, hour, minute, env.nssta);
     const int isst0 = (year - 1979) * 12 + month;
@@ -553,7 +565,8 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
     xform_qcorh(ctx, false);
     // geopotential of the rest state (prognostics.f90:123) so that an immediate output sees it
     launch_geopotential(ctx, 3);
-    M.sppt_first = true; M.sppt_counter = 0;
+    if (M.sppt_state.n != 2) M.sppt_state.alloc(2);
+    CUDA_CHECK(cudaMemsetAsync(M.sppt_state.p, 0, 2 * sizeof(int), ctx->stream));   // gen_sppt's `first` (sppt.f90:52)
     // ---- first_step (time_stepping.f90:12-24)
     if (speedy_first_step(ctx)) throw std::runtime_error(speedy_last_error());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -653,6 +666,16 @@ int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float*
     for (int f = 0; f < 5; f++)
         if (dst[f]) memcpy(dst[f], h.data() + (size_t)f * KXc * NG, KXc * NG * sizeof(float));
     if (ps) memcpy(ps, h.data() + (size_t)5 * KXc * NG, NG * sizeof(float));
+    API_END
+}
+
+// SPPT noise source: 1 (default) eta is drawn on the device by the counter generator; 0 eta is read
+// from the `sppt_eta` field (caller-supplied noise, e.g. to compare with another implementation)
+int speedy_set_sppt_draw(speedy_ctx* ctx, int on) {
+    API_BEGIN
+    check_ready(ctx);
+    ctx->model->sppt_draw = on != 0;
+    drop_graph(*ctx->model);   // the flag is a captured kernel argument
     API_END
 }
 

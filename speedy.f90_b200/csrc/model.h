@@ -93,8 +93,8 @@ struct Model {
     int day_graph_steps = 0;
     double implicit_dt = 0.0;
     // SPPT (sppt.f90): AR(1) state is device-resident; eta drawn on device unless supplied
-    bool sppt_first = true, sppt_draw = true;
-    long long sppt_counter = 0;
+    bool sppt_draw = true;
+    DevBuf<int> sppt_state;   // [0] AR(1) updates done so far (device-resident: CUDA-graph replays advance it), [1] block ticket
 };
 
 // ---- kernels (dynamics.cu / physics.cu) ------------------------------------------------

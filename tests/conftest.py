@@ -221,6 +221,13 @@ def ctx47(pkg):
     c.close()
 
 
+def bc_t47():
+    """synthetic T47 boundary pack (nearest-neighbour resampling of the T30 reference files), built on demand"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_t47_boundary
+    return make_t47_boundary.ensure()
+
+
 def random_spec(rng, lead, nx, mx, trunc, full_triangle=True):
     """uniform(-1,1) on the nsh2-active triangle (m+n <= trunc+1), zeros elsewhere"""
     s = rng.uniform(-1, 1, size=lead + (nx, mx)) + 1j * rng.uniform(-1, 1, size=lead + (nx, mx))

@@ -1,0 +1,108 @@
+"""BASELINE configs[2]: SPPT-perturbed ensemble, members batched per GPU (8/GPU on the 8-GPU
+box).  The reference seeds its noise from system_clock (sppt.f90:119-132), so bit-level parity
+is checked on caller-supplied noise (the oracle's `sppt_eta` hook), and the device generator is
+checked for its statistics, for freshness under CUDA-graph replay and for independence from the
+member partition."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+from conftest import ROOT, rel_rms
+
+pytestmark = pytest.mark.gpu
+BC = os.path.join(ROOT, "data", "bc_t30.bin")
+PROG = ("vor", "div", "t", "tr", "ps")
+
+
+def _ens(pkg):
+    return importlib.import_module("speedy_f90_b200.ensemble")
+
+
+def test_sppt_supplied_noise_matches_oracle(pkg, oracle):
+    """sppt.f90:45-99 + physics.f90:208-222 on identical eta: AR(1) pattern, clip and blend; 1e-10 after 24 h"""
+    o = oracle
+    rng = np.random.default_rng(11)
+    eta = (rng.standard_normal((o.kx, o.nx, o.mx)) + 1j * rng.standard_normal((o.kx, o.nx, o.mx)))
+    o.L.orc_set_sppt(1)
+    try:
+        o.set_field("sppt_eta", eta)
+        o.model_init(BC)
+        assert o.run(36) == 0
+        ref = o.state()
+    finally:
+        o.L.orc_set_sppt(0)
+    c = pkg.Speedy(trunc=30, sppt_on=1)
+    c.set_sppt_draw(False)
+    c.set_field("sppt_eta", eta)
+    c.model_init(BC)
+    assert c.run_steps(36) == 0
+    for n in PROG:
+        e = rel_rms(c.get_field(n), ref[n])
+        assert e < 1e-10, (n, e)
+    c.close()
+    # and the perturbation is not a no-op: the same run without SPPT differs
+    o.model_init(BC)
+    assert o.run(36) == 0
+    assert rel_rms(o.state()["t"], ref["t"]) > 1e-8
+
+
+def test_sppt_noise_statistics_and_graph_replay(pkg):
+    """device-drawn eta ~ N(0,1) per component; a replayed day graph draws fresh noise every step and
+    gives the same trajectory as plain launches"""
+    a = pkg.Speedy(trunc=30, nmembers=2, sppt_on=1, seed=7)
+    a.model_init(BC)
+    e0 = a.get_field("sppt_eta", all_members=True).copy()
+    x = np.concatenate([e0.real.ravel(), e0.imag.ravel()])
+    assert abs(x.mean()) < 0.02 and abs(x.std() - 1.0) < 0.02 and np.abs(x).max() <= 10.0
+    assert not np.array_equal(e0[0], e0[1])                       # members draw different noise
+    assert a.run_steps(72) == 0                                   # two replays of the 36-step graph
+    e2 = a.get_field("sppt_eta", all_members=True).copy()
+    b = pkg.Speedy(trunc=30, nmembers=2, sppt_on=1, seed=7)
+    b.set_graphs(False)
+    b.model_init(BC)
+    assert b.run_steps(36) == 0
+    e1 = b.get_field("sppt_eta", all_members=True).copy()
+    assert b.run_steps(36) == 0
+    assert not np.array_equal(e1, e2)                             # step 36's noise != step 72's (the graph does not replay its noise)
+    assert np.array_equal(b.get_field("sppt_eta", all_members=True), e2)
+    for n in PROG:
+        assert np.array_equal(a.get_field(n, all_members=True), b.get_field(n, all_members=True)), n
+    v = a.get_field("t", all_members=True)
+    assert rel_rms(v[0], v[1]) > 1e-9                             # the members have spread
+    a.close(); b.close()
+
+
+def test_member_trajectories_do_not_depend_on_the_partition(pkg):
+    """4 members in one context == blocks [0,2) and [2,4) in two contexts (what two ranks would hold)"""
+    ens = _ens(pkg)
+    whole = ens.Ensemble(pkg, 4, device=0, seed=3, rank=0, world=1)
+    whole.model_init(BC)
+    assert whole.run_steps(40) == 0
+    ref = {n: whole.ctx.get_field(n, all_members=True) for n in PROG}
+    for rank in range(2):
+        part = ens.Ensemble(pkg, 4, device=0, seed=3, rank=rank, world=2)
+        assert (part.lo, part.hi) == (2 * rank, 2 * rank + 2)
+        part.model_init(BC)
+        assert part.run_steps(40) == 0
+        for n in PROG:
+            assert np.array_equal(part.ctx.get_field(n, all_members=True), ref[n][part.lo:part.hi]), (rank, n)
+        part.close()
+    whole.close()
+
+
+def test_ensemble_mean_and_spread_on_device(pkg):
+    """speedy_ensemble_sums_dev + moments == mean/std of the members' output() fields"""
+    ens = _ens(pkg)
+    E = ens.Ensemble(pkg, 3, device=0, seed=5)
+    E.model_init(BC)
+    assert E.run_steps(36) == 0
+    mean, spread = E.mean_spread()
+    mean, spread = mean.cpu().numpy(), spread.cpu().numpy()
+    outs = [E.ctx.output_fields(member=e) for e in range(3)]
+    stack = np.stack([np.concatenate([o[n].reshape(-1, E.ctx.il, E.ctx.ix) for n in ("u", "v", "t", "q", "phi", "ps")]) for o in outs]).astype(np.float64)
+    scale = np.abs(stack).max(axis=(0, 2, 3), keepdims=True)[0]
+    assert np.all(np.abs(mean - stack.mean(0)) <= 2e-6 * scale)           # outputs are float32
+    assert np.all(np.abs(spread - stack.std(0)) <= 1e-4 * scale)
+    assert spread[16:24].max() > 0                                         # temperature spread is non-zero
+    E.close()

@@ -3,6 +3,7 @@ and the oracle's own invariants for the full model."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -106,3 +107,27 @@ def test_packed_boundary_file_layout():
         off += 20 + 4 * nrec * ix * il
     assert off == len(raw)
     assert names["ssta"] >= 40 and names["sst"] == 12 and names["orog"] == 1
+
+
+def test_t47_boundary_synthesis_and_oracle_start():
+    """BASELINE configs[3] input: the T47 pack is a nearest-neighbour resampling of the T30 files
+    (every value is a T30 value, zonal/meridional order preserved) and the T47 oracle starts from it"""
+    from conftest import bc_t47
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_t47_boundary as mk
+    path = bc_t47()
+    ix, il, f47 = mk.read_pack(path)
+    _, _, f30 = mk.read_pack(BC)
+    assert (ix, il) == (144, 72) and [n for n, _ in f47] == [n for n, _ in f30]
+    lat = mk.gauss_lat_deg(72)
+    assert np.all(np.diff(lat) > 0) and abs(lat[0] + lat[-1]) < 1e-12 and 87 < lat[-1] < 89
+    for (n, a47), (_, a30) in zip(f47, f30):
+        assert a47.shape[1:] == (72, 144)
+        assert np.isin(a47[0], a30[0]).all(), n
+    lsm47, lsm30 = dict(f47)["lsm"][0], dict(f30)["lsm"][0]
+    assert abs(lsm47.mean() - lsm30.mean()) < 0.02          # land fraction survives the resampling
+    o = Oracle("t47")
+    o.model_init(path)
+    assert o.run(3) == 0
+    rc, d = o.check_diagnostics(2)
+    assert rc == 0 and d[2].min() > 180 and d[2].max() < 320

@@ -6,7 +6,7 @@ RMS (north_star); integer fields (iptop, icltop, icnv) bit-exact."""
 import os
 import numpy as np
 import pytest
-from conftest import ROOT, rel_rms
+from conftest import ROOT, bc_t47, rel_rms
 
 pytestmark = pytest.mark.gpu
 BC = os.path.join(ROOT, "data", "bc_t30.bin")
@@ -141,3 +141,27 @@ def test_host_resident_main_loop(pkg):
     ref_out = np.concatenate([o[n].ravel() for n in ("u", "v", "t", "q", "phi", "ps")])
     assert np.array_equal(out, ref_out)
     a.close(); b.close()
+
+
+def test_48h_run_t47(pkg, oracle47):
+    """BASELINE configs[3]: T47 (144x72) L8 on synthetic boundaries (tools/make_t47_boundary.py), the reference's
+    time step; same 1e-10 tolerance on the prognostic spectral coefficients after 48 h, integer fields bit-exact"""
+    o = oracle47
+    bc = bc_t47()
+    o.model_init(bc)
+    assert o.run(72) == 0
+    c = pkg.Speedy(trunc=47)
+    assert (c.ix, c.il, c.mx, c.nx) == (144, 72, 48, 49)
+    c.model_init(bc)
+    assert c.run_steps(72) == 0
+    assert c.model_date() == o.date()
+    ref = o.state()
+    for n in PROG:
+        e = rel_rms(c.get_field(n), ref[n])
+        assert e < 1e-10, (n, e)
+    out, out0 = c.output_fields(), o.output_fields()
+    for n in out:
+        assert np.allclose(out[n], out0[n], rtol=2e-6, atol=1e-6 * np.abs(out0[n]).max()), n
+    for n in ("iptop", "icnv", "icltop"):
+        assert np.array_equal(c.get_field(n), o.ifield(n)), n
+    c.close()
