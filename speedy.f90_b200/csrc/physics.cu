@@ -12,6 +12,7 @@
 // operation (the checker is built with -ffp-contract=off).
 #include "model.h"
 #include "calendar.h"
+#include "tma.cuh"
 
 namespace spd {
 
@@ -55,39 +56,104 @@ struct ColumnArgs {
     int sppt_on;
 };
 
-__global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
+// ---- the column kernel -------------------------------------------------------------------
+// One CTA owns a tile of TC = 32 consecutive columns and runs FOUR warp roles on it (lane =
+// column), so that the dependent chain of a column is cut four ways and every role reads its
+// inputs from shared memory, where the tile was staged once by bulk asynchronous copies (TMA,
+// one 256-byte row per field, completion on two mbarriers):
+//   PHYS  prep, convection, condensation, [clouds + shortwave], longwave down, surface fluxes,
+//         longwave up, then the closing stage (tendency sums in the reference's order, SPPT)
+//   SLAB  couple_sea_land of the previous step + set_forcing(1) when due, then stages the
+//         surface fields the physics reads                                   -> BAR_SLAB
+//   DYN   tendencies.f90:109-197 and the products for the direct transforms  -> BAR_FINAL
+//   VDIF  vertical_diffusion.f90 (waits for PHYS's thermodynamic prep: BAR_PREP) -> BAR_FINAL
+constexpr int TC = 32;
+constexpr int COL_THREADS = 128;
+enum { ROLE_PHYS = 0, ROLE_SLAB = 1, ROLE_DYN = 2, ROLE_VDIF = 3 };
+enum { BAR_SLAB = 1, BAR_PREP = 2, BAR_FINAL = 3 };
+enum { SF_FMASK, SF_FSOL, SF_OZONE, SF_OZUPP, SF_ZENIT, SF_STRATZ, SF_ALBSFC, SF_PHIS0, SF_SST, SF_STL, SF_SOILW, SF_ALBL, SF_ALBS,
+       SF_SNOWC, SF_FOROG, SF_SSRD, SF_N };
+// shared-memory rows of TC doubles
+enum { R_GIN = 0, R_TAU2 = R_GIN + GI_N, R_STRATC = R_TAU2 + 4 * KX, R_RSW = R_STRATC + 2, R_SURF = R_RSW + KX, R_DYN = R_SURF + SF_N,
+       R_PREP = R_DYN + 4 * KX, R_CNV = R_PREP + 4 * KX, R_VD = R_CNV + 4 * KX, R_END = R_VD + 2 * KX };
+constexpr int NFBAND = 301 * 4;
+constexpr int LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
+static_assert(sizeof(LevelConsts) % 16 == 0 && (NFBAND * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
+constexpr size_t COL_SMEM = sizeof(double) * ((size_t)R_END * TC + NFBAND + LC_DOUBLES) + sizeof(int) * TC + 2 * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    double* sFband = smem + (size_t)R_END * TC;
+    double* sLc = sFband + NFBAND;
+    int* sIcnv = reinterpret_cast<int*>(sLc + LC_DOUBLES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sIcnv + TC);     // [0] physics inputs, [1] dynamics inputs
     const int ix = a.ix, il = a.il, N = ix * il;
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= N) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int col0 = blockIdx.x * TC, col = col0 + lane;
     const int e = blockIdx.y;
     const int j = col / ix;
     double* mb = a.base + (size_t)e * a.stride;
     int* ib = a.ibase + (size_t)e * a.L.istride;
-    const LevelConsts& lc = *a.lc;
-    const double* gin = mb + a.L.gin;
+    const LevelConsts& lc = *reinterpret_cast<const LevelConsts*>(sLc);
     double* gout = mb + a.L.gout;
-#define GIN(f) gin[(size_t)(f) * N + col]
+#define SROW(r) smem[(size_t)(r) * TC + lane]
+#define SG(f) SROW(R_GIN + (f))
+#define SURF(i) SROW(R_SURF + (i))
+#define STAU2(k, b) SROW(R_TAU2 + ((b)-1) * KX + ((k)-1))
+#define STRATC(i) SROW(R_STRATC + (i))
+#define RSW(k) SROW(R_RSW + (k)-1)
+#define DYN(v, k) SROW(R_DYN + (v) * KX + (k)-1)
+#define PREP(v, k) SROW(R_PREP + (v) * KX + (k)-1)
+#define CNV(v, k) SROW(R_CNV + (v) * KX + (k)-1)
+#define VD(v, k) SROW(R_VD + (v) * KX + (k)-1)
 #define GOUT(f) gout[(size_t)(f) * N + col]
 #define G2(off) mb[(off) + col]
 #define G3(off, k) mb[(off) + (size_t)((k)-1) * N + col]
+#define TAU2W(k, b, v) do { const double v_ = (v); mb[a.L.tau2 + ((size_t)((b)-1) * KX + ((k)-1)) * N + col] = v_; STAU2(k, b) = v_; } while (0)
 
-    double utend[KX + 1], vtend[KX + 1], ttend[KX + 1], qtend[KX + 1];
+    // ---- stage the tile: one bulk copy per field row, spread over the threads -------------------
+    const int ngin = a.sppt_on ? GI_N : GI_NBASE;
+    const int c_tau = ngin, c_str = c_tau + 4 * KX, c_rsw = c_str + 2, c_fb = c_rsw + KX, c_lc = c_fb + 1, ncopy = c_lc + 1;
+    const bool want_dyn = a.mode == 0;
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t row = TC * sizeof(double);
+        mbar_expect_tx(&bars[0], (uint32_t)((ngin - GI_U1) + 4 * KX + 2 + KX) * row + NFBAND * 8 + (uint32_t)sizeof(LevelConsts));
+        if (want_dyn) mbar_expect_tx(&bars[1], (uint32_t)GI_U1 * row);
+    }
+    for (int c = tid; c < ncopy; c += COL_THREADS) {
+        const uint32_t row = TC * sizeof(double);
+        if (c < ngin) {
+            if (c < GI_U1) { if (want_dyn) bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[1]); }
+            else bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[0]);
+        } else if (c < c_str) bulk_g2s(&smem[(size_t)(R_TAU2 + c - c_tau) * TC], mb + a.L.tau2 + (size_t)(c - c_tau) * N + col0, row, &bars[0]);
+        else if (c < c_rsw) bulk_g2s(&smem[(size_t)(R_STRATC + c - c_str) * TC], mb + a.L.stratc + (size_t)(c - c_str) * N + col0, row, &bars[0]);
+        else if (c < c_fb) bulk_g2s(&smem[(size_t)(R_RSW + c - c_rsw) * TC], mb + a.L.tt_rsw + (size_t)(c - c_rsw) * N + col0, row, &bars[0]);
+        else if (c == c_fb) bulk_g2s(sFband, a.fband, NFBAND * 8, &bars[0]);
+        else bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), &bars[0]);
+    }
 
-    if (a.mode == 0) {
+    if (warp == ROLE_DYN) {
         // ============================ tendencies.f90:109-197 ============================
+        double utend[KX + 1], vtend[KX + 1], ttend[KX + 1], qtend[KX + 1];
+        if (a.mode == 0) {
+            const double cor = a.coriol[j];
+            mbar_wait(&bars[0], 0);     // level constants
+            mbar_wait(&bars[1], 0);
         double ug[KX + 1], vg[KX + 1], tg[KX + 1], vorg[KX + 1], divg[KX + 1], trg[KX + 1], tgg[KX + 1], puv[KX + 1];
         double sigdt[KX + 2], sigm[KX + 2], temp[KX + 2];
-        const double cor = a.coriol[j];
+        
 #pragma unroll
         for (int k = 1; k <= KX; k++) {
-            vorg[k] = GIN(GI_VOR + k - 1) + cor;   // :103-107
-            divg[k] = GIN(GI_DIV + k - 1);
-            tg[k] = GIN(GI_T + k - 1);
-            trg[k] = GIN(GI_TR + k - 1);
-            ug[k] = GIN(GI_U + k - 1);
-            vg[k] = GIN(GI_V + k - 1);
+            vorg[k] = SG(GI_VOR + k - 1) + cor;   // :103-107
+            divg[k] = SG(GI_DIV + k - 1);
+            tg[k] = SG(GI_T + k - 1);
+            trg[k] = SG(GI_TR + k - 1);
+            ug[k] = SG(GI_U + k - 1);
+            vg[k] = SG(GI_V + k - 1);
         }
-        const double px = GIN(GI_PX), py = GIN(GI_PY);
+        const double px = SG(GI_PX), py = SG(GI_PY);
         double umean = 0.0, vmean = 0.0, dmean = 0.0;
 #pragma unroll
         for (int k = 1; k <= KX; k++) {
@@ -136,36 +202,118 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             GOUT(f + 6) = -ug[k] * trg[k];
             GOUT(f + 7) = -vg[k] * trg[k];
         }
-    } else {
+        } else {
 #pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            const int f = GO_PER * (k - 1);
-            utend[k] = GOUT(f + 0); vtend[k] = GOUT(f + 1); ttend[k] = GOUT(f + 5); qtend[k] = GOUT(f + 8);
+            for (int k = 1; k <= KX; k++) {
+                const int f = GO_PER * (k - 1);
+                utend[k] = GOUT(f + 0); vtend[k] = GOUT(f + 1); ttend[k] = GOUT(f + 5); qtend[k] = GOUT(f + 8);
+            }
         }
+#pragma unroll
+        for (int k = 1; k <= KX; k++) { DYN(0, k) = utend[k]; DYN(1, k) = vtend[k]; DYN(2, k) = ttend[k]; DYN(3, k) = qtend[k]; }
+        named_arrive(BAR_FINAL, 96);
+        return;
     }
 
-    // ===== main loop only: couple_sea_land of the previous step (speedy.f90:53) and set_forcing(1) (speedy.f90:29-32),
-    // both column-local, ride in front of the physics that consumes them
-    if (a.merged) {
-        if (a.clk->slab_pending) slab_point(mb, a.L, a.sh, *a.clk, lc, N, col, 0);
-        if (a.clk->do_forcing) forcing_point(mb, a.L, a.sh, *a.clk, lc, ix, il, col);
+    if (warp == ROLE_SLAB) {
+        // ===== main loop only: couple_sea_land of the previous step (speedy.f90:53) and set_forcing(1) (speedy.f90:29-32),
+        // both column-local, in front of the physics that consumes them
+        if (a.merged) {
+            const int pending = a.clk->slab_pending, forcing = a.clk->do_forcing;
+            if (pending | forcing) mbar_wait(&bars[0], 0);     // level constants
+            if (pending) slab_point(mb, a.L, a.sh, *a.clk, lc, N, col, 0);
+            if (forcing) forcing_point(mb, a.L, a.sh, *a.clk, lc, ix, il, col);
+        }
+        SURF(SF_FMASK) = G2(a.L.fmask_l); SURF(SF_FSOL) = G2(a.L.fsol); SURF(SF_OZONE) = G2(a.L.ozone); SURF(SF_OZUPP) = G2(a.L.ozupp);
+        SURF(SF_ZENIT) = G2(a.L.zenit); SURF(SF_STRATZ) = G2(a.L.stratz); SURF(SF_ALBSFC) = G2(a.L.albsfc); SURF(SF_PHIS0) = G2(a.L.phis0);
+        SURF(SF_SST) = G2(a.L.sst_am); SURF(SF_STL) = G2(a.L.stl_am); SURF(SF_SOILW) = G2(a.L.soilw_am); SURF(SF_ALBL) = G2(a.L.alb_l);
+        SURF(SF_ALBS) = G2(a.L.alb_s); SURF(SF_SNOWC) = G2(a.L.snowc); SURF(SF_FOROG) = G2(a.L.forog); SURF(SF_SSRD) = G2(a.L.ssrd);
+        named_arrive(BAR_SLAB, 64);
+        return;
     }
 
-    // ================================ physics.f90:110-205 ================================
+    if (warp == ROLE_VDIF) {
+        double se[KX + 1], rh[KX + 1], qsat[KX + 1], qg[KX + 1], phig[KX + 1];
+        mbar_wait(&bars[0], 0);
+#pragma unroll
+        for (int k = 1; k <= KX; k++) phig[k] = SG(GI_PHI + k - 1);
+        named_sync(BAR_PREP, 64);
+#pragma unroll
+        for (int k = 1; k <= KX; k++) { se[k] = PREP(0, k); qsat[k] = PREP(1, k); rh[k] = PREP(2, k); qg[k] = PREP(3, k); }
+        // ------------------- vertical_diffusion.f90:30-143 -------------------
+        {
+            const double trshc = 6.0, trvdi = 24.0, trvds = 6.0, redshc = 0.5, rhgrad = 0.5, segrad = F32(0.1);
+            const int nl1 = KX - 1;
+            double rsig[KX + 1], rsig1[KX + 1], ttenvd[KX + 1], qtenvd[KX + 1];
+            const double cshc = lc.dhs[KX - 1] / 3600.0;
+            const double cvdi = (lc.sigh[nl1] - lc.sigh[1]) / ((nl1 - 1) * 3600.0);
+            const double fshcq = cshc / trshc, fshcse = cshc / (trshc * lc.cp);
+            const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * lc.cp);
+#pragma unroll
+            for (int k = 1; k <= nl1; k++) { rsig[k] = 1.0 / lc.dhs[k - 1]; rsig1[k] = 1.0 / (1.0 - lc.sigh[k]); }
+            rsig[KX] = 1.0 / lc.dhs[KX - 1];
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { ttenvd[k] = 0.0; qtenvd[k] = 0.0; }
+            double drh0 = rhgrad * (lc.fsg[KX - 1] - lc.fsg[nl1 - 1]);
+            double fvdiq2 = fvdiq * lc.sigh[nl1];
+            {
+                const double dmse = se[KX] - se[nl1] + lc.alhc * (qg[KX] - qsat[nl1]);
+                const double drh = rh[KX] - rh[nl1];
+                double fcnv = 1.0;
+                if (dmse >= 0.0) {
+                    if (sIcnv[lane] > 0) fcnv = redshc;
+                    const double fluxse = fcnv * fshcse * dmse;
+                    ttenvd[nl1] = fluxse * rsig[nl1];
+                    ttenvd[KX] = -fluxse * rsig[KX];
+                    if (drh >= 0.0) {
+                        const double fluxq = fcnv * fshcq * qsat[KX] * drh;
+                        qtenvd[nl1] = fluxq * rsig[nl1];
+                        qtenvd[KX] = -fluxq * rsig[KX];
+                    }
+                } else if (drh > drh0) {
+                    const double fluxq = fvdiq2 * qsat[nl1] * drh;
+                    qtenvd[nl1] = fluxq * rsig[nl1];
+                    qtenvd[KX] = -fluxq * rsig[KX];
+                }
+            }
+            for (int k = 3; k <= KX - 2; k++) {
+                if (lc.sigh[k] > 0.5) {
+                    drh0 = rhgrad * (lc.fsg[k] - lc.fsg[k - 1]);
+                    fvdiq2 = fvdiq * lc.sigh[k];
+                    const double drh = rh[k + 1] - rh[k];
+                    if (drh >= drh0) {
+                        const double fluxq = fvdiq2 * qsat[k] * drh;
+                        qtenvd[k] = qtenvd[k] + fluxq * rsig[k];
+                        qtenvd[k + 1] = qtenvd[k + 1] - fluxq * rsig[k + 1];
+                    }
+                }
+            }
+            for (int k = 1; k <= nl1; k++) {
+                const double se0 = se[k + 1] + segrad * (phig[k] - phig[k + 1]);
+                if (se[k] < se0) {
+                    const double fluxse = fvdise * (se0 - se[k]);
+                    ttenvd[k] = ttenvd[k] + fluxse * rsig[k];
+                    for (int k1 = k + 1; k1 <= KX; k1++) ttenvd[k1] = ttenvd[k1] - fluxse * rsig1[k];
+                }
+            }
+
+#pragma unroll
+            for (int k = 1; k <= KX; k++) { VD(0, k) = ttenvd[k]; VD(1, k) = qtenvd[k]; }
+        }
+        named_arrive(BAR_FINAL, 96);
+        return;
+    }
+
+    // ================================ physics.f90:110-205 (ROLE_PHYS) ================================
     {
-        double ug[KX + 1], vg[KX + 1], tg[KX + 1], qg[KX + 1], phig[KX + 1], se[KX + 1], rh[KX + 1], qsat[KX + 1];
-        double ut_dyn[KX + 1], vt_dyn[KX + 1], tt_dyn[KX + 1], qt_dyn[KX + 1];
+        double tg[KX + 1], qg[KX + 1], phig[KX + 1], se[KX + 1], rh[KX + 1], qsat[KX + 1];
         const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
-        if (a.sppt_on) {
+        const double coa_j = a.coa[j];
+        mbar_wait(&bars[0], 0);
 #pragma unroll
-            for (int k = 1; k <= KX; k++) { ut_dyn[k] = utend[k]; vt_dyn[k] = vtend[k]; tt_dyn[k] = ttend[k]; qt_dyn[k] = qtend[k]; }
-        }
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            ug[k] = GIN(GI_U1 + k - 1); vg[k] = GIN(GI_V1 + k - 1); tg[k] = GIN(GI_T1 + k - 1);
-            qg[k] = GIN(GI_Q1 + k - 1); phig[k] = GIN(GI_PHI + k - 1);
-        }
-        const double psg = exp(GIN(GI_PSL));
+        for (int k = 1; k <= KX; k++) { tg[k] = SG(GI_T1 + k - 1); qg[k] = SG(GI_Q1 + k - 1); phig[k] = SG(GI_PHI + k - 1); }
+        const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);   // only the lowest-level wind is used (surface fluxes)
+        const double psg = exp(SG(GI_PSL));
         const double rps = 1.0 / psg;
 #pragma unroll
         for (int k = 1; k <= KX; k++) {
@@ -173,6 +321,7 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             se[k] = lc.cp * tg[k] + phig[k];
             qsat[k] = qsat_pt(tg[k], lc.fsg[k - 1] * psg);
             rh[k] = qg[k] / qsat[k];
+            PREP(0, k) = se[k]; PREP(1, k) = qsat[k]; PREP(2, k) = rh[k]; PREP(3, k) = qg[k];
         }
         const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
 
@@ -280,6 +429,8 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             dtlsc[1] = 0.0; dqlsc[1] = 0.0;
             const int icnv_ = KX - iptop;   // physics.f90:132, before LSC lowers iptop
             ib[a.L.icnv + col] = icnv_;
+            sIcnv[lane] = icnv_;
+            named_arrive(BAR_PREP, 64);          // se/qsat/rh/qg + icnv are in shared memory: the vertical-diffusion warp may start
 #pragma unroll
             for (int k = 2; k <= KX; k++) {
                 const double sig2 = lc.fsg[k - 1] * lc.fsg[k - 1];
@@ -304,14 +455,14 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             }
             precls = precls * psg;
 #pragma unroll
-            for (int k = 1; k <= KX; k++) {   // physics.f90:137-138
-                ttend[k] = ttend[k] + dfse[k] + dtlsc[k];
-                qtend[k] = qtend[k] + dfqa[k] + dqlsc[k];
+            for (int k = 1; k <= KX; k++) {   // physics.f90:137-138: added to the tendencies in the closing stage, in the reference's order
+                CNV(0, k) = dfse[k]; CNV(1, k) = dtlsc[k]; CNV(2, k) = dfqa[k]; CNV(3, k) = dqlsc[k];
             }
             G2(a.L.precnv) = precnv; G2(a.L.precls) = precls; G2(a.L.cbmf) = cbmf;
             ib[a.L.iptop + col] = iptop;
 
             // ------------------------- shortwave (every nstrad-th step) -------------------------
+            named_sync(BAR_SLAB, 64);          // surface / forcing fields of this step are staged (slab warp)
             if (csw) {
                 const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
                 const double clsmax = F32(0.60), clsminl = F32(0.15), gse_s0 = 0.25, gse_s1 = F32(0.40);
@@ -342,14 +493,14 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
                     const double fstab = dmax(0.0, dmin(1.0, rgse * (gse - gse_s0)));
                     clstr = fstab * dmax(clsmax - clfact * cloudc, 0.0);
                     const double clstrl = dmax(clstr, clsminl) * rh[KX];
-                    const double fm = G2(a.L.fmask_l);
+                    const double fm = SURF(SF_FMASK);
                     clstr = clstr + fm * (clstrl - clstr);
                 }
                 ib[a.L.icltop + col] = icltop;
                 G2(a.L.qcloud) = qcloud; G2(a.L.cloudc) = cloudc; G2(a.L.clstr) = clstr;
                 // get_shortwave_rad_fluxes  shortwave_radiation.f90:74-234
-                const double fsol = G2(a.L.fsol), ozone = G2(a.L.ozone), ozupp = G2(a.L.ozupp), zenit = G2(a.L.zenit), stratz = G2(a.L.stratz);
-                const double albsfc = G2(a.L.albsfc);
+                const double fsol = SURF(SF_FSOL), ozone = SURF(SF_OZONE), ozupp = SURF(SF_OZUPP), zenit = SURF(SF_ZENIT), stratz = SURF(SF_STRATZ);
+                const double albsfc = SURF(SF_ALBSFC);
                 const double fband2 = F32(0.05), fband1 = 1.0 - fband2;
                 double tau1[KX + 1], tau2_[KX + 1], tau3[KX + 1], dfabs[KX + 1];
 #pragma unroll
@@ -400,20 +551,19 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
                     flux1 = flux1 + tau3[k];
                 }
                 ftop = ftop - flux1;
-                G2(a.L.ssrd) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
+                G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
 #pragma unroll
-                for (int k = 1; k <= KX; k++) G3(a.L.tt_rsw, k) = dfabs[k] * rps * lc.grdscp[k - 1];   // physics.f90:160-162
+                for (int k = 1; k <= KX; k++) { const double v = dfabs[k] * rps * lc.grdscp[k - 1]; G3(a.L.tt_rsw, k) = v; RSW(k) = v; }   // physics.f90:160-162
                 // longwave transmissivities :190-233 -> persistent tau2(ix,il,kx,4)
-#define TAU2(k, b) mb[a.L.tau2 + ((size_t)((b)-1) * KX + ((k)-1)) * N + col]
-                TAU2(1, 1) = exp(-psg * lc.dhs[0] * ablwin);
-                TAU2(1, 2) = exp(-psg * lc.dhs[0] * ablco2);
-                TAU2(1, 3) = 1.0;
-                TAU2(1, 4) = 1.0;
+                TAU2W(1, 1, exp(-psg * lc.dhs[0] * ablwin));
+                TAU2W(1, 2, exp(-psg * lc.dhs[0] * ablco2));
+                TAU2W(1, 3, 1.0);
+                TAU2W(1, 4, 1.0);
                 for (int k = 2; k <= KX; k += KX - 2) {
-                    TAU2(k, 1) = exp(-psg * lc.dhs[k - 1] * ablwin);
-                    TAU2(k, 2) = exp(-psg * lc.dhs[k - 1] * ablco2);
-                    TAU2(k, 3) = exp(-psg * lc.dhs[k - 1] * ablwv1 * qg[k]);
-                    TAU2(k, 4) = exp(-psg * lc.dhs[k - 1] * ablwv2 * qg[k]);
+                    TAU2W(k, 1, exp(-psg * lc.dhs[k - 1] * ablwin));
+                    TAU2W(k, 2, exp(-psg * lc.dhs[k - 1] * ablco2));
+                    TAU2W(k, 3, exp(-psg * lc.dhs[k - 1] * ablwv1 * qg[k]));
+                    TAU2W(k, 4, exp(-psg * lc.dhs[k - 1] * ablwv2 * qg[k]));
                 }
                 acloud = cloudc * ablcl2;
                 for (int k = 3; k <= nl1; k++) {
@@ -421,14 +571,14 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
                     double acloud1;
                     if (k < icltop) acloud1 = acloud;
                     else acloud1 = ablcl1 * cloudc;
-                    TAU2(k, 1) = exp(-deltap * (ablwin + acloud1));
-                    TAU2(k, 2) = exp(-deltap * ablco2);
-                    TAU2(k, 3) = exp(-deltap * dmax(ablwv1 * qg[k], acloud));
-                    TAU2(k, 4) = exp(-deltap * dmax(ablwv2 * qg[k], acloud));
+                    TAU2W(k, 1, exp(-deltap * (ablwin + acloud1)));
+                    TAU2W(k, 2, exp(-deltap * ablco2));
+                    TAU2W(k, 3, exp(-deltap * dmax(ablwv1 * qg[k], acloud)));
+                    TAU2W(k, 4, exp(-deltap * dmax(ablwv2 * qg[k], acloud)));
                 }
                 const double eps1 = epslw / (lc.dhs[0] + lc.dhs[1]);
-                mb[a.L.stratc + col] = stratz * psg;
-                mb[a.L.stratc + N + col] = eps1 * psg;
+                mb[a.L.stratc + col] = STRATC(0) = stratz * psg;
+                mb[a.L.stratc + N + col] = STRATC(1) = eps1 * psg;
             }
         }
 
@@ -466,17 +616,17 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
 #pragma unroll
             for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;   // nint(T) -> row of fband(100:400,:)
             for (int jb = 1; jb <= 2; jb++) {
-                const double emis = 1.0 - TAU2(1, jb);
-                const double brad = a.fband[nt[1] + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
+                const double emis = 1.0 - STAU2(1, jb);
+                const double brad = sFband[nt[1] + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
                 flux[jb] = emis * brad;
                 tt_rlw[1] = tt_rlw[1] - flux[jb];
             }
             flux[3] = 0.0; flux[4] = 0.0;
             for (int jb = 1; jb <= 4; jb++)
                 for (int k = 2; k <= KX; k++) {
-                    const double tau = TAU2(k, jb);
+                    const double tau = STAU2(k, jb);
                     const double emis = 1.0 - tau;
-                    const double brad = a.fband[nt[k] + 301 * (jb - 1)] * (st4a1[k] + emis * st4a2[k]);
+                    const double brad = sFband[nt[k] + 301 * (jb - 1)] * (st4a1[k] + emis * st4a2[k]);
                     tt_rlw[k] = tt_rlw[k] + flux[jb];
                     flux[jb] = tau * flux[jb] + emis * brad;
                     tt_rlw[k] = tt_rlw[k] - flux[jb];
@@ -496,10 +646,10 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             const double vgust = 5.0, ctday = F32(1.0e-2), dtheta = 3.0, fstab = F32(0.67), clambda = 7.0, clambsn = 7.0;
             const double esbc = emisfc * lc.sbc;
             const int nl1 = KX - 1;
-            const double phi0 = G2(a.L.phis0), fmask = G2(a.L.fmask_l), tsea = G2(a.L.sst_am), stl_am = G2(a.L.stl_am);
-            const double soilw_am = G2(a.L.soilw_am), alb_l = G2(a.L.alb_l), alb_s = G2(a.L.alb_s), snowc = G2(a.L.snowc), forog = G2(a.L.forog);
-            const double ssrd = G2(a.L.ssrd);
-            const double u0 = fwind0 * ug[KX], v0 = fwind0 * vg[KX];
+            const double phi0 = SURF(SF_PHIS0), fmask = SURF(SF_FMASK), tsea = SURF(SF_SST), stl_am = SURF(SF_STL);
+            const double soilw_am = SURF(SF_SOILW), alb_l = SURF(SF_ALBL), alb_s = SURF(SF_ALBS), snowc = SURF(SF_SNOWC), forog = SURF(SF_FOROG);
+            const double ssrd = SURF(SF_SSRD);
+            const double u0 = fwind0 * ug8, v0 = fwind0 * vg8;
             const double gtemp0 = 1.0 - ftemp0, rcp = 1.0 / lc.cp;
             const double dt1 = wvi2[KX] * (tg[KX] - tg[nl1]);
             double t1_1 = tg[KX] + dt1;
@@ -515,14 +665,14 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             }
             double t0 = t1_2 + fmask * (t1_1 - t1_2);
             const double denvvs0 = (lc.p0 * psg / (lc.rgas * t0)) * sqrt(u0 * u0 + v0 * v0 + vgust * vgust);
-            double tskin = stl_am + ctday * sqrt(a.coa[j]) * ssrd * (1.0 - alb_l) * psg;
+            double tskin = stl_am + ctday * sqrt(coa_j) * ssrd * (1.0 - alb_l) * psg;
             const double rdth = fstab / dtheta, astab = 0.5;
             double dthl;
             if (tskin > t2_1) dthl = dmin(dtheta, tskin - t2_1);
             else dthl = dmax(-dtheta, astab * (tskin - t2_1));
             const double denvvs1 = denvvs0 * (1.0 + dthl * rdth);
             const double cdldv = cdl * denvvs0 * forog;
-            const double ustr1 = -cdldv * ug[KX], vstr1 = -cdldv * vg[KX];
+            const double ustr1 = -cdldv * ug8, vstr1 = -cdldv * vg8;
             const double chlcp = chl * lc.cp;
             double shf1 = chlcp * denvvs1 * (tskin - t1_1);
             const double q1_1 = qg[KX];
@@ -552,7 +702,7 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             const double denvvs2 = denvvs0 * (1.0 + dths * rdth);
             const double q1_2 = qg[KX];
             const double cdsdv = cds * denvvs2;
-            const double ustr2 = -cdsdv * ug[KX], vstr2 = -cdsdv * vg[KX];
+            const double ustr2 = -cdsdv * ug8, vstr2 = -cdsdv * vg8;
             const double shf2 = chs * lc.cp * denvvs2 * (tsea - t1_2);
             const double qsat0_s = qsat_pt(tsea, psg);
             const double evap2 = chs * denvvs2 * (qsat0_s - q1_2);
@@ -581,29 +731,29 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             const double fsfcu = slru3;
             G2(a.L.slr) = fsfcu - slrd;
             const int nts = (int)round(ts) - 100;
-            for (int jb = 1; jb <= 4; jb++) flux[jb] = a.fband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
+            for (int jb = 1; jb <= 4; jb++) flux[jb] = sFband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
             tt_rlw[KX] = tt_rlw[KX] + epslw * fsfcu;
             int nt[KX + 1];
 #pragma unroll
             for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;
             for (int jb = 1; jb <= 4; jb++)
                 for (int k = KX; k >= 2; k--) {
-                    const double tau = TAU2(k, jb);
+                    const double tau = STAU2(k, jb);
                     const double emis = 1.0 - tau;
-                    const double brad = a.fband[nt[k] + 301 * (jb - 1)] * (st4a1[k] - emis * st4a2[k]);
+                    const double brad = sFband[nt[k] + 301 * (jb - 1)] * (st4a1[k] - emis * st4a2[k]);
                     tt_rlw[k] = tt_rlw[k] + flux[jb];
                     flux[jb] = tau * flux[jb] + emis * brad;
                     tt_rlw[k] = tt_rlw[k] - flux[jb];
                 }
             for (int jb = 1; jb <= 2; jb++) {
-                const double tau = TAU2(1, jb);
+                const double tau = STAU2(1, jb);
                 const double emis = 1.0 - tau;
-                const double brad = a.fband[nt[1] + 301 * (jb - 1)] * (st4a1[1] - emis * st4a2[1]);
+                const double brad = sFband[nt[1] + 301 * (jb - 1)] * (st4a1[1] - emis * st4a2[1]);
                 tt_rlw[1] = tt_rlw[1] + flux[jb];
                 flux[jb] = tau * flux[jb] + emis * brad;
                 tt_rlw[1] = tt_rlw[1] - flux[jb];
             }
-            const double stratc1 = mb[a.L.stratc + col], stratc2 = mb[a.L.stratc + N + col];
+            const double stratc1 = STRATC(0), stratc2 = STRATC(1);
             const double corlw1 = lc.dhs[0] * stratc2 * st4a1[1] + stratc1;
             const double corlw2 = lc.dhs[1] * stratc2 * st4a1[2];
             tt_rlw[1] = tt_rlw[1] - corlw1;
@@ -612,101 +762,55 @@ __global__ void __launch_bounds__(64) k_grid_columns(ColumnArgs a) {
             for (int jb = 1; jb <= 4; jb++) ftop = ftop + flux[jb];
             G2(a.L.olr) = ftop;
 #pragma unroll
-            for (int k = 1; k <= KX; k++) {   // physics.f90:182-186
-                tt_rlw[k] = tt_rlw[k] * rps * lc.grdscp[k - 1];
-                ttend[k] = ttend[k] + G3(a.L.tt_rsw, k) + tt_rlw[k];
-            }
+            for (int k = 1; k <= KX; k++) tt_rlw[k] = tt_rlw[k] * rps * lc.grdscp[k - 1];   // physics.f90:182-186, added in the closing stage
         }
 
-        // ------------------- vertical_diffusion.f90:30-143 -------------------
+        // ------------------- closing stage: physics.f90:137-138, 182-186, 197-205, 208-222 -------------------
+        named_sync(BAR_FINAL, 96);     // dynamics tendencies and vertical-diffusion fluxes are in shared memory
         {
-            const double trshc = 6.0, trvdi = 24.0, trvds = 6.0, redshc = 0.5, rhgrad = 0.5, segrad = F32(0.1);
-            const int nl1 = KX - 1;
-            double rsig[KX + 1], rsig1[KX + 1], ttenvd[KX + 1], qtenvd[KX + 1];
-            const double cshc = lc.dhs[KX - 1] / 3600.0;
-            const double cvdi = (lc.sigh[nl1] - lc.sigh[1]) / ((nl1 - 1) * 3600.0);
-            const double fshcq = cshc / trshc, fshcse = cshc / (trshc * lc.cp);
-            const double fvdiq = cvdi / trvdi, fvdise = cvdi / (trvds * lc.cp);
-#pragma unroll
-            for (int k = 1; k <= nl1; k++) { rsig[k] = 1.0 / lc.dhs[k - 1]; rsig1[k] = 1.0 / (1.0 - lc.sigh[k]); }
-            rsig[KX] = 1.0 / lc.dhs[KX - 1];
-#pragma unroll
-            for (int k = 1; k <= KX; k++) { ttenvd[k] = 0.0; qtenvd[k] = 0.0; }
-            double drh0 = rhgrad * (lc.fsg[KX - 1] - lc.fsg[nl1 - 1]);
-            double fvdiq2 = fvdiq * lc.sigh[nl1];
-            {
-                const double dmse = se[KX] - se[nl1] + lc.alhc * (qg[KX] - qsat[nl1]);
-                const double drh = rh[KX] - rh[nl1];
-                double fcnv = 1.0;
-                if (dmse >= 0.0) {
-                    if (ib[a.L.icnv + col] > 0) fcnv = redshc;
-                    const double fluxse = fcnv * fshcse * dmse;
-                    ttenvd[nl1] = fluxse * rsig[nl1];
-                    ttenvd[KX] = -fluxse * rsig[KX];
-                    if (drh >= 0.0) {
-                        const double fluxq = fcnv * fshcq * qsat[KX] * drh;
-                        qtenvd[nl1] = fluxq * rsig[nl1];
-                        qtenvd[KX] = -fluxq * rsig[KX];
-                    }
-                } else if (drh > drh0) {
-                    const double fluxq = fvdiq2 * qsat[nl1] * drh;
-                    qtenvd[nl1] = fluxq * rsig[nl1];
-                    qtenvd[KX] = -fluxq * rsig[KX];
-                }
-            }
-            for (int k = 3; k <= KX - 2; k++) {
-                if (lc.sigh[k] > 0.5) {
-                    drh0 = rhgrad * (lc.fsg[k] - lc.fsg[k - 1]);
-                    fvdiq2 = fvdiq * lc.sigh[k];
-                    const double drh = rh[k + 1] - rh[k];
-                    if (drh >= drh0) {
-                        const double fluxq = fvdiq2 * qsat[k] * drh;
-                        qtenvd[k] = qtenvd[k] + fluxq * rsig[k];
-                        qtenvd[k + 1] = qtenvd[k + 1] - fluxq * rsig[k + 1];
-                    }
-                }
-            }
-            for (int k = 1; k <= nl1; k++) {
-                const double se0 = se[k + 1] + segrad * (phig[k] - phig[k + 1]);
-                if (se[k] < se0) {
-                    const double fluxse = fvdise * (se0 - se[k]);
-                    ttenvd[k] = ttenvd[k] + fluxse * rsig[k];
-                    for (int k1 = k + 1; k1 <= KX; k1++) ttenvd[k1] = ttenvd[k1] - fluxse * rsig1[k];
-                }
-            }
-            // physics.f90:197-205 (ut_pbl, vt_pbl are zero above the lowest level)
             const double ut8 = 0.0 + ustr3 * rps * lc.grdsig[KX - 1];
             const double vt8 = 0.0 + vstr3 * rps * lc.grdsig[KX - 1];
-            ttenvd[KX] = ttenvd[KX] + shf3 * rps * lc.grdscp[KX - 1];
-            qtenvd[KX] = qtenvd[KX] + evap3 * rps * lc.grdsig[KX - 1];
-#pragma unroll
-            for (int k = 1; k <= KX - 1; k++) { utend[k] = utend[k] + 0.0; vtend[k] = vtend[k] + 0.0; }
-            utend[KX] = utend[KX] + ut8;
-            vtend[KX] = vtend[KX] + vt8;
-#pragma unroll
-            for (int k = 1; k <= KX; k++) { ttend[k] = ttend[k] + ttenvd[k]; qtend[k] = qtend[k] + qtenvd[k]; }
-        }
-
-        // ------------------- SPPT blend  physics.f90:208-222 (mu(k) = 1) -------------------
-        if (a.sppt_on) {
 #pragma unroll
             for (int k = 1; k <= KX; k++) {
-                double p = GIN(GI_SPPT + k - 1);
-                p = dmin(1.0, fabs(p)) * copysign(1.0, p);   // sppt.f90:98
-                const double f = (1 + p * 1.0);
-                utend[k] = f * (utend[k] - ut_dyn[k]) + ut_dyn[k];
-                vtend[k] = f * (vtend[k] - vt_dyn[k]) + vt_dyn[k];
-                ttend[k] = f * (ttend[k] - tt_dyn[k]) + tt_dyn[k];
-                qtend[k] = f * (qtend[k] - qt_dyn[k]) + qt_dyn[k];
+                const double ut_dyn = DYN(0, k), vt_dyn = DYN(1, k), tt_dyn = DYN(2, k), qt_dyn = DYN(3, k);
+                double ut = ut_dyn, vt = vt_dyn, tt = tt_dyn, qt = qt_dyn;
+                tt = tt + CNV(0, k) + CNV(1, k);
+                qt = qt + CNV(2, k) + CNV(3, k);
+                tt = tt + RSW(k) + tt_rlw[k];
+                double ttenvd = VD(0, k), qtenvd = VD(1, k);
+                if (k == KX) {
+                    ttenvd = ttenvd + shf3 * rps * lc.grdscp[KX - 1];
+                    qtenvd = qtenvd + evap3 * rps * lc.grdsig[KX - 1];
+                    ut = ut + ut8; vt = vt + vt8;
+                } else {
+                    ut = ut + 0.0; vt = vt + 0.0;
+                }
+                tt = tt + ttenvd; qt = qt + qtenvd;
+                if (a.sppt_on) {
+                    double p = SG(GI_SPPT + k - 1);
+                    p = dmin(1.0, fabs(p)) * copysign(1.0, p);   // sppt.f90:98
+                    const double f = (1 + p * 1.0);
+                    ut = f * (ut - ut_dyn) + ut_dyn;
+                    vt = f * (vt - vt_dyn) + vt_dyn;
+                    tt = f * (tt - tt_dyn) + tt_dyn;
+                    qt = f * (qt - qt_dyn) + qt_dyn;
+                }
+                const int f0 = GO_PER * (k - 1);
+                GOUT(f0 + 0) = ut; GOUT(f0 + 1) = vt; GOUT(f0 + 5) = tt; GOUT(f0 + 8) = qt;
             }
         }
     }
-#pragma unroll
-    for (int k = 1; k <= KX; k++) {
-        const int f = GO_PER * (k - 1);
-        GOUT(f + 0) = utend[k]; GOUT(f + 1) = vtend[k]; GOUT(f + 5) = ttend[k]; GOUT(f + 8) = qtend[k];
-    }
-#undef TAU2
+#undef SROW
+#undef SG
+#undef SURF
+#undef STAU2
+#undef STRATC
+#undef RSW
+#undef DYN
+#undef PREP
+#undef CNV
+#undef VD
+#undef TAU2W
 }
 
 // ------------------------------------------------------------------------------------------
@@ -908,8 +1012,11 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on;
     const int N = ctx->d.ngrid();
-    dim3 grid((N + 63) / 64, ctx->nmembers);
-    k_grid_columns<<<grid, 64, 0, ctx->stream>>>(a);
+    if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM)); attr_set = true; }
+    dim3 grid(N / TC, ctx->nmembers);
+    k_grid_columns<<<grid, COL_THREADS, COL_SMEM, ctx->stream>>>(a);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }
