@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIBPATH = os.path.join(_HERE, "libspeedy_b200.so")
+_LIBPATH = os.environ.get("SPEEDY_B200_LIB") or os.path.join(_HERE, "libspeedy_b200.so")   # override: A/B builds of the same library
 _lib = None
 BC_T30 = os.path.join(os.path.dirname(_HERE), "data", "bc_t30.bin")   # packed reference boundary files (tools/pack_boundary.py)
 

@@ -33,6 +33,15 @@ void upload_tables(speedy_ctx* ctx) {
     DevTables& v = ctx->dv;
     v.trunc = t.d.trunc; v.ix = t.d.ix; v.iy = t.d.iy; v.il = t.d.il; v.kx = t.d.kx; v.nx = t.d.nx; v.mx = t.d.mx;
     v.poly = up(ctx, "poly", t.poly);
+    {   // device-only copy of P grouped by zonal wavenumber: one contiguous tile per CTA of the streaming direct transform
+        const int ng = polyd_groups(t.d.trunc), mg = polyd_mg(t.d.trunc), iy = t.d.iy, nx = t.d.nx, mx = t.d.mx;
+        std::vector<double> pd((size_t)ng * iy * nx * mg, 0.0);
+        for (int gq = 0; gq < ng; gq++) for (int j = 0; j < iy; j++) for (int n = 0; n < nx; n++) for (int ml = 0; ml < mg; ml++) {
+            const int m = gq * mg + ml;
+            if (m < mx) pd[(((size_t)gq * iy + j) * nx + n) * mg + ml] = t.poly[((size_t)j * nx + n) * mx + m];
+        }
+        v.polyd = up(ctx, "polyd", pd);
+    }
     v.finv = up(ctx, "finv", t.finv);
     v.ffwd = up(ctx, "ffwd", t.ffwd);
     v.wt = up(ctx, "wt", t.wt);
@@ -119,6 +128,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->seed = cfg->seed;
         ctx->member_offset = cfg->member_offset;
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
+        CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
         setup_transform_kernels();
         upload_tables(ctx);

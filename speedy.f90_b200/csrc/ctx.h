@@ -13,6 +13,7 @@ namespace spd {
 struct DevTables {
     int trunc, ix, iy, il, kx, nx, mx;
     const double* poly;     // [iy][nx][mx]
+    const double* polyd;    // [grp][iy][nx][mg]: P re-laid out per group of mg zonal wavenumbers (streaming direct transform)
     const double* finv;     // [ix][k2pad]
     const double* ffwd;     // [k2pad][ix]
     const double* wt;       // iy
@@ -54,7 +55,8 @@ struct XDesc {
 template <class T>
 struct DevBuf {
     T* p = nullptr; size_t n = 0;
-    void alloc(size_t cnt) { free(); n = cnt; if (cnt) { CUDA_CHECK(cudaMalloc(&p, cnt * sizeof(T))); CUDA_CHECK(cudaMemset(p, 0, cnt * sizeof(T))); } }
+    // the memset runs on the legacy default stream, which does not order against the context's non-blocking stream: wait for it
+    void alloc(size_t cnt) { free(); n = cnt; if (cnt) { CUDA_CHECK(cudaMalloc(&p, cnt * sizeof(T))); CUDA_CHECK(cudaMemset(p, 0, cnt * sizeof(T))); CUDA_CHECK(cudaDeviceSynchronize()); } }
     void upload(const std::vector<T>& v) { if (v.size() != n) alloc(v.size()); if (n) CUDA_CHECK(cudaMemcpy(p, v.data(), n * sizeof(T), cudaMemcpyHostToDevice)); }
     void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DevBuf() { free(); }
@@ -71,6 +73,7 @@ struct speedy_ctx {
     int device = 0;
     int sppt_on = 0;
     unsigned long long seed = 0;
+    int num_sms = 148;
     int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
     cudaStream_t stream = nullptr;
     long long launches = 0;
@@ -100,6 +103,8 @@ void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_membe
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
                          int nmembers, int mode, const int* gate = nullptr);
 void setup_transform_kernels();
+int polyd_groups(int trunc);
+int polyd_mg(int trunc);
 // spectral_ops.cu ---------------------------------------------------------------------
 void launch_spectral_op(speedy_ctx* ctx, int op, const double* a, const double* b, double* o1, double* o2, int nbatch);
 enum { OP_LAPLACIAN = 0, OP_INVLAPLACIAN, OP_GRAD, OP_VDS, OP_UVSPEC, OP_TRUNCT };

@@ -26,7 +26,9 @@ __device__ __forceinline__ double dmax(double a, double b) { return a > b ? a : 
 // 12k-instruction body and it stalls on instruction fetch (ncu: 40 % "no instruction").  One
 // shared out-of-line copy keeps the body inside the instruction cache.  Same libdevice routine.
 __device__ __noinline__ double exp_ol(double x) { return exp(x); }
+#ifndef SPD_EXP_INLINE
 #define exp(x) exp_ol(x)
+#endif
 
 // humidity.f90:44-78 for one point; p = sig*ps (or ps(1,1) for sig <= 0)
 __device__ __forceinline__ double qsat_pt(double ta, double p) {
@@ -75,7 +77,7 @@ enum { SF_FMASK, SF_FSOL, SF_OZONE, SF_OZUPP, SF_ZENIT, SF_STRATZ, SF_ALBSFC, SF
        SF_SNOWC, SF_FOROG, SF_SSRD, SF_N };
 // shared-memory rows of TC doubles
 enum { R_GIN = 0, R_TAU2 = R_GIN + GI_N, R_STRATC = R_TAU2 + 4 * KX, R_RSW = R_STRATC + 2, R_SURF = R_RSW + KX, R_DYN = R_SURF + SF_N,
-       R_PREP = R_DYN + 4 * KX, R_CNV = R_PREP + 4 * KX, R_VD = R_CNV + 4 * KX, R_END = R_VD + 2 * KX };
+       R_PREP = R_DYN + 4 * KX, R_CNV = R_PREP + 4 * KX, R_VD = R_CNV + 4 * KX, R_LW = R_VD + 2 * KX, R_END = R_LW + 3 * KX };
 constexpr int NFBAND = 301 * 4;
 constexpr int LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static_assert(sizeof(LevelConsts) % 16 == 0 && (NFBAND * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
@@ -106,6 +108,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #define PREP(v, k) SROW(R_PREP + (v) * KX + (k)-1)
 #define CNV(v, k) SROW(R_CNV + (v) * KX + (k)-1)
 #define VD(v, k) SROW(R_VD + (v) * KX + (k)-1)
+#define LWS(v, k) SROW(R_LW + (v) * KX + (k)-1)
 #define GOUT(f) gout[(size_t)(f) * N + col]
 #define G2(off) mb[(off) + col]
 #define G3(off, k) mb[(off) + (size_t)((k)-1) * N + col]
@@ -612,28 +615,48 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             double fsfcd = 0.0;
 #pragma unroll
             for (int k = 1; k <= KX; k++) tt_rlw[k] = 0.0;
-            int nt[KX + 1];
+            // Band sweep with the level loop rolled (the body is fetched once and stays in the L0 instruction
+            // cache; the unrolled 4 x 7 sweep was a third of this role's instruction stream).  For a fixed
+            // level the bands are visited in order and for a fixed band the levels in order, i.e. every
+            // tt_rlw(k) and flux(jb) sees the reference's sequence of operations (longwave_radiation.f90:93-105).
 #pragma unroll
-            for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;   // nint(T) -> row of fband(100:400,:)
-            for (int jb = 1; jb <= 2; jb++) {
-                const double emis = 1.0 - STAU2(1, jb);
-                const double brad = sFband[nt[1] + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
-                flux[jb] = emis * brad;
-                tt_rlw[1] = tt_rlw[1] - flux[jb];
+            for (int k = 1; k <= KX; k++) { LWS(0, k) = st4a1[k]; LWS(1, k) = st4a2[k]; }
+            {
+                const int nt1 = (int)round(tg[1]) - 100;   // nint(T) -> row of fband(100:400,:)
+                for (int jb = 1; jb <= 2; jb++) {
+                    const double emis = 1.0 - STAU2(1, jb);
+                    const double brad = sFband[nt1 + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
+                    flux[jb] = emis * brad;
+                    tt_rlw[1] = tt_rlw[1] - flux[jb];
+                }
             }
             flux[3] = 0.0; flux[4] = 0.0;
-            for (int jb = 1; jb <= 4; jb++)
+            LWS(2, 1) = tt_rlw[1];
+            {
+                double f1 = flux[1], f2 = flux[2], f3 = flux[3], f4 = flux[4];
+#pragma unroll 1
                 for (int k = 2; k <= KX; k++) {
-                    const double tau = STAU2(k, jb);
-                    const double emis = 1.0 - tau;
-                    const double brad = sFband[nt[k] + 301 * (jb - 1)] * (st4a1[k] + emis * st4a2[k]);
-                    tt_rlw[k] = tt_rlw[k] + flux[jb];
-                    flux[jb] = tau * flux[jb] + emis * brad;
-                    tt_rlw[k] = tt_rlw[k] - flux[jb];
+                    const double s1 = LWS(0, k), s2 = LWS(1, k);
+                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
+                    double t = 0.0;
+#define LW_BAND(fl, jb)                                                           \
+    {                                                                             \
+        const double tau = STAU2(k, jb);                                          \
+        const double emis = 1.0 - tau;                                            \
+        const double brad = sFband[ntk + 301 * ((jb)-1)] * (s1 + emis * s2);      \
+        t = t + fl;                                                               \
+        fl = tau * fl + emis * brad;                                              \
+        t = t - fl;                                                               \
+    }
+                    LW_BAND(f1, 1) LW_BAND(f2, 2) LW_BAND(f3, 3) LW_BAND(f4, 4)
+#undef LW_BAND
+                    LWS(2, k) = t;
                 }
+                flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
+            }
             for (int jb = 1; jb <= 4; jb++) fsfcd = fsfcd + emisfc * flux[jb];
             const double corlw = epslw * emisfc * st4a1[KX];
-            tt_rlw[KX] = tt_rlw[KX] - corlw;
+            LWS(2, KX) = LWS(2, KX) - corlw;
             fsfcd = fsfcd + corlw;
             slrd = fsfcd;
             G2(a.L.slrd) = slrd;
@@ -732,27 +755,44 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             G2(a.L.slr) = fsfcu - slrd;
             const int nts = (int)round(ts) - 100;
             for (int jb = 1; jb <= 4; jb++) flux[jb] = sFband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
-            tt_rlw[KX] = tt_rlw[KX] + epslw * fsfcu;
-            int nt[KX + 1];
-#pragma unroll
-            for (int k = 1; k <= KX; k++) nt[k] = (int)round(tg[k]) - 100;
-            for (int jb = 1; jb <= 4; jb++)
-                for (int k = KX; k >= 2; k--) {
-                    const double tau = STAU2(k, jb);
-                    const double emis = 1.0 - tau;
-                    const double brad = sFband[nt[k] + 301 * (jb - 1)] * (st4a1[k] - emis * st4a2[k]);
-                    tt_rlw[k] = tt_rlw[k] + flux[jb];
-                    flux[jb] = tau * flux[jb] + emis * brad;
-                    tt_rlw[k] = tt_rlw[k] - flux[jb];
+            LWS(2, KX) = LWS(2, KX) + epslw * fsfcu;
+            {
+                double f1 = flux[1], f2 = flux[2], f3 = flux[3], f4 = flux[4];
+#pragma unroll 1
+                for (int k = KX; k >= 2; k--) {     // longwave_radiation.f90:155-167, level loop rolled as in the downward sweep
+                    const double s1 = LWS(0, k), s2 = LWS(1, k);
+                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
+                    double t = LWS(2, k);
+#define LW_BAND(fl, jb)                                                           \
+    {                                                                             \
+        const double tau = STAU2(k, jb);                                          \
+        const double emis = 1.0 - tau;                                            \
+        const double brad = sFband[ntk + 301 * ((jb)-1)] * (s1 - emis * s2);      \
+        t = t + fl;                                                               \
+        fl = tau * fl + emis * brad;                                              \
+        t = t - fl;                                                               \
+    }
+                    LW_BAND(f1, 1) LW_BAND(f2, 2) LW_BAND(f3, 3) LW_BAND(f4, 4)
+#undef LW_BAND
+                    LWS(2, k) = t;
                 }
-            for (int jb = 1; jb <= 2; jb++) {
-                const double tau = STAU2(1, jb);
-                const double emis = 1.0 - tau;
-                const double brad = sFband[nt[1] + 301 * (jb - 1)] * (st4a1[1] - emis * st4a2[1]);
-                tt_rlw[1] = tt_rlw[1] + flux[jb];
-                flux[jb] = tau * flux[jb] + emis * brad;
-                tt_rlw[1] = tt_rlw[1] - flux[jb];
+                flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
             }
+            {
+                const int nt1 = (int)round(tg[1]) - 100;
+                double t = LWS(2, 1);
+                for (int jb = 1; jb <= 2; jb++) {
+                    const double tau = STAU2(1, jb);
+                    const double emis = 1.0 - tau;
+                    const double brad = sFband[nt1 + 301 * (jb - 1)] * (st4a1[1] - emis * st4a2[1]);
+                    t = t + flux[jb];
+                    flux[jb] = tau * flux[jb] + emis * brad;
+                    t = t - flux[jb];
+                }
+                LWS(2, 1) = t;
+            }
+#pragma unroll
+            for (int k = 1; k <= KX; k++) tt_rlw[k] = LWS(2, k);
             const double stratc1 = STRATC(0), stratc2 = STRATC(1);
             const double corlw1 = lc.dhs[0] * stratc2 * st4a1[1] + stratc1;
             const double corlw2 = lc.dhs[1] * stratc2 * st4a1[2];
@@ -810,6 +850,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #undef PREP
 #undef CNV
 #undef VD
+#undef LWS
 #undef TAU2W
 }
 

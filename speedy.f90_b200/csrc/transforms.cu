@@ -19,6 +19,7 @@
 // (uvspec / grad, spectral.f90:124-196), which removes a kernel from the time step.
 #include "ctx.h"
 #include "spectral_ops.cuh"
+#include "tma.cuh"
 
 namespace spd {
 
@@ -235,17 +236,299 @@ k_grid_to_spec(const double* __restrict__ in_base, long long in_ms, const XDesc*
     }
 }
 
+
+// ==========================================================================================
+// Streaming variants of K1 / K2 (mode 0, the time-step path).
+//
+// One persistent CTA per SM owns a slice of the transform — a latitude group (K1) or a group of
+// Fourier rows (K2) — and streams a chunk of FIELDS through it.  Everything that does not depend
+// on the field is staged once per CTA by bulk asynchronous copies (TMA): the P_n^m tile of the
+// slice (contiguous in [j][n][m]; re-laid out per wavenumber group for the direct transform) and
+// the rows of the dense Fourier operator.  The fields themselves arrive through one mbarrier-
+// tracked staging buffer: as soon as a field has been consumed into the working buffer the copy
+// of the next field is issued, so its L2/HBM latency hides behind the Legendre + Fourier work of
+// the current one.  The only global loads left on the dependent chain are per-field scalars.
+// ==========================================================================================
+template <int TRUNC>
+struct SCfg : TCfg<TRUNC> {
+    using B = TCfg<TRUNC>;
+    // K1: latitude groups sized so that the P tile + staging fit in 227 KB
+    static constexpr int LG = (TRUNC == 30) ? 3 : 9, JG = B::IY / LG, NR = 2 * JG;
+    static constexpr int XS = padmod16(NR, 4);
+    static constexpr int PT = JG * B::NX * B::MX;                 // P tile, doubles
+    static constexpr int MP = (B::MX + 31) / 32 * 32;             // m padded to whole warps
+    static constexpr int K1_THREADS = B::IX / 8 * 32;
+    static constexpr size_t K1_SMEM = sizeof(double) * (PT + 3 * B::NSPEC2 + B::KP * XS) + 2 * sizeof(uint64_t);
+    // K2: groups of 16 Fourier rows = 8 zonal wavenumbers
+    static constexpr int RG = 16, CG = B::KP / RG, MG = RG / 2;
+    static constexpr int GS = padmod16(B::IX, 4), FS = GS, YS = padmod16(B::IL, 8), ES = B::IY + 1 - (B::IY & 1);   // ES odd
+    static constexpr bool P_SMEM = (TRUNC == 30);                 // T47: 113 KB tile does not fit beside the grid buffer
+    static constexpr int PD = B::IY * B::NX * MG;                 // re-laid-out P tile [jh][n][mloc]
+    static constexpr int MT = RG / 8, NT = B::IL / 8;
+    static constexpr int K2_THREADS = 32 * (MT * NT < 18 ? MT * NT : 18);
+    static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
+    static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + 2 * RG * ES + 2 + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
+    static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG * MP <= K1_THREADS, "K1 tiling");
+    static_assert(B::KP % RG == 0 && (PT * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
+    static_assert(K1_SMEM <= 232448 && K2_SMEM <= 232448, "shared memory budget");
+};
+
+template <int TRUNC>
+__global__ void __launch_bounds__(SCfg<TRUNC>::K1_THREADS, 1)
+k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
+             double* __restrict__ out_base, long long out_ms, DevTables tv) {
+    using C = SCfg<TRUNC>;
+    extern __shared__ __align__(16) double smem[];
+    double* sP = smem;
+    double* sA = sP + C::PT;                 // staging: source field(s) of the current transform
+    double* sB = sA + C::NSPEC2;
+    double* sIn = sB + C::NSPEC2;
+    double* sX = sIn + C::NSPEC2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + C::KP * C::XS);   // [0] P tile, [1] staging
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int grp = blockIdx.x % C::LG, chunk = blockIdx.x / C::LG, e = blockIdx.y;
+    const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
+    const double* mbase = in_base + (size_t)e * in_ms;
+    const int j0 = grp * C::JG;
+    auto row_lat = [&](int r) { return (r < C::JG) ? (j0 + r) : (C::IL - 1 - (j0 + (r - C::JG))); };
+    auto issue = [&](int f) {                // one thread: bulk copies of field f's source(s)
+        const XDesc d = desc[f];
+        const uint32_t bytes = C::NSPEC2 * sizeof(double);
+        const bool two = d.op == 1 || d.op == 2;
+        mbar_expect_tx(&bars[1], two ? 2 * bytes : bytes);
+        bulk_g2s(sA, mbase + d.off, bytes, &bars[1]);
+        if (two) bulk_g2s(sB, mbase + d.off2, bytes, &bars[1]);
+    };
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        if (f0 < f1) issue(f0);
+        mbar_expect_tx(&bars[0], C::PT * sizeof(double));
+        bulk_g2s(sP, tv.poly + (size_t)j0 * C::NX * C::MX, C::PT * sizeof(double), &bars[0]);
+    }
+    // this warp's A fragments of the dense backward Fourier operator stay in registers for every field
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    double a[C::KP / 4];
+    {
+        const double* A = tv.finv + (size_t)(8 * w + g) * C::KP + q;
+#pragma unroll
+        for (int ks = 0; ks < C::KP / 4; ks++) a[ks] = A[4 * ks];
+    }
+    for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
+    const int jl0 = tid / C::MP, m0 = tid - jl0 * C::MP;
+    const bool leg = jl0 < C::JG && m0 < C::MX;
+
+    for (int f = f0; f < f1; f++) {
+        const XDesc dsc = desc[f];
+        // latitude factors of the epilogue (fourier.f90:47-51, tendencies.f90:103): loaded before the wait
+        const bool sc = dsc.flags & 1, ad = dsc.flags & 2;
+        double fsc[C::NR / 4], fad[C::NR / 4];
+#pragma unroll
+        for (int nt = 0; nt < C::NR / 8; nt++) {
+            const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
+            fsc[2 * nt] = sc ? tv.cosgr[ja] : 1.0; fsc[2 * nt + 1] = sc ? tv.cosgr[jb] : 1.0;
+            fad[2 * nt] = ad ? tv.coriol[ja] : 0.0; fad[2 * nt + 1] = ad ? tv.coriol[jb] : 0.0;
+        }
+        mbar_wait(&bars[1], (f - f0) & 1);
+        // ---- input stage.  Coefficients outside the triangle m+n <= trunc+1 are never read by the
+        // reference (legendre.f90:38 nsh2); they are zeroed so that the sums have a fixed trip count.
+        if (dsc.op == 0) {
+            for (int t = tid; t < C::NSPEC2; t += nthr) {
+                const int n = t / C::K2, c = t - n * C::K2;
+                sIn[t] = ((c >> 1) + n <= C::MX) ? sA[t] : 0.0;
+            }
+        } else {
+            // derived input: 1 ucos, 2 vcos = uvspec(vor, div) (spectral.f90:173-196); 3 d/dx, 4 d/dy = grad(ps) (:124-144)
+            for (int t = tid; t < C::MX * C::NX; t += nthr) {
+                const int n = t / C::MX, m = t - n * C::MX;
+                cd r0, r1;
+                if (dsc.op <= 2) dev_uvspec(tv, sA, sB, m, n, r0, r1);
+                else dev_grad(tv, sA, m, n, r0, r1);
+                cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
+                if (m + n > C::MX) r = cd{0.0, 0.0};
+                st(sIn, C::MX, m, n, r);
+            }
+        }
+        __syncthreads();                      // sIn complete, staging free
+        if (tid == 0 && f + 1 < f1) issue(f + 1);
+        if (f == f0) mbar_wait(&bars[0], 0);
+        // ---- inverse Legendre for this CTA's latitude pairs (legendre.f90:74-111): one thread per
+        // (latitude pair, m); real and imaginary sums share the P values
+        if (leg) {
+            const double* P = sP + (size_t)jl0 * C::NX * C::MX + m0;
+            const double2* X = reinterpret_cast<const double2*>(sIn) + m0;
+            double evr = 0.0, evi = 0.0, odr = 0.0, odi = 0.0;
+#pragma unroll
+            for (int n = 0; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[n * C::MX]; evr += x.x * pn; evi += x.y * pn; }
+#pragma unroll
+            for (int n = 1; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[n * C::MX]; odr += x.x * pn; odi += x.y * pn; }
+            double* xr = sX + (2 * m0) * C::XS;
+            xr[jl0] = evr - odr;  xr[C::XS + jl0] = evi - odi;                       // row j (southern)
+            xr[C::JG + jl0] = evr + odr;  xr[C::XS + C::JG + jl0] = evi + odi;       // row il+1-j (northern)
+        }
+        __syncthreads();
+        // ---- dense backward Fourier operator on the FP64 tensor pipe:
+        //   grid[i][r] = sum_c finv[i][c] * X[c][r],  M = IX, N = NR, K = KP
+        double* out = out_base + (size_t)e * out_ms + (size_t)f * C::IX * C::IL;
+        const int i = 8 * w + g;
+#pragma unroll
+        for (int nt = 0; nt < C::NR / 8; nt++) {
+            double c0 = 0.0, c1 = 0.0;
+            const double* Bf = sX + q * C::XS + 8 * nt + g;
+#pragma unroll
+            for (int ks = 0; ks < C::KP / 4; ks++) dmma884(c0, c1, a[ks], Bf[4 * ks * C::XS]);
+            const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
+            if (sc) { c0 *= fsc[2 * nt]; c1 *= fsc[2 * nt + 1]; }
+            if (ad) { c0 += fad[2 * nt]; c1 += fad[2 * nt + 1]; }
+            out[(size_t)ja * C::IX + i] = c0;
+            out[(size_t)jb * C::IX + i] = c1;
+        }
+        // the next field's Legendre stage rewrites sX only after the next __syncthreads pair
+    }
+}
+
+template <int TRUNC>
+__global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, 1)
+k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
+             double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
+    using C = SCfg<TRUNC>;
+    extern __shared__ __align__(16) double smem[];
+    double* sG = smem;                                  // [IL][GS] grid field (rows padded)
+    double* sF = sG + C::IL * C::GS;                    // [RG][FS] rows of the dense forward Fourier operator
+    double* sY = sF + C::RG * C::FS;                    // [RG][YS] Fourier coefficients of this group
+    double* sE = sY + C::RG * C::YS;                    // even / odd folds
+    double* sO = sE + C::OOFF;
+    double* sPd = sE + 2 * C::RG * C::ES + 2;           // [IY][NX][MG]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + (C::P_SMEM ? C::PD : 0));   // [0] operator + P tiles, [1] grid field
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int grp = blockIdx.x % C::CG, chunk = blockIdx.x / C::CG, e = blockIdx.y;
+    const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
+    const double* mbase = in_base + (size_t)e * in_ms;
+    const int c0row = grp * C::RG;
+    const int gate_open = gate ? *gate : 1;             // in-graph conditional work (the daily forcing transform)
+    auto live = [&](int f) { return gate_open || !(desc[f].flags & 4); };
+    auto next_live = [&](int f) { while (f < f1 && !live(f)) f++; return f; };
+    const uint32_t rowb = C::IX * sizeof(double);
+    auto issue = [&](int f) {                           // threads 0..IL-1: one row copy each; thread 0 arms the barrier
+        const double* src = mbase + desc[f].off;
+        if (tid == 0) mbar_expect_tx(&bars[1], C::IL * rowb);
+        if (tid < C::IL) bulk_g2s(sG + tid * C::GS, src + (size_t)tid * C::IX, rowb, &bars[1]);
+    };
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    int f = next_live(f0);
+    if (f < f1) issue(f);
+    if (tid == 0) mbar_expect_tx(&bars[0], C::RG * rowb + (C::P_SMEM ? C::PD * sizeof(double) : 0));
+    if (tid < C::RG) bulk_g2s(sF + tid * C::FS, tv.ffwd + (size_t)(c0row + tid) * C::IX, rowb, &bars[0]);
+    if (C::P_SMEM && tid == C::RG) bulk_g2s(sPd, tv.polyd + (size_t)grp * C::PD, C::PD * sizeof(double), &bars[0]);
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, nw = nthr >> 5;
+    int it = 0;
+    for (; f < f1; it++) {
+        const XDesc dsc = desc[f];
+        const double* scl = (dsc.flags & 1) ? tv.cosgr : ((dsc.flags & 2) ? tv.cosgr2 : nullptr);
+        if (it == 0) mbar_wait(&bars[0], 0);
+        mbar_wait(&bars[1], it & 1);
+        // ---- dense forward Fourier operator for this CTA's rows (fourier.f90:56-82):
+        //   Y[c][j] = sum_i ffwd[c][i] * (g[i][j] * scl[j]),  M = RG, N = IL, K = IX
+        for (int tile = w; tile < C::MT * C::NT; tile += nw) {
+            const int mt = tile / C::NT, nt = tile - mt * C::NT;
+            const double* A = sF + (8 * mt + g) * C::FS + q;
+            const double* Bf = sG + (8 * nt + g) * C::GS + q;
+            const double s = scl ? scl[8 * nt + g] : 1.0;
+            double c0 = 0.0, c1 = 0.0;
+            if (scl) {
+#pragma unroll
+                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks] * s);
+            } else {
+#pragma unroll
+                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks]);
+            }
+            *reinterpret_cast<double2*>(sY + (8 * mt + g) * C::YS + 8 * nt + 2 * q) = make_double2(c0, c1);
+        }
+        __syncthreads();                                // sY complete, grid buffer free
+        const int fn = next_live(f + 1);
+        if (fn < f1) issue(fn);
+        // Gaussian-weighted even/odd fold (legendre.f90:127-133)
+        for (int t = tid; t < C::RG * C::IY; t += nthr) {
+            const int cl = t / C::IY, jh = t - cl * C::IY;
+            const double south = sY[cl * C::YS + jh], north = sY[cl * C::YS + (C::IL - 1 - jh)];
+            const double wgt = tv.wt[jh];
+            sE[cl * C::ES + jh] = (north + south) * wgt;
+            sO[cl * C::ES + jh] = (north - south) * wgt;
+        }
+        __syncthreads();
+        // direct Legendre (legendre.f90:142-154): one thread per (n, m), real and imaginary sums share P
+        double* out = out_base + (size_t)e * out_ms + (size_t)f * C::K2 * C::NX;
+        for (int t = tid; t < C::NX * C::MG; t += nthr) {
+            const int n = t / C::MG, ml = t - n * C::MG;
+            const int m = grp * C::MG + ml;
+            if (m >= C::MX) continue;
+            double sr = 0.0, si = 0.0;
+            if (n <= TRUNC && m + n <= C::MX) {
+                const double* Fr = ((n & 1) ? sO : sE) + (2 * ml) * C::ES;
+                if (C::P_SMEM) {
+                    const double* P = sPd + (size_t)n * C::MG + ml;
+#pragma unroll
+                    for (int jh = 0; jh < C::IY; jh++) { const double pj = P[(size_t)jh * C::NX * C::MG]; sr += pj * Fr[jh]; si += pj * Fr[C::ES + jh]; }
+                } else {
+                    const double* P = tv.poly + (size_t)n * C::MX + m;
+#pragma unroll
+                    for (int jh = 0; jh < C::IY; jh++) { const double pj = P[(size_t)jh * C::NX * C::MX]; sr += pj * Fr[jh]; si += pj * Fr[C::ES + jh]; }
+                }
+            }
+            *reinterpret_cast<double2*>(out + n * C::K2 + 2 * m) = make_double2(sr, si);
+        }
+        f = fn;
+    }
+}
+
 void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K2_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K2_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM));
 }
+
+// fields per persistent CTA: spread (slices x members x chunks) over the SMs, one CTA each
+static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch) {
+    int nchunk = ctx->num_sms / (slices * nmembers);
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > nbatch) nchunk = nbatch;
+    return nchunk;
+}
+
+template <int TRUNC>
+static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
+                              double* d_out, long long out_ms, int nmembers) {
+    using C = SCfg<TRUNC>;
+    const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch);
+    dim3 grid(nchunk * C::LG, nmembers);
+    k_s2g_stream<TRUNC><<<grid, C::K1_THREADS, C::K1_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv);
+}
+template <int TRUNC>
+static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
+                              double* d_out, long long out_ms, int nmembers, const int* gate) {
+    using C = SCfg<TRUNC>;
+    const int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);
+    dim3 grid(nchunk * C::CG, nmembers);
+    k_g2s_stream<TRUNC><<<grid, C::K2_THREADS, C::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate);
+}
+
+// layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
+int polyd_groups(int trunc) { return trunc == 30 ? SCfg<30>::CG : SCfg<47>::CG; }
+int polyd_mg(int trunc) { return trunc == 30 ? SCfg<30>::MG : SCfg<47>::MG; }
 
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                          double* d_out, long long out_ms, int nmembers, int mode) {
     if (nbatch <= 0) return;
-    if (ctx->d.trunc == 30) {
+    if (mode == 0) {
+        if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);
+        else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);
+    } else if (ctx->d.trunc == 30) {
         dim3 grid(nbatch * TCfg<30>::LG, nmembers);
         k_spec_to_grid<30><<<grid, TCfg<30>::K1_THREADS, TCfg<30>::K1_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode);
     } else {
@@ -259,7 +542,10 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, c
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                          double* d_out, long long out_ms, int nmembers, int mode, const int* gate) {
     if (nbatch <= 0) return;
-    if (ctx->d.trunc == 30) {
+    if (mode == 0) {
+        if (ctx->d.trunc == 30) launch_g2s_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+        else launch_g2s_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+    } else if (ctx->d.trunc == 30) {
         dim3 grid(nbatch * TCfg<30>::CG, nmembers);
         k_grid_to_spec<30><<<grid, TCfg<30>::K2_THREADS, TCfg<30>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode, gate);
     } else {
