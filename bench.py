@@ -251,9 +251,9 @@ def run_b200(args):
     nact = sum(2 * min(c.mx, c.trunc + 2 - n) for n in range(c.nx))      # 1054 active reals (legendre.f90:33-41)
     NG = c.ix * c.il
     alg = {  # algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)
-        "spec_to_grid": M * 91 * (8 * nact + 8 * NG),
+        "spec_to_grid": M * 77 * (8 * nact + 8 * NG),                   # 91 of the reference minus the 14 level-1 wind fields nobody reads
         "grid_to_spec": M * 73 * (8 * NG + 8 * (nact - 2)),
-        "grid_columns": M * NG * 8 * (91 + 73 + 45 + 8 + 32 + 2),       # 91 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
+        "grid_columns": M * NG * 8 * (77 + 73 + 45 + 8 + 32 + 2),       # 77 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
         "spec_step": M * c.mx * c.nx * 16 * 165,
     }
     tot = sum(kt_warm.values())

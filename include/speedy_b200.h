@@ -169,6 +169,10 @@ int speedy_set_graphs(speedy_ctx* ctx, int on);
  * nsteps plain-launch steps; ms[10] in the order of speedy_kernel_names() */
 int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms);
 const char* speedy_kernel_names(void);
+/* in-graph timeline (debug aid): per-step duration of each kernel and the idle gap in front of it, microseconds;
+ * out9 = 4 durations, 4 gaps, number of steps traced */
+int speedy_trace(speedy_ctx* ctx, int on);
+int speedy_trace_read(speedy_ctx* ctx, double* out9);
 /* host-only: date.f90:109-157 newdate applied nsteps times to ymdhm[5] (no GPU needed) */
 int speedy_host_calendar(int* ymdhm, int nsteps, double* tmonth, double* tyear, int* imont1);
 

@@ -325,6 +325,17 @@ class Speedy:
         _chk(self.L.speedy_time_kernels(self.h, int(nsteps), int(flush_l2), _p(ms)))
         return dict(zip(names, ms.tolist()))
 
+    def trace(self, on=True):
+        """in-graph timeline of the four main-loop kernels (GPU global timer); read with trace_read()"""
+        _chk(self.L.speedy_trace(self.h, int(bool(on))))
+
+    def trace_read(self):
+        o = np.zeros(9)
+        _chk(self.L.speedy_trace_read(self.h, _p(o)))
+        self.L.speedy_kernel_names.restype = ctypes.c_char_p
+        names = self.L.speedy_kernel_names().decode().split()
+        return {"us": dict(zip(names, o[:4].tolist())), "gap_before_us": dict(zip(names, o[4:8].tolist())), "steps": int(o[8])}
+
     def state_len(self):
         return int(self.L.speedy_state_len(self.h))
 

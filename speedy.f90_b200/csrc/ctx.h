@@ -29,6 +29,7 @@ struct DevTables {
     const double *dmp, *dmpd, *dmps, *dmp1, *dmp1d, *dmp1s, *elz;
     const double *xj, *xc, *xd;          // Fortran order (kx,kx[,l])
     const double* fband;                 // (301,4)
+    unsigned long long* trace;           // nullptr, or the in-graph timeline buffer (speedy_trace)
 };
 
 // small per-level constants go to __constant__ memory (see consts.cuh)
@@ -48,6 +49,7 @@ struct XDesc {
     int flags;       // K1: bit0 scale by cosgr(j), bit1 add coriol(j);  K2: bit0 scale by cosgr, bit1 scale by cosgr2, bit2 gated
     int op;          // K1 input: 0 the field at `off`; 1 ucos, 2 vcos of uvspec(vor@off, div@off2); 3 d/dx, 4 d/dy of grad(ps@off)
     long long off2;
+    int oslot1;      // K1: 0 -> the transform's own index is its output slot; else output slot + 1 (compact field lists)
 };
 
 #define CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw std::runtime_error(std::string(#x) + ": " + cudaGetErrorString(e_)); } while (0)
@@ -74,13 +76,14 @@ struct speedy_ctx {
     int sppt_on = 0;
     unsigned long long seed = 0;
     int num_sms = 148;
+    spd::DevBuf<unsigned long long> trace;
     int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
     cudaStream_t stream = nullptr;
     long long launches = 0;
     bool use_graphs = true;
     // device tables
     std::map<std::string, spd::DevBuf<double>> dtab;
-    spd::DevTables dv;
+    spd::DevTables dv{};
     // scratch for host-pointer API calls
     spd::DevBuf<double> scratch_a, scratch_b, scratch_c, scratch_d;
     std::map<unsigned long long, spd::DevBuf<spd::XDesc>> desc_cache;

@@ -12,6 +12,7 @@
 #include "model.h"
 #include "spectral_ops.cuh"
 #include "calendar.h"
+#include "tma.cuh"
 
 namespace spd {
 
@@ -67,7 +68,9 @@ __global__ void k_geopotential(SpecArgs a) {
 //            check_diagnostics partial sums, and let the LAST block to arrive close the step
 //            (final diagnostics reduction in fixed order, range guard, calendar advance).
 #define SC 32
-__global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
+constexpr int SPEC_LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
+static size_t spec_step_smem(int mx, int nx) { return sizeof(double) * (SPEC_LC_DOUBLES + 2 * KX * KX + (size_t)KX * KX * (mx + nx + 1)) + sizeof(uint64_t); }
+__global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers: fits beside a CTA of K2 (PDL overlap)
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
     const int c = threadIdx.x, k = threadIdx.y;
     const int r = blockIdx.x * SC + c;
@@ -75,13 +78,53 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     const int rr = valid ? r : nsp - 1;
     const int n = rr / mx, m = rr - n * mx;
     double* mb = a.base + (size_t)blockIdx.y * a.stride;
-    const LevelConsts& lc = *a.lc;
     const DevTables& tv = a.tv;
     const size_t q = rr;
-    const double el2 = tv.el2[q];
     const cd zero{0.0, 0.0};
     __shared__ cd s_a[KX][SC], s_b[KX][SC], s_phi[KX][SC], s_sig[KX + 1][SC];
     __shared__ cd s_dmeanc[SC], s_psdt[SC];
+    // The level constants and the three semi-implicit matrices (implicit.f90:36-165) are staged in shared
+    // memory by bulk asynchronous copies; every other global operand of this thread's chain is loaded HERE,
+    // before the first barrier, so that the kernel exposes one L2 round trip instead of one per stage.
+    extern __shared__ __align__(16) double dsm[];
+    double* sLc = dsm;
+    double* sXd = sLc + SPEC_LC_DOUBLES;
+    double* sXc = sXd + KX * KX;
+    double* sXj = sXc + KX * KX;
+    const int nl = mx + nx + 1;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(sXj + (size_t)KX * KX * nl);
+    const int tid = k * SC + c;
+    if (tid == 0) trace_begin(tv.trace, 3);
+    if (tid == 0) { mbar_init(bar, 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t mb64 = KX * KX * sizeof(double);
+        mbar_expect_tx(bar, (uint32_t)sizeof(LevelConsts) + 2 * mb64 + mb64 * nl);
+        bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), bar);
+        bulk_g2s(sXd, tv.xd, mb64, bar);
+        bulk_g2s(sXc, tv.xc, mb64, bar);
+        bulk_g2s(sXj, tv.xj, mb64 * nl, bar);
+    }
+    const LevelConsts& lc = *reinterpret_cast<const LevelConsts*>(sLc);
+    const double el2 = tv.el2[q], elz_q = tv.elz[q], trf_q = tv.trfilt[q], elm2_q = tv.elm2[q];
+    const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
+    pdl_wait();                 // everything above reads constant tables only; the fields below come from the previous kernel
+    pdl_trigger();
+    const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
+    const cd qcorh_old = ld(mb + a.L.qcorh, mx, m, n);
+    const cd qcorh_new = (a.flag & 2) ? ld(sfield(mb, a.L.sout, nsp, GO_QCORH), mx, m, n) : zero;
+    const int do_forcing = (a.flag & 2) ? a.clk->do_forcing : 0;
+    const cd psdt_in = ld(sfield(mb, a.L.sout, nsp, GO_PSDT), mx, m, n);
+    const cd phis_q = ld(mb + a.L.phis, mx, m, n);
+    // time level j1 of the prognostics for the filter (time_stepping.f90:163-166); j1 == 1 re-uses level 1
+    cd vorj = zero, divj = zero, tj = zero, trj = zero, psj = zero;
+    if (a.j1 != 1) {
+        vorj = ld(sfield(mb, a.L.vor, nsp, KX + k), mx, m, n);
+        divj = ld(sfield(mb, a.L.div, nsp, KX + k), mx, m, n);
+        tj = ld(sfield(mb, a.L.t, nsp, KX + k), mx, m, n);
+        trj = ld(sfield(mb, a.L.tr, nsp, KX + k), mx, m, n);
+        psj = ld(sfield(mb, a.L.ps, nsp, 1), mx, m, n);
+    }
 
     // ---- tendencies.f90:212-234: spectral assembly of the transformed grid-point tendencies
     cd vordt, divdt, tdt, trdt, psdt = zero;
@@ -103,12 +146,13 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     const cd t1 = ld(sfield(mb, a.L.t, nsp, k), mx, m, n);
     const cd tr1 = ld(sfield(mb, a.L.tr, nsp, k), mx, m, n);
     const cd ps1 = ld(sfield(mb, a.L.ps, nsp, 0), mx, m, n);
+    mbar_wait(bar, 0);
     s_a[k][c] = div1;
     s_b[k][c] = t1;
     __syncthreads();
     // ---- get_spectral_tendencies  tendencies.f90:242-293 (level-coupled parts: one warp each)
     if (k == 0) {
-        psdt = ld(sfield(mb, a.L.sout, nsp, GO_PSDT), mx, m, n);
+        psdt = psdt_in;
         if (rr == 0) psdt = zero;                                        // tendencies.f90:126
         cd dmeanc = zero;
 #pragma unroll
@@ -124,7 +168,7 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
         s_sig[KX][c] = zero;
     } else if (k == 1) {
         // get_geopotential(t(:,:,:,1), phis)  geopotential.f90:33-57 (tendencies.f90:288)
-        cd ph = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
+        cd ph = phis_q + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
         s_phi[KX - 1][c] = ph;
 #pragma unroll
         for (int kk = KX - 2; kk >= 0; kk--) { ph = (ph + lc.xgeop2[kk + 1] * s_b[kk + 1][c]) + lc.xgeop1[kk] * s_b[kk][c]; s_phi[kk][c] = ph; }
@@ -151,14 +195,14 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     {
         cd s = zero;
 #pragma unroll
-        for (int k1 = 0; k1 < KX; k1++) s = s + tv.xd[k + KX * k1] * s_a[k1][c];
+        for (int k1 = 0; k1 < KX; k1++) s = s + sXd[k + KX * k1] * s_a[k1][c];
         const cd ye = s + lc.tref1[k] * s_psdt[c];
-        s_b[k][c] = divdt + tv.elz[q] * ye;       // yf
+        s_b[k][c] = divdt + elz_q * ye;       // yf
     }
     __syncthreads();
     divdt = zero;
     if (m + n != 0) {
-        const double* xj = tv.xj + (size_t)KX * KX * (m + n - 1);   // xj(:,:,l), l = total wavenumber
+        const double* xj = sXj + (size_t)KX * KX * (m + n - 1);   // xj(:,:,l), l = total wavenumber
 #pragma unroll
         for (int k1 = 0; k1 < KX; k1++) divdt = divdt + xj[k + KX * k1] * s_b[k1][c];
     }
@@ -170,7 +214,7 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
         for (int kk = 0; kk < KX; kk++) psdt = psdt - lc.dhsx[kk] * s_a[kk][c];
     }
 #pragma unroll
-    for (int k1 = 0; k1 < KX; k1++) tdt = tdt + tv.xc[k + KX * k1] * s_a[k1][c];
+    for (int k1 = 0; k1 < KX; k1++) tdt = tdt + sXc[k + KX * k1] * s_a[k1][c];
 
     if (a.flag & 1) {
         if (valid) {
@@ -184,14 +228,12 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     }
     // ---- horizontal diffusion + drag  time_stepping.f90:63-96
     {
-        const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
-        const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
         cd qcorh;
-        if ((a.flag & 2) && a.clk->do_forcing) {       // qcorh = grid_to_spec(corh) of today's set_forcing (forcing.f90:99)
-            qcorh = ld(sfield(mb, a.L.sout, nsp, GO_QCORH), mx, m, n);
+        if (do_forcing) {       // qcorh = grid_to_spec(corh) of today's set_forcing (forcing.f90:99)
+            qcorh = qcorh_new;
             if (k == 0 && valid) st(mb + a.L.qcorh, mx, m, n, qcorh);
         } else {
-            qcorh = ld(mb + a.L.qcorh, mx, m, n);
+            qcorh = qcorh_old;
         }
         vordt = dmp1 * (vordt - dmp * vor1);
         divdt = dmp1d * (divdt - dmpd * div1);
@@ -211,13 +253,13 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     cd vor2n = zero, div2n = zero, t2n = zero, t1n = zero;
     {
         const double eps = (a.j1 == 1) ? 0.0 : lc.rob;
-        const double trf = tv.trfilt[q];
+        const double trf = trf_q;
         const double c1 = lc.wil * eps, c2 = (1.0 - lc.wil) * eps;
-        auto stepf = [&](long long off, int nlev_fields, int kk, cd fdt, cd f1, cd* new_level1 = nullptr) -> cd {
+        auto stepf = [&](long long off, int nlev_fields, int kk, cd fdt, cd f1, cd fj_in, cd* new_level1 = nullptr) -> cd {
             double* p1 = sfield(mb, off, nsp, kk);
             double* p2 = sfield(mb, off, nsp, nlev_fields + kk);
             fdt = trf * fdt;
-            const cd fj = (a.j1 == 1) ? f1 : ld(p2, mx, m, n);
+            const cd fj = (a.j1 == 1) ? f1 : fj_in;
             const cd fnew = f1 + a.dt * fdt;
             const cd f1n = fj + c1 * ((f1 - 2.0 * fj) + fnew);
             const cd fj2 = (a.j1 == 1) ? f1n : fj;     // :166 re-reads output(:,:,j1) after :163 overwrote level 1
@@ -226,11 +268,11 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
             if (new_level1) *new_level1 = f1n;
             return f2n;
         };
-        if (k == 0) stepf(a.L.ps, 1, 0, psdt, ps1);
-        vor2n = stepf(a.L.vor, KX, k, vordt, vor1);
-        div2n = stepf(a.L.div, KX, k, divdt, div1);
-        t2n = stepf(a.L.t, KX, k, tdt, t1, &t1n);
-        stepf(a.L.tr, KX, k, trdt, tr1);
+        if (k == 0) stepf(a.L.ps, 1, 0, psdt, ps1, psj);
+        vor2n = stepf(a.L.vor, KX, k, vordt, vor1, vorj);
+        div2n = stepf(a.L.div, KX, k, divdt, div1, divj);
+        t2n = stepf(a.L.t, KX, k, tdt, t1, tj, &t1n);
+        stepf(a.L.tr, KX, k, trdt, tr1, trj);
     }
     if (!(a.flag & 2)) return;
     // ---- geopotential of the NEW time level 1: the field the next step's physics transforms (physics.f90:103,
@@ -239,7 +281,7 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     s_b[k][c] = t1n;
     __syncthreads();
     if (k == 1) {
-        cd ph = ld(mb + a.L.phis, mx, m, n) + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
+        cd ph = phis_q + lc.xgeop1[KX - 1] * s_b[KX - 1][c];
         s_phi[KX - 1][c] = ph;
 #pragma unroll
         for (int kk = KX - 2; kk >= 0; kk--) { ph = (ph + lc.xgeop2[kk + 1] * s_b[kk + 1][c]) + lc.xgeop1[kk] * s_b[kk][c]; s_phi[kk][c] = ph; }
@@ -254,7 +296,7 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
     {
         double s1 = 0.0, s2 = 0.0;
         if (valid && m >= 1) {
-            const double e = tv.elm2[q];
+            const double e = elm2_q;
             const cd tv_ = neg(e * vor2n), td = neg(e * div2n);
             s1 = -(tv_.re * vor2n.re - tv_.im * (-vor2n.im));
             s2 = -(td.re * div2n.re - td.im * (-div2n.im));
@@ -296,6 +338,20 @@ __global__ void __launch_bounds__(SC * KX) k_spec_step(SpecArgs a) {
         a.clk->ticket = 0;
         cal_advance(*a.clk);          // speedy.f90:44-47
         a.clk->slab_pending = 1;      // couple_sea_land of this step rides in the next column kernel
+        if (tv.trace) {               // close the step's timeline: durations [8..11], gaps before each kernel [12..15], steps [16]
+            unsigned long long* tr = tv.trace;
+            tr[4 + 3] = gtimer();
+            unsigned long long prev = tr[17];
+            for (int sl = 0; sl < 4; sl++) {
+                const unsigned long long t0 = tr[sl], t1 = tr[4 + sl];
+                tr[8 + sl] += t1 - t0;
+                if (prev && t0 > prev) tr[12 + sl] += t0 - prev;
+                prev = t1;
+                tr[sl] = ~0ull; tr[4 + sl] = 0ull;
+            }
+            tr[17] = prev;
+            tr[16] += 1;
+        }
     }
 }
 
@@ -459,7 +515,10 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     dim3 grid((ctx->d.nspec() + SC - 1) / SC, ctx->nmembers);
     const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
     if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }
-    k_spec_step<<<grid, dim3(SC, KX), 0, ctx->stream>>>(a);
+    const size_t smem = spec_step_smem(ctx->d.mx, ctx->d.nx);
+    static bool attr_set = false;
+    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_spec_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
+    CUDA_CHECK(launch_pdl(k_spec_step, grid, dim3(SC, KX), smem, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

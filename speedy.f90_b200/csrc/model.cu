@@ -151,6 +151,22 @@ void model_create(speedy_ctx* ctx) {
             D[GI_PSL] = XDesc{L.ps, 0, 0, 0};
         }
         M.desc_inv.upload(h);
+        // per-step list: the physics uses the level-1 wind at the lowest level only (surface fluxes), so the
+        // uvspec + transform of u,v at levels 1..kx-1 (physics.f90:95-96) is dead work and is not enqueued
+        {
+            std::vector<XDesc> cs;
+            const int nf = ctx->sppt_on ? GI_N : GI_NBASE;
+            for (int j2 = 1; j2 <= 2; j2++)
+                for (int f = 0; f < nf; f++) {
+                    const bool dead = (f >= GI_U1 && f < GI_U1 + KXc - 1) || (f >= GI_V1 && f < GI_V1 + KXc - 1);
+                    if (dead) continue;
+                    XDesc x = h[(size_t)(j2 - 1) * GI_N + f];
+                    x.oslot1 = f + 1;
+                    cs.push_back(x);
+                }
+            M.nstep_fields = (int)cs.size() / 2;
+            M.desc_step.upload(cs);
+        }
         // output(): the 41 level-1 fields with the module variable phi (input_output.f90:184-192)
         std::vector<XDesc> o(h.begin() + GI_U1, h.begin() + GI_U1 + 41);
         for (int k = 0; k < KXc; k++) o[GI_PHI - GI_U1 + k].off = L.phi + k * NS2;
@@ -182,6 +198,12 @@ static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_inv.p + (size_t)(j2 - 1) * GI_N + first, count,
                         M.mem.p + M.L.gin + first * NG, M.L.stride, ctx->nmembers, 0);
 }
+// the inverse transforms of one time step (tendencies.f90:89-123 + physics.f90:95-104), compact list
+static void xform_step(speedy_ctx* ctx, int j2) {
+    Model& M = *ctx->model;
+    launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_step.p + (size_t)(j2 - 1) * M.nstep_fields, M.nstep_fields,
+                        M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0);
+}
 static void xform_output(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_out.p, 41, M.mem.p + M.L.gin + (long long)GI_U1 * ctx->d.ngrid(), M.L.stride, ctx->nmembers, 0);
@@ -201,7 +223,7 @@ static void xform_qcorh(speedy_ctx* ctx, bool gated) {
 static void enqueue_tendency_front(speedy_ctx* ctx, int j2, int csw_override) {
     launch_geopotential(ctx, 3);
     if (ctx->sppt_on) launch_sppt_update(ctx);
-    xform_inverse(ctx, j2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
+    xform_step(ctx, j2);
     launch_grid_columns(ctx, 0, csw_override);
     xform_direct(ctx);
 }
@@ -217,7 +239,7 @@ static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
     if (ctx->sppt_on) launch_sppt_update(ctx);
-    xform_inverse(ctx, 2, 0, ctx->sppt_on ? GI_N : GI_NBASE);
+    xform_step(ctx, 2);
     launch_grid_columns(ctx, 0, -1, 1);
     xform_direct(ctx, true);
     launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1);
@@ -679,6 +701,44 @@ int speedy_set_sppt_draw(speedy_ctx* ctx, int on) {
     API_END
 }
 
+// In-graph timeline of the main-loop kernels (debug aid): on != 0 makes every kernel stamp the GPU's global
+// timer; speedy_trace_read returns, in microseconds per step, the duration of each of the four kernels
+// (order of speedy_kernel_names) and the idle gap in front of each, then the number of steps traced.
+int speedy_trace(speedy_ctx* ctx, int on) {
+    API_BEGIN
+    check_ready(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    drop_graph(*ctx->model);
+    if (on) {
+        std::vector<unsigned long long> h(64, 0ull);
+        for (int i = 0; i < 4; i++) h[i] = ~0ull;
+        ctx->trace.upload(h);
+        ctx->dv.trace = ctx->trace.p;
+    } else {
+        ctx->dv.trace = nullptr;
+    }
+    API_END
+}
+int speedy_trace_read(speedy_ctx* ctx, double* out9) {
+    API_BEGIN
+    check_ready(ctx);
+    if (!ctx->dv.trace) throw std::runtime_error("tracing is off");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[32];
+    CUDA_CHECK(cudaMemcpy(h, ctx->trace.p, sizeof(h), cudaMemcpyDeviceToHost));
+    const double n = h[16] ? (double)h[16] : 1.0;
+    for (int i = 0; i < 4; i++) { out9[i] = 1e-3 * (double)h[8 + i] / n; out9[4 + i] = 1e-3 * (double)h[12 + i] / n; }
+    out9[8] = (double)h[16];
+    if (getenv("SPEEDY_TRACE_STAMPS")) {   // column-kernel role stamps of one CTA (physics.cu STAMP), microseconds after the CTA's start
+        unsigned long long st[32];
+        CUDA_CHECK(cudaMemcpy(st, ctx->trace.p + 32, sizeof(st), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "column stamps (us):");
+        for (int i = 0; i < 13; i++) fprintf(stderr, " [%d] %.2f", i, 1e-3 * (double)st[i] / n);
+        fprintf(stderr, "\n");
+    }
+    API_END
+}
+
 int speedy_ensemble_sums_dev(speedy_ctx* ctx, double* d_sum, double* d_sumsq) {
     API_BEGIN
     check_ready(ctx);
@@ -713,7 +773,7 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
             if (flush_l2) CUDA_CHECK(cudaMemsetAsync(flush.p, s & 1, flush.n * sizeof(double), ctx->stream));
             CUDA_CHECK(cudaEventRecord(ev[i][0], ctx->stream));
             switch (i) {
-                case 0: xform_inverse(ctx, 2, 0, GI_NBASE); break;
+                case 0: xform_step(ctx, 2); break;
                 case 1: launch_grid_columns(ctx, 0, -1, 1); break;
                 case 2: xform_direct(ctx, true); break;
                 case 3: launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1); break;

@@ -81,6 +81,8 @@ struct Model {
     DevBuf<LevelConsts> lc;
     DevBuf<float> outbuf;          // output() staging (input_output.f90:201-206)
     DevBuf<double> diag_partial;   // [member][block][kx][2] + [member][kx] partial sums of check_diagnostics
+    DevBuf<XDesc> desc_step;       // compact per-step list (two time levels): the fields the column kernel actually reads
+    int nstep_fields = 0;
     DevBuf<XDesc> desc_inv, desc_dir, desc_out, desc_one_dir, desc_sppt;
     std::map<std::string, FieldInfo> fields;
     // host-side calendar mirror

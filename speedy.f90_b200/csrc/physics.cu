@@ -56,6 +56,7 @@ struct ColumnArgs {
     int mode;                // 0: dynamics + physics -> K2 inputs; 1: physics only, tendencies in/out in gout slots
     int csw_override;        // -1: take compute_shortwave from the device clock
     int sppt_on;
+    unsigned long long* trace;
 };
 
 // ---- the column kernel -------------------------------------------------------------------
@@ -91,6 +92,9 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(sIcnv + TC);     // [0] physics inputs, [1] dynamics inputs
     const int ix = a.ix, il = a.il, N = ix * il;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) trace_begin(a.trace, 1);
+    const unsigned long long tk0 = a.trace ? gtimer() : 0ull;
+#define STAMP(i) do { if (a.trace && lane == 0 && blockIdx.x == 40 && blockIdx.y == 0) a.trace[32 + (i)] += gtimer() - tk0; } while (0)
     const int col0 = blockIdx.x * TC, col = col0 + lane;
     const int e = blockIdx.y;
     const int j = col / ix;
@@ -116,7 +120,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 
     // ---- stage the tile: one bulk copy per field row, spread over the threads -------------------
     const int ngin = a.sppt_on ? GI_N : GI_NBASE;
-    const int c_tau = ngin, c_str = c_tau + 4 * KX, c_rsw = c_str + 2, c_fb = c_rsw + KX, c_lc = c_fb + 1, ncopy = c_lc + 1;
+    const int c_tau = ngin, c_str = c_tau + 4 * KX, c_rsw = c_str + 2, c_fb = c_rsw + KX;
     const bool want_dyn = a.mode == 0;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -124,17 +128,20 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         const uint32_t row = TC * sizeof(double);
         mbar_expect_tx(&bars[0], (uint32_t)((ngin - GI_U1) + 4 * KX + 2 + KX) * row + NFBAND * 8 + (uint32_t)sizeof(LevelConsts));
         if (want_dyn) mbar_expect_tx(&bars[1], (uint32_t)GI_U1 * row);
+        // constant tables first: they may be fetched while the previous kernel is still draining (PDL)
+        bulk_g2s(sFband, a.fband, NFBAND * 8, &bars[0]);
+        bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), &bars[0]);
     }
-    for (int c = tid; c < ncopy; c += COL_THREADS) {
+    pdl_wait();                                        // the grid fields of the previous kernel are complete
+    pdl_trigger();
+    for (int c = tid; c < c_fb; c += COL_THREADS) {
         const uint32_t row = TC * sizeof(double);
         if (c < ngin) {
             if (c < GI_U1) { if (want_dyn) bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[1]); }
             else bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[0]);
         } else if (c < c_str) bulk_g2s(&smem[(size_t)(R_TAU2 + c - c_tau) * TC], mb + a.L.tau2 + (size_t)(c - c_tau) * N + col0, row, &bars[0]);
         else if (c < c_rsw) bulk_g2s(&smem[(size_t)(R_STRATC + c - c_str) * TC], mb + a.L.stratc + (size_t)(c - c_str) * N + col0, row, &bars[0]);
-        else if (c < c_fb) bulk_g2s(&smem[(size_t)(R_RSW + c - c_rsw) * TC], mb + a.L.tt_rsw + (size_t)(c - c_rsw) * N + col0, row, &bars[0]);
-        else if (c == c_fb) bulk_g2s(sFband, a.fband, NFBAND * 8, &bars[0]);
-        else bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), &bars[0]);
+        else bulk_g2s(&smem[(size_t)(R_RSW + c - c_rsw) * TC], mb + a.L.tt_rsw + (size_t)(c - c_rsw) * N + col0, row, &bars[0]);
     }
 
     if (warp == ROLE_DYN) {
@@ -214,6 +221,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         }
 #pragma unroll
         for (int k = 1; k <= KX; k++) { DYN(0, k) = utend[k]; DYN(1, k) = vtend[k]; DYN(2, k) = ttend[k]; DYN(3, k) = qtend[k]; }
+        STAMP(10);
         named_arrive(BAR_FINAL, 96);
         return;
     }
@@ -231,6 +239,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         SURF(SF_ZENIT) = G2(a.L.zenit); SURF(SF_STRATZ) = G2(a.L.stratz); SURF(SF_ALBSFC) = G2(a.L.albsfc); SURF(SF_PHIS0) = G2(a.L.phis0);
         SURF(SF_SST) = G2(a.L.sst_am); SURF(SF_STL) = G2(a.L.stl_am); SURF(SF_SOILW) = G2(a.L.soilw_am); SURF(SF_ALBL) = G2(a.L.alb_l);
         SURF(SF_ALBS) = G2(a.L.alb_s); SURF(SF_SNOWC) = G2(a.L.snowc); SURF(SF_FOROG) = G2(a.L.forog); SURF(SF_SSRD) = G2(a.L.ssrd);
+        STAMP(11);
         named_arrive(BAR_SLAB, 64);
         return;
     }
@@ -303,6 +312,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #pragma unroll
             for (int k = 1; k <= KX; k++) { VD(0, k) = ttenvd[k]; VD(1, k) = qtenvd[k]; }
         }
+        STAMP(12);
         named_arrive(BAR_FINAL, 96);
         return;
     }
@@ -313,6 +323,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
         const double coa_j = a.coa[j];
         mbar_wait(&bars[0], 0);
+        STAMP(0);
 #pragma unroll
         for (int k = 1; k <= KX; k++) { tg[k] = SG(GI_T1 + k - 1); qg[k] = SG(GI_Q1 + k - 1); phig[k] = SG(GI_PHI + k - 1); }
         const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);   // only the lowest-level wind is used (surface fluxes)
@@ -326,6 +337,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             rh[k] = qg[k] / qsat[k];
             PREP(0, k) = se[k]; PREP(1, k) = qsat[k]; PREP(2, k) = rh[k]; PREP(3, k) = qg[k];
         }
+        STAMP(1);
         const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
 
         // ---------------------------- convection.f90:27-245 ----------------------------
@@ -465,6 +477,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             ib[a.L.iptop + col] = iptop;
 
             // ------------------------- shortwave (every nstrad-th step) -------------------------
+            STAMP(2);
             named_sync(BAR_SLAB, 64);          // surface / forcing fields of this step are staged (slab warp)
             if (csw) {
                 const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
@@ -585,6 +598,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             }
         }
 
+        STAMP(3);
         // ------------------- downward longwave  longwave_radiation.f90:16-117 -------------------
         const double emisfc = F32(0.98), epslw = F32(0.05);
         double st4a1[KX + 1], st4a2[KX + 1], tt_rlw[KX + 1], flux[5];
@@ -662,6 +676,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             G2(a.L.slrd) = slrd;
         }
 
+        STAMP(4);
         // ------------------------- surface_fluxes.f90:42-296 (lfluxland = .true.) -------------------------
         double ts, shf3, evap3, ustr3, vstr3, slru3;
         {
@@ -748,6 +763,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             G2(a.L.ts) = ts; G2(a.L.tskin) = tskin; G2(a.L.u0) = u0; G2(a.L.v0) = v0; G2(a.L.t0) = t0;
         }
 
+        STAMP(5);
         // ------------------- upward longwave  longwave_radiation.f90:120-194 -------------------
         {
             const double refsfc = 1.0 - emisfc;
@@ -806,6 +822,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         }
 
         // ------------------- closing stage: physics.f90:137-138, 182-186, 197-205, 208-222 -------------------
+        STAMP(6);
         named_sync(BAR_FINAL, 96);     // dynamics tendencies and vertical-diffusion fluxes are in shared memory
         {
             const double ut8 = 0.0 + ustr3 * rps * lc.grdsig[KX - 1];
@@ -839,6 +856,8 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
                 GOUT(f0 + 0) = ut; GOUT(f0 + 1) = vt; GOUT(f0 + 5) = tt; GOUT(f0 + 8) = qt;
             }
         }
+        STAMP(7);
+        if (lane == 0) trace_end(a.trace, 1);
     }
 #undef SROW
 #undef SG
@@ -852,6 +871,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #undef VD
 #undef LWS
 #undef TAU2W
+#undef STAMP
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1051,13 +1071,13 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.sh = M.sh; a.merged = merged;
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
-    a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on;
+    a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on; a.trace = ctx->dv.trace;
     const int N = ctx->d.ngrid();
     if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
     static bool attr_set = false;
     if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM)); attr_set = true; }
     dim3 grid(N / TC, ctx->nmembers);
-    k_grid_columns<<<grid, COL_THREADS, COL_SMEM, ctx->stream>>>(a);
+    CUDA_CHECK(launch_pdl(k_grid_columns, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -46,4 +46,29 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_pdl() may start while its
+// predecessor in the stream / graph is still draining; everything before pdl_wait() must not touch data
+// the predecessor writes (barrier set-up, staging of constant tables), everything after sees it complete.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- in-graph timeline (debug aid, speedy_trace): per kernel slot the earliest CTA start and the latest
+// CTA end on the GPU's global nanosecond timer.  trace == nullptr in production launches.
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void trace_begin(unsigned long long* trace, int slot) { if (trace) atomicMin(&trace[slot], gtimer()); }
+__device__ __forceinline__ void trace_end(unsigned long long* trace, int slot) { if (trace) atomicMax(&trace[4 + slot], gtimer()); }
+
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 }  // namespace spd

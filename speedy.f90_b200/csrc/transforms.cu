@@ -274,7 +274,7 @@ struct SCfg : TCfg<TRUNC> {
 };
 
 template <int TRUNC>
-__global__ void __launch_bounds__(SCfg<TRUNC>::K1_THREADS, 1)
+__global__ void __maxnreg__(96)    // <= 96 registers: a CTA of the column kernel must fit beside it (PDL overlap)
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv) {
     using C = SCfg<TRUNC>;
@@ -286,6 +286,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     double* sX = sIn + C::NSPEC2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + C::KP * C::XS);   // [0] P tile, [1] staging
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) trace_begin(tv.trace, 0);
     const int grp = blockIdx.x % C::LG, chunk = blockIdx.x / C::LG, e = blockIdx.y;
     const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
     const double* mbase = in_base + (size_t)e * in_ms;
@@ -301,8 +302,8 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     };
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
+    // prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
     if (tid == 0) {
-        if (f0 < f1) issue(f0);
         mbar_expect_tx(&bars[0], C::PT * sizeof(double));
         bulk_g2s(sP, tv.poly + (size_t)j0 * C::NX * C::MX, C::PT * sizeof(double), &bars[0]);
     }
@@ -315,6 +316,9 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         for (int ks = 0; ks < C::KP / 4; ks++) a[ks] = A[4 * ks];
     }
     for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
+    pdl_wait();                                        // the spectral fields of the previous kernel are complete
+    pdl_trigger();
+    if (tid == 0 && f0 < f1) issue(f0);
     const int jl0 = tid / C::MP, m0 = tid - jl0 * C::MP;
     const bool leg = jl0 < C::JG && m0 < C::MX;
 
@@ -369,7 +373,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         __syncthreads();
         // ---- dense backward Fourier operator on the FP64 tensor pipe:
         //   grid[i][r] = sum_c finv[i][c] * X[c][r],  M = IX, N = NR, K = KP
-        double* out = out_base + (size_t)e * out_ms + (size_t)f * C::IX * C::IL;
+        double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : f) * C::IX * C::IL;
         const int i = 8 * w + g;
 #pragma unroll
         for (int nt = 0; nt < C::NR / 8; nt++) {
@@ -385,6 +389,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         }
         // the next field's Legendre stage rewrites sX only after the next __syncthreads pair
     }
+    if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 0); }
 }
 
 template <int TRUNC>
@@ -401,11 +406,12 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     double* sPd = sE + 2 * C::RG * C::ES + 2;           // [IY][NX][MG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + (C::P_SMEM ? C::PD : 0));   // [0] operator + P tiles, [1] grid field
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) trace_begin(tv.trace, 2);
     const int grp = blockIdx.x % C::CG, chunk = blockIdx.x / C::CG, e = blockIdx.y;
     const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
     const double* mbase = in_base + (size_t)e * in_ms;
     const int c0row = grp * C::RG;
-    const int gate_open = gate ? *gate : 1;             // in-graph conditional work (the daily forcing transform)
+    int gate_open = 1;
     auto live = [&](int f) { return gate_open || !(desc[f].flags & 4); };
     auto next_live = [&](int f) { while (f < f1 && !live(f)) f++; return f; };
     const uint32_t rowb = C::IX * sizeof(double);
@@ -416,11 +422,15 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     };
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
-    int f = next_live(f0);
-    if (f < f1) issue(f);
+    // prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
     if (tid == 0) mbar_expect_tx(&bars[0], C::RG * rowb + (C::P_SMEM ? C::PD * sizeof(double) : 0));
     if (tid < C::RG) bulk_g2s(sF + tid * C::FS, tv.ffwd + (size_t)(c0row + tid) * C::IX, rowb, &bars[0]);
     if (C::P_SMEM && tid == C::RG) bulk_g2s(sPd, tv.polyd + (size_t)grp * C::PD, C::PD * sizeof(double), &bars[0]);
+    pdl_wait();                                        // the grid fields of the previous kernel are complete
+    pdl_trigger();
+    gate_open = gate ? *gate : 1;                       // in-graph conditional work (the daily forcing transform)
+    int f = next_live(f0);
+    if (f < f1) issue(f);
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, nw = nthr >> 5;
     int it = 0;
     for (; f < f1; it++) {
@@ -480,6 +490,7 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         }
         f = fn;
     }
+    if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 2); }
 }
 
 void setup_transform_kernels() {
@@ -507,7 +518,7 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
     using C = SCfg<TRUNC>;
     const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch);
     dim3 grid(nchunk * C::LG, nmembers);
-    k_s2g_stream<TRUNC><<<grid, C::K1_THREADS, C::K1_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv);
+    CUDA_CHECK(launch_pdl(k_s2g_stream<TRUNC>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv));
 }
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
@@ -515,7 +526,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     using C = SCfg<TRUNC>;
     const int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);
     dim3 grid(nchunk * C::CG, nmembers);
-    k_g2s_stream<TRUNC><<<grid, C::K2_THREADS, C::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate);
+    CUDA_CHECK(launch_pdl(k_g2s_stream<TRUNC>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
 }
 
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]

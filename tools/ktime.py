@@ -23,6 +23,11 @@ for _ in range(days):
     c.run_steps(36)
 c.synchronize()
 dt = time.perf_counter() - t0
+c.trace(True)
+c.run_steps(36 * 5)
+tr = c.trace_read()
+c.trace(False)
+print("in-graph timeline (us/step):", {k: round(v, 2) for k, v in tr["us"].items()}, "gaps:", {k: round(v, 2) for k, v in tr["gap_before_us"].items()}, "steps", tr["steps"])
 kt = c.time_kernels(36, False)
 print("members %d T%d: %.2f us/step (graph, wall)  %.1f member-days/s | kernels warm (us): %s | sum %.1f" % (
     members, trunc, 1e6 * dt / (days * 36), days * members / dt, {k: round(1e3 * v, 2) for k, v in kt.items()}, 1e3 * sum(kt.values())))
