@@ -60,41 +60,52 @@ struct ColumnArgs {
 };
 
 // ---- the column kernel -------------------------------------------------------------------
-// One CTA owns a tile of TC = 32 consecutive columns and runs FOUR warp roles on it (lane =
-// column), so that the dependent chain of a column is cut four ways and every role reads its
-// inputs from shared memory, where the tile was staged once by bulk asynchronous copies (TMA,
-// one 256-byte row per field, completion on two mbarriers):
-//   PHYS  prep, convection, condensation, [clouds + shortwave], longwave down, surface fluxes,
-//         longwave up, then the closing stage (tendency sums in the reference's order, SPPT)
-//   SLAB  couple_sea_land of the previous step + set_forcing(1) when due, then stages the
-//         surface fields the physics reads                                   -> BAR_SLAB
-//   DYN   tendencies.f90:109-197 and the products for the direct transforms  -> BAR_FINAL
-//   VDIF  vertical_diffusion.f90 (waits for PHYS's thermodynamic prep: BAR_PREP) -> BAR_FINAL
+// One CTA owns a tile of TC = 32 consecutive columns (lane = column).  The tile is staged once in
+// shared memory by bulk asynchronous copies (TMA, one 256-byte row per field, two mbarriers) and
+// worked on by TEN warps:
+//   * eight LEVEL warps, warp k <-> sigma level k.  Everything that is local to a level — the
+//     thermodynamic prep (qsat, rh, static energy), large-scale condensation, the long-wave source
+//     terms, the whole of tendencies.f90:109-197, the short/long-wave transmissivities (all the exp()
+//     of the radiation) and the closing sum of the tendencies — runs level-parallel, so the dependent
+//     FP64 chain of a column is 1/8 as long as in a thread-per-column sweep (a B200 DFMA has 8.7 cycles of
+//     dependent-issue latency, exp() 160: profiles/r1g).  The vertical sweeps that are inherently serial
+//     (convection, the radiative flux recurrences, the surface-flux balance) run on level warp 1 (the sea
+//     half of the surface fluxes on level warp 2) between the wide phases;
+//   * SLAB: couple_sea_land of the previous step + set_forcing(1) when due, then stages the surface fields;
+//   * VDIF: vertical_diffusion.f90 (column-serial, off the critical path).
+// Hand-offs are named barriers; every sum keeps the reference's order of operations.
 constexpr int TC = 32;
-constexpr int COL_THREADS = 128;
-enum { ROLE_PHYS = 0, ROLE_SLAB = 1, ROLE_DYN = 2, ROLE_VDIF = 3 };
-enum { BAR_SLAB = 1, BAR_PREP = 2, BAR_FINAL = 3 };
+enum { W_SLAB = KX, W_VDIF = KX + 1, COL_WARPS = KX + 2 };
+constexpr int COL_THREADS = COL_WARPS * 32;
+constexpr int LEV_THREADS = KX * 32;
+enum { BAR_LEV = 1, BAR_MID = 2, BAR_SEA = 3, BAR_END = 4 };
 enum { SF_FMASK, SF_FSOL, SF_OZONE, SF_OZUPP, SF_ZENIT, SF_STRATZ, SF_ALBSFC, SF_PHIS0, SF_SST, SF_STL, SF_SOILW, SF_ALBL, SF_ALBS,
        SF_SNOWC, SF_FOROG, SF_SSRD, SF_N };
+// scalar rows (one value per column)
+enum { S_PSG, S_CLOUDC, S_QCLOUD, S_T1_1, S_T1_2, S_T2_1, S_DENVVS0, S_T0, S_U0, S_V0, S_USTR2, S_VSTR2, S_SHF2, S_EVAP2, S_SLRU2,
+       S_UT8, S_VT8, S_SHFT, S_EVAPT, S_N };
+enum { I_ICNV, I_ICLTOP, I_LSC, I_N = I_LSC + KX };
 // shared-memory rows of TC doubles
 enum { R_GIN = 0, R_TAU2 = R_GIN + GI_N, R_STRATC = R_TAU2 + 4 * KX, R_RSW = R_STRATC + 2, R_SURF = R_RSW + KX, R_DYN = R_SURF + SF_N,
-       R_PREP = R_DYN + 4 * KX, R_CNV = R_PREP + 4 * KX, R_VD = R_CNV + 4 * KX, R_LW = R_VD + 2 * KX, R_END = R_LW + 3 * KX };
+       R_SE = R_DYN + 4 * KX, R_QSAT = R_SE + KX, R_RH = R_QSAT + KX, R_QG = R_RH + KX, R_DFSE = R_QG + KX, R_DFQA = R_DFSE + KX,
+       R_DTLSC = R_DFQA + KX, R_DQLSC = R_DTLSC + KX, R_VD = R_DQLSC + KX, R_LW = R_VD + 2 * KX, R_TAU1 = R_LW + 3 * KX,
+       R_TAU2S = R_TAU1 + KX, R_SC = R_TAU2S + KX, R_END = R_SC + S_N };
 constexpr int NFBAND = 301 * 4;
 constexpr int LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static_assert(sizeof(LevelConsts) % 16 == 0 && (NFBAND * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
-constexpr size_t COL_SMEM = sizeof(double) * ((size_t)R_END * TC + NFBAND + LC_DOUBLES) + sizeof(int) * TC + 2 * sizeof(uint64_t);
+constexpr size_t COL_SMEM = sizeof(double) * ((size_t)R_END * TC + NFBAND + LC_DOUBLES) + sizeof(int) * TC * I_N + 2 * sizeof(uint64_t);
 
-__global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
+__global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
     extern __shared__ __align__(16) double smem[];
     double* sFband = smem + (size_t)R_END * TC;
     double* sLc = sFband + NFBAND;
-    int* sIcnv = reinterpret_cast<int*>(sLc + LC_DOUBLES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sIcnv + TC);     // [0] physics inputs, [1] dynamics inputs
+    int* sInt = reinterpret_cast<int*>(sLc + LC_DOUBLES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sInt + TC * I_N);     // [0] physics inputs, [1] dynamics inputs
     const int ix = a.ix, il = a.il, N = ix * il;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) trace_begin(a.trace, 1);
-    const unsigned long long tk0 = a.trace ? gtimer() : 0ull;
-#define STAMP(i) do { if (a.trace && lane == 0 && blockIdx.x == 40 && blockIdx.y == 0) a.trace[32 + (i)] += gtimer() - tk0; } while (0)
+    unsigned long long tk0 = 0ull;
+#define STAMP(i) do { if (a.trace && lane == 0 && (warp == 0 || warp >= KX) && blockIdx.x == 40 && blockIdx.y == 0) a.trace[32 + (i)] += gtimer() - tk0; } while (0)
     const int col0 = blockIdx.x * TC, col = col0 + lane;
     const int e = blockIdx.y;
     const int j = col / ix;
@@ -109,10 +120,20 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #define STRATC(i) SROW(R_STRATC + (i))
 #define RSW(k) SROW(R_RSW + (k)-1)
 #define DYN(v, k) SROW(R_DYN + (v) * KX + (k)-1)
-#define PREP(v, k) SROW(R_PREP + (v) * KX + (k)-1)
-#define CNV(v, k) SROW(R_CNV + (v) * KX + (k)-1)
+#define SE(k) SROW(R_SE + (k)-1)
+#define QSAT(k) SROW(R_QSAT + (k)-1)
+#define RH(k) SROW(R_RH + (k)-1)
+#define QG(k) SROW(R_QG + (k)-1)
+#define DFSE(k) SROW(R_DFSE + (k)-1)
+#define DFQA(k) SROW(R_DFQA + (k)-1)
+#define DTLSC(k) SROW(R_DTLSC + (k)-1)
+#define DQLSC(k) SROW(R_DQLSC + (k)-1)
 #define VD(v, k) SROW(R_VD + (v) * KX + (k)-1)
 #define LWS(v, k) SROW(R_LW + (v) * KX + (k)-1)
+#define TAU1(k) SROW(R_TAU1 + (k)-1)
+#define TAU2S(k) SROW(R_TAU2S + (k)-1)
+#define SC(i) SROW(R_SC + (i))
+#define SI(i) sInt[(i) * TC + lane]
 #define GOUT(f) gout[(size_t)(f) * N + col]
 #define G2(off) mb[(off) + col]
 #define G3(off, k) mb[(off) + (size_t)((k)-1) * N + col]
@@ -134,6 +155,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
     }
     pdl_wait();                                        // the grid fields of the previous kernel are complete
     pdl_trigger();
+    if (a.trace) tk0 = gtimer();
     for (int c = tid; c < c_fb; c += COL_THREADS) {
         const uint32_t row = TC * sizeof(double);
         if (c < ngin) {
@@ -144,89 +166,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         else bulk_g2s(&smem[(size_t)(R_RSW + c - c_rsw) * TC], mb + a.L.tt_rsw + (size_t)(c - c_rsw) * N + col0, row, &bars[0]);
     }
 
-    if (warp == ROLE_DYN) {
-        // ============================ tendencies.f90:109-197 ============================
-        double utend[KX + 1], vtend[KX + 1], ttend[KX + 1], qtend[KX + 1];
-        if (a.mode == 0) {
-            const double cor = a.coriol[j];
-            mbar_wait(&bars[0], 0);     // level constants
-            mbar_wait(&bars[1], 0);
-        double ug[KX + 1], vg[KX + 1], tg[KX + 1], vorg[KX + 1], divg[KX + 1], trg[KX + 1], tgg[KX + 1], puv[KX + 1];
-        double sigdt[KX + 2], sigm[KX + 2], temp[KX + 2];
-        
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            vorg[k] = SG(GI_VOR + k - 1) + cor;   // :103-107
-            divg[k] = SG(GI_DIV + k - 1);
-            tg[k] = SG(GI_T + k - 1);
-            trg[k] = SG(GI_TR + k - 1);
-            ug[k] = SG(GI_U + k - 1);
-            vg[k] = SG(GI_V + k - 1);
-        }
-        const double px = SG(GI_PX), py = SG(GI_PY);
-        double umean = 0.0, vmean = 0.0, dmean = 0.0;
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            umean = umean + ug[k] * lc.dhs[k - 1];
-            vmean = vmean + vg[k] * lc.dhs[k - 1];
-            dmean = dmean + divg[k] * lc.dhs[k - 1];
-        }
-        GOUT(GO_PSDT) = -umean * px - vmean * py;   // :125
-        sigdt[1] = 0.0; sigm[1] = 0.0;
-#pragma unroll
-        for (int k = 1; k <= KX; k++) puv[k] = (ug[k] - umean) * px + (vg[k] - vmean) * py;
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {   // :140-143 (the loop also overwrites level kx+1)
-            sigdt[k + 1] = sigdt[k] - lc.dhs[k - 1] * (puv[k] + divg[k] - dmean);
-            sigm[k + 1] = sigm[k] - lc.dhs[k - 1] * puv[k];
-        }
-#pragma unroll
-        for (int k = 1; k <= KX; k++) tgg[k] = tg[k] - lc.tref[k - 1];
-        temp[1] = 0.0; temp[KX + 1] = 0.0;
-#pragma unroll
-        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (ug[k] - ug[k - 1]);
-#pragma unroll
-        for (int k = 1; k <= KX; k++) utend[k] = vg[k] * vorg[k] - tgg[k] * lc.rgas * px - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
-#pragma unroll
-        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (vg[k] - vg[k - 1]);
-#pragma unroll
-        for (int k = 1; k <= KX; k++) vtend[k] = -ug[k] * vorg[k] - tgg[k] * lc.rgas * py - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
-#pragma unroll
-        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (tgg[k] - tgg[k - 1]) + sigm[k] * (lc.tref[k - 1] - lc.tref[k - 2]);
-#pragma unroll
-        for (int k = 1; k <= KX; k++)
-            ttend[k] = tgg[k] * divg[k] - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1] + lc.fsgr[k - 1] * tgg[k] * (sigdt[k + 1] + sigdt[k]) +
-                       lc.tref3[k - 1] * (sigm[k + 1] + sigm[k]) + lc.akap * (tg[k] * puv[k] - tgg[k] * dmean);
-#pragma unroll
-        for (int k = 2; k <= KX; k++) temp[k] = sigdt[k] * (trg[k] - trg[k - 1]);
-        temp[2] = 0.0; temp[3] = 0.0;   // :192
-#pragma unroll
-        for (int k = 1; k <= KX; k++) qtend[k] = trg[k] * divg[k] - (temp[k + 1] + temp[k]) * lc.dhsr[k - 1];
-        // products for the direct transforms (tendencies.f90:219-232)
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            const int f = GO_PER * (k - 1);
-            GOUT(f + 2) = 0.5 * (ug[k] * ug[k] + vg[k] * vg[k]);
-            GOUT(f + 3) = -ug[k] * tgg[k];
-            GOUT(f + 4) = -vg[k] * tgg[k];
-            GOUT(f + 6) = -ug[k] * trg[k];
-            GOUT(f + 7) = -vg[k] * trg[k];
-        }
-        } else {
-#pragma unroll
-            for (int k = 1; k <= KX; k++) {
-                const int f = GO_PER * (k - 1);
-                utend[k] = GOUT(f + 0); vtend[k] = GOUT(f + 1); ttend[k] = GOUT(f + 5); qtend[k] = GOUT(f + 8);
-            }
-        }
-#pragma unroll
-        for (int k = 1; k <= KX; k++) { DYN(0, k) = utend[k]; DYN(1, k) = vtend[k]; DYN(2, k) = ttend[k]; DYN(3, k) = qtend[k]; }
-        STAMP(10);
-        named_arrive(BAR_FINAL, 96);
-        return;
-    }
-
-    if (warp == ROLE_SLAB) {
+    if (warp == W_SLAB) {
         // ===== main loop only: couple_sea_land of the previous step (speedy.f90:53) and set_forcing(1) (speedy.f90:29-32),
         // both column-local, in front of the physics that consumes them
         if (a.merged) {
@@ -240,18 +180,18 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
         SURF(SF_SST) = G2(a.L.sst_am); SURF(SF_STL) = G2(a.L.stl_am); SURF(SF_SOILW) = G2(a.L.soilw_am); SURF(SF_ALBL) = G2(a.L.alb_l);
         SURF(SF_ALBS) = G2(a.L.alb_s); SURF(SF_SNOWC) = G2(a.L.snowc); SURF(SF_FOROG) = G2(a.L.forog); SURF(SF_SSRD) = G2(a.L.ssrd);
         STAMP(11);
-        named_arrive(BAR_SLAB, 64);
+        named_arrive(BAR_MID, COL_THREADS);
         return;
     }
 
-    if (warp == ROLE_VDIF) {
+    if (warp == W_VDIF) {
         double se[KX + 1], rh[KX + 1], qsat[KX + 1], qg[KX + 1], phig[KX + 1];
         mbar_wait(&bars[0], 0);
 #pragma unroll
         for (int k = 1; k <= KX; k++) phig[k] = SG(GI_PHI + k - 1);
-        named_sync(BAR_PREP, 64);
+        named_sync(BAR_MID, COL_THREADS);      // thermodynamic prep (level warps) and icnv (convection) are in shared memory
 #pragma unroll
-        for (int k = 1; k <= KX; k++) { se[k] = PREP(0, k); qsat[k] = PREP(1, k); rh[k] = PREP(2, k); qg[k] = PREP(3, k); }
+        for (int k = 1; k <= KX; k++) { se[k] = SE(k); qsat[k] = QSAT(k); rh[k] = RH(k); qg[k] = QG(k); }
         // ------------------- vertical_diffusion.f90:30-143 -------------------
         {
             const double trshc = 6.0, trvdi = 24.0, trvds = 6.0, redshc = 0.5, rhgrad = 0.5, segrad = F32(0.1);
@@ -273,7 +213,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
                 const double drh = rh[KX] - rh[nl1];
                 double fcnv = 1.0;
                 if (dmse >= 0.0) {
-                    if (sIcnv[lane] > 0) fcnv = redshc;
+                    if (SI(I_ICNV) > 0) fcnv = redshc;
                     const double fluxse = fcnv * fshcse * dmse;
                     ttenvd[nl1] = fluxse * rsig[nl1];
                     ttenvd[KX] = -fluxse * rsig[KX];
@@ -313,36 +253,144 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             for (int k = 1; k <= KX; k++) { VD(0, k) = ttenvd[k]; VD(1, k) = qtenvd[k]; }
         }
         STAMP(12);
-        named_arrive(BAR_FINAL, 96);
+        named_arrive(BAR_END, 9 * 32);
         return;
     }
 
-    // ================================ physics.f90:110-205 (ROLE_PHYS) ================================
-    {
-        double tg[KX + 1], qg[KX + 1], phig[KX + 1], se[KX + 1], rh[KX + 1], qsat[KX + 1];
-        const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
-        const double coa_j = a.coa[j];
-        mbar_wait(&bars[0], 0);
-        STAMP(0);
-#pragma unroll
-        for (int k = 1; k <= KX; k++) { tg[k] = SG(GI_T1 + k - 1); qg[k] = SG(GI_Q1 + k - 1); phig[k] = SG(GI_PHI + k - 1); }
-        const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);   // only the lowest-level wind is used (surface fluxes)
-        const double psg = exp(SG(GI_PSL));
-        const double rps = 1.0 / psg;
-#pragma unroll
-        for (int k = 1; k <= KX; k++) {
-            qg[k] = dmax(qg[k], 0.0);
-            se[k] = lc.cp * tg[k] + phig[k];
-            qsat[k] = qsat_pt(tg[k], lc.fsg[k - 1] * psg);
-            rh[k] = qg[k] / qsat[k];
-            PREP(0, k) = se[k]; PREP(1, k) = qsat[k]; PREP(2, k) = rh[k]; PREP(3, k) = qg[k];
-        }
-        STAMP(1);
-        const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
 
-        // ---------------------------- convection.f90:27-245 ----------------------------
-        int iptop;
-        double cbmf = 0.0, precnv = 0.0;
+    // ======================= level warps: warp k-1 <-> sigma level k =======================
+    const int k = warp + 1;
+    const int nl1 = KX - 1, nlp = KX + 1;
+    const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
+    const double cor = a.coriol[j], coa_j = a.coa[j];
+    mbar_wait(&bars[0], 0);
+    STAMP(0);
+    // ---------------- phase A (wide): thermodynamic prep, physics.f90:110-122 ----------------
+    const double tgk = SG(GI_T1 + k - 1), phigk = SG(GI_PHI + k - 1);
+    const double psg = exp(SG(GI_PSL));
+    const double rps = 1.0 / psg;
+    const double qgk = dmax(SG(GI_Q1 + k - 1), 0.0);
+    const double sek = lc.cp * tgk + phigk;
+    const double qsatk = qsat_pt(tgk, lc.fsg[k - 1] * psg);
+    const double rhk = qgk / qsatk;
+    SE(k) = sek; QSAT(k) = qsatk; RH(k) = rhk; QG(k) = qgk;
+    if (k == 1) SC(S_PSG) = psg;
+    // ---------------- large_scale_condensation.f90:33-95, the level-local part ----------------
+    {
+        const double trlsc = 4.0, rhlsc = F32(0.9), drhlsc = F32(0.1), rhblsc = F32(0.95), qsmax = 10.0;
+        const double rtlsc = 1.0 / (trlsc * 3600.0), tfact = lc.alhc / lc.cp;
+        const double psa2 = psg * psg;
+        double dtl = 0.0, dql = 0.0;
+        int hit = 0;
+        if (k >= 2) {
+            const double sig2 = lc.fsg[k - 1] * lc.fsg[k - 1];
+            double rhref = rhlsc + drhlsc * (sig2 - 1.0);
+            if (k == KX) rhref = dmax(rhref, rhblsc);
+            const double dqmax = qsmax * sig2 * rtlsc;
+            const double dqa = rhref * qsatk - qgk;
+            if (dqa < 0.0) {
+                hit = 1;
+                dql = dqa * rtlsc;
+                dtl = tfact * dmin(-dql, dqmax * psa2);
+            }
+        }
+        DTLSC(k) = dtl; DQLSC(k) = dql; SI(I_LSC + k - 1) = hit;
+    }
+    // ---------------- long-wave source terms, longwave_radiation.f90:40-76 ----------------
+    {
+        const double anis = 1.0;
+        const double tgm = (k > 1) ? SG(GI_T1 + k - 2) : 0.0, tgp = (k < KX) ? SG(GI_T1 + k) : 0.0;
+        const double si_k = (k <= nl1) ? tgk + lc.wvi[7 + k] * (tgp - tgk) : 0.0;            // st4a(k,1) before the power
+        const double si_m = (k >= 2) ? tgm + lc.wvi[7 + k - 1] * (tgk - tgm) : 0.0;          // st4a(k-1,1)
+        double s1, s2;
+        if (k <= 2) {
+            const double x = (k == 1) ? 0.75 * tgk + 0.25 * si_k : 0.50 * tgk + 0.25 * (si_m + si_k);
+            s1 = lc.sbc * ((x * x) * (x * x));
+            s2 = 0.0;
+        } else {
+            const double d = (k <= nl1) ? 0.5 * anis * dmax(si_k - si_m, 0.0) : anis * dmax(tgk - si_m, 0.0);
+            const double x = tgk;
+            const double st3a = lc.sbc * ((x * x) * x);
+            s1 = st3a * tgk;
+            s2 = 4.0 * st3a * d;
+        }
+        LWS(0, k) = s1; LWS(1, k) = s2;
+    }
+    // ---------------- tendencies.f90:109-197 for level k ----------------
+    if (a.mode == 0) {
+        mbar_wait(&bars[1], 0);
+        const double px = SG(GI_PX), py = SG(GI_PY);
+        double umean = 0.0, vmean = 0.0, dmean = 0.0;
+#pragma unroll
+        for (int kk = 1; kk <= KX; kk++) {
+            umean = umean + SG(GI_U + kk - 1) * lc.dhs[kk - 1];
+            vmean = vmean + SG(GI_V + kk - 1) * lc.dhs[kk - 1];
+            dmean = dmean + SG(GI_DIV + kk - 1) * lc.dhs[kk - 1];
+        }
+        if (k == 1) GOUT(GO_PSDT) = -umean * px - vmean * py;   // :125
+        // sigma-dot and its mean-flow part at the two interfaces of level k (:140-143 prefix sums, re-done per level)
+        double sd_lo = 0.0, sm_lo = 0.0, sd_hi = 0.0, sm_hi = 0.0;    // interfaces k and k+1
+        double puvk = 0.0;
+        {
+            double sd = 0.0, sm = 0.0;
+#pragma unroll
+            for (int kk = 1; kk <= KX; kk++) {
+                const double puv = (SG(GI_U + kk - 1) - umean) * px + (SG(GI_V + kk - 1) - vmean) * py;
+                if (kk == k) { sd_lo = sd; sm_lo = sm; puvk = puv; }
+                sd = sd - lc.dhs[kk - 1] * (puv + SG(GI_DIV + kk - 1) - dmean);
+                sm = sm - lc.dhs[kk - 1] * puv;
+                if (kk == k) { sd_hi = sd; sm_hi = sm; }
+            }
+        }
+        const double ugk = SG(GI_U + k - 1), vgk = SG(GI_V + k - 1), tg2k = SG(GI_T + k - 1), trgk = SG(GI_TR + k - 1);
+        const double divgk = SG(GI_DIV + k - 1), vorgk = SG(GI_VOR + k - 1) + cor;   // :103-107
+        const double tggk = tg2k - lc.tref[k - 1];
+        // neighbours (level k-1 for the lower-index interface, k+1 for the upper one)
+        const double ugm = (k > 1) ? SG(GI_U + k - 2) : 0.0, ugp = (k < KX) ? SG(GI_U + k) : 0.0;
+        const double vgm = (k > 1) ? SG(GI_V + k - 2) : 0.0, vgp = (k < KX) ? SG(GI_V + k) : 0.0;
+        const double tggm = (k > 1) ? SG(GI_T + k - 2) - lc.tref[k - 2] : 0.0, tggp = (k < KX) ? SG(GI_T + k) - lc.tref[k] : 0.0;
+        const double trgm = (k > 1) ? SG(GI_TR + k - 2) : 0.0, trgp = (k < KX) ? SG(GI_TR + k) : 0.0;
+        // temp(k) lives on interface k (k = 2..kx), temp(1) = temp(kx+1) = 0
+        double t_lo, t_hi;
+        t_lo = (k >= 2) ? sd_lo * (ugk - ugm) : 0.0;
+        t_hi = (k < KX) ? sd_hi * (ugp - ugk) : 0.0;
+        const double utend = vgk * vorgk - tggk * lc.rgas * px - (t_hi + t_lo) * lc.dhsr[k - 1];
+        t_lo = (k >= 2) ? sd_lo * (vgk - vgm) : 0.0;
+        t_hi = (k < KX) ? sd_hi * (vgp - vgk) : 0.0;
+        const double vtend = -ugk * vorgk - tggk * lc.rgas * py - (t_hi + t_lo) * lc.dhsr[k - 1];
+        t_lo = (k >= 2) ? sd_lo * (tggk - tggm) + sm_lo * (lc.tref[k - 1] - lc.tref[k - 2]) : 0.0;
+        t_hi = (k < KX) ? sd_hi * (tggp - tggk) + sm_hi * (lc.tref[k] - lc.tref[k - 1]) : 0.0;
+        const double ttend = tggk * divgk - (t_hi + t_lo) * lc.dhsr[k - 1] + lc.fsgr[k - 1] * tggk * (sd_hi + sd_lo) +
+                             lc.tref3[k - 1] * (sm_hi + sm_lo) + lc.akap * (tg2k * puvk - tggk * dmean);
+        t_lo = (k >= 4) ? sd_lo * (trgk - trgm) : 0.0;            // :192 the tracer flux is zeroed at interfaces 2 and 3
+        t_hi = (k < KX && k + 1 >= 4) ? sd_hi * (trgp - trgk) : 0.0;
+        const double qtend = trgk * divgk - (t_hi + t_lo) * lc.dhsr[k - 1];
+        DYN(0, k) = utend; DYN(1, k) = vtend; DYN(2, k) = ttend; DYN(3, k) = qtend;
+        // products for the direct transforms (tendencies.f90:219-232)
+        const int f = GO_PER * (k - 1);
+        GOUT(f + 2) = 0.5 * (ugk * ugk + vgk * vgk);
+        GOUT(f + 3) = -ugk * tggk;
+        GOUT(f + 4) = -vgk * tggk;
+        GOUT(f + 6) = -ugk * trgk;
+        GOUT(f + 7) = -vgk * trgk;
+    } else {
+        const int f = GO_PER * (k - 1);
+        DYN(0, k) = GOUT(f + 0); DYN(1, k) = GOUT(f + 1); DYN(2, k) = GOUT(f + 5); DYN(3, k) = GOUT(f + 8);
+    }
+    STAMP(1);
+    named_sync(BAR_LEV, LEV_THREADS);
+
+    // ---------------- phase B (level warp 1): convection.f90:27-245 + the LSC reductions ----------------
+    int iptop = 0, icltop = 0;
+    double cloudc = 0.0, clstr = 0.0, qcloud = 0.0, precnv = 0.0, precls = 0.0;
+    double se[KX + 1], qg[KX + 1], qsat[KX + 1], rh[KX + 1], tg[KX + 1], phig[KX + 1];
+    const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
+    if (k == 1) {
+#pragma unroll
+        for (int kk = 1; kk <= KX; kk++) {
+            se[kk] = SE(kk); qg[kk] = QG(kk); qsat[kk] = QSAT(kk); rh[kk] = RH(kk); tg[kk] = SG(GI_T1 + kk - 1); phig[kk] = SG(GI_PHI + kk - 1);
+        }
+        double cbmf = 0.0;
         {
             const double psmin = F32(0.8), trcnv = 6.0, rhbl = F32(0.9), rhil = F32(0.7), entmax = 0.5, smf = F32(0.8);
             const int nl1 = KX - 1, nlp = KX + 1;
@@ -436,196 +484,209 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
                 dfse[k] = dfse[k] * rps * lc.grdscp[k - 1];
                 dfqa[k] = dfqa[k] * rps * lc.grdsig[k - 1];
             }
-            // ---------------------- large_scale_condensation.f90:33-95 ----------------------
-            const double trlsc = 4.0, rhlsc = F32(0.9), drhlsc = F32(0.1), rhblsc = F32(0.95), qsmax = 10.0;
-            const double rtlsc = 1.0 / (trlsc * 3600.0), tfact = lc.alhc / lc.cp, prg = lc.p0 / lc.grav;
-            const double psa2 = psg * psg;
-            double dtlsc[KX + 1], dqlsc[KX + 1];
-            dtlsc[1] = 0.0; dqlsc[1] = 0.0;
-            const int icnv_ = KX - iptop;   // physics.f90:132, before LSC lowers iptop
-            ib[a.L.icnv + col] = icnv_;
-            sIcnv[lane] = icnv_;
-            named_arrive(BAR_PREP, 64);          // se/qsat/rh/qg + icnv are in shared memory: the vertical-diffusion warp may start
 #pragma unroll
-            for (int k = 2; k <= KX; k++) {
-                const double sig2 = lc.fsg[k - 1] * lc.fsg[k - 1];
-                double rhref = rhlsc + drhlsc * (sig2 - 1.0);
-                if (k == KX) rhref = dmax(rhref, rhblsc);
-                const double dqmax = qsmax * sig2 * rtlsc;
-                const double dqa = rhref * qsat[k] - qg[k];
-                if (dqa < 0.0) {
-                    iptop = min(k, iptop);
-                    dqlsc[k] = dqa * rtlsc;
-                    dtlsc[k] = tfact * dmin(-dqlsc[k], dqmax * psa2);
-                } else {
-                    dqlsc[k] = 0.0;
-                    dtlsc[k] = 0.0;
-                }
-            }
-            double precls = 0.0;
+            for (int k = 1; k <= KX; k++) { DFSE(k) = dfse[k]; DFQA(k) = dfqa[k]; }
+        }
+        const int icnv_ = KX - iptop;   // physics.f90:132, before LSC lowers iptop
+        ib[a.L.icnv + col] = icnv_;
+        SI(I_ICNV) = icnv_;
+        {   // large_scale_condensation.f90:60-93: cloud top and precipitation from the level-local results
+            const double prg = lc.p0 / lc.grav;
 #pragma unroll
-            for (int k = 2; k <= KX; k++) {
-                const double pfact = lc.dhs[k - 1] * prg;
-                precls = precls - pfact * dqlsc[k];
+            for (int kk = 2; kk <= KX; kk++) if (SI(I_LSC + kk - 1)) iptop = min(kk, iptop);
+#pragma unroll
+            for (int kk = 2; kk <= KX; kk++) {
+                const double pfact = lc.dhs[kk - 1] * prg;
+                precls = precls - pfact * DQLSC(kk);
             }
             precls = precls * psg;
-#pragma unroll
-            for (int k = 1; k <= KX; k++) {   // physics.f90:137-138: added to the tendencies in the closing stage, in the reference's order
-                CNV(0, k) = dfse[k]; CNV(1, k) = dtlsc[k]; CNV(2, k) = dfqa[k]; CNV(3, k) = dqlsc[k];
-            }
-            G2(a.L.precnv) = precnv; G2(a.L.precls) = precls; G2(a.L.cbmf) = cbmf;
-            ib[a.L.iptop + col] = iptop;
+        }
+        G2(a.L.precnv) = precnv; G2(a.L.precls) = precls; G2(a.L.cbmf) = cbmf;
+        ib[a.L.iptop + col] = iptop;
+        STAMP(2);
+    }
+    named_sync(BAR_MID, COL_THREADS);          // + surface / forcing fields staged by the slab warp; icnv for the diffusion warp
 
-            // ------------------------- shortwave (every nstrad-th step) -------------------------
-            STAMP(2);
-            named_sync(BAR_SLAB, 64);          // surface / forcing fields of this step are staged (slab warp)
-            if (csw) {
-                const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
-                const double clsmax = F32(0.60), clsminl = F32(0.15), gse_s0 = 0.25, gse_s1 = F32(0.40);
-                const double albcl = F32(0.43), albcls = 0.50;
-                const double absdry = F32(0.033), absaer = F32(0.033), abswv1 = F32(0.022), abswv2 = 15.000, abscl1 = F32(0.015), abscl2 = F32(0.15);
-                const double ablwin = F32(0.3), ablco2 = 6.0, ablwv1 = F32(0.7), ablwv2 = 50.0, ablcl1 = 12.0, ablcl2 = F32(0.6);
-                const double epslw = F32(0.05);
-                const double gse = (se[KX - 1] - se[KX]) / (phig[KX - 1] - phig[KX]);   // physics.f90:147
-                // clouds  shortwave_radiation.f90:332-410
-                double cloudc, clstr;
-                int icltop;
-                const double rrcl = 1. / (rhcl2 - rhcl1);
-                if (rh[nl1] > rhcl1) { cloudc = rh[nl1] - rhcl1; icltop = nl1; }
-                else { cloudc = 0.0; icltop = nlp; }
-                for (int k = 3; k <= KX - 2; k++) {
-                    const double drh = rh[k] - rhcl1;
-                    if (drh > cloudc && qg[k] > qacl) { cloudc = drh; icltop = k; }
-                }
-                {
-                    const double pr1 = dmin(pmaxcl, F32(86.4) * (precnv + precls));
-                    const double cc = dmin(1.0, cloudc * rrcl);
-                    cloudc = dmin(1.0, wpcl * sqrt(pr1) + cc * cc);
-                    icltop = min(iptop, icltop);
-                }
-                const double qcloud = qg[nl1];
-                {
-                    const double clfact = F32(1.2), rgse = 1.0 / (gse_s1 - gse_s0);
-                    const double fstab = dmax(0.0, dmin(1.0, rgse * (gse - gse_s0)));
-                    clstr = fstab * dmax(clsmax - clfact * cloudc, 0.0);
-                    const double clstrl = dmax(clstr, clsminl) * rh[KX];
-                    const double fm = SURF(SF_FMASK);
-                    clstr = clstr + fm * (clstrl - clstr);
-                }
-                ib[a.L.icltop + col] = icltop;
-                G2(a.L.qcloud) = qcloud; G2(a.L.cloudc) = cloudc; G2(a.L.clstr) = clstr;
-                // get_shortwave_rad_fluxes  shortwave_radiation.f90:74-234
-                const double fsol = SURF(SF_FSOL), ozone = SURF(SF_OZONE), ozupp = SURF(SF_OZUPP), zenit = SURF(SF_ZENIT), stratz = SURF(SF_STRATZ);
-                const double albsfc = SURF(SF_ALBSFC);
-                const double fband2 = F32(0.05), fband1 = 1.0 - fband2;
-                double tau1[KX + 1], tau2_[KX + 1], tau3[KX + 1], dfabs[KX + 1];
-#pragma unroll
-                for (int k = 1; k <= KX; k++) tau3[k] = 0.0;
-                if (icltop <= KX) tau3[icltop] = albcl * cloudc;
-                tau3[KX] = albcls * clstr;
-                const double psaz = psg * zenit;
-                double acloud = cloudc * dmin(abscl1 * qcloud, abscl2);
-                tau1[1] = exp(-psaz * lc.dhs[0] * absdry);
-                for (int k = 2; k <= nl1; k++) {
-                    const double abs1 = absdry + absaer * (lc.fsg[k - 1] * lc.fsg[k - 1]);
-                    if (k >= icltop) tau1[k] = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qg[k] + acloud));
-                    else tau1[k] = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qg[k]));
-                }
-                {
-                    const double abs1 = absdry + absaer * (lc.fsg[KX - 1] * lc.fsg[KX - 1]);
-                    tau1[KX] = exp(-psaz * lc.dhs[KX - 1] * (abs1 + abswv1 * qg[KX]));
-                }
-                tau2_[1] = 0.0;
-                for (int k = 2; k <= KX; k++) tau2_[k] = exp(-psaz * lc.dhs[k - 1] * abswv2 * qg[k]);
-                double ftop = fsol;
-                double flux1 = fsol * fband1, flux2 = fsol * fband2;
-                dfabs[1] = flux1;
-                flux1 = tau1[1] * (flux1 - ozupp * psg);
-                dfabs[1] = dfabs[1] - flux1;
-                dfabs[2] = flux1;
-                flux1 = tau1[2] * (flux1 - ozone * psg);
-                dfabs[2] = dfabs[2] - flux1;
-                for (int k = 3; k <= KX; k++) {
-                    tau3[k] = flux1 * tau3[k];
-                    flux1 = flux1 - tau3[k];
-                    dfabs[k] = flux1;
-                    flux1 = tau1[k] * flux1;
-                    dfabs[k] = dfabs[k] - flux1;
-                }
-                for (int k = 2; k <= KX; k++) {
-                    dfabs[k] = dfabs[k] + flux2;
-                    flux2 = tau2_[k] * flux2;
-                    dfabs[k] = dfabs[k] - flux2;
-                }
-                const double fsfcd = flux1 + flux2;
-                flux1 = flux1 * albsfc;
-                const double fsfc = fsfcd - flux1;
-                for (int k = KX; k >= 1; k--) {
-                    dfabs[k] = dfabs[k] + flux1;
-                    flux1 = tau1[k] * flux1;
-                    dfabs[k] = dfabs[k] - flux1;
-                    flux1 = flux1 + tau3[k];
-                }
-                ftop = ftop - flux1;
-                G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
-#pragma unroll
-                for (int k = 1; k <= KX; k++) { const double v = dfabs[k] * rps * lc.grdscp[k - 1]; G3(a.L.tt_rsw, k) = v; RSW(k) = v; }   // physics.f90:160-162
-                // longwave transmissivities :190-233 -> persistent tau2(ix,il,kx,4)
+    // ---------------- shortwave (every nstrad-th step), shortwave_radiation.f90 ----------------
+    if (csw) {
+        const double albcl = F32(0.43), albcls = 0.50;
+        const double absdry = F32(0.033), absaer = F32(0.033), abswv1 = F32(0.022), abswv2 = 15.000, abscl1 = F32(0.015), abscl2 = F32(0.15);
+        const double ablwin = F32(0.3), ablco2 = 6.0, ablwv1 = F32(0.7), ablwv2 = 50.0, ablcl1 = 12.0, ablcl2 = F32(0.6);
+        const double epslw = F32(0.05);
+        if (k == 1) {
+            // clouds  shortwave_radiation.f90:332-410
+            const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
+            const double clsmax = F32(0.60), clsminl = F32(0.15), gse_s0 = 0.25, gse_s1 = F32(0.40);
+            const double gse = (se[KX - 1] - se[KX]) / (phig[KX - 1] - phig[KX]);   // physics.f90:147
+            const double rrcl = 1. / (rhcl2 - rhcl1);
+            if (rh[nl1] > rhcl1) { cloudc = rh[nl1] - rhcl1; icltop = nl1; }
+            else { cloudc = 0.0; icltop = nlp; }
+            for (int kk = 3; kk <= KX - 2; kk++) {
+                const double drh = rh[kk] - rhcl1;
+                if (drh > cloudc && qg[kk] > qacl) { cloudc = drh; icltop = kk; }
+            }
+            {
+                const double pr1 = dmin(pmaxcl, F32(86.4) * (precnv + precls));
+                const double cc = dmin(1.0, cloudc * rrcl);
+                cloudc = dmin(1.0, wpcl * sqrt(pr1) + cc * cc);
+                icltop = min(iptop, icltop);
+            }
+            qcloud = qg[nl1];
+            {
+                const double clfact = F32(1.2), rgse = 1.0 / (gse_s1 - gse_s0);
+                const double fstab = dmax(0.0, dmin(1.0, rgse * (gse - gse_s0)));
+                clstr = fstab * dmax(clsmax - clfact * cloudc, 0.0);
+                const double clstrl = dmax(clstr, clsminl) * rh[KX];
+                const double fm = SURF(SF_FMASK);
+                clstr = clstr + fm * (clstrl - clstr);
+            }
+            ib[a.L.icltop + col] = icltop;
+            G2(a.L.qcloud) = qcloud; G2(a.L.cloudc) = cloudc; G2(a.L.clstr) = clstr;
+            SC(S_CLOUDC) = cloudc; SC(S_QCLOUD) = qcloud; SI(I_ICLTOP) = icltop;
+        }
+        named_sync(BAR_LEV, LEV_THREADS);
+        // ---- phase C (wide): every transmissivity of level k (shortwave_radiation.f90:130-150, 190-233)
+        {
+            const double cloudc_ = SC(S_CLOUDC), qcloud_ = SC(S_QCLOUD);
+            const int icltop_ = SI(I_ICLTOP);
+            const double zenit = SURF(SF_ZENIT);
+            const double psaz = psg * zenit;
+            double acloud = cloudc_ * dmin(abscl1 * qcloud_, abscl2);
+            double t1;
+            if (k == 1) {
+                t1 = exp(-psaz * lc.dhs[0] * absdry);
+            } else if (k <= nl1) {
+                const double abs1 = absdry + absaer * (lc.fsg[k - 1] * lc.fsg[k - 1]);
+                if (k >= icltop_) t1 = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qgk + acloud));
+                else t1 = exp(-psaz * lc.dhs[k - 1] * (abs1 + abswv1 * qgk));
+            } else {
+                const double abs1 = absdry + absaer * (lc.fsg[KX - 1] * lc.fsg[KX - 1]);
+                t1 = exp(-psaz * lc.dhs[KX - 1] * (abs1 + abswv1 * qgk));
+            }
+            TAU1(k) = t1;
+            TAU2S(k) = (k == 1) ? 0.0 : exp(-psaz * lc.dhs[k - 1] * abswv2 * qgk);
+            // longwave transmissivities :190-233 -> persistent tau2(ix,il,kx,4)
+            if (k == 1) {
                 TAU2W(1, 1, exp(-psg * lc.dhs[0] * ablwin));
                 TAU2W(1, 2, exp(-psg * lc.dhs[0] * ablco2));
                 TAU2W(1, 3, 1.0);
                 TAU2W(1, 4, 1.0);
-                for (int k = 2; k <= KX; k += KX - 2) {
-                    TAU2W(k, 1, exp(-psg * lc.dhs[k - 1] * ablwin));
-                    TAU2W(k, 2, exp(-psg * lc.dhs[k - 1] * ablco2));
-                    TAU2W(k, 3, exp(-psg * lc.dhs[k - 1] * ablwv1 * qg[k]));
-                    TAU2W(k, 4, exp(-psg * lc.dhs[k - 1] * ablwv2 * qg[k]));
-                }
-                acloud = cloudc * ablcl2;
-                for (int k = 3; k <= nl1; k++) {
-                    const double deltap = psg * lc.dhs[k - 1];
-                    double acloud1;
-                    if (k < icltop) acloud1 = acloud;
-                    else acloud1 = ablcl1 * cloudc;
-                    TAU2W(k, 1, exp(-deltap * (ablwin + acloud1)));
-                    TAU2W(k, 2, exp(-deltap * ablco2));
-                    TAU2W(k, 3, exp(-deltap * dmax(ablwv1 * qg[k], acloud)));
-                    TAU2W(k, 4, exp(-deltap * dmax(ablwv2 * qg[k], acloud)));
-                }
-                const double eps1 = epslw / (lc.dhs[0] + lc.dhs[1]);
-                mb[a.L.stratc + col] = STRATC(0) = stratz * psg;
-                mb[a.L.stratc + N + col] = STRATC(1) = eps1 * psg;
+            } else if (k == 2 || k == KX) {
+                TAU2W(k, 1, exp(-psg * lc.dhs[k - 1] * ablwin));
+                TAU2W(k, 2, exp(-psg * lc.dhs[k - 1] * ablco2));
+                TAU2W(k, 3, exp(-psg * lc.dhs[k - 1] * ablwv1 * qgk));
+                TAU2W(k, 4, exp(-psg * lc.dhs[k - 1] * ablwv2 * qgk));
+            } else {
+                acloud = cloudc_ * ablcl2;
+                const double deltap = psg * lc.dhs[k - 1];
+                double acloud1;
+                if (k < icltop_) acloud1 = acloud;
+                else acloud1 = ablcl1 * cloudc_;
+                TAU2W(k, 1, exp(-deltap * (ablwin + acloud1)));
+                TAU2W(k, 2, exp(-deltap * ablco2));
+                TAU2W(k, 3, exp(-deltap * dmax(ablwv1 * qgk, acloud)));
+                TAU2W(k, 4, exp(-deltap * dmax(ablwv2 * qgk, acloud)));
             }
         }
+        named_sync(BAR_LEV, LEV_THREADS);
+        if (k == 1) {
+            // get_shortwave_rad_fluxes  shortwave_radiation.f90:74-234: the flux sweeps
+            const double fsol = SURF(SF_FSOL), ozone = SURF(SF_OZONE), ozupp = SURF(SF_OZUPP), stratz = SURF(SF_STRATZ);
+            const double albsfc = SURF(SF_ALBSFC);
+            const double fband2 = F32(0.05), fband1 = 1.0 - fband2;
+            double tau1[KX + 1], tau2_[KX + 1], tau3[KX + 1], dfabs[KX + 1];
+#pragma unroll
+            for (int kk = 1; kk <= KX; kk++) { tau1[kk] = TAU1(kk); tau2_[kk] = TAU2S(kk); tau3[kk] = 0.0; }
+            if (icltop <= KX) tau3[icltop] = albcl * cloudc;
+            tau3[KX] = albcls * clstr;
+            double ftop = fsol;
+            double flux1 = fsol * fband1, flux2 = fsol * fband2;
+            dfabs[1] = flux1;
+            flux1 = tau1[1] * (flux1 - ozupp * psg);
+            dfabs[1] = dfabs[1] - flux1;
+            dfabs[2] = flux1;
+            flux1 = tau1[2] * (flux1 - ozone * psg);
+            dfabs[2] = dfabs[2] - flux1;
+            for (int kk = 3; kk <= KX; kk++) {
+                tau3[kk] = flux1 * tau3[kk];
+                flux1 = flux1 - tau3[kk];
+                dfabs[kk] = flux1;
+                flux1 = tau1[kk] * flux1;
+                dfabs[kk] = dfabs[kk] - flux1;
+            }
+            for (int kk = 2; kk <= KX; kk++) {
+                dfabs[kk] = dfabs[kk] + flux2;
+                flux2 = tau2_[kk] * flux2;
+                dfabs[kk] = dfabs[kk] - flux2;
+            }
+            const double fsfcd = flux1 + flux2;
+            flux1 = flux1 * albsfc;
+            const double fsfc = fsfcd - flux1;
+            for (int kk = KX; kk >= 1; kk--) {
+                dfabs[kk] = dfabs[kk] + flux1;
+                flux1 = tau1[kk] * flux1;
+                dfabs[kk] = dfabs[kk] - flux1;
+                flux1 = flux1 + tau3[kk];
+            }
+            ftop = ftop - flux1;
+            G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
+#pragma unroll
+            for (int kk = 1; kk <= KX; kk++) { const double v = dfabs[kk] * rps * lc.grdscp[kk - 1]; G3(a.L.tt_rsw, kk) = v; RSW(kk) = v; }   // physics.f90:160-162
+            const double eps1 = epslw / (lc.dhs[0] + lc.dhs[1]);
+            mb[a.L.stratc + col] = STRATC(0) = stratz * psg;
+            mb[a.L.stratc + N + col] = STRATC(1) = eps1 * psg;
+        }
+    }
+    STAMP(3);
 
-        STAMP(3);
+    // ---------------- surface_fluxes.f90:42-296: level warp 2 prepares the shared terms and the sea half ----------------
+    const double emisfc = F32(0.98), epslw = F32(0.05);
+    const double fwind0 = F32(0.95), ftemp0 = 1.0, cdl = F32(2.4e-3), cds = F32(1.0e-3), chl = F32(1.2e-3), chs = F32(0.9e-3);
+    const double vgust = 5.0, ctday = F32(1.0e-2), dtheta = 3.0, fstab = F32(0.67), clambda = 7.0, clambsn = 7.0;
+    const double esbc = emisfc * lc.sbc;
+    const double rdth = fstab / dtheta, astab = 0.5;
+    if (k == 2) {
+        const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);   // only the lowest-level wind is used
+        const double tg8 = SG(GI_T1 + KX - 1), tg7 = SG(GI_T1 + nl1 - 1), qg8 = QG(KX), phig8 = SG(GI_PHI + KX - 1);
+        const double phi0 = SURF(SF_PHIS0), fmask = SURF(SF_FMASK), tsea = SURF(SF_SST);
+        const double u0 = fwind0 * ug8, v0 = fwind0 * vg8;
+        const double gtemp0 = 1.0 - ftemp0, rcp = 1.0 / lc.cp;
+        const double dt1 = lc.wvi[7 + KX] * (tg8 - tg7);
+        double t1_1 = tg8 + dt1;
+        double t1_2 = t1_1 - phi0 * dt1 / (lc.rgas * 288.0 * lc.sigl[KX - 1]);
+        const double t2_2 = tg8 + rcp * phig8;
+        const double t2_1 = t2_2 - rcp * phi0;
+        if (tg8 > tg7) {
+            t1_1 = ftemp0 * t1_1 + gtemp0 * t2_1;
+            t1_2 = ftemp0 * t1_2 + gtemp0 * t2_2;
+        } else {
+            t1_1 = tg8;
+            t1_2 = tg8;
+        }
+        const double t0 = t1_2 + fmask * (t1_1 - t1_2);
+        const double denvvs0 = (lc.p0 * psg / (lc.rgas * t0)) * sqrt(u0 * u0 + v0 * v0 + vgust * vgust);
+        double dths;
+        if (tsea > t2_2) dths = dmin(dtheta, tsea - t2_2);
+        else dths = dmax(-dtheta, astab * (tsea - t2_2));
+        const double denvvs2 = denvvs0 * (1.0 + dths * rdth);
+        const double q1_2 = qg8;
+        const double cdsdv = cds * denvvs2;
+        const double ustr2 = -cdsdv * ug8, vstr2 = -cdsdv * vg8;
+        const double shf2 = chs * lc.cp * denvvs2 * (tsea - t1_2);
+        const double qsat0_s = qsat_pt(tsea, psg);
+        const double evap2 = chs * denvvs2 * (qsat0_s - q1_2);
+        const double slru2 = esbc * ((tsea * tsea) * (tsea * tsea));
+        SC(S_T1_1) = t1_1; SC(S_T1_2) = t1_2; SC(S_T2_1) = t2_1; SC(S_DENVVS0) = denvvs0; SC(S_T0) = t0; SC(S_U0) = u0; SC(S_V0) = v0;
+        SC(S_USTR2) = ustr2; SC(S_VSTR2) = vstr2; SC(S_SHF2) = shf2; SC(S_EVAP2) = evap2; SC(S_SLRU2) = slru2;
+        named_arrive(BAR_SEA, 64);
+    }
+    if (k == 1) {
         // ------------------- downward longwave  longwave_radiation.f90:16-117 -------------------
-        const double emisfc = F32(0.98), epslw = F32(0.05);
         double st4a1[KX + 1], st4a2[KX + 1], tt_rlw[KX + 1], flux[5];
         double slrd;
+#pragma unroll
+        for (int kk = 1; kk <= KX; kk++) { st4a1[kk] = LWS(0, kk); st4a2[kk] = LWS(1, kk); }
         {
-            const int nl1 = KX - 1;
-#pragma unroll
-            for (int k = 1; k <= nl1; k++) st4a1[k] = tg[k] + wvi2[k] * (tg[k + 1] - tg[k]);
-            st4a2[1] = 0.75 * tg[1] + 0.25 * st4a1[1];
-            st4a2[2] = 0.50 * tg[2] + 0.25 * (st4a1[1] + st4a1[2]);
-            const double anis = 1.0;
-#pragma unroll
-            for (int k = 3; k <= nl1; k++) st4a2[k] = 0.5 * anis * dmax(st4a1[k] - st4a1[k - 1], 0.0);
-            st4a2[KX] = anis * dmax(tg[KX] - st4a1[nl1], 0.0);
-#pragma unroll
-            for (int k = 1; k <= 2; k++) {
-                const double x = st4a2[k];
-                st4a1[k] = lc.sbc * ((x * x) * (x * x));
-                st4a2[k] = 0.0;
-            }
-#pragma unroll
-            for (int k = 3; k <= KX; k++) {
-                const double x = tg[k];
-                const double st3a = lc.sbc * ((x * x) * x);
-                st4a1[k] = st3a * tg[k];
-                st4a2[k] = 4.0 * st3a * st4a2[k];
-            }
             double fsfcd = 0.0;
 #pragma unroll
             for (int k = 1; k <= KX; k++) tt_rlw[k] = 0.0;
@@ -633,8 +694,6 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             // cache; the unrolled 4 x 7 sweep was a third of this role's instruction stream).  For a fixed
             // level the bands are visited in order and for a fixed band the levels in order, i.e. every
             // tt_rlw(k) and flux(jb) sees the reference's sequence of operations (longwave_radiation.f90:93-105).
-#pragma unroll
-            for (int k = 1; k <= KX; k++) { LWS(0, k) = st4a1[k]; LWS(1, k) = st4a2[k]; }
             {
                 const int nt1 = (int)round(tg[1]) - 100;   // nint(T) -> row of fband(100:400,:)
                 for (int jb = 1; jb <= 2; jb++) {
@@ -676,35 +735,19 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             G2(a.L.slrd) = slrd;
         }
 
+
         STAMP(4);
-        // ------------------------- surface_fluxes.f90:42-296 (lfluxland = .true.) -------------------------
+        // ------------------------- surface_fluxes.f90:42-296 (lfluxland = .true.): land half and the blend -------------------------
+        named_sync(BAR_SEA, 64);
         double ts, shf3, evap3, ustr3, vstr3, slru3;
         {
-            const double fwind0 = F32(0.95), ftemp0 = 1.0, cdl = F32(2.4e-3), cds = F32(1.0e-3), chl = F32(1.2e-3), chs = F32(0.9e-3);
-            const double vgust = 5.0, ctday = F32(1.0e-2), dtheta = 3.0, fstab = F32(0.67), clambda = 7.0, clambsn = 7.0;
-            const double esbc = emisfc * lc.sbc;
-            const int nl1 = KX - 1;
-            const double phi0 = SURF(SF_PHIS0), fmask = SURF(SF_FMASK), tsea = SURF(SF_SST), stl_am = SURF(SF_STL);
+            const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);
+            const double fmask = SURF(SF_FMASK), tsea = SURF(SF_SST), stl_am = SURF(SF_STL);
             const double soilw_am = SURF(SF_SOILW), alb_l = SURF(SF_ALBL), alb_s = SURF(SF_ALBS), snowc = SURF(SF_SNOWC), forog = SURF(SF_FOROG);
             const double ssrd = SURF(SF_SSRD);
-            const double u0 = fwind0 * ug8, v0 = fwind0 * vg8;
-            const double gtemp0 = 1.0 - ftemp0, rcp = 1.0 / lc.cp;
-            const double dt1 = wvi2[KX] * (tg[KX] - tg[nl1]);
-            double t1_1 = tg[KX] + dt1;
-            double t1_2 = t1_1 - phi0 * dt1 / (lc.rgas * 288.0 * lc.sigl[KX - 1]);
-            const double t2_2 = tg[KX] + rcp * phig[KX];
-            const double t2_1 = t2_2 - rcp * phi0;
-            if (tg[KX] > tg[nl1]) {
-                t1_1 = ftemp0 * t1_1 + gtemp0 * t2_1;
-                t1_2 = ftemp0 * t1_2 + gtemp0 * t2_2;
-            } else {
-                t1_1 = tg[KX];
-                t1_2 = tg[KX];
-            }
-            double t0 = t1_2 + fmask * (t1_1 - t1_2);
-            const double denvvs0 = (lc.p0 * psg / (lc.rgas * t0)) * sqrt(u0 * u0 + v0 * v0 + vgust * vgust);
+            const double t1_1 = SC(S_T1_1), t1_2 = SC(S_T1_2), t2_1 = SC(S_T2_1), denvvs0 = SC(S_DENVVS0);
+            const double u0 = SC(S_U0), v0 = SC(S_V0);
             double tskin = stl_am + ctday * sqrt(coa_j) * ssrd * (1.0 - alb_l) * psg;
-            const double rdth = fstab / dtheta, astab = 0.5;
             double dthl;
             if (tskin > t2_1) dthl = dmin(dtheta, tskin - t2_1);
             else dthl = dmax(-dtheta, astab * (tskin - t2_1));
@@ -734,17 +777,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
                 slru1 = slru1 + dslr * dtskin;
                 hfluxn1 = clamb * (tskin - stl_am);
             }
-            double dths;
-            if (tsea > t2_2) dths = dmin(dtheta, tsea - t2_2);
-            else dths = dmax(-dtheta, astab * (tsea - t2_2));
-            const double denvvs2 = denvvs0 * (1.0 + dths * rdth);
-            const double q1_2 = qg[KX];
-            const double cdsdv = cds * denvvs2;
-            const double ustr2 = -cdsdv * ug8, vstr2 = -cdsdv * vg8;
-            const double shf2 = chs * lc.cp * denvvs2 * (tsea - t1_2);
-            const double qsat0_s = qsat_pt(tsea, psg);
-            const double evap2 = chs * denvvs2 * (qsat0_s - q1_2);
-            const double slru2 = esbc * ((tsea * tsea) * (tsea * tsea));
+            const double ustr2 = SC(S_USTR2), vstr2 = SC(S_VSTR2), shf2 = SC(S_SHF2), evap2 = SC(S_EVAP2), slru2 = SC(S_SLRU2);
             const double hfluxn2 = ssrd * (1.0 - alb_s) + slrd - slru2 + shf2 + lc.alhc * evap2;
             ustr3 = ustr2 + fmask * (ustr1 - ustr2);
             vstr3 = vstr2 + fmask * (vstr1 - vstr2);
@@ -753,7 +786,7 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             slru3 = slru2 + fmask * (slru1 - slru2);
             ts = tsea + fmask * (stl_am - tsea);
             tskin = tsea + fmask * (tskin - tsea);
-            t0 = t1_2 + fmask * (t1_1 - t1_2);
+            const double t0 = t1_2 + fmask * (t1_1 - t1_2);
             mb[a.L.ustr + col] = ustr1; mb[a.L.ustr + N + col] = ustr2; mb[a.L.ustr + 2 * N + col] = ustr3;
             mb[a.L.vstr + col] = vstr1; mb[a.L.vstr + N + col] = vstr2; mb[a.L.vstr + 2 * N + col] = vstr3;
             mb[a.L.shf + col] = shf1; mb[a.L.shf + N + col] = shf2; mb[a.L.shf + 2 * N + col] = shf3;
@@ -762,7 +795,6 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             mb[a.L.hfluxn + col] = hfluxn1; mb[a.L.hfluxn + N + col] = hfluxn2;
             G2(a.L.ts) = ts; G2(a.L.tskin) = tskin; G2(a.L.u0) = u0; G2(a.L.v0) = v0; G2(a.L.t0) = t0;
         }
-
         STAMP(5);
         // ------------------- upward longwave  longwave_radiation.f90:120-194 -------------------
         {
@@ -821,44 +853,47 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
             for (int k = 1; k <= KX; k++) tt_rlw[k] = tt_rlw[k] * rps * lc.grdscp[k - 1];   // physics.f90:182-186, added in the closing stage
         }
 
-        // ------------------- closing stage: physics.f90:137-138, 182-186, 197-205, 208-222 -------------------
-        STAMP(6);
-        named_sync(BAR_FINAL, 96);     // dynamics tendencies and vertical-diffusion fluxes are in shared memory
-        {
-            const double ut8 = 0.0 + ustr3 * rps * lc.grdsig[KX - 1];
-            const double vt8 = 0.0 + vstr3 * rps * lc.grdsig[KX - 1];
+
+        // hand the column-serial results to the level warps (physics.f90:197-205)
+        SC(S_UT8) = 0.0 + ustr3 * rps * lc.grdsig[KX - 1];
+        SC(S_VT8) = 0.0 + vstr3 * rps * lc.grdsig[KX - 1];
+        SC(S_SHFT) = shf3 * rps * lc.grdscp[KX - 1];
+        SC(S_EVAPT) = evap3 * rps * lc.grdsig[KX - 1];
 #pragma unroll
-            for (int k = 1; k <= KX; k++) {
-                const double ut_dyn = DYN(0, k), vt_dyn = DYN(1, k), tt_dyn = DYN(2, k), qt_dyn = DYN(3, k);
-                double ut = ut_dyn, vt = vt_dyn, tt = tt_dyn, qt = qt_dyn;
-                tt = tt + CNV(0, k) + CNV(1, k);
-                qt = qt + CNV(2, k) + CNV(3, k);
-                tt = tt + RSW(k) + tt_rlw[k];
-                double ttenvd = VD(0, k), qtenvd = VD(1, k);
-                if (k == KX) {
-                    ttenvd = ttenvd + shf3 * rps * lc.grdscp[KX - 1];
-                    qtenvd = qtenvd + evap3 * rps * lc.grdsig[KX - 1];
-                    ut = ut + ut8; vt = vt + vt8;
-                } else {
-                    ut = ut + 0.0; vt = vt + 0.0;
-                }
-                tt = tt + ttenvd; qt = qt + qtenvd;
-                if (a.sppt_on) {
-                    double p = SG(GI_SPPT + k - 1);
-                    p = dmin(1.0, fabs(p)) * copysign(1.0, p);   // sppt.f90:98
-                    const double f = (1 + p * 1.0);
-                    ut = f * (ut - ut_dyn) + ut_dyn;
-                    vt = f * (vt - vt_dyn) + vt_dyn;
-                    tt = f * (tt - tt_dyn) + tt_dyn;
-                    qt = f * (qt - qt_dyn) + qt_dyn;
-                }
-                const int f0 = GO_PER * (k - 1);
-                GOUT(f0 + 0) = ut; GOUT(f0 + 1) = vt; GOUT(f0 + 5) = tt; GOUT(f0 + 8) = qt;
-            }
-        }
-        STAMP(7);
-        if (lane == 0) trace_end(a.trace, 1);
+        for (int kk = 1; kk <= KX; kk++) LWS(2, kk) = tt_rlw[kk];
+        STAMP(6);
     }
+    // ---------------- closing stage (wide): physics.f90:137-138, 182-186, 197-205, 208-222 for level k ----------------
+    named_sync(BAR_END, 9 * 32);     // serial results of level warp 1 and the vertical-diffusion fluxes are in shared memory
+    {
+        const double ut_dyn = DYN(0, k), vt_dyn = DYN(1, k), tt_dyn = DYN(2, k), qt_dyn = DYN(3, k);
+        double ut = ut_dyn, vt = vt_dyn, tt = tt_dyn, qt = qt_dyn;
+        tt = tt + DFSE(k) + DTLSC(k);
+        qt = qt + DFQA(k) + DQLSC(k);
+        tt = tt + RSW(k) + LWS(2, k);
+        double ttenvd = VD(0, k), qtenvd = VD(1, k);
+        if (k == KX) {
+            ttenvd = ttenvd + SC(S_SHFT);
+            qtenvd = qtenvd + SC(S_EVAPT);
+            ut = ut + SC(S_UT8); vt = vt + SC(S_VT8);
+        } else {
+            ut = ut + 0.0; vt = vt + 0.0;
+        }
+        tt = tt + ttenvd; qt = qt + qtenvd;
+        if (a.sppt_on) {
+            double p = SG(GI_SPPT + k - 1);
+            p = dmin(1.0, fabs(p)) * copysign(1.0, p);   // sppt.f90:98
+            const double f = (1 + p * 1.0);
+            ut = f * (ut - ut_dyn) + ut_dyn;
+            vt = f * (vt - vt_dyn) + vt_dyn;
+            tt = f * (tt - tt_dyn) + tt_dyn;
+            qt = f * (qt - qt_dyn) + qt_dyn;
+        }
+        const int f0 = GO_PER * (k - 1);
+        GOUT(f0 + 0) = ut; GOUT(f0 + 1) = vt; GOUT(f0 + 5) = tt; GOUT(f0 + 8) = qt;
+    }
+    STAMP(7);
+    if (lane == 0) trace_end(a.trace, 1);
 #undef SROW
 #undef SG
 #undef SURF
@@ -866,10 +901,20 @@ __global__ void __launch_bounds__(COL_THREADS) k_grid_columns(ColumnArgs a) {
 #undef STRATC
 #undef RSW
 #undef DYN
-#undef PREP
-#undef CNV
+#undef SE
+#undef QSAT
+#undef RH
+#undef QG
+#undef DFSE
+#undef DFQA
+#undef DTLSC
+#undef DQLSC
 #undef VD
 #undef LWS
+#undef TAU1
+#undef TAU2S
+#undef SC
+#undef SI
 #undef TAU2W
 #undef STAMP
 }
