@@ -98,9 +98,10 @@ void upload_level_consts(speedy_ctx* ctx);      // consts in dynamics.cu
 
 // transforms.cu ----------------------------------------------------------------------
 // mode: 0 full spec->grid, 1 legendre_inv only (out = (2mx,il)), 2 fourier_inv only (in = (2mx,il))
+struct CloseArgs;   // close_step.cuh
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
-                         int nmembers, int mode);
+                         int nmembers, int mode, const CloseArgs* close = nullptr);
 // mode: 0 full grid->spec, 1 fourier_dir only (out = (2mx,il)), 2 legendre_dir only (in = (2mx,il))
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,

@@ -13,6 +13,7 @@
 #include "spectral_ops.cuh"
 #include "calendar.h"
 #include "tma.cuh"
+#include "close_step.cuh"
 
 namespace spd {
 
@@ -307,53 +308,13 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
         if (c == 0) { part[k] = s1; part[KX + k] = s2; }
         if (valid && rr == 0) a.partial[(size_t)gridDim.y * gridDim.x * 2 * KX + (size_t)blockIdx.y * KX + k] = t2n.re;
     }
-    // ---- the last block to arrive closes the step
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (c == 0 && k == 0) s_last = (atomicAdd(&a.clk->ticket, 1) == (int)(gridDim.x * gridDim.y) - 1);
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const int nb = gridDim.x, ne = gridDim.y;
-    // warp k reduces the (member, level) pairs k, k+8, ...: lanes take blocks in a fixed order, then a fixed shuffle tree
-    for (int idx = k; idx < ne * KX; idx += KX) {
-        const int e = idx / KX, kk = idx - e * KX;
-        double d1 = 0.0, d2 = 0.0;
-        for (int b = c; b < nb; b += SC) {
-            const double* part = a.partial + ((size_t)e * nb + b) * (2 * KX);
-            d1 += __ldcg(part + kk); d2 += __ldcg(part + KX + kk);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
-        if (c == 0) {
-            const double d3 = (double)sqrtf(0.5f) * __ldcg(a.partial + (size_t)ne * nb * 2 * KX + (size_t)e * KX + kk);
-            if (e == 0) { a.clk->diag[kk] = d1; a.clk->diag[KX + kk] = d2; a.clk->diag[2 * KX + kk] = d3; }
-            const bool bad = !(d1 <= 500.0) || !(d2 <= 500.0) || !(d3 >= 180.0) || !(d3 <= 320.0);
-            if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
-        }
-    }
-    __syncthreads();
-    if (c == 0 && k == 0) {
-        a.clk->ticket = 0;
-        cal_advance(*a.clk);          // speedy.f90:44-47
-        a.clk->slab_pending = 1;      // couple_sea_land of this step rides in the next column kernel
-        if (tv.trace) {               // close the step's timeline: durations [8..11], gaps before each kernel [12..15], steps [16]
-            unsigned long long* tr = tv.trace;
-            tr[4 + 3] = gtimer();
-            unsigned long long prev = tr[17];
-            for (int sl = 0; sl < 4; sl++) {
-                const unsigned long long t0 = tr[sl], t1 = tr[4 + sl];
-                tr[8 + sl] += t1 - t0;
-                if (prev && t0 > prev) tr[12 + sl] += t0 - prev;
-                prev = t1;
-                tr[sl] = ~0ull; tr[4 + sl] = 0ull;
-            }
-            tr[17] = prev;
-            tr[16] += 1;
-        }
-    }
+    // ---- the step is closed (final diagnostics reduction, range guard, calendar) by an extra CTA of the next
+    // step's spec->grid kernel, or by k_close_step when no step follows: nothing here waits for the other blocks
+    if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && k == 0) a.clk->close_pending = 1;
+    if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 3); }
 }
+
+__global__ void k_close_step(CloseArgs cl) { close_step_cta(cl, threadIdx.x); }
 
 // check_diagnostics (diagnostics.f90:16-75): one block per level, tree reduction over (m,n)
 __global__ void k_diagnostics(SpecArgs a) {
@@ -518,7 +479,15 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     const size_t smem = spec_step_smem(ctx->d.mx, ctx->d.nx);
     static bool attr_set = false;
     if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_spec_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
-    CUDA_CHECK(launch_pdl(k_spec_step, grid, dim3(SC, KX), smem, ctx->stream, a));
+    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step, grid, dim3(SC, KX), smem, ctx->stream, a));
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_close_step(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + SC - 1) / SC), ctx->nmembers, ctx->dv.trace};
+    k_close_step<<<1, 256, 0, ctx->stream>>>(cl);
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -4,6 +4,7 @@
 #include "../../include/speedy_b200.h"
 #include "model.h"
 #include "calendar.h"
+#include "close_step.cuh"
 #include "abi_util.h"
 #include <cmath>
 #include <cstring>
@@ -199,10 +200,12 @@ static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
                         M.mem.p + M.L.gin + first * NG, M.L.stride, ctx->nmembers, 0);
 }
 // the inverse transforms of one time step (tendencies.f90:89-123 + physics.f90:95-104), compact list
-static void xform_step(speedy_ctx* ctx, int j2) {
+// with_close: an extra CTA of the kernel closes the previous main-loop step if one is pending (close_step.cuh)
+static void xform_step(speedy_ctx* ctx, int j2, bool with_close = false) {
     Model& M = *ctx->model;
+    const CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + 31) / 32), ctx->nmembers, nullptr};
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_step.p + (size_t)(j2 - 1) * M.nstep_fields, M.nstep_fields,
-                        M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0);
+                        M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0, with_close ? &cl : nullptr);
 }
 static void xform_output(speedy_ctx* ctx) {
     Model& M = *ctx->model;
@@ -238,15 +241,18 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
 static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
+    const bool tracing = ctx->dv.trace != nullptr;      // trace mode closes each step with the stand-alone kernel (exact timeline)
     if (ctx->sppt_on) launch_sppt_update(ctx);
-    xform_step(ctx, 2);
+    xform_step(ctx, 2, !tracing);
     launch_grid_columns(ctx, 0, -1, 1);
     xform_direct(ctx, true);
     launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1);
+    if (tracing) launch_close_step(ctx);
 }
 // the coupler call of the last step (speedy.f90:53) when no further step follows in this call
 static void flush_pending_slab(speedy_ctx* ctx) {
     Model& M = *ctx->model;
+    launch_close_step(ctx);      // diagnostics + calendar of the last step (no-op if already closed)
     launch_slab(ctx, 0);
     CUDA_CHECK(cudaMemsetAsync(&M.clock.p->slab_pending, 0, sizeof(int), ctx->stream));
 }
@@ -773,7 +779,7 @@ int speedy_time_kernels(speedy_ctx* ctx, int nsteps, int flush_l2, double* ms) {
             if (flush_l2) CUDA_CHECK(cudaMemsetAsync(flush.p, s & 1, flush.n * sizeof(double), ctx->stream));
             CUDA_CHECK(cudaEventRecord(ev[i][0], ctx->stream));
             switch (i) {
-                case 0: xform_step(ctx, 2); break;
+                case 0: xform_step(ctx, 2, true); break;
                 case 1: launch_grid_columns(ctx, 0, -1, 1); break;
                 case 2: xform_direct(ctx, true); break;
                 case 3: launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1); break;

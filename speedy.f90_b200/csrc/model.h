@@ -25,7 +25,7 @@ struct DevClock {
     int diag_fail;       // sticky: check_diagnostics range violation (diagnostics.f90:60-70); holds the failing step
     int nssta;           // records in the resident ssta window
     int slab_pending;    // the coupler call of the last completed step has not run yet (it rides in the next column kernel)
-    int ticket;          // arrival counter of the spectral-step blocks (last block closes the step)
+    int close_pending;   // the step's closing (diagnostics reduction + calendar) has not run yet: it rides in the next spec->grid kernel
     double tmonth, tyear;
     double diag[24];     // (kx,3) of the last check_diagnostics
 };
@@ -103,6 +103,7 @@ struct Model {
 void launch_geopotential(speedy_ctx* ctx, int which);   // which: bit0 module phi, bit1 phi_next (K1's physics input)
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged = 0);   // mode 0 dyn+phys, 1 physics only on resident tendencies
 void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step = 0);
+void launch_close_step(speedy_ctx* ctx);   // stand-alone closing of a pending step
 void launch_diagnostics(speedy_ctx* ctx, int level);
 void launch_slab(speedy_ctx* ctx, int day0);
 void launch_daily_forcing(speedy_ctx* ctx, int force);

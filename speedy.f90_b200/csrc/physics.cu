@@ -1122,7 +1122,7 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     static bool attr_set = false;
     if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM)); attr_set = true; }
     dim3 grid(N / TC, ctx->nmembers);
-    CUDA_CHECK(launch_pdl(k_grid_columns, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
+    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -20,6 +20,7 @@
 #include "ctx.h"
 #include "spectral_ops.cuh"
 #include "tma.cuh"
+#include "close_step.cuh"
 
 namespace spd {
 
@@ -276,8 +277,14 @@ struct SCfg : TCfg<TRUNC> {
 template <int TRUNC>
 __global__ void __maxnreg__(96)    // <= 96 registers: a CTA of the column kernel must fit beside it (PDL overlap)
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
-             double* __restrict__ out_base, long long out_ms, DevTables tv) {
+             double* __restrict__ out_base, long long out_ms, DevTables tv, CloseArgs cl) {
     using C = SCfg<TRUNC>;
+    if (blockIdx.x == (unsigned)(nchunk * C::LG)) {     // the extra CTA: closes the previous step, off the critical path
+        pdl_wait();
+        pdl_trigger();
+        if (blockIdx.y == 0) close_step_cta(cl, threadIdx.x);     // one closer for the whole member batch
+        return;
+    }
     extern __shared__ __align__(16) double smem[];
     double* sP = smem;
     double* sA = sP + C::PT;                 // staging: source field(s) of the current transform
@@ -505,8 +512,8 @@ void setup_transform_kernels() {
 }
 
 // fields per persistent CTA: spread (slices x members x chunks) over the SMs, one CTA each
-static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch) {
-    int nchunk = ctx->num_sms / (slices * nmembers);
+static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch, int reserved_sms = 0) {
+    int nchunk = (ctx->num_sms - reserved_sms) / (slices * nmembers);
     if (nchunk < 1) nchunk = 1;
     if (nchunk > nbatch) nchunk = nbatch;
     return nchunk;
@@ -514,11 +521,12 @@ static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch) 
 
 template <int TRUNC>
 static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                              double* d_out, long long out_ms, int nmembers) {
+                              double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
     using C = SCfg<TRUNC>;
-    const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch);
-    dim3 grid(nchunk * C::LG, nmembers);
-    CUDA_CHECK(launch_pdl(k_s2g_stream<TRUNC>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv));
+    // one SM is left to the closing CTA when a step is to be closed
+    const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch, cl.clk ? 1 : 0);
+    dim3 grid(nchunk * C::LG + (cl.clk ? 1 : 0), nmembers);
+    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
 }
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
@@ -526,7 +534,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     using C = SCfg<TRUNC>;
     const int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);
     dim3 grid(nchunk * C::CG, nmembers);
-    CUDA_CHECK(launch_pdl(k_g2s_stream<TRUNC>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
 }
 
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
@@ -534,11 +542,12 @@ int polyd_groups(int trunc) { return trunc == 30 ? SCfg<30>::CG : SCfg<47>::CG; 
 int polyd_mg(int trunc) { return trunc == 30 ? SCfg<30>::MG : SCfg<47>::MG; }
 
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                         double* d_out, long long out_ms, int nmembers, int mode) {
+                         double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close) {
     if (nbatch <= 0) return;
     if (mode == 0) {
-        if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);
-        else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);
+        const CloseArgs cl = close ? *close : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
+        if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
+        else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
     } else if (ctx->d.trunc == 30) {
         dim3 grid(nbatch * TCfg<30>::LG, nmembers);
         k_spec_to_grid<30><<<grid, TCfg<30>::K1_THREADS, TCfg<30>::K1_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode);
