@@ -740,6 +740,8 @@ int speedy_trace_read(speedy_ctx* ctx, double* out9) {
         CUDA_CHECK(cudaMemcpy(st, ctx->trace.p + 32, sizeof(st), cudaMemcpyDeviceToHost));
         fprintf(stderr, "column stamps (us):");
         for (int i = 0; i < 13; i++) fprintf(stderr, " [%d] %.2f", i, 1e-3 * (double)st[i] / n);
+        fprintf(stderr, "\nK1 stamps (us) [wait,input,legendre,mma] per field:");
+        for (int i = 16; i < 24; i++) fprintf(stderr, " %.2f", 1e-3 * (double)st[i] / n);
         fprintf(stderr, "\n");
     }
     API_END

@@ -256,7 +256,8 @@ struct SCfg : TCfg<TRUNC> {
     // K1: latitude groups sized so that the P tile + staging fit in 227 KB
     static constexpr int LG = (TRUNC == 30) ? 3 : 9, JG = B::IY / LG, NR = 2 * JG;
     static constexpr int XS = padmod16(NR, 4);
-    static constexpr int PT = JG * B::NX * B::MX;                 // P tile, doubles
+    static constexpr int PS = B::NX * B::MX + 8;                  // P tile row (one latitude) padded by 64 B: the 4 latitudes a warp reads fall in alternating bank halves
+    static constexpr int PT = JG * PS;                            // P tile, doubles
     static constexpr int MP = (B::MX + 31) / 32 * 32;             // m padded to whole warps
     static constexpr int K1_THREADS = B::IX / 8 * 32;
     static constexpr size_t K1_SMEM = sizeof(double) * (PT + 3 * B::NSPEC2 + B::KP * XS) + 2 * sizeof(uint64_t);
@@ -269,8 +270,8 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int K2_THREADS = 32 * (MT * NT < 18 ? MT * NT : 18);
     static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
     static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + 2 * RG * ES + 2 + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
-    static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG * MP <= K1_THREADS, "K1 tiling");
-    static_assert(B::KP % RG == 0 && (PT * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
+    static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && JG * MP <= K1_THREADS, "K1 tiling");
+    static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && (B::NX * B::MX * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
     static_assert(K1_SMEM <= 232448 && K2_SMEM <= 232448, "shared memory budget");
 };
 
@@ -299,8 +300,10 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     const double* mbase = in_base + (size_t)e * in_ms;
     const int j0 = grp * C::JG;
     auto row_lat = [&](int r) { return (r < C::JG) ? (j0 + r) : (C::IL - 1 - (j0 + (r - C::JG))); };
+    __shared__ XDesc sDesc[104];             // descriptors of this CTA's fields (constant data: fetched in the prologue)
+    for (int t = tid; t < f1 - f0 && t < 104; t += nthr) sDesc[t] = desc[f0 + t];
     auto issue = [&](int f) {                // one thread: bulk copies of field f's source(s)
-        const XDesc d = desc[f];
+        const XDesc d = (f - f0 < 104) ? sDesc[f - f0] : desc[f];
         const uint32_t bytes = C::NSPEC2 * sizeof(double);
         const bool two = d.op == 1 || d.op == 2;
         mbar_expect_tx(&bars[1], two ? 2 * bytes : bytes);
@@ -310,10 +313,8 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     // prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], C::PT * sizeof(double));
-        bulk_g2s(sP, tv.poly + (size_t)j0 * C::NX * C::MX, C::PT * sizeof(double), &bars[0]);
-    }
+    if (tid == 0) mbar_expect_tx(&bars[0], C::JG * C::NX * C::MX * sizeof(double));
+    if (tid < C::JG) bulk_g2s(sP + tid * C::PS, tv.poly + (size_t)(j0 + tid) * C::NX * C::MX, C::NX * C::MX * sizeof(double), &bars[0]);
     // this warp's A fragments of the dense backward Fourier operator stay in registers for every field
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     double a[C::KP / 4];
@@ -323,24 +324,30 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         for (int ks = 0; ks < C::KP / 4; ks++) a[ks] = A[4 * ks];
     }
     for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
+    // latitude factors of the epilogue (fourier.f90:47-51, tendencies.f90:103) for this thread's output rows
+    double cg[C::NR / 4], cf[C::NR / 4];
+#pragma unroll
+    for (int nt = 0; nt < C::NR / 8; nt++) {
+        const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
+        cg[2 * nt] = tv.cosgr[ja]; cg[2 * nt + 1] = tv.cosgr[jb];
+        cf[2 * nt] = tv.coriol[ja]; cf[2 * nt + 1] = tv.coriol[jb];
+    }
     pdl_wait();                                        // the spectral fields of the previous kernel are complete
     pdl_trigger();
+    const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
+#define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 10 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)
     if (tid == 0 && f0 < f1) issue(f0);
-    const int jl0 = tid / C::MP, m0 = tid - jl0 * C::MP;
-    const bool leg = jl0 < C::JG && m0 < C::MX;
+    // Legendre work items: a warp takes 4 latitude pairs x 8 zonal wavenumbers, so that the spectral
+    // coefficients it reads are one 128-byte broadcast and the P values 2 conflict-free wavefronts
+    const int jl0 = 4 * (w % (C::JG / 4)) + (lane >> 3), m0 = 8 * (w / (C::JG / 4)) + (lane & 7);
+    const bool leg = w < C::JG * C::MP / 32 && m0 < C::MX;
+    __syncthreads();                                   // sDesc
 
     for (int f = f0; f < f1; f++) {
-        const XDesc dsc = desc[f];
-        // latitude factors of the epilogue (fourier.f90:47-51, tendencies.f90:103): loaded before the wait
+        const XDesc dsc = (f - f0 < 104) ? sDesc[f - f0] : desc[f];      // beyond the prefetched window: a plain (cached) load
         const bool sc = dsc.flags & 1, ad = dsc.flags & 2;
-        double fsc[C::NR / 4], fad[C::NR / 4];
-#pragma unroll
-        for (int nt = 0; nt < C::NR / 8; nt++) {
-            const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
-            fsc[2 * nt] = sc ? tv.cosgr[ja] : 1.0; fsc[2 * nt + 1] = sc ? tv.cosgr[jb] : 1.0;
-            fad[2 * nt] = ad ? tv.coriol[ja] : 0.0; fad[2 * nt + 1] = ad ? tv.coriol[jb] : 0.0;
-        }
         mbar_wait(&bars[1], (f - f0) & 1);
+        KSTAMP(4 * (f - f0) + 0);
         // ---- input stage.  Coefficients outside the triangle m+n <= trunc+1 are never read by the
         // reference (legendre.f90:38 nsh2); they are zeroed so that the sums have a fixed trip count.
         if (dsc.op == 0) {
@@ -363,10 +370,11 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         __syncthreads();                      // sIn complete, staging free
         if (tid == 0 && f + 1 < f1) issue(f + 1);
         if (f == f0) mbar_wait(&bars[0], 0);
+        KSTAMP(4 * (f - f0) + 1);
         // ---- inverse Legendre for this CTA's latitude pairs (legendre.f90:74-111): one thread per
         // (latitude pair, m); real and imaginary sums share the P values
         if (leg) {
-            const double* P = sP + (size_t)jl0 * C::NX * C::MX + m0;
+            const double* P = sP + (size_t)jl0 * C::PS + m0;
             const double2* X = reinterpret_cast<const double2*>(sIn) + m0;
             double evr = 0.0, evi = 0.0, odr = 0.0, odi = 0.0;
 #pragma unroll
@@ -378,6 +386,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             xr[C::JG + jl0] = evr + odr;  xr[C::XS + C::JG + jl0] = evi + odi;       // row il+1-j (northern)
         }
         __syncthreads();
+        KSTAMP(4 * (f - f0) + 2);
         // ---- dense backward Fourier operator on the FP64 tensor pipe:
         //   grid[i][r] = sum_c finv[i][c] * X[c][r],  M = IX, N = NR, K = KP
         double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : f) * C::IX * C::IL;
@@ -389,13 +398,15 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
 #pragma unroll
             for (int ks = 0; ks < C::KP / 4; ks++) dmma884(c0, c1, a[ks], Bf[4 * ks * C::XS]);
             const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
-            if (sc) { c0 *= fsc[2 * nt]; c1 *= fsc[2 * nt + 1]; }
-            if (ad) { c0 += fad[2 * nt]; c1 += fad[2 * nt + 1]; }
+            if (sc) { c0 *= cg[2 * nt]; c1 *= cg[2 * nt + 1]; }
+            if (ad) { c0 += cf[2 * nt]; c1 += cf[2 * nt + 1]; }
             out[(size_t)ja * C::IX + i] = c0;
             out[(size_t)jb * C::IX + i] = c1;
         }
+        KSTAMP(4 * (f - f0) + 3);
         // the next field's Legendre stage rewrites sX only after the next __syncthreads pair
     }
+#undef KSTAMP
     if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 0); }
 }
 
