@@ -247,6 +247,12 @@ def run_b200(args):
     hbm = float(peaks.get("hbm_gbs", 6650.0))
     kt_cold = c.time_kernels(NSTEPS_PER_DAY, flush_l2=True)
     kt_warm = c.time_kernels(NSTEPS_PER_DAY, flush_l2=False)
+    # the same kernels on the GPU's own nanosecond timer inside the replayed graph (first CTA start -> last CTA end,
+    # programmatic dependent launch off so that the kernels do not overlap): no event / launch overhead in these
+    c.trace(True)
+    c.run_steps(3 * NSTEPS_PER_DAY)
+    timeline = c.trace_read()
+    c.trace(False)
     M = args.members
     nact = sum(2 * min(c.mx, c.trunc + 2 - n) for n in range(c.nx))      # 1054 active reals (legendre.f90:33-41)
     NG = c.ix * c.il
@@ -257,7 +263,7 @@ def run_b200(args):
         "spec_step": M * c.mx * c.nx * 16 * 165,
     }
     tot = sum(kt_warm.values())
-    dom = max(alg, key=lambda k: kt_warm[k])
+    dom = max(alg, key=lambda k: timeline["us"][k])     # the longest kernel of the step on the GPU's own timer
     ach = alg[dom] / (kt_cold[dom] * 1e-3) / 1e9
     traffic, traffic_src = _ncu_traffic(dom, M)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
@@ -266,9 +272,11 @@ def run_b200(args):
                 "achieved_warm_l2": alg[dom] / (kt_warm[dom] * 1e-3) / 1e9,
                 "share_of_step": kt_warm[dom] / tot,
                 "kernel_ms_cold": kt_cold, "kernel_ms_warm": kt_warm,
+                "kernel_us_gpu_timer": timeline["us"], "gap_before_us_gpu_timer": timeline["gap_before_us"],
+                "gpu_timer_note": "in-graph durations on %globaltimer with programmatic dependent launch disabled; the CUDA-event figures above carry ~5 us of event+launch overhead per kernel",
                 "legendre": {k: {"GBps_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9, "frac_hbm_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9 / hbm,
                                  "GBps_warm": alg[k] / (kt_warm[k] * 1e-3) / 1e9} for k in ("spec_to_grid", "grid_to_spec")},
-                "note": "single-member T30 is launch/latency-bound (SURVEY.md F12): 7.4 MB of transform traffic per step is 1 us at HBM speed"}
+                "note": "single-member T30 is latency-bound (SURVEY.md F12): one step moves ~19 MB (3 us of HBM time); each kernel is a chain of dependent FP64 operations (DFMA 8.7 cycles, exp 160 cycles dependent issue on B200, tools/dmma_probe.cu)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

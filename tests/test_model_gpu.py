@@ -165,3 +165,21 @@ def test_48h_run_t47(pkg, oracle47):
     for n in ("iptop", "icnv", "icltop"):
         assert np.array_equal(c.get_field(n), o.ifield(n)), n
     c.close()
+
+
+def test_one_year_integration(pkg):
+    """BASELINE configs[1]: T30/L8 single member, 1-year integration (13 140 steps), fp64: check_diagnostics
+    never trips, the calendar lands on 1983-01-01 and the climate stays physical"""
+    c = pkg.Speedy(trunc=30)
+    c.model_init(BC)
+    assert c.run_steps(36 * 365) == 0
+    (y, m, d, h, mi), step = c.model_date()
+    assert (y, m, d, h, mi) == (1983, 1, 1, 0, 0) and step == 36 * 365 + 1
+    rc, diag = c.check_diagnostics(2)
+    assert rc == 0
+    assert diag[0].max() < 500 and diag[1].max() < 500 and 180 < diag[2].min() and diag[2].max() < 320
+    out = c.output_fields()
+    assert 180 < out["t"].min() and out["t"].max() < 330
+    assert 4.5e4 < out["ps"].min() and out["ps"].max() < 1.1e5
+    assert np.abs(out["u"]).max() < 150 and out["q"].min() > -1e-3 and out["q"].max() < 0.04
+    c.close()
