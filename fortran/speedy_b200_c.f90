@@ -98,6 +98,16 @@ module speedy_b200_c
             import; type(c_ptr), value :: ctx; integer(c_int), value :: member
             real(c_float), intent(out) :: u(*), v(*), t(*), q(*), phi(*), ps(*)
         end function
+        ! ensembles: sppt.f90:45-99 noise source, on-device moments of the 41 output levels (device pointers)
+        integer(c_int) function speedy_set_sppt_draw(ctx, on) bind(C, name="speedy_set_sppt_draw")
+            import; type(c_ptr), value :: ctx; integer(c_int), value :: on
+        end function
+        integer(c_int) function speedy_ensemble_sums_dev(ctx, d_sum, d_sumsq) bind(C, name="speedy_ensemble_sums_dev")
+            import; type(c_ptr), value :: ctx, d_sum, d_sumsq
+        end function
+        integer(c_int) function speedy_model_date(ctx, ymdhm, model_step) bind(C, name="speedy_model_date")
+            import; type(c_ptr), value :: ctx; integer(c_int), intent(out) :: ymdhm(5); integer(c_long_long), intent(out) :: model_step
+        end function
     end interface
 
     type(c_ptr), save :: b200_ctx = c_null_ptr   !! one context per process, like the reference's module state

@@ -23,6 +23,12 @@ void upload_implicit(speedy_ctx* ctx) {
     ctx->dv.dmp1s = up(ctx, "dmp1s", p.dmp1s);
     ctx->dv.elz = up(ctx, "elz", p.elz);
     ctx->dv.xj = up(ctx, "xj", p.xj);
+    {   // xj(k,k1,l) transposed to [k + kx*k1][l]: the spectral-step kernel reads one l per lane (conflict-free shared memory)
+        const int nl = (int)(p.xj.size() / 64);
+        std::vector<double> t(p.xj.size());
+        for (int l = 0; l < nl; l++) for (int e = 0; e < 64; e++) t[(size_t)e * nl + l] = p.xj[(size_t)l * 64 + e];
+        ctx->dv.xjt = up(ctx, "xjt", t);
+    }
     ctx->dv.xc = up(ctx, "xc", p.xc);
     ctx->dv.xd = up(ctx, "xd", p.xd);
     upload_level_consts(ctx);

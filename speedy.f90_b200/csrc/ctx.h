@@ -28,6 +28,7 @@ struct DevTables {
     // dynamics
     const double *dmp, *dmpd, *dmps, *dmp1, *dmp1d, *dmp1s, *elz;
     const double *xj, *xc, *xd;          // Fortran order (kx,kx[,l])
+    const double* xjt;                   // xj transposed: [k + kx*k1][l]
     const double* fband;                 // (301,4)
     unsigned long long* trace;           // nullptr, or the in-graph timeline buffer (speedy_trace)
 };

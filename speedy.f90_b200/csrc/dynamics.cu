@@ -104,13 +104,15 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
         bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), bar);
         bulk_g2s(sXd, tv.xd, mb64, bar);
         bulk_g2s(sXc, tv.xc, mb64, bar);
-        bulk_g2s(sXj, tv.xj, mb64 * nl, bar);
+        bulk_g2s(sXj, tv.xjt, mb64 * nl, bar);
     }
     const LevelConsts& lc = *reinterpret_cast<const LevelConsts*>(sLc);
     const double el2 = tv.el2[q], elz_q = tv.elz[q], trf_q = tv.trfilt[q], elm2_q = tv.elm2[q];
     const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
     pdl_wait();                 // everything above reads constant tables only; the fields below come from the previous kernel
     pdl_trigger();
+    const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
+#define SSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 5 && blockIdx.y == 0) tv.trace[56 + (i)] += gtimer() - tk0; } while (0)
     const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
     const cd qcorh_old = ld(mb + a.L.qcorh, mx, m, n);
     const cd qcorh_new = (a.flag & 2) ? ld(sfield(mb, a.L.sout, nsp, GO_QCORH), mx, m, n) : zero;
@@ -148,6 +150,7 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
     const cd tr1 = ld(sfield(mb, a.L.tr, nsp, k), mx, m, n);
     const cd ps1 = ld(sfield(mb, a.L.ps, nsp, 0), mx, m, n);
     mbar_wait(bar, 0);
+    SSTAMP(0);
     s_a[k][c] = div1;
     s_b[k][c] = t1;
     __syncthreads();
@@ -190,6 +193,7 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
         if (valid) st(sfield(mb, a.L.phi, nsp, k), mx, m, n, s_phi[k][c]);   // module phi (tendencies.f90:288), read by output()
     }
     __syncthreads();          // s_a (div1) and s_b (t1) are free again
+    SSTAMP(1);
     // ---- implicit_terms  implicit.f90:168-217
     s_a[k][c] = tdt;
     __syncthreads();
@@ -203,9 +207,9 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
     __syncthreads();
     divdt = zero;
     if (m + n != 0) {
-        const double* xj = sXj + (size_t)KX * KX * (m + n - 1);   // xj(:,:,l), l = total wavenumber
+        const double* xj = sXj + (m + n - 1);                      // xj(:,:,l) transposed, l = total wavenumber
 #pragma unroll
-        for (int k1 = 0; k1 < KX; k1++) divdt = divdt + xj[k + KX * k1] * s_b[k1][c];
+        for (int k1 = 0; k1 < KX; k1++) divdt = divdt + xj[(size_t)(k + KX * k1) * nl] * s_b[k1][c];
     }
     __syncthreads();          // all reads of tdt (s_a) done
     s_a[k][c] = divdt;
@@ -227,6 +231,7 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
         }
         return;
     }
+    SSTAMP(2);
     // ---- horizontal diffusion + drag  time_stepping.f90:63-96
     {
         cd qcorh;
@@ -275,6 +280,7 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
         t2n = stepf(a.L.t, KX, k, tdt, t1, tj, &t1n);
         stepf(a.L.tr, KX, k, trdt, tr1, trj);
     }
+    SSTAMP(3);
     if (!(a.flag & 2)) return;
     // ---- geopotential of the NEW time level 1: the field the next step's physics transforms (physics.f90:103,
     // tendencies.f90:203); the module variable phi above keeps the reference's one-step-old value for output()
@@ -293,6 +299,7 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
     }
     __syncthreads();
     if (valid) st(sfield(mb, a.L.phi_next, nsp, k), mx, m, n, s_phi[k][c]);
+    SSTAMP(4);
     // ---- check_diagnostics on the new time level 2 (diagnostics.f90:16-75): per-block partial sums
     {
         double s1 = 0.0, s2 = 0.0;
@@ -311,6 +318,8 @@ __global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers
     // ---- the step is closed (final diagnostics reduction, range guard, calendar) by an extra CTA of the next
     // step's spec->grid kernel, or by k_close_step when no step follows: nothing here waits for the other blocks
     if (blockIdx.x == 0 && blockIdx.y == 0 && c == 0 && k == 0) a.clk->close_pending = 1;
+    SSTAMP(5);
+#undef SSTAMP
     if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 3); }
 }
 
