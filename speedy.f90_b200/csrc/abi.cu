@@ -47,6 +47,18 @@ void upload_tables(speedy_ctx* ctx) {
             if (m < mx) pd[(((size_t)gq * iy + j) * nx + n) * mg + ml] = t.poly[((size_t)j * nx + n) * mx + m];
         }
         v.polyd = up(ctx, "polyd", pd);
+        // packed triangle per latitude for the streaming inverse transform: row n holds m = 0..min(mx-1, mx-n)
+        const int tr = polyt_row(t.d.trunc);
+        std::vector<double> pt((size_t)iy * tr, 0.0);
+        for (int j = 0; j < iy; j++) {
+            size_t o = (size_t)j * tr;
+            for (int n = 0; n < nx; n++) {
+                const int cnt = std::min(mx, mx - n + 1);
+                for (int m = 0; m < cnt; m++) pt[o + m] = t.poly[((size_t)j * nx + n) * mx + m];
+                o += cnt;
+            }
+        }
+        v.polyt = up(ctx, "polyt", pt);
     }
     v.finv = up(ctx, "finv", t.finv);
     v.ffwd = up(ctx, "ffwd", t.ffwd);

@@ -13,6 +13,7 @@ namespace spd {
 struct DevTables {
     int trunc, ix, iy, il, kx, nx, mx;
     const double* poly;     // [iy][nx][mx]
+    const double* polyt;    // [iy][TR]: per latitude the triangle m+n <= trunc+1 of P, rows of n packed (streaming inverse transform)
     const double* polyd;    // [grp][iy][nx][mg]: P re-laid out per group of mg zonal wavenumbers (streaming direct transform)
     const double* finv;     // [ix][k2pad]
     const double* ffwd;     // [k2pad][ix]
@@ -110,6 +111,7 @@ void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_membe
 void setup_transform_kernels();
 int polyd_groups(int trunc);
 int polyd_mg(int trunc);
+int polyt_row(int trunc);
 // spectral_ops.cu ---------------------------------------------------------------------
 void launch_spectral_op(speedy_ctx* ctx, int op, const double* a, const double* b, double* o1, double* o2, int nbatch);
 enum { OP_LAPLACIAN = 0, OP_INVLAPLACIAN, OP_GRAD, OP_VDS, OP_UVSPEC, OP_TRUNCT };

@@ -256,7 +256,12 @@ struct SCfg : TCfg<TRUNC> {
     // K1: latitude groups sized so that the P tile + staging fit in 227 KB
     static constexpr int LG = (TRUNC == 30) ? 3 : 9, JG = B::IY / LG, NR = 2 * JG;
     static constexpr int XS = padmod16(NR, 4);
-    static constexpr int PS = B::NX * B::MX + 8;                  // P tile row (one latitude) padded by 64 B: the 4 latitudes a warp reads fall in alternating bank halves
+    // P tile: per latitude only the triangle m + n <= trunc + 1 (legendre.f90:38), rows of n packed back to back.
+    // A read past the end of a row meets the next row (finite) times a masked-out coefficient (zero).
+    __host__ __device__ static constexpr int tri_cnt(int n) { return (B::MX - n + 1 < B::MX) ? (B::MX - n + 1) : B::MX; }
+    __host__ __device__ static constexpr int tri_off(int n) { int o = 0; for (int i = 0; i < n; i++) o += tri_cnt(i); return o; }
+    static constexpr int TR = (tri_off(B::NX) + 1) / 2 * 2;       // doubles per latitude in the packed table (even: 16-byte rows)
+    static constexpr int PS = TR + B::MX + (24 - (TR + B::MX) % 16) % 16;   // shared row: >= MX zeroed pad, stride = 8 mod 16 (alternating bank halves)
     static constexpr int PT = JG * PS;                            // P tile, doubles
     static constexpr int MP = (B::MX + 31) / 32 * 32;             // m padded to whole warps
     static constexpr int K1_THREADS = B::IX / 8 * 32;
@@ -271,12 +276,12 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
     static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + 2 * RG * ES + 2 + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
     static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && JG * MP <= K1_THREADS, "K1 tiling");
-    static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && (B::NX * B::MX * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
+    static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && PS % 16 == 8 && PS >= TR + B::MX && (TR * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
     static_assert(K1_SMEM <= 232448 && K2_SMEM <= 232448, "shared memory budget");
 };
 
 template <int TRUNC>
-__global__ void __maxnreg__(96)    // <= 96 registers: a CTA of the column kernel must fit beside it (PDL overlap)
+__global__ void __maxnreg__(80)    // <= 80 registers: two CTAs per SM at T30 (their Legendre and DMMA phases overlap)
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, CloseArgs cl) {
     using C = SCfg<TRUNC>;
@@ -313,8 +318,9 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     // prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
-    if (tid == 0) mbar_expect_tx(&bars[0], C::JG * C::NX * C::MX * sizeof(double));
-    if (tid < C::JG) bulk_g2s(sP + tid * C::PS, tv.poly + (size_t)(j0 + tid) * C::NX * C::MX, C::NX * C::MX * sizeof(double), &bars[0]);
+    if (tid == 0) mbar_expect_tx(&bars[0], C::JG * C::TR * sizeof(double));
+    if (tid < C::JG) bulk_g2s(sP + tid * C::PS, tv.polyt + (size_t)(j0 + tid) * C::TR, C::TR * sizeof(double), &bars[0]);
+    for (int t = tid; t < C::JG * (C::PS - C::TR); t += nthr) sP[(t / (C::PS - C::TR)) * C::PS + C::TR + t % (C::PS - C::TR)] = 0.0;   // row pads
     // this warp's A fragments of the dense backward Fourier operator stay in registers for every field
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     double a[C::KP / 4];
@@ -378,9 +384,9 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             const double2* X = reinterpret_cast<const double2*>(sIn) + m0;
             double evr = 0.0, evi = 0.0, odr = 0.0, odi = 0.0;
 #pragma unroll
-            for (int n = 0; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[n * C::MX]; evr += x.x * pn; evi += x.y * pn; }
+            for (int n = 0; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[C::tri_off(n)]; evr += x.x * pn; evi += x.y * pn; }
 #pragma unroll
-            for (int n = 1; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[n * C::MX]; odr += x.x * pn; odi += x.y * pn; }
+            for (int n = 1; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[C::tri_off(n)]; odr += x.x * pn; odi += x.y * pn; }
             double* xr = sX + (2 * m0) * C::XS;
             xr[jl0] = evr - odr;  xr[C::XS + jl0] = evi - odi;                       // row j (southern)
             xr[C::JG + jl0] = evr + odr;  xr[C::XS + C::JG + jl0] = evi + odi;       // row il+1-j (northern)
@@ -523,8 +529,8 @@ void setup_transform_kernels() {
 }
 
 // fields per persistent CTA: spread (slices x members x chunks) over the SMs, one CTA each
-static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch, int reserved_sms = 0) {
-    int nchunk = (ctx->num_sms - reserved_sms) / (slices * nmembers);
+static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch, int reserved_sms = 0, int ctas_per_sm = 1) {
+    int nchunk = (ctx->num_sms * ctas_per_sm - reserved_sms) / (slices * nmembers);
     if (nchunk < 1) nchunk = 1;
     if (nchunk > nbatch) nchunk = nbatch;
     return nchunk;
@@ -535,7 +541,9 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
                               double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
     using C = SCfg<TRUNC>;
     // one SM is left to the closing CTA when a step is to be closed
-    const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch, cl.clk ? 1 : 0);
+    static int occ = 0;       // resident CTAs per SM of this kernel (2 at T30, 1 at T47)
+    if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC>, C::K1_THREADS, C::K1_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
+    const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch, cl.clk ? 1 : 0, occ);
     dim3 grid(nchunk * C::LG + (cl.clk ? 1 : 0), nmembers);
     CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
 }
@@ -551,6 +559,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
 int polyd_groups(int trunc) { return trunc == 30 ? SCfg<30>::CG : SCfg<47>::CG; }
 int polyd_mg(int trunc) { return trunc == 30 ? SCfg<30>::MG : SCfg<47>::MG; }
+int polyt_row(int trunc) { return trunc == 30 ? SCfg<30>::TR : SCfg<47>::TR; }
 
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                          double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close) {
