@@ -742,6 +742,12 @@ int speedy_trace_read(speedy_ctx* ctx, double* out9) {
         for (int i = 0; i < 13; i++) fprintf(stderr, " [%d] %.2f", i, 1e-3 * (double)st[i] / n);
         fprintf(stderr, "\nK1 stamps (us) [wait,input,legendre,mma] per field:");
         for (int i = 16; i < 24; i++) fprintf(stderr, " %.2f", 1e-3 * (double)st[i] / n);
+        {
+            unsigned long long k2[8];
+            CUDA_CHECK(cudaMemcpy(k2, ctx->trace.p + 24, sizeof(k2), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "\nK2 stamps (us) [wait,dft,fold,legendre] per field:");
+            for (int i = 0; i < 8; i++) fprintf(stderr, " %.2f", 1e-3 * (double)k2[i] / n);
+        }
         fprintf(stderr, "\nspec_step stamps (us) [operands, spectral tendencies, implicit, leapfrog, geopotential, end]:");
         for (int i = 24; i < 30; i++) fprintf(stderr, " %.2f", 1e-3 * (double)st[i] / n);
         fprintf(stderr, "\n");

@@ -275,12 +275,13 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int K2_THREADS = 32 * (MT * NT < 18 ? MT * NT : 18);
     static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
     static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + 2 * RG * ES + 2 + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
-    static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && JG * MP <= K1_THREADS, "K1 tiling");
+    static constexpr size_t K2_SMEM_BATCH = K2_SMEM + sizeof(double) * B::IL * B::IX;   // + the raw field buffer of the one-copy path (at the end)
+    static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && 32 % (JG / 2) == 0 && JG * MP <= K1_THREADS, "K1 tiling");
     static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && PS % 16 == 8 && PS >= TR + B::MX && (TR * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
-    static_assert(K1_SMEM <= 232448 && K2_SMEM <= 232448, "shared memory budget");
+    static_assert(K1_SMEM <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
 };
 
-template <int TRUNC>
+template <int TRUNC, bool BATCH>
 __global__ void __maxnreg__(80)    // <= 80 registers: two CTAs per SM at T30 (their Legendre and DMMA phases overlap)
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, CloseArgs cl) {
@@ -306,7 +307,6 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     const int j0 = grp * C::JG;
     auto row_lat = [&](int r) { return (r < C::JG) ? (j0 + r) : (C::IL - 1 - (j0 + (r - C::JG))); };
     __shared__ XDesc sDesc[104];             // descriptors of this CTA's fields (constant data: fetched in the prologue)
-    for (int t = tid; t < f1 - f0 && t < 104; t += nthr) sDesc[t] = desc[f0 + t];
     auto issue = [&](int f) {                // one thread: bulk copies of field f's source(s)
         const XDesc d = (f - f0 < 104) ? sDesc[f - f0] : desc[f];
         const uint32_t bytes = C::NSPEC2 * sizeof(double);
@@ -321,6 +321,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     if (tid == 0) mbar_expect_tx(&bars[0], C::JG * C::TR * sizeof(double));
     if (tid < C::JG) bulk_g2s(sP + tid * C::PS, tv.polyt + (size_t)(j0 + tid) * C::TR, C::TR * sizeof(double), &bars[0]);
     for (int t = tid; t < C::JG * (C::PS - C::TR); t += nthr) sP[(t / (C::PS - C::TR)) * C::PS + C::TR + t % (C::PS - C::TR)] = 0.0;   // row pads
+    for (int t = tid; t < f1 - f0 && t < 104; t += nthr) sDesc[t] = desc[f0 + t];
     // this warp's A fragments of the dense backward Fourier operator stay in registers for every field
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     double a[C::KP / 4];
@@ -343,10 +344,18 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
 #define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 10 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)
     if (tid == 0 && f0 < f1) issue(f0);
+    // BATCH = false (1-2 fields per CTA, the single-member step): latency matters, 8 warps share the Legendre sums
     // Legendre work items: a warp takes 4 latitude pairs x 8 zonal wavenumbers, so that the spectral
     // coefficients it reads are one 128-byte broadcast and the P values 2 conflict-free wavefronts
     const int jl0 = 4 * (w % (C::JG / 4)) + (lane >> 3), m0 = 8 * (w / (C::JG / 4)) + (lane & 7);
-    const bool leg = w < C::JG * C::MP / 32 && m0 < C::MX;
+    const bool leg1 = !BATCH && w < C::JG * C::MP / 32 && m0 < C::MX;
+    // BATCH = true (long chunks: ensemble batches): the stage is bound by shared-memory bandwidth
+    // Legendre work items: one thread owns a zonal wavenumber m and TWO latitude pairs (jlA, jlA + JG/2), so that the
+    // spectral coefficients it reads serve 8 sums (the stage is bound by shared-memory bandwidth); a warp covers
+    // JG/2 latitude pairs x 32/(JG/2) wavenumbers: P reads fall in alternating bank halves (row stride = 8 mod 16)
+    constexpr int JH = C::JG / 2, MW = 32 / JH;
+    const int jlA = lane / MW, jlB = jlA + JH, m2 = MW * w + lane % MW;
+    const bool leg2 = BATCH && w < C::MP / MW && m2 < C::MX;
     __syncthreads();                                   // sDesc
 
     for (int f = f0; f < f1; f++) {
@@ -379,7 +388,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         KSTAMP(4 * (f - f0) + 1);
         // ---- inverse Legendre for this CTA's latitude pairs (legendre.f90:74-111): one thread per
         // (latitude pair, m); real and imaginary sums share the P values
-        if (leg) {
+        if (leg1) {
             const double* P = sP + (size_t)jl0 * C::PS + m0;
             const double2* X = reinterpret_cast<const double2*>(sIn) + m0;
             double evr = 0.0, evi = 0.0, odr = 0.0, odi = 0.0;
@@ -390,6 +399,27 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             double* xr = sX + (2 * m0) * C::XS;
             xr[jl0] = evr - odr;  xr[C::XS + jl0] = evi - odi;                       // row j (southern)
             xr[C::JG + jl0] = evr + odr;  xr[C::XS + C::JG + jl0] = evi + odi;       // row il+1-j (northern)
+        }
+        if (leg2) {
+            const double* PA = sP + (size_t)jlA * C::PS + m2;
+            const double* PB = sP + (size_t)jlB * C::PS + m2;
+            const double2* X = reinterpret_cast<const double2*>(sIn) + m2;
+            double ear = 0.0, eai = 0.0, oar = 0.0, oai = 0.0, ebr = 0.0, ebi = 0.0, obr = 0.0, obi = 0.0;
+#pragma unroll
+            for (int n = 0; n < C::NX; n += 2) {
+                const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
+                ear += x.x * pa; eai += x.y * pa; ebr += x.x * pb; ebi += x.y * pb;
+            }
+#pragma unroll
+            for (int n = 1; n < C::NX; n += 2) {
+                const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
+                oar += x.x * pa; oai += x.y * pa; obr += x.x * pb; obi += x.y * pb;
+            }
+            double* xr = sX + (2 * m2) * C::XS;
+            xr[jlA] = ear - oar;  xr[C::XS + jlA] = eai - oai;                       // row j (southern)
+            xr[C::JG + jlA] = ear + oar;  xr[C::XS + C::JG + jlA] = eai + oai;       // row il+1-j (northern)
+            xr[jlB] = ebr - obr;  xr[C::XS + jlB] = ebi - obi;
+            xr[C::JG + jlB] = ebr + obr;  xr[C::XS + C::JG + jlB] = ebi + obi;
         }
         __syncthreads();
         KSTAMP(4 * (f - f0) + 2);
@@ -416,19 +446,20 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 0); }
 }
 
-template <int TRUNC>
+template <int TRUNC, bool BATCH>
 __global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, 1)
 k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
     using C = SCfg<TRUNC>;
     extern __shared__ __align__(16) double smem[];
-    double* sG = smem;                                  // [IL][GS] grid field (rows padded)
+    double* sG = smem;                                  // [IL][GS] grid field, rows padded for conflict-free B fragments
     double* sF = sG + C::IL * C::GS;                    // [RG][FS] rows of the dense forward Fourier operator
     double* sY = sF + C::RG * C::FS;                    // [RG][YS] Fourier coefficients of this group
     double* sE = sY + C::RG * C::YS;                    // even / odd folds
     double* sO = sE + C::OOFF;
     double* sPd = sE + 2 * C::RG * C::ES + 2;           // [IY][NX][MG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + (C::P_SMEM ? C::PD : 0));   // [0] operator + P tiles, [1] grid field
+    double* sRaw = reinterpret_cast<double*>(bars + 2);  // BATCH only: [IL][IX] grid field as it arrives (one bulk copy)
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) trace_begin(tv.trace, 2);
     const int grp = blockIdx.x % C::CG, chunk = blockIdx.x / C::CG, e = blockIdx.y;
@@ -439,10 +470,16 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     auto live = [&](int f) { return gate_open || !(desc[f].flags & 4); };
     auto next_live = [&](int f) { while (f < f1 && !live(f)) f++; return f; };
     const uint32_t rowb = C::IX * sizeof(double);
-    auto issue = [&](int f) {                           // threads 0..IL-1: one row copy each; thread 0 arms the barrier
+    // Two ways to bring a field in.  Long chunks (ensemble batches): ONE bulk copy into the raw buffer, then a re-layout
+    // pass to padded rows — 48 row copies take ~1 us to drain through the TMA unit, the single copy half of that, and the
+    // next copy overlaps the whole field.  Short chunks (1-2 fields per CTA, the single-member step): row copies straight
+    // into the padded buffer, no extra pass on the critical path.
+    constexpr bool one_copy = BATCH;
+    auto issue = [&](int f) {
         const double* src = mbase + desc[f].off;
         if (tid == 0) mbar_expect_tx(&bars[1], C::IL * rowb);
-        if (tid < C::IL) bulk_g2s(sG + tid * C::GS, src + (size_t)tid * C::IX, rowb, &bars[1]);
+        if (one_copy) { if (tid == 0) bulk_g2s(sRaw, src, C::IL * rowb, &bars[1]); }
+        else if (tid < C::IL) bulk_g2s(sG + tid * C::GS, src + (size_t)tid * C::IX, rowb, &bars[1]);
     };
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -462,26 +499,38 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         const double* scl = (dsc.flags & 1) ? tv.cosgr : ((dsc.flags & 2) ? tv.cosgr2 : nullptr);
         if (it == 0) mbar_wait(&bars[0], 0);
         mbar_wait(&bars[1], it & 1);
+        const int fn = next_live(f + 1);
+        if (one_copy) {
+            // ---- re-layout to padded rows with the cosgr / cosgr2 pre-scale of vdspec (spectral.f90:208-222)
+            for (int t = tid; t < C::IL * C::IX / 2; t += nthr) {
+                const int j = (2 * t) / C::IX, i = 2 * t - j * C::IX;
+                double2 v = *reinterpret_cast<const double2*>(sRaw + 2 * t);
+                if (scl) { const double sj = scl[j]; v.x *= sj; v.y *= sj; }
+                *reinterpret_cast<double2*>(sG + j * C::GS + i) = v;
+            }
+            __syncthreads();                            // sG complete, raw buffer free
+            if (fn < f1) issue(fn);
+            scl = nullptr;
+        }
         // ---- dense forward Fourier operator for this CTA's rows (fourier.f90:56-82):
         //   Y[c][j] = sum_i ffwd[c][i] * (g[i][j] * scl[j]),  M = RG, N = IL, K = IX
         for (int tile = w; tile < C::MT * C::NT; tile += nw) {
             const int mt = tile / C::NT, nt = tile - mt * C::NT;
             const double* A = sF + (8 * mt + g) * C::FS + q;
             const double* Bf = sG + (8 * nt + g) * C::GS + q;
-            const double s = scl ? scl[8 * nt + g] : 1.0;
             double c0 = 0.0, c1 = 0.0;
             if (scl) {
+                const double sj = scl[8 * nt + g];
 #pragma unroll
-                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks] * s);
+                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks] * sj);
             } else {
 #pragma unroll
                 for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks]);
             }
             *reinterpret_cast<double2*>(sY + (8 * mt + g) * C::YS + 8 * nt + 2 * q) = make_double2(c0, c1);
         }
-        __syncthreads();                                // sY complete, grid buffer free
-        const int fn = next_live(f + 1);
-        if (fn < f1) issue(fn);
+        __syncthreads();                                // sY complete, padded grid buffer free
+        if (!one_copy && fn < f1) issue(fn);
         // Gaussian-weighted even/odd fold (legendre.f90:127-133)
         for (int t = tid; t < C::RG * C::IY; t += nthr) {
             const int cl = t / C::IY, jh = t - cl * C::IY;
@@ -522,10 +571,14 @@ void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K2_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K2_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM_BATCH));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM_BATCH));
 }
 
 // fields per persistent CTA: spread (slices x members x chunks) over the SMs, one CTA each
@@ -542,10 +595,14 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
     using C = SCfg<TRUNC>;
     // one SM is left to the closing CTA when a step is to be closed
     static int occ = 0;       // resident CTAs per SM of this kernel (2 at T30, 1 at T47)
-    if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC>, C::K1_THREADS, C::K1_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
+    if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false>, C::K1_THREADS, C::K1_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
     const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch, cl.clk ? 1 : 0, occ);
     dim3 grid(nchunk * C::LG + (cl.clk ? 1 : 0), nmembers);
-    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
+    // chunks of >= 3 fields (ensemble batches) take the throughput-oriented variant, the single-member step the latency-oriented one
+    if ((nbatch + nchunk - 1) / nchunk >= 3)
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC, true>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
+    else
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC, false>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
 }
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
@@ -553,7 +610,10 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     using C = SCfg<TRUNC>;
     const int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);
     dim3 grid(nchunk * C::CG, nmembers);
-    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+    if ((nbatch + nchunk - 1) / nchunk >= 3)
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+    else
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC, false>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
 }
 
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
