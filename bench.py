@@ -287,6 +287,24 @@ def run_b200(args):
                     "days": e2e_days},
             "gpu_launches": int(launches), "us_per_model_step": 1e6 * dev_s / (args.steps * NSTEPS_PER_DAY),
             "wall_s_timed_region": t_wall, "roofline": roofline}
+    if world == 1 and args.members == 1:
+        # BASELINE configs[2] in passing (not the headline): 8 SPPT members resident on this GPU, 5 simulated days
+        try:
+            c8 = pkg.Speedy(trunc=30, nmembers=8, device=local, sppt_on=1, seed=1)
+            c8.model_init(BC)
+            for _ in range(2):
+                assert c8.run_steps(NSTEPS_PER_DAY) == 0
+            c8.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                assert c8.run_steps(NSTEPS_PER_DAY) == 0
+            c8.synchronize()
+            dt8 = time.perf_counter() - t0
+            line["ensemble_8_members_per_gpu"] = {"member_days_per_s": 8 * 5 / dt8, "us_per_step": 1e6 * dt8 / (5 * NSTEPS_PER_DAY),
+                                                  "note": "SPPT on, wall clock, device-resident; per-GPU figure of the 64-member / 8-GPU config"}
+            c8.close()
+        except Exception as ex:
+            line["ensemble_8_members_per_gpu"] = {"error": str(ex)}
     if not args.no_cpu_baseline and world == 1:
         try:
             L = _oracle_fast()

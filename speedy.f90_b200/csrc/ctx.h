@@ -43,6 +43,9 @@ struct LevelConsts {
     double sigl[8], sigh[9], grdsig[8], grdscp[8], wvi[16];
     double rgas, akap, cp, p0, grav, alhc, alhs, sbc, rearth, refrh1, gamma;
     double rob, wil, sdrag;
+    // loop-invariant quotients of the column-serial sweeps, evaluated once on the host with the reference's expressions
+    // (an fp64 division is ~130 cycles of dependent latency on the critical warp): convection.f90:118-131, LSC :52, SW :227
+    double entr[8], ralhc, fm0, rdps, prg, tfact, eps1, rcp, pad_;
 };
 
 // descriptor of one transform in a batch

@@ -46,6 +46,25 @@ void upload_level_consts(speedy_ctx* ctx) {
     h.sbc = c.sbc; h.rearth = c.rearth; h.refrh1 = c.refrh1; h.gamma = c.gamma;
     h.rob = c.rob; h.wil = c.wil;
     h.sdrag = 1.0 / (c.tdrs * 3600.0);   // time_stepping.f90:77
+    {   // convection.f90:118-131 entrainment profile and mass-flux constants; large_scale_condensation.f90:52; shortwave_radiation.f90:227
+        const double psmin = (double)0.8f, trcnv = 6.0, entmax = 0.5, epslw = (double)0.05f;
+        double sentr = 0.0;
+        for (int k = 2; k <= 7; k++) {
+            const double d = h.fsg[k - 1] - 0.5;
+            const double ee = 0.0 > d ? 0.0 : d;
+            h.entr[k - 1] = ee * ee;
+            sentr = sentr + h.entr[k - 1];
+        }
+        sentr = entmax / sentr;
+        for (int k = 2; k <= 7; k++) h.entr[k - 1] = h.entr[k - 1] * sentr;
+        h.ralhc = 1.0 / c.alhc;
+        h.fm0 = c.p0 * h.dhs[7] / (c.grav * trcnv * 3600.0);
+        h.rdps = 2.0 / (1.0 - psmin);
+        h.prg = c.p0 / c.grav;
+        h.tfact = c.alhc / c.cp;
+        h.eps1 = epslw / (h.dhs[0] + h.dhs[1]);
+        h.rcp = 1.0 / c.cp;
+    }
     Model& M = *ctx->model;
     if (!M.lc.p) M.lc.alloc(1);
     CUDA_CHECK(cudaMemcpyAsync(M.lc.p, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));

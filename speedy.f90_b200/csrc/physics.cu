@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
     // ---------------- large_scale_condensation.f90:33-95, the level-local part ----------------
     {
         const double trlsc = 4.0, rhlsc = F32(0.9), drhlsc = F32(0.1), rhblsc = F32(0.95), qsmax = 10.0;
-        const double rtlsc = 1.0 / (trlsc * 3600.0), tfact = lc.alhc / lc.cp;
+        const double rtlsc = 1.0 / (trlsc * 3600.0), tfact = lc.tfact;
         const double psa2 = psg * psg;
         double dtl = 0.0, dql = 0.0;
         int hit = 0;
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
                     const bool lqthr = (qg[KX] > qthr0 && qg[nl1] > qthr1);
                     if (ktop2 < KX) {
                         itop = ktop1;
-                        qdif = dmax(qg[KX] - qthr0, (mse0 - msthr) * (1.0 / lc.alhc));
+                        qdif = dmax(qg[KX] - qthr0, (mse0 - msthr) * lc.ralhc);
                     } else if (lqthr) {
                         itop = ktop1;
                         qdif = qg[KX] - qthr0;
@@ -427,17 +427,10 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
             }
             if (itop != nlp) {
                 const double fqmax = 5.0;
-                const double fm0 = lc.p0 * lc.dhs[KX - 1] / (lc.grav * trcnv * 3600.0);
-                const double rdps = 2.0 / (1.0 - psmin);
+                const double fm0 = lc.fm0, rdps = lc.rdps;          // p0*dhs(kx)/(grav*trcnv*3600), 2/(1-psmin): host-evaluated
                 double entr[KX + 1];
-                double sentr = 0.0;
-                for (int k = 2; k <= nl1; k++) {
-                    const double ee = dmax(0.0, lc.fsg[k - 1] - 0.5);
-                    entr[k] = ee * ee;
-                    sentr = sentr + entr[k];
-                }
-                sentr = entmax / sentr;
-                for (int k = 2; k <= nl1; k++) entr[k] = entr[k] * sentr;
+#pragma unroll
+                for (int k = 2; k <= nl1; k++) entr[k] = lc.entr[k - 1]; // convection.f90:118-131, host-evaluated
                 int k = KX, k1 = k - 1;
                 const double qmax = dmax(F32(1.01) * qg[k], qsat[k]);
                 double sb = se[k1] + wvi2[k1] * (se[k] - se[k1]);
@@ -491,7 +484,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
         ib[a.L.icnv + col] = icnv_;
         SI(I_ICNV) = icnv_;
         {   // large_scale_condensation.f90:60-93: cloud top and precipitation from the level-local results
-            const double prg = lc.p0 / lc.grav;
+            const double prg = lc.prg;
 #pragma unroll
             for (int kk = 2; kk <= KX; kk++) if (SI(I_LSC + kk - 1)) iptop = min(kk, iptop);
 #pragma unroll
@@ -632,7 +625,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
             G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
 #pragma unroll
             for (int kk = 1; kk <= KX; kk++) { const double v = dfabs[kk] * rps * lc.grdscp[kk - 1]; G3(a.L.tt_rsw, kk) = v; RSW(kk) = v; }   // physics.f90:160-162
-            const double eps1 = epslw / (lc.dhs[0] + lc.dhs[1]);
+            const double eps1 = lc.eps1;
             mb[a.L.stratc + col] = STRATC(0) = stratz * psg;
             mb[a.L.stratc + N + col] = STRATC(1) = eps1 * psg;
         }
@@ -650,7 +643,7 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
         const double tg8 = SG(GI_T1 + KX - 1), tg7 = SG(GI_T1 + nl1 - 1), qg8 = QG(KX), phig8 = SG(GI_PHI + KX - 1);
         const double phi0 = SURF(SF_PHIS0), fmask = SURF(SF_FMASK), tsea = SURF(SF_SST);
         const double u0 = fwind0 * ug8, v0 = fwind0 * vg8;
-        const double gtemp0 = 1.0 - ftemp0, rcp = 1.0 / lc.cp;
+        const double gtemp0 = 1.0 - ftemp0, rcp = lc.rcp;
         const double dt1 = lc.wvi[7 + KX] * (tg8 - tg7);
         double t1_1 = tg8 + dt1;
         double t1_2 = t1_1 - phi0 * dt1 / (lc.rgas * 288.0 * lc.sigl[KX - 1]);
