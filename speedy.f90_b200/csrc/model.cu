@@ -207,6 +207,7 @@ void model_create(speedy_ctx* ctx) {
 void model_destroy(speedy_ctx* ctx) {
     if (!ctx->model) return;
     drop_graph(*ctx->model);
+    free_column_maps(*ctx->model);
     delete ctx->model;
     ctx->model = nullptr;
 }

@@ -96,6 +96,7 @@ struct Model {
     double implicit_dt = 0.0;
     // SPPT (sppt.f90): AR(1) state is device-resident; eta drawn on device unless supplied
     bool sppt_draw = true;
+    void* colmaps = nullptr;       // tensor maps of the column kernel's tiles (physics.cu)
     DevBuf<int> sppt_state;   // [0] AR(1) updates done so far (device-resident: CUDA-graph replays advance it), [1] block ticket
 };
 
@@ -103,7 +104,8 @@ struct Model {
 void launch_geopotential(speedy_ctx* ctx, int which);   // which: bit0 module phi, bit1 phi_next (K1's physics input)
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged = 0);   // mode 0 dyn+phys, 1 physics only on resident tendencies
 void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step = 0);
-void launch_close_step(speedy_ctx* ctx);   // stand-alone closing of a pending step
+void launch_close_step(speedy_ctx* ctx);
+void free_column_maps(Model& M);   // stand-alone closing of a pending step
 void launch_diagnostics(speedy_ctx* ctx, int level);
 void launch_slab(speedy_ctx* ctx, int day0);
 void launch_daily_forcing(speedy_ctx* ctx, int force);

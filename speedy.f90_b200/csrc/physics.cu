@@ -13,6 +13,7 @@
 #include "model.h"
 #include "calendar.h"
 #include "tma.cuh"
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace spd {
 
@@ -57,6 +58,8 @@ struct ColumnArgs {
     int csw_override;        // -1: take compute_shortwave from the device clock
     int sppt_on;
     unsigned long long* trace;
+    // [member][row][column] tensor maps: box = rows x 32 columns, one TMA instruction per tile
+    CUtensorMap m_dyn, m_phys, m_tau2, m_stratc, m_rsw;
 };
 
 // ---- the column kernel -------------------------------------------------------------------
@@ -95,8 +98,8 @@ constexpr int LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static_assert(sizeof(LevelConsts) % 16 == 0 && (NFBAND * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
 constexpr size_t COL_SMEM = sizeof(double) * ((size_t)R_END * TC + NFBAND + LC_DOUBLES) + sizeof(int) * TC * I_N + 2 * sizeof(uint64_t);
 
-__global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
-    extern __shared__ __align__(16) double smem[];
+__global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(const __grid_constant__ ColumnArgs a) {
+    extern __shared__ __align__(128) double smem[];
     double* sFband = smem + (size_t)R_END * TC;
     double* sLc = sFband + NFBAND;
     int* sInt = reinterpret_cast<int*>(sLc + LC_DOUBLES);
@@ -141,7 +144,6 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
 
     // ---- stage the tile: one bulk copy per field row, spread over the threads -------------------
     const int ngin = a.sppt_on ? GI_N : GI_NBASE;
-    const int c_tau = ngin, c_str = c_tau + 4 * KX, c_rsw = c_str + 2, c_fb = c_rsw + KX;
     const bool want_dyn = a.mode == 0;
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -156,14 +158,12 @@ __global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(ColumnArgs a) {
     pdl_wait();                                        // the grid fields of the previous kernel are complete
     pdl_trigger();
     if (a.trace) tk0 = gtimer();
-    for (int c = tid; c < c_fb; c += COL_THREADS) {
-        const uint32_t row = TC * sizeof(double);
-        if (c < ngin) {
-            if (c < GI_U1) { if (want_dyn) bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[1]); }
-            else bulk_g2s(&smem[(size_t)(R_GIN + c) * TC], mb + a.L.gin + (size_t)c * N + col0, row, &bars[0]);
-        } else if (c < c_str) bulk_g2s(&smem[(size_t)(R_TAU2 + c - c_tau) * TC], mb + a.L.tau2 + (size_t)(c - c_tau) * N + col0, row, &bars[0]);
-        else if (c < c_rsw) bulk_g2s(&smem[(size_t)(R_STRATC + c - c_str) * TC], mb + a.L.stratc + (size_t)(c - c_str) * N + col0, row, &bars[0]);
-        else bulk_g2s(&smem[(size_t)(R_RSW + c - c_rsw) * TC], mb + a.L.tt_rsw + (size_t)(c - c_rsw) * N + col0, row, &bars[0]);
+    if (tid == 0) {     // five tile copies (UTMALDG) instead of ~140 row copies: small bulk copies drain slowly through the TMA unit
+        tensor_g2s_3d(&smem[(size_t)(R_GIN + GI_U1) * TC], &a.m_phys, col0, GI_U1, e, &bars[0]);
+        tensor_g2s_3d(&smem[(size_t)R_TAU2 * TC], &a.m_tau2, col0, 0, e, &bars[0]);
+        tensor_g2s_3d(&smem[(size_t)R_STRATC * TC], &a.m_stratc, col0, 0, e, &bars[0]);
+        tensor_g2s_3d(&smem[(size_t)R_RSW * TC], &a.m_rsw, col0, 0, e, &bars[0]);
+        if (want_dyn) tensor_g2s_3d(&smem[(size_t)R_GIN * TC], &a.m_dyn, col0, 0, e, &bars[1]);
     }
 
     if (warp == W_SLAB) {
@@ -1102,6 +1102,44 @@ __global__ void k_clock_advance(DevClock* c) {
     if (threadIdx.x == 0 && blockIdx.x == 0) cal_advance(*c);
 }
 
+// ---- tensor maps of the column kernel ---------------------------------------------------------
+struct ColMaps { CUtensorMap dyn, phys, tau2, stratc, rsw; int sppt_on; };
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static CUtensorMap make_map3(EncodeTiledFn enc, double* base, long long N, int rows, int nmembers, long long member_stride, int box_rows) {
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)rows, (cuuint64_t)nmembers};
+    const cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(double), (cuuint64_t)member_stride * sizeof(double)};
+    const cuuint32_t box[3] = {(cuuint32_t)TC, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return m;
+}
+static const ColMaps& column_maps(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    if (M.colmaps && static_cast<ColMaps*>(M.colmaps)->sppt_on == ctx->sppt_on) return *static_cast<ColMaps*>(M.colmaps);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
+    EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(fn);
+    const long long N = ctx->d.ngrid();
+    const int ngin = ctx->sppt_on ? GI_N : GI_NBASE;
+    ColMaps* cm = M.colmaps ? static_cast<ColMaps*>(M.colmaps) : new ColMaps();
+    cm->sppt_on = ctx->sppt_on;
+    cm->dyn = make_map3(enc, M.mem.p + M.L.gin, N, GI_N, ctx->nmembers, M.L.stride, GI_U1);
+    cm->phys = make_map3(enc, M.mem.p + M.L.gin, N, GI_N, ctx->nmembers, M.L.stride, ngin - GI_U1);
+    cm->tau2 = make_map3(enc, M.mem.p + M.L.tau2, N, 4 * KX, ctx->nmembers, M.L.stride, 4 * KX);
+    cm->stratc = make_map3(enc, M.mem.p + M.L.stratc, N, 2, ctx->nmembers, M.L.stride, 2);
+    cm->rsw = make_map3(enc, M.mem.p + M.L.tt_rsw, N, KX, ctx->nmembers, M.L.stride, KX);
+    M.colmaps = cm;
+    return *cm;
+}
+
+void free_column_maps(Model& M) { delete static_cast<ColMaps*>(M.colmaps); M.colmaps = nullptr; }
+
 // ---- launchers ------------------------------------------------------------------------------
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged) {
     Model& M = *ctx->model;
@@ -1110,6 +1148,10 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on; a.trace = ctx->dv.trace;
+    {
+        const ColMaps& cm = column_maps(ctx);
+        a.m_dyn = cm.dyn; a.m_phys = cm.phys; a.m_tau2 = cm.tau2; a.m_stratc = cm.stratc; a.m_rsw = cm.rsw;
+    }
     const int N = ctx->d.ngrid();
     if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
     static bool attr_set = false;

@@ -37,6 +37,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// global -> shared TILE copy through a tensor map (cp.async.bulk.tensor, SASS UTMALDG): one instruction moves a
+// [rows x 32-column] box of a [member][field][column] array; coordinates are element indices, innermost first
+__device__ __forceinline__ void tensor_g2s_3d(void* dst_smem, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 // named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-off between warp roles
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {
     __threadfence_block();   // the arriving side's shared/global writes are ordered before the arrival
