@@ -71,7 +71,10 @@ __global__ void k_geopotential(SpecArgs a) {
 #define SC 32
 constexpr int SPEC_LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static size_t spec_step_smem(int mx, int nx) { return sizeof(double) * (SPEC_LC_DOUBLES + 2 * KX * KX + (size_t)KX * KX * (mx + nx + 1)) + sizeof(uint64_t); }
-__global__ void __maxnreg__(120) k_spec_step(SpecArgs a) {   // <= 120 registers: fits beside a CTA of K2 (PDL overlap)
+// BATCH = false (single-member step): no register cap, every operand load of a thread is in flight at once;
+// BATCH = true (ensemble batches): two CTAs per SM
+template <bool BATCH>
+__global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a) {
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
     const int c = threadIdx.x, k = threadIdx.y;
     const int r = blockIdx.x * SC + c;
@@ -487,8 +490,13 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }
     const size_t smem = spec_step_smem(ctx->d.mx, ctx->d.nx);
     static bool attr_set = false;
-    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_spec_step, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr_set = true; }
-    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step, grid, dim3(SC, KX), smem, ctx->stream, a));
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_set = true;
+    }
+    if (ctx->nmembers >= 4) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step<true>, grid, dim3(SC, KX), smem, ctx->stream, a));
+    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step<false>, grid, dim3(SC, KX), smem, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }
