@@ -98,7 +98,8 @@ constexpr int LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static_assert(sizeof(LevelConsts) % 16 == 0 && (NFBAND * 8) % 16 == 0, "bulk copies move multiples of 16 bytes");
 constexpr size_t COL_SMEM = sizeof(double) * ((size_t)R_END * TC + NFBAND + LC_DOUBLES) + sizeof(int) * TC * I_N + 2 * sizeof(uint64_t);
 
-__global__ void __launch_bounds__(COL_THREADS, 2) k_grid_columns(const __grid_constant__ ColumnArgs a) {
+template <bool BATCH>
+__global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(const __grid_constant__ ColumnArgs a) {
     extern __shared__ __align__(128) double smem[];
     double* sFband = smem + (size_t)R_END * TC;
     double* sLc = sFband + NFBAND;
@@ -1155,9 +1156,14 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     const int N = ctx->d.ngrid();
     if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
     static bool attr_set = false;
-    if (!attr_set) { CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM)); attr_set = true; }
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
+        attr_set = true;
+    }
     dim3 grid(N / TC, ctx->nmembers);
-    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
+    if (ctx->nmembers >= 2) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns<true>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
+    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns<false>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }
