@@ -274,8 +274,11 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int MT = RG / 8, NT = B::IL / 8;
     static constexpr int K2_THREADS = 32 * (MT * NT < 18 ? MT * NT : 18);
     static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
-    static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + 2 * RG * ES + 2 + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
-    static constexpr size_t K2_SMEM_BATCH = K2_SMEM + sizeof(double) * B::IL * B::IX;   // + the raw field buffer of the one-copy path (at the end)
+    // latency variant: the even/odd folds alias the grid buffer (dead after the Fourier stage), 107 KB at T30: two CTAs per SM;
+    // batch variant: separate fold buffers (the next field is already streaming into the grid buffer) + the raw field buffer
+    static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
+    static constexpr size_t K2_SMEM_BATCH = K2_SMEM + sizeof(double) * (2 * RG * ES + 2 + B::IL * B::IX);
+    static_assert(2 * RG * ES + 2 <= B::IL * GS, "fold buffers fit in the grid buffer");
     static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && 32 % (JG / 2) == 0 && JG * MP <= K1_THREADS, "K1 tiling");
     static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && PS % 16 == 8 && PS >= TR + B::MX && (TR * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
     static_assert(K1_SMEM <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
@@ -447,7 +450,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
 }
 
 template <int TRUNC, bool BATCH>
-__global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, 1)
+__global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, (!BATCH && TRUNC == 30) ? 2 : 1)
 k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
     using C = SCfg<TRUNC>;
@@ -455,11 +458,11 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     double* sG = smem;                                  // [IL][GS] grid field, rows padded for conflict-free B fragments
     double* sF = sG + C::IL * C::GS;                    // [RG][FS] rows of the dense forward Fourier operator
     double* sY = sF + C::RG * C::FS;                    // [RG][YS] Fourier coefficients of this group
-    double* sE = sY + C::RG * C::YS;                    // even / odd folds
-    double* sO = sE + C::OOFF;
-    double* sPd = sE + 2 * C::RG * C::ES + 2;           // [IY][NX][MG]
+    double* sPd = sY + C::RG * C::YS;                   // [IY][NX][MG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + (C::P_SMEM ? C::PD : 0));   // [0] operator + P tiles, [1] grid field
-    double* sRaw = reinterpret_cast<double*>(bars + 2);  // BATCH only: [IL][IX] grid field as it arrives (one bulk copy)
+    double* sE = BATCH ? reinterpret_cast<double*>(bars + 2) : sG;   // even / odd folds (latency variant: in the dead grid buffer)
+    double* sO = sE + C::OOFF;
+    double* sRaw = sE + 2 * C::RG * C::ES + 2;          // BATCH only: [IL][IX] grid field as it arrives (one bulk copy)
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) trace_begin(tv.trace, 2);
     const int grp = blockIdx.x % C::CG, chunk = blockIdx.x / C::CG, e = blockIdx.y;
@@ -530,7 +533,6 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             *reinterpret_cast<double2*>(sY + (8 * mt + g) * C::YS + 8 * nt + 2 * q) = make_double2(c0, c1);
         }
         __syncthreads();                                // sY complete, padded grid buffer free
-        if (!one_copy && fn < f1) issue(fn);
         // Gaussian-weighted even/odd fold (legendre.f90:127-133)
         for (int t = tid; t < C::RG * C::IY; t += nthr) {
             const int cl = t / C::IY, jh = t - cl * C::IY;
@@ -560,6 +562,10 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
                 }
             }
             *reinterpret_cast<double2*>(out + n * C::K2 + 2 * m) = make_double2(sr, si);
+        }
+        if (!BATCH && fn < f1) {                        // the folds live in the grid buffer: the next field may only come now
+            __syncthreads();
+            issue(fn);
         }
         f = fn;
     }
@@ -608,7 +614,10 @@ template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                               double* d_out, long long out_ms, int nmembers, const int* gate) {
     using C = SCfg<TRUNC>;
-    const int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);
+    static int occ = 0;       // resident CTAs per SM of the latency variant (2 at T30, 1 at T47)
+    if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2s_stream<TRUNC, false>, C::K2_THREADS, C::K2_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
+    int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ);
+    if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);   // batch variant: one CTA per SM
     dim3 grid(nchunk * C::CG, nmembers);
     if ((nbatch + nchunk - 1) / nchunk >= 3)
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
