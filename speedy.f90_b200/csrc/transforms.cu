@@ -347,18 +347,12 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
 #define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 10 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)
     if (tid == 0 && f0 < f1) issue(f0);
-    // BATCH = false (1-2 fields per CTA, the single-member step): latency matters, 8 warps share the Legendre sums
-    // Legendre work items: a warp takes 4 latitude pairs x 8 zonal wavenumbers, so that the spectral
-    // coefficients it reads are one 128-byte broadcast and the P values 2 conflict-free wavefronts
-    const int jl0 = 4 * (w % (C::JG / 4)) + (lane >> 3), m0 = 8 * (w / (C::JG / 4)) + (lane & 7);
-    const bool leg1 = !BATCH && w < C::JG * C::MP / 32 && m0 < C::MX;
-    // BATCH = true (long chunks: ensemble batches): the stage is bound by shared-memory bandwidth
     // Legendre work items: one thread owns a zonal wavenumber m and TWO latitude pairs (jlA, jlA + JG/2), so that the
     // spectral coefficients it reads serve 8 sums (the stage is bound by shared-memory bandwidth); a warp covers
     // JG/2 latitude pairs x 32/(JG/2) wavenumbers: P reads fall in alternating bank halves (row stride = 8 mod 16)
     constexpr int JH = C::JG / 2, MW = 32 / JH;
     const int jlA = lane / MW, jlB = jlA + JH, m2 = MW * w + lane % MW;
-    const bool leg2 = BATCH && w < C::MP / MW && m2 < C::MX;
+    const bool leg2 = w < C::MP / MW && m2 < C::MX;
     __syncthreads();                                   // sDesc
 
     for (int f = f0; f < f1; f++) {
@@ -391,18 +385,6 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         KSTAMP(4 * (f - f0) + 1);
         // ---- inverse Legendre for this CTA's latitude pairs (legendre.f90:74-111): one thread per
         // (latitude pair, m); real and imaginary sums share the P values
-        if (leg1) {
-            const double* P = sP + (size_t)jl0 * C::PS + m0;
-            const double2* X = reinterpret_cast<const double2*>(sIn) + m0;
-            double evr = 0.0, evi = 0.0, odr = 0.0, odi = 0.0;
-#pragma unroll
-            for (int n = 0; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[C::tri_off(n)]; evr += x.x * pn; evi += x.y * pn; }
-#pragma unroll
-            for (int n = 1; n < C::NX; n += 2) { const double2 x = X[n * C::MX]; const double pn = P[C::tri_off(n)]; odr += x.x * pn; odi += x.y * pn; }
-            double* xr = sX + (2 * m0) * C::XS;
-            xr[jl0] = evr - odr;  xr[C::XS + jl0] = evi - odi;                       // row j (southern)
-            xr[C::JG + jl0] = evr + odr;  xr[C::XS + C::JG + jl0] = evi + odi;       // row il+1-j (northern)
-        }
         if (leg2) {
             const double* PA = sP + (size_t)jlA * C::PS + m2;
             const double* PB = sP + (size_t)jlB * C::PS + m2;
@@ -542,26 +524,43 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             sO[cl * C::ES + jh] = (north - south) * wgt;
         }
         __syncthreads();
-        // direct Legendre (legendre.f90:142-154): one thread per (n, m), real and imaginary sums share P
+        // direct Legendre (legendre.f90:142-154): one thread per (m, two n of equal parity): the real and imaginary
+        // sums share P, the two n share the folded Fourier coefficients (the stage is shared-memory-bandwidth-bound)
         double* out = out_base + (size_t)e * out_ms + (size_t)f * C::K2 * C::NX;
-        for (int t = tid; t < C::NX * C::MG; t += nthr) {
-            const int n = t / C::MG, ml = t - n * C::MG;
+        constexpr int NP = 2 * ((C::NX + 3) / 4);
+        for (int t = tid; t < NP * C::MG; t += nthr) {
+            const int np = t / C::MG, ml = t - np * C::MG;
             const int m = grp * C::MG + ml;
             if (m >= C::MX) continue;
-            double sr = 0.0, si = 0.0;
-            if (n <= TRUNC && m + n <= C::MX) {
-                const double* Fr = ((n & 1) ? sO : sE) + (2 * ml) * C::ES;
+            const int nA = 4 * (np >> 1) + (np & 1), nB = nA + 2;
+            const bool vA = nA < C::NX, vB = nB < C::NX;
+            const bool cA = vA && nA <= TRUNC && m + nA <= C::MX, cB = vB && nB <= TRUNC && m + nB <= C::MX;
+            double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+            if (cA) {                                   // m + nB <= MX implies m + nA <= MX: cB only if cA
+                const double* Fr = ((np & 1) ? sO : sE) + (2 * ml) * C::ES;
                 if (C::P_SMEM) {
-                    const double* P = sPd + (size_t)n * C::MG + ml;
+                    const double* PA = sPd + (size_t)nA * C::MG + ml;
+                    const double* PB = sPd + (size_t)(cB ? nB : nA) * C::MG + ml;
 #pragma unroll
-                    for (int jh = 0; jh < C::IY; jh++) { const double pj = P[(size_t)jh * C::NX * C::MG]; sr += pj * Fr[jh]; si += pj * Fr[C::ES + jh]; }
+                    for (int jh = 0; jh < C::IY; jh++) {
+                        const double fr = Fr[jh], fi = Fr[C::ES + jh];
+                        const double pa = PA[(size_t)jh * C::NX * C::MG], pb = PB[(size_t)jh * C::NX * C::MG];
+                        ar += pa * fr; ai += pa * fi; br += pb * fr; bi += pb * fi;
+                    }
                 } else {
-                    const double* P = tv.poly + (size_t)n * C::MX + m;
+                    const double* PA = tv.poly + (size_t)nA * C::MX + m;
+                    const double* PB = tv.poly + (size_t)(cB ? nB : nA) * C::MX + m;
 #pragma unroll
-                    for (int jh = 0; jh < C::IY; jh++) { const double pj = P[(size_t)jh * C::NX * C::MX]; sr += pj * Fr[jh]; si += pj * Fr[C::ES + jh]; }
+                    for (int jh = 0; jh < C::IY; jh++) {
+                        const double fr = Fr[jh], fi = Fr[C::ES + jh];
+                        const double pa = PA[(size_t)jh * C::NX * C::MX], pb = PB[(size_t)jh * C::NX * C::MX];
+                        ar += pa * fr; ai += pa * fi; br += pb * fr; bi += pb * fi;
+                    }
                 }
+                if (!cB) { br = 0.0; bi = 0.0; }
             }
-            *reinterpret_cast<double2*>(out + n * C::K2 + 2 * m) = make_double2(sr, si);
+            if (vA) *reinterpret_cast<double2*>(out + nA * C::K2 + 2 * m) = make_double2(ar, ai);
+            if (vB) *reinterpret_cast<double2*>(out + nB * C::K2 + 2 * m) = make_double2(br, bi);
         }
         if (!BATCH && fn < f1) {                        // the folds live in the grid buffer: the next field may only come now
             __syncthreads();
