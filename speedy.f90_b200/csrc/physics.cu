@@ -86,7 +86,7 @@ enum { SF_FMASK, SF_FSOL, SF_OZONE, SF_OZUPP, SF_ZENIT, SF_STRATZ, SF_ALBSFC, SF
        SF_SNOWC, SF_FOROG, SF_SSRD, SF_N };
 // scalar rows (one value per column)
 enum { S_PSG, S_CLOUDC, S_QCLOUD, S_T1_1, S_T1_2, S_T2_1, S_DENVVS0, S_T0, S_U0, S_V0, S_USTR2, S_VSTR2, S_SHF2, S_EVAP2, S_SLRU2,
-       S_UT8, S_VT8, S_SHFT, S_EVAPT, S_N };
+       S_UT8, S_VT8, S_SHFT, S_EVAPT, S_SLRD, S_FLX1, S_FLX2, S_FLX3, S_FLX4, S_N };
 enum { I_ICNV, I_ICLTOP, I_LSC, I_N = I_LSC + KX };
 // shared-memory rows of TC doubles
 enum { R_GIN = 0, R_TAU2 = R_GIN + GI_N, R_STRATC = R_TAU2 + 4 * KX, R_RSW = R_STRATC + 2, R_SURF = R_RSW + KX, R_DYN = R_SURF + SF_N,
@@ -381,6 +381,71 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
     STAMP(1);
     named_sync(BAR_LEV, LEV_THREADS);
 
+    const double emisfc = F32(0.98), epslw = F32(0.05);
+    // level warp 3 sweeps the long wave downward while level warp 1 is busy with convection (or the short-wave sweeps):
+    // it needs only the transmissivities, the source terms of phase A and the band table
+    auto lw_down = [&]() {
+        // ------------------- downward longwave  longwave_radiation.f90:16-117 -------------------
+        double st4a1[KX + 1], st4a2[KX + 1], tt_rlw[KX + 1], flux[5];
+        double slrd;
+#pragma unroll
+        for (int kk = 1; kk <= KX; kk++) { st4a1[kk] = LWS(0, kk); st4a2[kk] = LWS(1, kk); }
+        {
+            double fsfcd = 0.0;
+#pragma unroll
+            for (int k = 1; k <= KX; k++) tt_rlw[k] = 0.0;
+            // Band sweep with the level loop rolled (the body is fetched once and stays in the L0 instruction
+            // cache; the unrolled 4 x 7 sweep was a third of this role's instruction stream).  For a fixed
+            // level the bands are visited in order and for a fixed band the levels in order, i.e. every
+            // tt_rlw(k) and flux(jb) sees the reference's sequence of operations (longwave_radiation.f90:93-105).
+            {
+                const int nt1 = (int)round(SG(GI_T1)) - 100;   // nint(T) -> row of fband(100:400,:)
+                for (int jb = 1; jb <= 2; jb++) {
+                    const double emis = 1.0 - STAU2(1, jb);
+                    const double brad = sFband[nt1 + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
+                    flux[jb] = emis * brad;
+                    tt_rlw[1] = tt_rlw[1] - flux[jb];
+                }
+            }
+            flux[3] = 0.0; flux[4] = 0.0;
+            LWS(2, 1) = tt_rlw[1];
+            {
+                double f1 = flux[1], f2 = flux[2], f3 = flux[3], f4 = flux[4];
+#pragma unroll 1
+                for (int k = 2; k <= KX; k++) {
+                    const double s1 = LWS(0, k), s2 = LWS(1, k);
+                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
+                    double t = 0.0;
+#define LW_BAND(fl, jb)                                                           \
+    {                                                                             \
+        const double tau = STAU2(k, jb);                                          \
+        const double emis = 1.0 - tau;                                            \
+        const double brad = sFband[ntk + 301 * ((jb)-1)] * (s1 + emis * s2);      \
+        t = t + fl;                                                               \
+        fl = tau * fl + emis * brad;                                              \
+        t = t - fl;                                                               \
+    }
+                    LW_BAND(f1, 1) LW_BAND(f2, 2) LW_BAND(f3, 3) LW_BAND(f4, 4)
+#undef LW_BAND
+                    LWS(2, k) = t;
+                }
+                flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
+            }
+            for (int jb = 1; jb <= 4; jb++) fsfcd = fsfcd + emisfc * flux[jb];
+            const double corlw = epslw * emisfc * st4a1[KX];
+            LWS(2, KX) = LWS(2, KX) - corlw;
+            fsfcd = fsfcd + corlw;
+            slrd = fsfcd;
+            G2(a.L.slrd) = slrd;
+            SC(S_SLRD) = slrd;
+            SC(S_FLX1) = flux[1]; SC(S_FLX2) = flux[2]; SC(S_FLX3) = flux[3]; SC(S_FLX4) = flux[4];
+        }
+
+
+        named_arrive(BAR_SEA, 96);
+    };
+    if (k == 3 && !csw) lw_down();
+
     // ---------------- phase B (level warp 1): convection.f90:27-245 + the LSC reductions ----------------
     int iptop = 0, icltop = 0;
     double cloudc = 0.0, clstr = 0.0, qcloud = 0.0, precnv = 0.0, precls = 0.0;
@@ -583,6 +648,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             }
         }
         named_sync(BAR_LEV, LEV_THREADS);
+        if (k == 3) lw_down();
         if (k == 1) {
             // get_shortwave_rad_fluxes  shortwave_radiation.f90:74-234: the flux sweeps
             const double fsol = SURF(SF_FSOL), ozone = SURF(SF_OZONE), ozupp = SURF(SF_OZUPP), stratz = SURF(SF_STRATZ);
@@ -634,7 +700,6 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
     STAMP(3);
 
     // ---------------- surface_fluxes.f90:42-296: level warp 2 prepares the shared terms and the sea half ----------------
-    const double emisfc = F32(0.98), epslw = F32(0.05);
     const double fwind0 = F32(0.95), ftemp0 = 1.0, cdl = F32(2.4e-3), cds = F32(1.0e-3), chl = F32(1.2e-3), chs = F32(0.9e-3);
     const double vgust = 5.0, ctday = F32(1.0e-2), dtheta = 3.0, fstab = F32(0.67), clambda = 7.0, clambsn = 7.0;
     const double esbc = emisfc * lc.sbc;
@@ -672,67 +737,18 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         const double slru2 = esbc * ((tsea * tsea) * (tsea * tsea));
         SC(S_T1_1) = t1_1; SC(S_T1_2) = t1_2; SC(S_T2_1) = t2_1; SC(S_DENVVS0) = denvvs0; SC(S_T0) = t0; SC(S_U0) = u0; SC(S_V0) = v0;
         SC(S_USTR2) = ustr2; SC(S_VSTR2) = vstr2; SC(S_SHF2) = shf2; SC(S_EVAP2) = evap2; SC(S_SLRU2) = slru2;
-        named_arrive(BAR_SEA, 64);
+        named_arrive(BAR_SEA, 96);
     }
     if (k == 1) {
-        // ------------------- downward longwave  longwave_radiation.f90:16-117 -------------------
+        // ------------------- downward longwave: done by level warp 3 (lw_down), results in shared memory -------------------
         double st4a1[KX + 1], st4a2[KX + 1], tt_rlw[KX + 1], flux[5];
-        double slrd;
-#pragma unroll
-        for (int kk = 1; kk <= KX; kk++) { st4a1[kk] = LWS(0, kk); st4a2[kk] = LWS(1, kk); }
-        {
-            double fsfcd = 0.0;
-#pragma unroll
-            for (int k = 1; k <= KX; k++) tt_rlw[k] = 0.0;
-            // Band sweep with the level loop rolled (the body is fetched once and stays in the L0 instruction
-            // cache; the unrolled 4 x 7 sweep was a third of this role's instruction stream).  For a fixed
-            // level the bands are visited in order and for a fixed band the levels in order, i.e. every
-            // tt_rlw(k) and flux(jb) sees the reference's sequence of operations (longwave_radiation.f90:93-105).
-            {
-                const int nt1 = (int)round(tg[1]) - 100;   // nint(T) -> row of fband(100:400,:)
-                for (int jb = 1; jb <= 2; jb++) {
-                    const double emis = 1.0 - STAU2(1, jb);
-                    const double brad = sFband[nt1 + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
-                    flux[jb] = emis * brad;
-                    tt_rlw[1] = tt_rlw[1] - flux[jb];
-                }
-            }
-            flux[3] = 0.0; flux[4] = 0.0;
-            LWS(2, 1) = tt_rlw[1];
-            {
-                double f1 = flux[1], f2 = flux[2], f3 = flux[3], f4 = flux[4];
-#pragma unroll 1
-                for (int k = 2; k <= KX; k++) {
-                    const double s1 = LWS(0, k), s2 = LWS(1, k);
-                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
-                    double t = 0.0;
-#define LW_BAND(fl, jb)                                                           \
-    {                                                                             \
-        const double tau = STAU2(k, jb);                                          \
-        const double emis = 1.0 - tau;                                            \
-        const double brad = sFband[ntk + 301 * ((jb)-1)] * (s1 + emis * s2);      \
-        t = t + fl;                                                               \
-        fl = tau * fl + emis * brad;                                              \
-        t = t - fl;                                                               \
-    }
-                    LW_BAND(f1, 1) LW_BAND(f2, 2) LW_BAND(f3, 3) LW_BAND(f4, 4)
-#undef LW_BAND
-                    LWS(2, k) = t;
-                }
-                flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
-            }
-            for (int jb = 1; jb <= 4; jb++) fsfcd = fsfcd + emisfc * flux[jb];
-            const double corlw = epslw * emisfc * st4a1[KX];
-            LWS(2, KX) = LWS(2, KX) - corlw;
-            fsfcd = fsfcd + corlw;
-            slrd = fsfcd;
-            G2(a.L.slrd) = slrd;
-        }
-
-
         STAMP(4);
         // ------------------------- surface_fluxes.f90:42-296 (lfluxland = .true.): land half and the blend -------------------------
-        named_sync(BAR_SEA, 64);
+        named_sync(BAR_SEA, 96);                // sea half of the fluxes (warp 2), long-wave down (warp 3)
+        const double slrd = SC(S_SLRD);
+#pragma unroll
+        for (int kk = 1; kk <= KX; kk++) { st4a1[kk] = LWS(0, kk); st4a2[kk] = LWS(1, kk); }
+        flux[1] = SC(S_FLX1); flux[2] = SC(S_FLX2); flux[3] = SC(S_FLX3); flux[4] = SC(S_FLX4);
         double ts, shf3, evap3, ustr3, vstr3, slru3;
         {
             const double ug8 = SG(GI_U1 + KX - 1), vg8 = SG(GI_V1 + KX - 1);
