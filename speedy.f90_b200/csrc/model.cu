@@ -273,8 +273,7 @@ static void enqueue_main_loop_step(speedy_ctx* ctx) {
 static void flush_pending_slab(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     launch_close_step(ctx);      // diagnostics + calendar of the last step (no-op if already closed)
-    launch_slab(ctx, 0);
-    CUDA_CHECK(cudaMemsetAsync(&M.clock.p->slab_pending, 0, sizeof(int), ctx->stream));
+    launch_slab(ctx, 0);     // also clears slab_pending
 }
 
 static void set_implicit(speedy_ctx* ctx, double dt) {
@@ -285,9 +284,11 @@ static void set_implicit(speedy_ctx* ctx, double dt) {
     M.implicit_dt = dt;
 }
 
-static void check_ready(speedy_ctx* ctx) {
+// keeps_phi_next: only the device-resident main loop leaves phi_next valid; every other entry point may change the state
+static void check_ready(speedy_ctx* ctx, bool keeps_phi_next = false) {
     if (!ctx || !ctx->model) throw std::runtime_error("null context");
     CUDA_CHECK(cudaSetDevice(ctx->device));
+    if (!keeps_phi_next) ctx->model->phi_next_valid = false;
 }
 
 static void set_all_members(speedy_ctx* ctx, long long off, const double* host, size_t len) {
@@ -629,7 +630,9 @@ static void run_steps_core(speedy_ctx* ctx, int nsteps) {
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
     int left = nsteps;
     const int G = 36;
-    if (nsteps > 0) launch_geopotential(ctx, 2);   // phi_next of the current level-1 T (the state may have been set from the host)
+    // phi_next of the current level-1 T: every main-loop step leaves it up to date; it is recomputed only after another
+    // entry point of the library ran in between (which may have changed the state)
+    if (nsteps > 0 && !M.phi_next_valid) launch_geopotential(ctx, 2);
     if (ctx->use_graphs && left >= G) {
         if (!M.day_graph) {
             cudaGraph_t graph;
@@ -651,7 +654,7 @@ static void run_steps_core(speedy_ctx* ctx, int nsteps) {
         }
     }
     for (int s = 0; s < left; s++) enqueue_main_loop_step(ctx);
-    if (nsteps > 0) flush_pending_slab(ctx);
+    if (nsteps > 0) { flush_pending_slab(ctx); M.phi_next_valid = true; }
 }
 static int finish_run(speedy_ctx* ctx) {
     Model& M = *ctx->model;
@@ -662,7 +665,7 @@ static int finish_run(speedy_ctx* ctx) {
 
 int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
     API_BEGIN
-    check_ready(ctx);
+    check_ready(ctx, true);
     run_steps_core(ctx, nsteps);
     if (finish_run(ctx)) return 1;
     API_END

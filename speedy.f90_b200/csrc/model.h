@@ -88,6 +88,7 @@ struct Model {
     // host-side calendar mirror
     DevClock hclock;
     bool initialized = false;
+    bool phi_next_valid = false;   // phi_next matches the resident level-1 temperature (true after main-loop steps)
     // host copies needed by the daily/implicit logic
     std::vector<double> h_phis0;
     // CUDA graph of one day (36 steps) of the main loop

@@ -1056,6 +1056,7 @@ __device__ __forceinline__ void slab_point(double* mb, const Layout& L_, const S
 __global__ void k_slab(SlabArgs a) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.N) return;
+    if (q == 0 && blockIdx.y == 0 && !a.day0) a.clk->slab_pending = 0;   // the coupler call of the last step is being applied (no thread here reads the flag)
     slab_point(a.base + (size_t)blockIdx.y * a.stride, a.L, a.sh, *a.clk, *a.lc, a.N, q, a.day0);
 }
 
