@@ -40,6 +40,8 @@ typedef struct speedy_cfg {
     int member_offset; /* global index of this context's member 0 in a sharded ensemble: the SPPT noise of
                         * member e is keyed by (seed, step, member_offset + e, coefficient), so a member's
                         * trajectory does not depend on how the ensemble is spread over GPUs */
+    int nsteps;        /* params.f90:30 time steps per day; 0 = the reference's 36 (delt = 2400 s).  A compile-time
+                        * parameter in the reference: T47 needs 72 to stay stable beyond a month */
 } speedy_cfg;
 
 /* ---- life cycle -------------------------------------------------------------------- */

@@ -43,8 +43,11 @@ constexpr int kx = 8;
 constexpr int nx = trunc_ + 2;
 constexpr int mx = trunc_ + 1;
 constexpr int ntr = 1;
-constexpr int nsteps = 36;
-constexpr double delt = 2400.0;            /* 86400.0/nsteps in real32 = 2400 exactly */
+#ifndef NSTEPS
+#define NSTEPS 36                          /* params.f90:30; a compile-time parameter of the reference as well */
+#endif
+constexpr int nsteps = NSTEPS;
+constexpr double delt = (double)(86400.0f / (float)NSTEPS);   /* params.f90:31 in real32: 2400 exactly at 36 steps/day */
 const double rob = (double)0.05f;
 const double wil = (double)0.53f;
 constexpr double alph = 0.5;

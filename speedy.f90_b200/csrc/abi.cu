@@ -138,7 +138,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
     CUDA_CHECK(cudaSetDevice(cfg->device));
     speedy_ctx* ctx = new speedy_ctx();
     try {
-        build_tables(cfg->trunc, ctx->tab);
+        build_tables(cfg->trunc, ctx->tab, cfg->nsteps ? cfg->nsteps : 36);
         ctx->d = ctx->tab.d;
         ctx->nmembers = cfg->nmembers;
         ctx->device = cfg->device;

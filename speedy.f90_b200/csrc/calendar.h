@@ -34,7 +34,7 @@ SPD_HD inline void cal_fractions(DevClock& c) {
 
 // flags for the step that is about to run
 SPD_HD inline void cal_step_flags(DevClock& c) {
-    c.do_forcing = ((c.model_step - 1) % 36 == 0) ? 1 : 0;   // speedy.f90:29
+    c.do_forcing = ((c.model_step - 1) % c.nsteps == 0) ? 1 : 0;   // speedy.f90:29
     c.csw = (c.model_step % 3 == 1) ? 1 : 0;                 // speedy.f90:35, nstrad = 3
 }
 
@@ -42,7 +42,7 @@ SPD_HD inline void cal_step_flags(DevClock& c) {
 // call of this step sees (couple_sea_atm: obs_ssta on every step of day 1 of a month)
 SPD_HD inline void cal_advance(DevClock& c) {
     c.model_step += 1;
-    c.minute += 24 * 60 / 36;
+    c.minute += 24 * 60 / c.nsteps;                             // date.f90:113
     if (c.minute >= 60) { c.minute = c.minute % 60; c.hour += 1; }
     if (c.hour >= 24) { c.hour = c.hour % 24; c.day += 1; }
     if (c.year % 4 == 0 && c.month == 2) {

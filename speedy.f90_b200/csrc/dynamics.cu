@@ -403,7 +403,7 @@ __global__ void k_ensemble_sums(const double* __restrict__ base, long long strid
 // drawn with a counter-based generator: flag bit0 = first step, bit1 = draw eta on device
 struct SpptArgs {
     double* base; long long stride; Layout L; DevTables tv;
-    unsigned long long seed; int* state; int member0; int draw; double rearth;   // state[0] = updates done so far, state[1] = block ticket
+    unsigned long long seed; int* state; int member0; int draw; int nsteps; double rearth;   // state[0] = updates done so far, state[1] = block ticket
 };
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -425,7 +425,7 @@ __global__ void k_sppt_update(SpptArgs a) {
     const bool first = counter == 0;
     double* mb = a.base + (size_t)e * a.stride;
     const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
-    const double phi = exp(-(24 / 36.0) / time_decorr);
+    const double phi = exp(-(24 / (double)a.nsteps) / time_decorr);   // sppt.f90:32
     double f0 = 0.0;
     const double rr = len_decorr / a.rearth;
     for (int nn = 1; nn <= a.tv.trunc; nn++) f0 = f0 + (2 * nn + 1) * exp(-0.5 * (rr * rr) * nn * (nn + 1));
@@ -530,7 +530,7 @@ void launch_sppt_update(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpptArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv;
-    a.seed = ctx->seed; a.state = M.sppt_state.p; a.member0 = ctx->member_offset; a.draw = M.sppt_draw ? 1 : 0; a.rearth = ctx->tab.c.rearth;
+    a.seed = ctx->seed; a.state = M.sppt_state.p; a.member0 = ctx->member_offset; a.draw = M.sppt_draw ? 1 : 0; a.nsteps = ctx->tab.c.nsteps; a.rearth = ctx->tab.c.rearth;
     const int total = KX * ctx->d.nspec();
     dim3 grid((total + 127) / 128, ctx->nmembers);
     k_sppt_update<<<grid, 128, 0, ctx->stream>>>(a);

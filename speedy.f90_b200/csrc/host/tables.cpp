@@ -623,12 +623,15 @@ void build_implicit(Tables& t, double dt) {   // implicit.f90:36-165
     for (auto& v : p.xc) v = v * xi;
 }
 
-void build_tables(int trunc, Tables& t) {
+void build_tables(int trunc, Tables& t, int nsteps) {
     if (trunc != 30 && trunc != 47) throw std::runtime_error("only T30 and T47 are supported");
+    if (nsteps < 1 || (24 * 60) % nsteps != 0) throw std::runtime_error("nsteps must divide the 1440 minutes of a day (date.f90:113)");
     t.d.trunc = trunc;
     t.d.ix = (trunc == 30) ? 96 : 144;
     t.d.iy = t.d.ix / 4; t.d.il = 2 * t.d.iy; t.d.kx = 8; t.d.nx = trunc + 2; t.d.mx = trunc + 1; t.d.ntr = 1;
     t.c = make_consts();
+    t.c.nsteps = nsteps;
+    t.c.delt = (double)(86400.0f / (float)nsteps);   // params.f90:31, a real32 quotient (2400 at the reference's 36 steps/day)
     build_geometry(t);
     factorize(t.d.ix, t.fft_fac);
     make_twiddles(t.d.ix, t.fft_fac, t.fft_work);

@@ -73,7 +73,7 @@ struct Tables {
     std::map<std::string, std::vector<double>*> named();
 };
 
-void build_tables(int trunc, Tables& t);
+void build_tables(int trunc, Tables& t, int nsteps = 36);   // nsteps: time steps per day (params.f90:30)
 void build_implicit(Tables& t, double dt);
 // product-side real FFT (FFTPACK algorithm, reference constants); x has n elements, in place
 void rfft_forward(const Tables& t, double* x);

@@ -15,12 +15,13 @@ namespace spd {
 
 static const int KXc = 8;
 
-void calendar_init(DevClock& c, int y, int m, int d, int h, int mi, int nssta) {
+void calendar_init(DevClock& c, int y, int m, int d, int h, int mi, int nssta, int nsteps) {
     memset(&c, 0, sizeof(c));
     c.year = y; c.month = m; c.day = d; c.hour = h; c.minute = mi;
     c.start_year = y;
     c.model_step = 1;
     c.nssta = nssta;
+    c.nsteps = nsteps;
     cal_fractions(c);
     cal_step_flags(c);
 }
@@ -137,7 +138,7 @@ void model_create(speedy_ctx* ctx) {
     M.mem.alloc((size_t)L.stride * ctx->nmembers);
     M.imem.alloc((size_t)L.istride * ctx->nmembers);
     M.clock.alloc(1);
-    calendar_init(M.hclock, 1982, 1, 1, 0, 0, 0);
+    calendar_init(M.hclock, 1982, 1, 1, 0, 0, 0, ctx->tab.c.nsteps);
     CUDA_CHECK(cudaMemcpy(M.clock.p, &M.hclock, sizeof(DevClock), cudaMemcpyHostToDevice));
     upload_level_consts(ctx);
     {
@@ -536,7 +537,7 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
         CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + M.L.sppt_eta, keep_eta.data() + e * eta_len, eta_len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     // date.f90:53-105, initialization.f90:37
-    calendar_init(M.hclock, year, month, day, hour, minute, env.nssta);
+    calendar_init(M.hclock, year, month, day, hour, minute, env.nssta, ctx->tab.c.nsteps);
     const int isst0 = (year - 1979) * 12 + month;
     if (isst0 - 1 < 1 || isst0 + 1 > env.nssta) throw std::runtime_error("start date outside the resident SST-anomaly window of the boundary file");
     push_clock(ctx);
@@ -629,7 +630,7 @@ static void run_steps_core(speedy_ctx* ctx, int nsteps) {
     if (!M.initialized) throw std::runtime_error("speedy_model_init has not been called");
     if (M.implicit_dt != 2 * ctx->tab.c.delt) set_implicit(ctx, 2 * ctx->tab.c.delt);
     int left = nsteps;
-    const int G = 36;
+    const int G = ctx->tab.c.nsteps;      // one simulated day per graph
     // phi_next of the current level-1 T: every main-loop step leaves it up to date; it is recomputed only after another
     // entry point of the library ran in between (which may have changed the state)
     if (nsteps > 0 && !M.phi_next_valid) launch_geopotential(ctx, 2);

@@ -25,6 +25,7 @@ struct DevClock {
     int diag_fail;       // sticky: check_diagnostics range violation (diagnostics.f90:60-70); holds the failing step
     int nssta;           // records in the resident ssta window
     int slab_pending;    // the coupler call of the last completed step has not run yet (it rides in the next column kernel)
+    int nsteps;          // time steps per day (params.f90:30)
     int close_pending;   // the step's closing (diagnostics reduction + calendar) has not run yet: it rides in the next spec->grid kernel
     double tmonth, tyear;
     double diag[24];     // (kx,3) of the last check_diagnostics
@@ -126,7 +127,7 @@ struct HostEnv {
     std::vector<double> solar;                                   // [365][5][il]
 };
 void load_host_env(const char* bc_path, const Tables& tab, HostEnv& env);   // throws on error
-void calendar_init(DevClock& c, int y, int m, int d, int h, int mi, int nssta);
+void calendar_init(DevClock& c, int y, int m, int d, int h, int mi, int nssta, int nsteps = 36);
 void calendar_advance(DevClock& c);   // speedy.f90:44-47 + flags for the next step (same arithmetic as the device kernel)
 
 }  // namespace spd

@@ -31,6 +31,10 @@ __device__ __noinline__ double exp_ol(double x) { return exp(x); }
 #define exp(x) exp_ol(x)
 #endif
 
+// nint(T) -> row of fband(100:400,:) (longwave_radiation.f90:84,99).  The clamp only matters once the model has left its
+// accepted range (diagnostics.f90:60-70): the reference would index out of bounds there, this must not fault the GPU.
+__device__ __forceinline__ int band_row(double t) { const int n = (int)round(t) - 100; return min(max(n, 0), 300); }
+
 // humidity.f90:44-78 for one point; p = sig*ps (or ps(1,1) for sig <= 0)
 __device__ __forceinline__ double qsat_pt(double ta, double p) {
     const double e0 = 6.108e-3, c1 = F32(17.269), c2 = F32(21.875), t0 = F32(273.16), t1 = F32(35.86), t2 = F32(7.66);
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             // level the bands are visited in order and for a fixed band the levels in order, i.e. every
             // tt_rlw(k) and flux(jb) sees the reference's sequence of operations (longwave_radiation.f90:93-105).
             {
-                const int nt1 = (int)round(SG(GI_T1)) - 100;   // nint(T) -> row of fband(100:400,:)
+                const int nt1 = band_row(SG(GI_T1));   // nint(T) -> row of fband(100:400,:)
                 for (int jb = 1; jb <= 2; jb++) {
                     const double emis = 1.0 - STAU2(1, jb);
                     const double brad = sFband[nt1 + 301 * (jb - 1)] * (st4a1[1] + emis * st4a2[1]);
@@ -414,7 +418,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
 #pragma unroll 1
                 for (int k = 2; k <= KX; k++) {
                     const double s1 = LWS(0, k), s2 = LWS(1, k);
-                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
+                    const int ntk = band_row(SG(GI_T1 + k - 1));
                     double t = 0.0;
 #define LW_BAND(fl, jb)                                                           \
     {                                                                             \
@@ -811,7 +815,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             const double refsfc = 1.0 - emisfc;
             const double fsfcu = slru3;
             G2(a.L.slr) = fsfcu - slrd;
-            const int nts = (int)round(ts) - 100;
+            const int nts = band_row(ts);
             for (int jb = 1; jb <= 4; jb++) flux[jb] = sFband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
             LWS(2, KX) = LWS(2, KX) + epslw * fsfcu;
             {
@@ -819,7 +823,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
 #pragma unroll 1
                 for (int k = KX; k >= 2; k--) {     // longwave_radiation.f90:155-167, level loop rolled as in the downward sweep
                     const double s1 = LWS(0, k), s2 = LWS(1, k);
-                    const int ntk = (int)round(SG(GI_T1 + k - 1)) - 100;
+                    const int ntk = band_row(SG(GI_T1 + k - 1));
                     double t = LWS(2, k);
 #define LW_BAND(fl, jb)                                                           \
     {                                                                             \
@@ -837,7 +841,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
             }
             {
-                const int nt1 = (int)round(tg[1]) - 100;
+                const int nt1 = band_row(tg[1]);
                 double t = LWS(2, 1);
                 for (int jb = 1; jb <= 2; jb++) {
                     const double tau = STAU2(1, jb);

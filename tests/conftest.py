@@ -208,6 +208,11 @@ def oracle47():
 
 
 @pytest.fixture(scope="session")
+def oracle47_n72():
+    return Oracle("t47_n72")
+
+
+@pytest.fixture(scope="session")
 def ctx(pkg):
     c = pkg.Speedy(trunc=30)
     yield c

@@ -131,3 +131,12 @@ def test_t47_boundary_synthesis_and_oracle_start():
     assert o.run(3) == 0
     rc, d = o.check_diagnostics(2)
     assert rc == 0 and d[2].min() > 180 and d[2].max() < 320
+
+
+def test_oracle_steps_per_day_variant():
+    """the oracle built with NSTEPS=72 (delt = 1200 s): 72 steps are one calendar day"""
+    from conftest import bc_t47
+    o = Oracle("t47_n72")
+    o.model_init(bc_t47())
+    assert o.run(72) == 0
+    assert o.date() == ((1982, 1, 2, 0, 0), 73)

@@ -183,3 +183,29 @@ def test_one_year_integration(pkg):
     assert 4.5e4 < out["ps"].min() and out["ps"].max() < 1.1e5
     assert np.abs(out["u"]).max() < 150 and out["q"].min() > -1e-3 and out["q"].max() < 0.04
     c.close()
+
+
+def test_t47_at_72_steps_per_day(pkg, oracle47_n72):
+    """params.f90:30 nsteps is a run-time setting here (speedy_cfg.nsteps).  T47 at 72 steps/day (delt = 1200 s):
+    48 h parity against the oracle built with the same setting, then two months without leaving the
+    check_diagnostics bounds; at the reference's 36 steps/day the same model blows up within 40 days."""
+    o = oracle47_n72
+    bc = bc_t47()
+    o.model_init(bc)
+    assert o.run(144) == 0
+    c = pkg.Speedy(trunc=47, nsteps=72)
+    c.model_init(bc)
+    assert c.run_steps(144) == 0
+    assert c.model_date() == o.date() and c.model_date()[0] == (1982, 1, 3, 0, 0)
+    ref = o.state()
+    for n in PROG:
+        e = rel_rms(c.get_field(n), ref[n])
+        assert e < 1e-10, (n, e)
+    assert c.run_steps(72 * 58) == 0                       # 60 days in all
+    rc, diag = c.check_diagnostics(2)
+    assert rc == 0 and diag[0].max() < 500 and diag[1].max() < 500
+    c.close()
+    c36 = pkg.Speedy(trunc=47)
+    c36.model_init(bc)
+    assert c36.run_steps(36 * 40) == 1                      # 'Model variables out of accepted range' (diagnostics.f90:68)
+    c36.close()
