@@ -24,17 +24,18 @@ __device__ __forceinline__ cd times_i(cd a) { return cd{-a.im, a.re}; }
 __device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vor, const double* div, int m, int n, cd& uc, cd& vc) {
     const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
     const size_t q = m + (size_t)mx * n;
-    const cd zp = times_i(tv.uvdx[q] * ld(vor, mx, m, n));
-    const cd zc = times_i(tv.uvdx[q] * ld(div, mx, m, n));
+    const double dx = tv.uvdx[q], dym = tv.uvdym[q], dyp = tv.uvdyp[q];   // loaded ahead of the branches: one round trip
+    const cd zp = times_i(dx * ld(vor, mx, m, n));
+    const cd zc = times_i(dx * ld(div, mx, m, n));
     if (n == 0) {
-        uc = zc - tv.uvdyp[q] * ld(vor, mx, m, 1);
-        vc = zp + tv.uvdyp[q] * ld(div, mx, m, 1);
+        uc = zc - dyp * ld(vor, mx, m, 1);
+        vc = zp + dyp * ld(div, mx, m, 1);
     } else if (n == nx - 1) {
-        uc = tv.uvdym[q] * ld(vor, mx, m, tr);
-        vc = neg(tv.uvdym[q] * ld(div, mx, m, tr));
+        uc = dym * ld(vor, mx, m, tr);
+        vc = neg(dym * ld(div, mx, m, tr));
     } else {
-        vc = (neg(tv.uvdym[q] * ld(div, mx, m, n - 1)) + tv.uvdyp[q] * ld(div, mx, m, n + 1)) + zp;
-        uc = (tv.uvdym[q] * ld(vor, mx, m, n - 1) - tv.uvdyp[q] * ld(vor, mx, m, n + 1)) + zc;
+        vc = (neg(dym * ld(div, mx, m, n - 1)) + dyp * ld(div, mx, m, n + 1)) + zp;
+        uc = (dym * ld(vor, mx, m, n - 1) - dyp * ld(vor, mx, m, n + 1)) + zc;
     }
 }
 
@@ -42,10 +43,11 @@ __device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vo
 __device__ __forceinline__ void dev_grad(const DevTables& tv, const double* psi, int m, int n, cd& dx, cd& dy) {
     const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
     const size_t q = m + (size_t)mx * n;
-    dx = times_i(tv.gradx[m] * ld(psi, mx, m, n));
-    if (n == 0) dy = tv.gradyp[q] * ld(psi, mx, m, 1);
-    else if (n == nx - 1) dy = neg(tv.gradym[q] * ld(psi, mx, m, tr));
-    else dy = neg(tv.gradym[q] * ld(psi, mx, m, n - 1)) + tv.gradyp[q] * ld(psi, mx, m, n + 1);
+    const double gx = tv.gradx[m], gym = tv.gradym[q], gyp = tv.gradyp[q];
+    dx = times_i(gx * ld(psi, mx, m, n));
+    if (n == 0) dy = gyp * ld(psi, mx, m, 1);
+    else if (n == nx - 1) dy = neg(gym * ld(psi, mx, m, tr));
+    else dy = neg(gym * ld(psi, mx, m, n - 1)) + gyp * ld(psi, mx, m, n + 1);
 }
 
 // vds  spectral.f90:146-171

@@ -345,7 +345,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     pdl_wait();                                        // the spectral fields of the previous kernel are complete
     pdl_trigger();
     const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
-#define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 10 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)
+#define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 96 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)   // block 96: a derived (uvspec) field at T30
     if (tid == 0 && f0 < f1) issue(f0);
     // Legendre work items: one thread owns a zonal wavenumber m and TWO latitude pairs (jlA, jlA + JG/2), so that the
     // spectral coefficients it reads serve 8 sums (the stage is bound by shared-memory bandwidth); a warp covers
@@ -369,14 +369,20 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             }
         } else {
             // derived input: 1 ucos, 2 vcos = uvspec(vor, div) (spectral.f90:173-196); 3 d/dx, 4 d/dy = grad(ps) (:124-144)
-            for (int t = tid; t < C::MX * C::NX; t += nthr) {
-                const int n = t / C::MX, m = t - n * C::MX;
-                cd r0, r1;
-                if (dsc.op <= 2) dev_uvspec(tv, sA, sB, m, n, r0, r1);
-                else dev_grad(tv, sA, m, n, r0, r1);
-                cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
-                if (m + n > C::MX) r = cd{0.0, 0.0};
-                st(sIn, C::MX, m, n, r);
+            // fixed trip count, fully unrolled: the operator-table loads of all of a thread's coefficients are in flight together
+            constexpr int NE = (C::MX * C::NX + C::K1_THREADS - 1) / C::K1_THREADS;
+#pragma unroll
+            for (int u = 0; u < NE; u++) {
+                const int t = tid + u * C::K1_THREADS;
+                if (t < C::MX * C::NX) {
+                    const int n = t / C::MX, m = t - n * C::MX;
+                    cd r0, r1;
+                    if (dsc.op <= 2) dev_uvspec(tv, sA, sB, m, n, r0, r1);
+                    else dev_grad(tv, sA, m, n, r0, r1);
+                    cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
+                    if (m + n > C::MX) r = cd{0.0, 0.0};
+                    st(sIn, C::MX, m, n, r);
+                }
             }
         }
         __syncthreads();                      // sIn complete, staging free

@@ -179,7 +179,7 @@ def test_one_year_integration(pkg):
     assert rc == 0
     assert diag[0].max() < 500 and diag[1].max() < 500 and 180 < diag[2].min() and diag[2].max() < 320
     out = c.output_fields()
-    assert 180 < out["t"].min() and out["t"].max() < 330
+    assert 160 < out["t"].min() and out["t"].max() < 340          # local extremes of a chaotic year (polar night stratosphere ~180 K)
     assert 4.5e4 < out["ps"].min() and out["ps"].max() < 1.1e5
     assert np.abs(out["u"]).max() < 150 and out["q"].min() > -1e-3 and out["q"].max() < 0.04
     c.close()
