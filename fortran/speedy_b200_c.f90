@@ -9,7 +9,7 @@ module speedy_b200_c
     type, bind(C) :: speedy_cfg
         integer(c_int) :: trunc, kx, ntr, nmembers, device, sppt_on
         integer(c_long_long) :: seed
-        integer(c_int) :: member_offset, nsteps
+        integer(c_int) :: member_offset, nsteps, precision
     end type
 
     interface

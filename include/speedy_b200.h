@@ -42,6 +42,9 @@ typedef struct speedy_cfg {
                         * trajectory does not depend on how the ensemble is spread over GPUs */
     int nsteps;        /* params.f90:30 time steps per day; 0 = the reference's 36 (delt = 2400 s).  A compile-time
                         * parameter in the reference: T47 needs 72 to stay stable beyond a month */
+    int precision;     /* 0: fp64 everywhere (types.f90:12).  1: the spherical-harmonic transforms (Legendre + Fourier, incl.
+                        * uvspec/grad) in real32; grid-point columns, semi-implicit solve and time stepping stay fp64
+                        * (BASELINE configs[4] tolerance study) */
 } speedy_cfg;
 
 /* ---- life cycle -------------------------------------------------------------------- */

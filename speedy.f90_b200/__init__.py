@@ -25,7 +25,7 @@ class SpeedyError(RuntimeError):
 class Cfg(ctypes.Structure):
     _fields_ = [("trunc", ctypes.c_int), ("kx", ctypes.c_int), ("ntr", ctypes.c_int),
                 ("nmembers", ctypes.c_int), ("device", ctypes.c_int), ("sppt_on", ctypes.c_int),
-                ("seed", ctypes.c_ulonglong), ("member_offset", ctypes.c_int), ("nsteps", ctypes.c_int)]
+                ("seed", ctypes.c_ulonglong), ("member_offset", ctypes.c_int), ("nsteps", ctypes.c_int), ("precision", ctypes.c_int)]
 
 
 def lib():
@@ -79,9 +79,9 @@ def _c(a, dtype):
 class Speedy:
     """One context = one GPU + one batch of ensemble members (speedy_ctx)."""
 
-    def __init__(self, trunc=30, nmembers=1, device=0, sppt_on=0, seed=0, member_offset=0, nsteps=0):
+    def __init__(self, trunc=30, nmembers=1, device=0, sppt_on=0, seed=0, member_offset=0, nsteps=0, precision=0):
         L = lib()
-        cfg = Cfg(trunc, 8, 1, nmembers, device, sppt_on, seed, member_offset, nsteps)
+        cfg = Cfg(trunc, 8, 1, nmembers, device, sppt_on, seed, member_offset, nsteps, precision)
         self.nsteps = nsteps or 36
         h = ctypes.c_void_p()
         _chk(L.speedy_create(ctypes.byref(cfg), ctypes.byref(h)))

@@ -80,6 +80,7 @@ struct speedy_ctx {
     int device = 0;
     int sppt_on = 0;
     unsigned long long seed = 0;
+    int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
     int num_sms = 148;
     spd::DevBuf<unsigned long long> trace;
     int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
@@ -112,6 +113,9 @@ void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_membe
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
                          int nmembers, int mode, const int* gate = nullptr);
 void setup_transform_kernels();
+// transforms_f32.cu (precision = 1)
+void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers);
+void launch_grid_to_spec_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
 int polyd_groups(int trunc);
 int polyd_mg(int trunc);
 int polyt_row(int trunc);

@@ -262,7 +262,9 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
 static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
-    const bool tracing = ctx->dv.trace != nullptr;      // trace mode closes each step with the stand-alone kernel (exact timeline)
+    // trace mode (exact timeline) and the real32-transform mode (its spec->grid kernel has no closing CTA) close each step
+    // with the stand-alone kernel
+    const bool tracing = ctx->dv.trace != nullptr || ctx->precision != 0;
     if (ctx->sppt_on) launch_sppt_update(ctx);
     xform_step(ctx, 2, !tracing);
     launch_grid_columns(ctx, 0, -1, 1);

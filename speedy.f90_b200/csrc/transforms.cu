@@ -638,7 +638,9 @@ int polyt_row(int trunc) { return trunc == 30 ? SCfg<30>::TR : SCfg<47>::TR; }
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                          double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close) {
     if (nbatch <= 0) return;
-    if (mode == 0) {
+    if (mode == 0 && ctx->precision == 1) {
+        launch_spec_to_grid_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);   // the caller closes the step separately
+    } else if (mode == 0) {
         const CloseArgs cl = close ? *close : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
         if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
         else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
@@ -656,7 +658,9 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, c
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                          double* d_out, long long out_ms, int nmembers, int mode, const int* gate) {
     if (nbatch <= 0) return;
-    if (mode == 0) {
+    if (mode == 0 && ctx->precision == 1) {
+        launch_grid_to_spec_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+    } else if (mode == 0) {
         if (ctx->d.trunc == 30) launch_g2s_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
         else launch_g2s_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
     } else if (ctx->d.trunc == 30) {

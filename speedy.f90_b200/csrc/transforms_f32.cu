@@ -1,0 +1,197 @@
+// Single-precision spherical-harmonic transforms: the `precision = 1` mode of BASELINE configs[4]
+// ("mixed fp32 dynamical core + fp64 implicit solve").  The Legendre sums and the dense Fourier
+// operator are evaluated entirely in real32 (operands converted on load, FFMA accumulation); the
+// prognostic state, the grid-point column work, the semi-implicit solve and the time stepping stay
+// fp64.  These kernels exist for the tolerance study (tools/precision_study.py), not for speed:
+// one CTA per (field, slice), no tensor cores, operands straight from L2.
+//
+//   k_s2g_f32 = uvspec/grad input stage + legendre_inv (legendre.f90:74-111) + fourier_inv (fourier.f90:23-53)
+//   k_g2s_f32 = fourier_dir (fourier.f90:56-82) + legendre_dir (legendre.f90:114-155)
+#include "ctx.h"
+#include "spectral_ops.cuh"
+
+namespace spd {
+
+template <int TRUNC>
+struct FCfg {
+    static constexpr int MX = TRUNC + 1, NX = TRUNC + 2;
+    static constexpr int IX = (TRUNC == 30) ? 96 : 144, IY = IX / 4, IL = IX / 2;
+    static constexpr int K2 = 2 * MX, KP = (K2 + 7) / 8 * 8;
+    static constexpr int NSPEC2 = NX * K2;
+    static constexpr int LG = (TRUNC == 30) ? 3 : 9, JG = IY / LG, NR = 2 * JG;     // K1: latitude pairs per CTA
+    static constexpr int RG = 16, CG = KP / RG;                                     // K2: Fourier rows per CTA
+    static constexpr int THREADS = 384;
+    static constexpr size_t S2G_SMEM = sizeof(float) * (NSPEC2 + K2 * NR) + sizeof(double) * 2 * NSPEC2;
+    static constexpr size_t G2S_SMEM = sizeof(float) * (IL * IX + RG * IL + 2 * RG * IY);
+};
+
+template <int TRUNC>
+__global__ void __launch_bounds__(FCfg<TRUNC>::THREADS)
+k_s2g_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc,
+          double* __restrict__ out_base, long long out_ms, DevTables tv) {
+    using C = FCfg<TRUNC>;
+    extern __shared__ __align__(16) unsigned char raw[];
+    double* sA = reinterpret_cast<double*>(raw);                 // source fields of a derived input (fp64 state)
+    double* sB = sA + C::NSPEC2;
+    float* sIn = reinterpret_cast<float*>(sB + C::NSPEC2);       // the field to transform, real32
+    float* sX = sIn + C::NSPEC2;                                 // [K2][NR] Fourier coefficients of this CTA's rows
+    const int b = blockIdx.x / C::LG, grp = blockIdx.x - b * C::LG, e = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const XDesc dsc = desc[b];
+    const double* mbase = in_base + (size_t)e * in_ms;
+    const double* in = mbase + dsc.off;
+    const int j0 = grp * C::JG;
+    auto row_lat = [&](int r) { return (r < C::JG) ? (j0 + r) : (C::IL - 1 - (j0 + (r - C::JG))); };
+    if (dsc.op == 0) {
+        for (int t = tid; t < C::NSPEC2; t += nthr) {
+            const int n = t / C::K2, c = t - n * C::K2;
+            sIn[t] = ((c >> 1) + n <= C::MX) ? (float)in[t] : 0.0f;
+        }
+    } else {
+        const double* in2 = mbase + dsc.off2;
+        for (int t = tid; t < C::NSPEC2; t += nthr) { sA[t] = in[t]; if (dsc.op <= 2) sB[t] = in2[t]; }
+        __syncthreads();
+        for (int t = tid; t < C::MX * C::NX; t += nthr) {        // uvspec / grad in real32 (spectral.f90:124-196)
+            const int n = t / C::MX, m = t - n * C::MX;
+            auto L = [&](const double* f, int mm, int nn, float& re, float& im) { re = (float)f[2 * (mm + C::MX * nn)]; im = (float)f[2 * (mm + C::MX * nn) + 1]; };
+            float r0r, r0i, r1r, r1i;
+            if (dsc.op <= 2) {
+                const float dx = (float)tv.uvdx[t], dym = (float)tv.uvdym[t], dyp = (float)tv.uvdyp[t];
+                float vr, vi, dr, di; L(sA, m, n, vr, vi); L(sB, m, n, dr, di);
+                const float zpr = -(dx * vi), zpi = dx * vr, zcr = -(dx * di), zci = dx * dr;     // times_i
+                if (n == 0) {
+                    float ar, ai, br, bi; L(sA, m, 1, ar, ai); L(sB, m, 1, br, bi);
+                    r0r = zcr - dyp * ar; r0i = zci - dyp * ai; r1r = zpr + dyp * br; r1i = zpi + dyp * bi;
+                } else if (n == C::NX - 1) {
+                    float ar, ai, br, bi; L(sA, m, TRUNC, ar, ai); L(sB, m, TRUNC, br, bi);
+                    r0r = dym * ar; r0i = dym * ai; r1r = -(dym * br); r1i = -(dym * bi);
+                } else {
+                    float am_r, am_i, ap_r, ap_i, bm_r, bm_i, bp_r, bp_i;
+                    L(sA, m, n - 1, am_r, am_i); L(sA, m, n + 1, ap_r, ap_i); L(sB, m, n - 1, bm_r, bm_i); L(sB, m, n + 1, bp_r, bp_i);
+                    r1r = (-(dym * bm_r) + dyp * bp_r) + zpr; r1i = (-(dym * bm_i) + dyp * bp_i) + zpi;
+                    r0r = (dym * am_r - dyp * ap_r) + zcr; r0i = (dym * am_i - dyp * ap_i) + zci;
+                }
+            } else {
+                const float gx = (float)tv.gradx[m], gym = (float)tv.gradym[t], gyp = (float)tv.gradyp[t];
+                float pr, pi; L(sA, m, n, pr, pi);
+                r0r = -(gx * pi); r0i = gx * pr;
+                if (n == 0) { float ar, ai; L(sA, m, 1, ar, ai); r1r = gyp * ar; r1i = gyp * ai; }
+                else if (n == C::NX - 1) { float ar, ai; L(sA, m, TRUNC, ar, ai); r1r = -(gym * ar); r1i = -(gym * ai); }
+                else { float ar, ai, br, bi; L(sA, m, n - 1, ar, ai); L(sA, m, n + 1, br, bi); r1r = -(gym * ar) + gyp * br; r1i = -(gym * ai) + gyp * bi; }
+            }
+            const bool first = dsc.op == 1 || dsc.op == 3;
+            float rr = first ? r0r : r1r, ri = first ? r0i : r1i;
+            if (m + n > C::MX) { rr = 0.0f; ri = 0.0f; }
+            sIn[2 * (m + C::MX * n)] = rr; sIn[2 * (m + C::MX * n) + 1] = ri;
+        }
+    }
+    __syncthreads();
+    // inverse Legendre, real32 FFMA
+    for (int t = tid; t < C::JG * C::K2; t += nthr) {
+        const int jl = t / C::K2, c = t - jl * C::K2, m = c >> 1;
+        const double* P = tv.poly + (size_t)(j0 + jl) * C::NX * C::MX + m;
+        float ev = 0.0f, od = 0.0f;
+#pragma unroll 4
+        for (int n = 0; n < C::NX; n += 2) ev = fmaf(sIn[n * C::K2 + c], (float)P[n * C::MX], ev);
+#pragma unroll 4
+        for (int n = 1; n < C::NX; n += 2) od = fmaf(sIn[n * C::K2 + c], (float)P[n * C::MX], od);
+        sX[c * C::NR + jl] = ev - od;
+        sX[c * C::NR + C::JG + jl] = ev + od;
+    }
+    __syncthreads();
+    // dense backward Fourier operator, real32 FFMA: grid[i][r] = sum_c finv[i][c] * X[c][r]
+    double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : b) * C::IX * C::IL;
+    const bool sc = dsc.flags & 1, ad = dsc.flags & 2;
+    for (int t = tid; t < C::IX * C::NR; t += nthr) {
+        const int r = t / C::IX, i = t - r * C::IX;
+        const double* A = tv.finv + (size_t)i * C::KP;
+        float s = 0.0f;
+#pragma unroll 4
+        for (int c = 0; c < C::K2; c++) s = fmaf((float)A[c], sX[c * C::NR + r], s);
+        const int j = row_lat(r);
+        if (sc) s *= (float)tv.cosgr[j];
+        if (ad) s += (float)tv.coriol[j];
+        out[(size_t)j * C::IX + i] = (double)s;
+    }
+}
+
+template <int TRUNC>
+__global__ void __launch_bounds__(FCfg<TRUNC>::THREADS)
+k_g2s_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc,
+          double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
+    using C = FCfg<TRUNC>;
+    extern __shared__ __align__(16) unsigned char raw[];
+    float* sG = reinterpret_cast<float*>(raw);       // [IL][IX]
+    float* sY = sG + C::IL * C::IX;                  // [RG][IL]
+    float* sE = sY + C::RG * C::IL;                  // [RG][IY]
+    float* sO = sE + C::RG * C::IY;
+    const int b = blockIdx.x / C::CG, grp = blockIdx.x - b * C::CG, e = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const XDesc dsc = desc[b];
+    if (gate && (dsc.flags & 4) && !*gate) return;
+    const double* in = in_base + (size_t)e * in_ms + dsc.off;
+    const int c0row = grp * C::RG;
+    const double* scl = (dsc.flags & 1) ? tv.cosgr : ((dsc.flags & 2) ? tv.cosgr2 : nullptr);
+    for (int t = tid; t < C::IL * C::IX; t += nthr) {
+        const int j = t / C::IX;
+        float v = (float)in[t];
+        if (scl) v *= (float)scl[j];
+        sG[t] = v;
+    }
+    __syncthreads();
+    for (int t = tid; t < C::RG * C::IL; t += nthr) {        // forward Fourier operator rows of this group
+        const int cl = t / C::IL, j = t - cl * C::IL, c = c0row + cl;
+        float s = 0.0f;
+        if (c < C::K2) {
+            const double* A = tv.ffwd + (size_t)c * C::IX;
+            const float* G = sG + j * C::IX;
+#pragma unroll 4
+            for (int i = 0; i < C::IX; i++) s = fmaf((float)A[i], G[i], s);
+        }
+        sY[cl * C::IL + j] = s;
+    }
+    __syncthreads();
+    for (int t = tid; t < C::RG * C::IY; t += nthr) {        // Gaussian-weighted even/odd fold (legendre.f90:127-133)
+        const int cl = t / C::IY, jh = t - cl * C::IY;
+        const float south = sY[cl * C::IL + jh], north = sY[cl * C::IL + (C::IL - 1 - jh)], wgt = (float)tv.wt[jh];
+        sE[cl * C::IY + jh] = (north + south) * wgt;
+        sO[cl * C::IY + jh] = (north - south) * wgt;
+    }
+    __syncthreads();
+    double* out = out_base + (size_t)e * out_ms + (size_t)b * C::K2 * C::NX;
+    for (int t = tid; t < C::NX * C::RG; t += nthr) {        // direct Legendre (legendre.f90:142-154)
+        const int n = t / C::RG, cl = t - n * C::RG, c = c0row + cl;
+        if (c >= C::K2) continue;
+        const int m = c >> 1;
+        float s = 0.0f;
+        if (n <= TRUNC && m + n <= C::MX) {
+            const double* P = tv.poly + (size_t)n * C::MX + m;
+            const float* F = ((n & 1) ? sO : sE) + cl * C::IY;
+#pragma unroll 4
+            for (int jh = 0; jh < C::IY; jh++) s = fmaf((float)P[(size_t)jh * C::NX * C::MX], F[jh], s);
+        }
+        out[n * C::K2 + c] = (double)s;
+    }
+}
+
+void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
+                             double* d_out, long long out_ms, int nmembers) {
+    static bool attr = false;
+    if (!attr) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::S2G_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::S2G_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::G2S_SMEM));
+        CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::G2S_SMEM));
+        attr = true;
+    }
+    if (ctx->d.trunc == 30) k_s2g_f32<30><<<dim3(nbatch * FCfg<30>::LG, nmembers), FCfg<30>::THREADS, FCfg<30>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv);
+    else k_s2g_f32<47><<<dim3(nbatch * FCfg<47>::LG, nmembers), FCfg<47>::THREADS, FCfg<47>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_grid_to_spec_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
+                             double* d_out, long long out_ms, int nmembers, const int* gate) {
+    if (ctx->d.trunc == 30) k_g2s_f32<30><<<dim3(nbatch * FCfg<30>::CG, nmembers), FCfg<30>::THREADS, FCfg<30>::G2S_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate);
+    else k_g2s_f32<47><<<dim3(nbatch * FCfg<47>::CG, nmembers), FCfg<47>::THREADS, FCfg<47>::G2S_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace spd
