@@ -66,8 +66,8 @@ __global__ void k_geopotential(SpecArgs a) {
 // shared memory in the reference's summation order; everything else is one thread per (m,n,k).
 // flag bit0: stop after implicit_terms and store the tendencies (get_tendencies drop-in)
 // flag bit1: main-loop step: take qcorh from the day's transform when due, add the
-//            check_diagnostics partial sums, and let the LAST block to arrive close the step
-//            (final diagnostics reduction in fixed order, range guard, calendar advance).
+//            check_diagnostics partial sums and flag the step as waiting to be closed (close_step.cuh: final
+//            diagnostics reduction in fixed order, range guard, calendar advance — in the next spec->grid kernel).
 #define SC 32
 constexpr int SPEC_LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static size_t spec_step_smem(int mx, int nx) { return sizeof(double) * (SPEC_LC_DOUBLES + 2 * KX * KX + (size_t)KX * KX * (mx + nx + 1)) + sizeof(uint64_t); }

@@ -258,7 +258,8 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
 }
 // main-loop body speedy.f90:27-54 in 4 launches.  The column kernel first applies the pending
 // couple_sea_land of the previous step and, when due, set_forcing(1); the spectral-step kernel
-// ends with check_diagnostics and the calendar advance (last block to arrive).
+// ends with the check_diagnostics partial sums; the step is closed (final reduction, range guard, calendar) by a spare CTA
+// of the next step's spec->grid kernel or by k_close_step.
 static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;

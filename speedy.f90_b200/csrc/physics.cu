@@ -2,9 +2,10 @@
 // (tendencies.f90:109-197) and the whole physics sweep (physics.f90:110-205 dispatching
 // convection.f90, large_scale_condensation.f90, shortwave_radiation.f90,
 // longwave_radiation.f90, surface_fluxes.f90, vertical_diffusion.f90) fused into ONE pass
-// over the (ix,il) columns: every parameterisation is column-local, so a thread owns a
-// column, keeps its 8 levels on chip and touches HBM once per input field and once per
-// output field.  Longitude is the fastest thread index = unit stride in every array.
+// over the (ix,il) columns: every parameterisation is column-local, so a CTA owns a tile of 32
+// columns, stages it once in shared memory (tensor-map TMA) and works on it level-parallel
+// (see "the column kernel" below); HBM is touched once per input field and once per output
+// field.  Longitude is the fastest index = unit stride in every array.
 // Also here: the per-step land/sea slab update (land_model.f90:184-239,
 // sea_model.f90:253-444), the daily forcing (forcing.f90:55-99) and the device calendar.
 //
