@@ -495,8 +495,8 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
         CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    if (ctx->nmembers >= 4) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step<true>, grid, dim3(SC, KX), smem, ctx->stream, a));
-    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_spec_step<false>, grid, dim3(SC, KX), smem, ctx->stream, a));
+    if (ctx->nmembers >= 4) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_spec_step<true>, grid, dim3(SC, KX), smem, ctx->stream, a));
+    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_spec_step<false>, grid, dim3(SC, KX), smem, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

@@ -1185,8 +1185,8 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     }
     dim3 grid(N / TC, ctx->nmembers);
     // more tiles than SMs (ensemble batches, T47): the two-CTAs-per-SM variant; otherwise the uncapped one
-    if ((long long)grid.x * grid.y > ctx->num_sms) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns<true>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
-    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_grid_columns<false>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
+    if ((long long)grid.x * grid.y > ctx->num_sms) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_grid_columns<true>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
+    else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_grid_columns<false>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }

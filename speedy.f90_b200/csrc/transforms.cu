@@ -611,9 +611,9 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
     dim3 grid(nchunk * C::LG + (cl.clk ? 1 : 0), nmembers);
     // chunks of >= 3 fields (ensemble batches) take the throughput-oriented variant, the single-member step the latency-oriented one
     if ((nbatch + nchunk - 1) / nchunk >= 3)
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC, true>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_stream<TRUNC, true>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
     else
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_s2g_stream<TRUNC, false>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_stream<TRUNC, false>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
 }
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
@@ -625,9 +625,9 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);   // batch variant: one CTA per SM
     dim3 grid(nchunk * C::CG, nmembers);
     if ((nbatch + nchunk - 1) / nchunk >= 3)
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
     else
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr, k_g2s_stream<TRUNC, false>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, false>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
 }
 
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
