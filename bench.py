@@ -262,6 +262,34 @@ def run_b200(args):
         "grid_columns": M * NG * 8 * (77 + 73 + 45 + 8 + 32 + 2),       # 77 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
         "spec_step": M * c.mx * c.nx * 16 * 165,
     }
+    # BASELINE metric (2), "Legendre GB/s vs roofline": the two transform kernels alone on a large device-resident batch
+    # (5824 = 91 fields x 8 levels x 8 members), CUDA events on the library stream, L2 flushed between reps
+    def _transform_batch(inverse, nb):
+        spec = torch.rand((nb, c.nx, c.mx, 2), dtype=torch.float64, device="cuda") * 2 - 1
+        grid = torch.rand((nb, c.il, c.ix), dtype=torch.float64, device="cuda") * 2 - 1
+        times = []
+        for rep in range(6):
+            flush.fill_(rep)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            if inverse:
+                rc = c.L.speedy_spec_to_grid_dev(c.h, ctypes.c_void_p(spec.data_ptr()), nb, None, ctypes.c_void_p(grid.data_ptr()))
+            else:
+                rc = c.L.speedy_grid_to_spec_dev(c.h, ctypes.c_void_p(grid.data_ptr()), nb, ctypes.c_void_p(spec.data_ptr()))
+            assert rc == 0
+            e1.record(stream)
+            e1.synchronize()
+            if rep >= 2:
+                times.append(e0.elapsed_time(e1) * 1e-3)
+        t = sorted(times)[len(times) // 2]
+        by = nb * ((8 * nact + 8 * NG) if inverse else (8 * NG + 8 * (nact - 2)))
+        return {"batch": nb, "us": 1e6 * t, "GBps": by / t / 1e9, "frac_hbm": by / t / 1e9 / hbm, "transforms_per_s": nb / t}
+    try:
+        legendre_batched = {"spec_to_grid": _transform_batch(True, 5824), "grid_to_spec": _transform_batch(False, 4672),
+                            "note": "algorithmic bytes per transform over the measured HBM copy bandwidth; at this batch the dense-operator transforms are FP64-pipe-bound (~40 % of the 36 TFLOP/s FP64 peak, profiles/r1l_transform_microbench_t30.json), not HBM-bound"}
+    except Exception as ex:
+        legendre_batched = {"error": str(ex)}
     tot = sum(kt_warm.values())
     dom = max(alg, key=lambda k: timeline["us"][k])     # the longest kernel of the step on the GPU's own timer
     ach = alg[dom] / (kt_cold[dom] * 1e-3) / 1e9
@@ -276,6 +304,7 @@ def run_b200(args):
                 "gpu_timer_note": "in-graph durations on %globaltimer with programmatic dependent launch disabled; the CUDA-event figures above carry ~5 us of event+launch overhead per kernel",
                 "legendre": {k: {"GBps_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9, "frac_hbm_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9 / hbm,
                                  "GBps_warm": alg[k] / (kt_warm[k] * 1e-3) / 1e9} for k in ("spec_to_grid", "grid_to_spec")},
+                "legendre_batched": legendre_batched,
                 "note": "single-member T30 is latency-bound (SURVEY.md F12): one step moves ~19 MB (3 us of HBM time); each kernel is a chain of dependent FP64 operations (DFMA 8.7 cycles, exp 160 cycles dependent issue on B200, tools/dmma_probe.cu)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
