@@ -98,6 +98,17 @@ module speedy_b200_c
             import; type(c_ptr), value :: ctx; integer(c_int), value :: member
             real(c_float), intent(out) :: u(*), v(*), t(*), q(*), phi(*), ps(*)
         end function
+        ! output() file (input_output.f90:95-217) written by the library, and restart files; dir / path are c_null_char-terminated
+        integer(c_int) function speedy_write_output(ctx, member, dir, path_out, path_cap) bind(C, name="speedy_write_output")
+            import; type(c_ptr), value :: ctx; integer(c_int), value :: member
+            character(kind=c_char), intent(in) :: dir(*); type(c_ptr), value :: path_out; integer(c_size_t), value :: path_cap
+        end function
+        integer(c_int) function speedy_save_restart(ctx, path) bind(C, name="speedy_save_restart")
+            import; type(c_ptr), value :: ctx; character(kind=c_char), intent(in) :: path(*)
+        end function
+        integer(c_int) function speedy_load_restart(ctx, path) bind(C, name="speedy_load_restart")
+            import; type(c_ptr), value :: ctx; character(kind=c_char), intent(in) :: path(*)
+        end function
         ! ensembles: sppt.f90:45-99 noise source, on-device moments of the 41 output levels (device pointers)
         integer(c_int) function speedy_set_sppt_draw(ctx, on) bind(C, name="speedy_set_sppt_draw")
             import; type(c_ptr), value :: ctx; integer(c_int), value :: on

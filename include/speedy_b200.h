@@ -144,6 +144,19 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
 int speedy_model_date(const speedy_ctx* ctx, int* ymdhm, long long* model_step);
 /* output() conversions input_output.f90:184-214: float32 u,v,t,q,phi (ix,il,kx) and ps (ix,il) */
 int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float* t, float* q, float* phi, float* ps);
+/* output() file writer, input_output.f90:95-217: one NetCDF classic (CDF-1) file `yyyymmddhhmm.nc` per output time
+ * with time/lon/lat/lev and float32 u,v,t,q,phi(lon,lat,lev,time), ps(lon,lat,time), names, attributes and coordinate
+ * arithmetic as in the reference; written without a NetCDF library.  speedy_write_output converts member `member`'s
+ * resident state on the device and writes the file into `dir` (path returned in path_out when non-NULL);
+ * speedy_write_output_file is the host-only writer underneath (timestep = model_step - 1, speedy.f90:50). */
+int speedy_write_output(speedy_ctx* ctx, int member, const char* dir, char* path_out, size_t path_cap);
+int speedy_write_output_file(const char* path, int trunc, int nsteps, const int* start_ymdhm, int timestep,
+                             const float* u, const float* v, const float* t, const float* q, const float* phi, const float* ps);
+/* restart files (absent in the reference, which always starts from rest, prognostics.f90:29-31): the complete
+ * device-resident state of all members + calendar + SPPT counters; a run continued from a restart file is bit-identical
+ * to the uninterrupted one.  Load into a context of the same configuration after speedy_model_init. */
+int speedy_save_restart(speedy_ctx* ctx, const char* path);
+int speedy_load_restart(speedy_ctx* ctx, const char* path);
 /* ensemble sums for the mean/spread diagnostic: writes sum and sum of squares of the 41
  * output levels over this ctx's members into device buffers (for NCCL all-reduce) */
 /* sppt.f90:45-99 noise source: on != 0 (default) draws eta on the device; 0 reads it from the

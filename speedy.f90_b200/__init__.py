@@ -48,6 +48,10 @@ def lib():
         _lib.speedy_step_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int]
         _lib.speedy_run_steps_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
         _lib.speedy_model_init.argtypes = [ctypes.c_void_p, ctypes.c_char_p] + [ctypes.c_int] * 5
+        _lib.speedy_write_output.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t]
+        _lib.speedy_write_output_file.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
+        _lib.speedy_save_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        _lib.speedy_load_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
     return _lib
 
 
@@ -70,6 +74,13 @@ def host_table(trunc, name):
     out = np.zeros(n)
     _chk(L.speedy_host_table(trunc, name.encode(), _p(out), ctypes.c_size_t(n)))
     return out
+
+
+def write_output_file(path, u, v, t, q, phi, ps, trunc=30, nsteps=36, start=(1982, 1, 1, 0, 0), timestep=0):
+    """Host-only writer of one output() file (input_output.f90:95-217) from float32 fields in C order (kx, il, ix) / (il, ix)."""
+    st = np.ascontiguousarray(start, dtype=np.int32)
+    f = [np.ascontiguousarray(a, dtype=np.float32) for a in (u, v, t, q, phi, ps)]
+    _chk(lib().speedy_write_output_file(str(path).encode(), int(trunc), int(nsteps), _p(st), int(timestep), *[_p(a) for a in f]))
 
 
 def _c(a, dtype):
@@ -312,6 +323,18 @@ class Speedy:
         o = [np.empty((k, il, ix), np.float32) for _ in range(5)] + [np.empty((il, ix), np.float32)]
         _chk(self.L.speedy_output_fields(self.h, member, *[_p(x) for x in o]))
         return dict(zip(("u", "v", "t", "q", "phi", "ps"), o))
+
+    def write_output(self, directory=".", member=0):
+        """output() (input_output.f90:95-217): writes `yyyymmddhhmm.nc` (NetCDF classic) for the resident state; returns the path."""
+        buf = ctypes.create_string_buffer(4096)
+        _chk(self.L.speedy_write_output(self.h, int(member), str(directory).encode(), buf, ctypes.c_size_t(len(buf))))
+        return buf.value.decode()
+
+    def save_restart(self, path):
+        _chk(self.L.speedy_save_restart(self.h, str(path).encode()))
+
+    def load_restart(self, path):
+        _chk(self.L.speedy_load_restart(self.h, str(path).encode()))
 
     def step_host(self, state, j1, j2, dt, compute_shortwave=True):
         a = _c(state, np.float64).copy()

@@ -6,6 +6,8 @@
 #include "calendar.h"
 #include "close_step.cuh"
 #include "abi_util.h"
+#include "host/netcdf_classic.h"
+#include <cstdio>
 #include <cmath>
 #include <cstring>
 
@@ -541,6 +543,7 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     // date.f90:53-105, initialization.f90:37
     calendar_init(M.hclock, year, month, day, hour, minute, env.nssta, ctx->tab.c.nsteps);
+    { const int st[5] = {year, month, day, hour, minute}; memcpy(M.start, st, sizeof st); }
     const int isst0 = (year - 1979) * 12 + month;
     if (isst0 - 1 < 1 || isst0 + 1 > env.nssta) throw std::runtime_error("start date outside the resident SST-anomaly window of the boundary file");
     push_clock(ctx);
@@ -721,6 +724,174 @@ int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float*
     for (int f = 0; f < 5; f++)
         if (dst[f]) memcpy(dst[f], h.data() + (size_t)f * KXc * NG, KXc * NG * sizeof(float));
     if (ps) memcpy(ps, h.data() + (size_t)5 * KXc * NG, NG * sizeof(float));
+    API_END
+}
+
+// ---- output files (input_output.f90:95-217) --------------------------------------------------------
+// One NetCDF classic file per output time, named yyyymmddhhmm.nc after the model date, holding the float32
+// u, v, t, q, phi (lon, lat, lev, time) and ps (lon, lat, time) of speedy_output_fields plus the coordinate
+// variables and attributes the reference writes.  Host-only: no device work, callable without a GPU.
+int speedy_write_output_file(const char* path, int trunc, int nsteps, const int* start_ymdhm, int timestep,
+                             const float* u, const float* v, const float* t, const float* q, const float* phi, const float* ps) {
+    API_BEGIN
+    if (!path || !start_ymdhm || !u || !v || !t || !q || !phi || !ps) throw std::runtime_error("speedy_write_output_file: null argument");
+    Tables tab;
+    build_tables(trunc, tab, nsteps > 0 ? nsteps : 36);
+    const int ix = tab.d.ix, il = tab.d.il;
+    NcClassicWriter nc;
+    char units[64];
+    snprintf(units, sizeof units, "hours since %04d-%02d-%02d %02d:%02d:0.0", start_ymdhm[0], start_ymdhm[1], start_ymdhm[2], start_ymdhm[3], start_ymdhm[4]);
+    // definition order as in the reference: time, lon, lat, lev, then the fields
+    const int dt = nc.def_dim("time", 0);
+    const int vt = nc.def_var("time", {dt});
+    nc.put_att(vt, "units", units);
+    const int dlon = nc.def_dim("lon", ix), dlat = nc.def_dim("lat", il), dlev = nc.def_dim("lev", KXc);
+    const int vlon = nc.def_var("lon", {dlon}); nc.put_att(vlon, "long_name", "longitude");
+    const int vlat = nc.def_var("lat", {dlat}); nc.put_att(vlat, "long_name", "latitude");
+    const int vlev = nc.def_var("lev", {dlev}); nc.put_att(vlev, "long_name", "atmosphere_sigma_coordinate");
+    struct F { const char *name, *long_name, *units; const float* data; };
+    const F f3[5] = {{"u", "eastward_wind", "m/s", u}, {"v", "northward_wind", "m/s", v}, {"t", "air_temperature", "K", t},
+                     {"q", "specific_humidity", "1", q}, {"phi", "geopotential_height", "m", phi}};
+    int vf[5];
+    for (int i = 0; i < 5; i++) {
+        vf[i] = nc.def_var(f3[i].name, {dt, dlev, dlat, dlon});   // Fortran (lon, lat, lev, time)
+        nc.put_att(vf[i], "long_name", f3[i].long_name);
+        nc.put_att(vf[i], "units", f3[i].units);
+    }
+    const int vps = nc.def_var("ps", {dt, dlat, dlon});
+    nc.put_att(vps, "long_name", "surface_air_pressure");
+    nc.put_att(vps, "units", "Pa");
+    // coordinate values, in the reference's mixed real32 / real64 arithmetic (input_output.f90:178-181)
+    const float hours = (float)timestep * 24.0f / (float)tab.c.nsteps;
+    nc.put_var(vt, &hours, 1);
+    std::vector<float> lon(ix), lat(il), lev(KXc);
+    const float dlon_deg = (float)(360.0 / ix);                    // 3.75 at T30
+    for (int k = 0; k < ix; k++) lon[k] = dlon_deg * (float)k;
+    const double quarter = (double)asinf(1.0f);
+    for (int k = 0; k < il; k++) lat[k] = (float)(tab.radang[k] * 90.0 / quarter);
+    for (int k = 0; k < KXc; k++) lev[k] = (float)tab.fsg[k];
+    nc.put_var(vlon, lon.data(), lon.size());
+    nc.put_var(vlat, lat.data(), lat.size());
+    nc.put_var(vlev, lev.data(), lev.size());
+    const size_t NG = (size_t)ix * il;
+    for (int i = 0; i < 5; i++) nc.put_var(vf[i], f3[i].data, (size_t)KXc * NG);
+    nc.put_var(vps, ps, NG);
+    nc.write(path);
+    API_END
+}
+
+// output() of the resident state of one member: converts on the device (speedy_output_fields), names the file after
+// the model date and writes it into `dir`; the path is returned in path_out (optional)
+int speedy_write_output(speedy_ctx* ctx, int member, const char* dir, char* path_out, size_t path_cap) {
+    API_BEGIN
+    check_ready(ctx);
+    if (member < 0 || member >= ctx->nmembers) throw std::runtime_error("bad member index");
+    Model& M = *ctx->model;
+    const size_t NG = ctx->d.ngrid(), n = speedy_output_len(ctx);
+    float* d = enqueue_output(ctx, member);
+    std::vector<float> h(n);
+    CUDA_CHECK(cudaMemcpyAsync(h.data(), d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    pull_clock(ctx);
+    const DevClock& c = M.hclock;
+    char name[32];
+    snprintf(name, sizeof name, "%04d%02d%02d%02d%02d.nc", c.year, c.month, c.day, c.hour, c.minute);
+    std::string path = (dir && *dir) ? std::string(dir) + "/" + name : std::string(name);
+    const float* f = h.data();
+    const size_t L3 = (size_t)KXc * NG;
+    if (speedy_write_output_file(path.c_str(), ctx->d.trunc, ctx->tab.c.nsteps, M.start, c.model_step - 1, f, f + L3, f + 2 * L3, f + 3 * L3, f + 4 * L3, f + 5 * L3))
+        throw std::runtime_error(speedy_last_error());
+    if (path_out && path_cap) { strncpy(path_out, path.c_str(), path_cap - 1); path_out[path_cap - 1] = 0; }
+    API_END
+}
+
+// ---- restart files -----------------------------------------------------------------------------------
+// The reference always starts from rest (prognostics.f90:29-31).  A restart file holds everything a context needs to
+// continue a run bit for bit: the members' device-resident state (prognostics at both time levels, tendencies, slab
+// models, radiation state, SPPT AR(1) state), the calendar and the SPPT draw counter.  The boundary data and tables
+// are not in the file: load into a context created with the same configuration after speedy_model_init.
+namespace {
+struct RestartHeader {
+    char magic[8];
+    int version, trunc, nmembers, nsteps, sppt_on, member_offset;
+    long long stride, istride;
+    unsigned long long seed;
+    int start[5];
+    int phi_next_valid;
+    double implicit_dt;
+    DevClock clock;
+};
+const char kRestartMagic[8] = {'S', 'P', 'D', 'B', '2', '0', '0', 'R'};
+}  // namespace
+
+int speedy_save_restart(speedy_ctx* ctx, const char* path) {
+    API_BEGIN
+    check_ready(ctx, true);
+    Model& M = *ctx->model;
+    if (!M.initialized) throw std::runtime_error("speedy_save_restart: model not initialized");
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    pull_clock(ctx);
+    RestartHeader h;
+    memset(&h, 0, sizeof h);
+    memcpy(h.magic, kRestartMagic, 8);
+    h.version = 1; h.trunc = ctx->d.trunc; h.nmembers = ctx->nmembers; h.nsteps = ctx->tab.c.nsteps; h.sppt_on = ctx->sppt_on;
+    h.member_offset = ctx->member_offset; h.stride = (long long)M.L.stride; h.istride = (long long)M.L.istride; h.seed = ctx->seed;
+    memcpy(h.start, M.start, sizeof h.start);
+    h.phi_next_valid = M.phi_next_valid ? 1 : 0;
+    h.implicit_dt = M.implicit_dt;
+    h.clock = M.hclock;
+    std::vector<double> mem(M.mem.n);
+    std::vector<int> imem(M.imem.n), sppt(M.sppt_state.n);
+    CUDA_CHECK(cudaMemcpy(mem.data(), M.mem.p, mem.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (!imem.empty()) CUDA_CHECK(cudaMemcpy(imem.data(), M.imem.p, imem.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (!sppt.empty()) CUDA_CHECK(cudaMemcpy(sppt.data(), M.sppt_state.p, sppt.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    FILE* f = fopen(path, "wb");
+    if (!f) throw std::runtime_error(std::string("speedy_save_restart: cannot create ") + path);
+    const unsigned long long cnt[3] = {mem.size(), imem.size(), sppt.size()};
+    bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(cnt, sizeof cnt, 1, f) == 1;
+    ok = ok && fwrite(mem.data(), sizeof(double), mem.size(), f) == mem.size();
+    ok = ok && fwrite(imem.data(), sizeof(int), imem.size(), f) == imem.size();
+    ok = ok && fwrite(sppt.data(), sizeof(int), sppt.size(), f) == sppt.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw std::runtime_error(std::string("speedy_save_restart: short write to ") + path);
+    API_END
+}
+
+int speedy_load_restart(speedy_ctx* ctx, const char* path) {
+    API_BEGIN
+    check_ready(ctx);
+    Model& M = *ctx->model;
+    if (!M.initialized) throw std::runtime_error("speedy_load_restart: call speedy_model_init first (boundary data and tables are not in the file)");
+    FILE* f = fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("speedy_load_restart: cannot open ") + path);
+    RestartHeader h;
+    unsigned long long cnt[3];
+    std::vector<double> mem;
+    std::vector<int> imem, sppt;
+    std::string err;
+    if (fread(&h, sizeof h, 1, f) != 1 || fread(cnt, sizeof cnt, 1, f) != 1 || memcmp(h.magic, kRestartMagic, 8) != 0 || h.version != 1) err = "not a restart file of this library";
+    else if (h.trunc != ctx->d.trunc || h.nmembers != ctx->nmembers || h.nsteps != ctx->tab.c.nsteps || h.sppt_on != ctx->sppt_on ||
+             h.stride != (long long)M.L.stride || h.istride != (long long)M.L.istride || cnt[0] != M.mem.n || cnt[1] != M.imem.n || cnt[2] != M.sppt_state.n)
+        err = "restart file was written by a context of another configuration (trunc / nmembers / nsteps / sppt_on)";
+    else {
+        mem.resize(cnt[0]); imem.resize(cnt[1]); sppt.resize(cnt[2]);
+        if (fread(mem.data(), sizeof(double), mem.size(), f) != mem.size() || fread(imem.data(), sizeof(int), imem.size(), f) != imem.size() ||
+            fread(sppt.data(), sizeof(int), sppt.size(), f) != sppt.size())
+            err = "truncated restart file";
+    }
+    fclose(f);
+    if (!err.empty()) throw std::runtime_error("speedy_load_restart: " + err + ": " + path);
+    drop_graph(M);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    CUDA_CHECK(cudaMemcpy(M.mem.p, mem.data(), mem.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (!imem.empty()) CUDA_CHECK(cudaMemcpy(M.imem.p, imem.data(), imem.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!sppt.empty()) CUDA_CHECK(cudaMemcpy(M.sppt_state.p, sppt.data(), sppt.size() * sizeof(int), cudaMemcpyHostToDevice));
+    memcpy(M.start, h.start, sizeof h.start);
+    M.hclock = h.clock;
+    push_clock(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (h.implicit_dt != M.implicit_dt && h.implicit_dt > 0.0 && speedy_initialize_implicit(ctx, h.implicit_dt)) throw std::runtime_error(speedy_last_error());
+    M.phi_next_valid = h.phi_next_valid != 0;
     API_END
 }
 

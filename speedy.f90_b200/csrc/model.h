@@ -88,6 +88,7 @@ struct Model {
     std::map<std::string, FieldInfo> fields;
     // host-side calendar mirror
     DevClock hclock;
+    int start[5] = {1982, 1, 1, 0, 0};   // start_datetime (date.f90:21), for the time axis of the output files
     bool initialized = false;
     bool phi_next_valid = false;   // phi_next matches the resident level-1 temperature (true after main-loop steps)
     // host copies needed by the daily/implicit logic
