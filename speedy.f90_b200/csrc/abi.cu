@@ -62,6 +62,7 @@ void upload_tables(speedy_ctx* ctx) {
     }
     v.finv = up(ctx, "finv", t.finv);
     v.ffwd = up(ctx, "ffwd", t.ffwd);
+    v.fftwa = up(ctx, "fftwa", t.fft_work);
     v.wt = up(ctx, "wt", t.wt);
     v.cosgr = up(ctx, "cosgr", t.cosgr);
     v.cosgr2 = up(ctx, "cosgr2", t.cosgr2);
@@ -147,6 +148,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->member_offset = cfg->member_offset;
         ctx->precision = cfg->precision;
         ctx->trace_pdl = getenv("SPEEDY_TRACE_PDL") != nullptr;
+        ctx->fft_inverse = getenv("SPEEDY_DENSE_INVERSE") == nullptr;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));

@@ -17,6 +17,7 @@ struct DevTables {
     const double* polyd;    // [grp][iy][nx][mg]: P re-laid out per group of mg zonal wavenumbers (streaming direct transform)
     const double* finv;     // [ix][k2pad]
     const double* ffwd;     // [k2pad][ix]
+    const double* fftwa;    // [ix] twiddle table of rffti1 (fftpack.f90:1-67)
     const double* wt;       // iy
     const double* cosgr;    // il
     const double* cosgr2;   // il
@@ -81,6 +82,7 @@ struct speedy_ctx {
     int sppt_on = 0;
     unsigned long long seed = 0;
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
+    bool fft_inverse = true; // T30 spec->grid: regrouped FFTPACK FFT (fft96.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
     int num_sms = 148;
     spd::DevBuf<unsigned long long> trace;

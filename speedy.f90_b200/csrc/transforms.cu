@@ -20,6 +20,7 @@
 #include "ctx.h"
 #include "spectral_ops.cuh"
 #include "tma.cuh"
+#include "fft96.cuh"
 #include "close_step.cuh"
 
 namespace spd {
@@ -266,6 +267,11 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int MP = (B::MX + 31) / 32 * 32;             // m padded to whole warps
     static constexpr int K1_THREADS = B::IX / 8 * 32;
     static constexpr size_t K1_SMEM = sizeof(double) * (PT + 3 * B::NSPEC2 + B::KP * XS) + 2 * sizeof(uint64_t);
+    // FFT variant of the Fourier stage (fft96.cuh, T30 only): half-complex rows + the buffer between its two stages, position-major
+    // with an odd row stride (the Legendre stage's scattered writes and the FFT's 16-row reads are both conflict-free), + twiddles
+    static constexpr int XF = 17;
+    static constexpr bool HAS_FFT = (B::IX == 96 && NR == 16);
+    static constexpr size_t K1_SMEM_FFT = sizeof(double) * (PT + 3 * B::NSPEC2 + 2 * B::IX * XF + B::IX) + 2 * sizeof(uint64_t);
     // K2: groups of 16 Fourier rows = 8 zonal wavenumbers
     static constexpr int RG = 16, CG = B::KP / RG, MG = RG / 2;
     static constexpr int GS = padmod16(B::IX, 4), FS = GS, YS = padmod16(B::IL, 8), ES = B::IY + 1 - (B::IY & 1);   // ES odd
@@ -284,8 +290,8 @@ struct SCfg : TCfg<TRUNC> {
     static_assert(K1_SMEM <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
 };
 
-template <int TRUNC, bool BATCH>
-__global__ void __maxnreg__(80)    // <= 80 registers: two CTAs per SM at T30 (their Legendre and DMMA phases overlap)
+template <int TRUNC, bool BATCH, bool FFT>
+__global__ void __maxnreg__(80)    // <= 80 registers: two CTAs per SM at T30 (their Legendre and Fourier phases overlap)
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, CloseArgs cl) {
     using C = SCfg<TRUNC>;
@@ -301,7 +307,9 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     double* sB = sA + C::NSPEC2;
     double* sIn = sB + C::NSPEC2;
     double* sX = sIn + C::NSPEC2;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + C::KP * C::XS);   // [0] P tile, [1] staging
+    double* sT = sX + C::IX * C::XF;         // FFT variant: between the two FFT stages
+    double* sWa = sT + C::IX * C::XF;        // FFT variant: twiddle table of rffti1
+    uint64_t* bars = reinterpret_cast<uint64_t*>(FFT ? sWa + C::IX : sX + C::KP * C::XS);   // [0] P tile, [1] staging
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) trace_begin(tv.trace, 0);
     const int grp = blockIdx.x % C::LG, chunk = blockIdx.x / C::LG, e = blockIdx.y;
@@ -327,20 +335,26 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
     for (int t = tid; t < f1 - f0 && t < 104; t += nthr) sDesc[t] = desc[f0 + t];
     // this warp's A fragments of the dense backward Fourier operator stay in registers for every field
     const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
-    double a[C::KP / 4];
-    {
+    double a[FFT ? 1 : C::KP / 4];
+    // latitude factors of the epilogue (fourier.f90:47-51, tendencies.f90:103) for this thread's output rows
+    double cg[FFT ? 1 : C::NR / 4], cf[FFT ? 1 : C::NR / 4];
+    if constexpr (FFT) {
+        // half-complex rows hold positions 0..2*trunc (fourier.f90:40-45); the zero padding up to ix is written once
+        for (int t = tid; t < (C::IX - (C::K2 - 1)) * C::XF; t += nthr) sX[(C::K2 - 1) * C::XF + t] = 0.0;
+        for (int t = tid; t < C::IX; t += nthr) sWa[t] = tv.fftwa[t];
+        const int jr = row_lat((tid >> 3) & (C::NR - 1));      // stage 2: thread = (row, k of the third pass)
+        cg[0] = tv.cosgr[jr]; cf[0] = tv.coriol[jr];
+    } else {
         const double* A = tv.finv + (size_t)(8 * w + g) * C::KP + q;
 #pragma unroll
         for (int ks = 0; ks < C::KP / 4; ks++) a[ks] = A[4 * ks];
-    }
-    for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
-    // latitude factors of the epilogue (fourier.f90:47-51, tendencies.f90:103) for this thread's output rows
-    double cg[C::NR / 4], cf[C::NR / 4];
+        for (int t = tid; t < (C::KP - C::K2) * C::XS; t += nthr) sX[C::K2 * C::XS + t] = 0.0;
 #pragma unroll
-    for (int nt = 0; nt < C::NR / 8; nt++) {
-        const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
-        cg[2 * nt] = tv.cosgr[ja]; cg[2 * nt + 1] = tv.cosgr[jb];
-        cf[2 * nt] = tv.coriol[ja]; cf[2 * nt + 1] = tv.coriol[jb];
+        for (int nt = 0; nt < C::NR / 8; nt++) {
+            const int ja = row_lat(8 * nt + 2 * q), jb = row_lat(8 * nt + 2 * q + 1);
+            cg[2 * nt] = tv.cosgr[ja]; cg[2 * nt + 1] = tv.cosgr[jb];
+            cf[2 * nt] = tv.coriol[ja]; cf[2 * nt + 1] = tv.coriol[jb];
+        }
     }
     pdl_wait();                                        // the spectral fields of the previous kernel are complete
     pdl_trigger();
@@ -406,17 +420,53 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
                 const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
                 oar += x.x * pa; oai += x.y * pa; obr += x.x * pb; obi += x.y * pb;
             }
-            double* xr = sX + (2 * m2) * C::XS;
-            xr[jlA] = ear - oar;  xr[C::XS + jlA] = eai - oai;                       // row j (southern)
-            xr[C::JG + jlA] = ear + oar;  xr[C::XS + C::JG + jlA] = eai + oai;       // row il+1-j (northern)
-            xr[jlB] = ebr - obr;  xr[C::XS + jlB] = ebi - obi;
-            xr[C::JG + jlB] = ebr + obr;  xr[C::XS + C::JG + jlB] = ebi + obi;
+            if constexpr (FFT) {
+                // FFTPACK's half-complex order (fourier.f90:40-45): a0, then (re, im) of m = 1..; the imaginary part of m = 0 is dropped
+                double* xr = sX + (m2 == 0 ? 0 : 2 * m2 - 1) * C::XF;
+                xr[jlA] = ear - oar;  xr[C::JG + jlA] = ear + oar;
+                xr[jlB] = ebr - obr;  xr[C::JG + jlB] = ebr + obr;
+                if (m2) {
+                    xr[C::XF + jlA] = eai - oai;  xr[C::XF + C::JG + jlA] = eai + oai;
+                    xr[C::XF + jlB] = ebi - obi;  xr[C::XF + C::JG + jlB] = ebi + obi;
+                }
+            } else {
+                double* xr = sX + (2 * m2) * C::XS;
+                xr[jlA] = ear - oar;  xr[C::XS + jlA] = eai - oai;                       // row j (southern)
+                xr[C::JG + jlA] = ear + oar;  xr[C::XS + C::JG + jlA] = eai + oai;       // row il+1-j (northern)
+                xr[jlB] = ebr - obr;  xr[C::XS + jlB] = ebi - obi;
+                xr[C::JG + jlB] = ebr + obr;  xr[C::XS + C::JG + jlB] = ebi + obi;
+            }
         }
         __syncthreads();
         KSTAMP(4 * (f - f0) + 2);
+        double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : f) * C::IX * C::IL;
+        if constexpr (FFT) {
+            // ---- backward FFT per latitude row, FFTPACK's passes regrouped into two register-resident stages (fft96.cuh).
+            // stage 1: half-warp = one closed input set x the 16 rows
+            if (tid < 128) {
+                const int h = tid >> 4, r = tid & 15;
+                if (h < 5) Fft96::stage1_general<C::XF>(sX + r, sT + r, sWa, 3 + 2 * h);
+                else if (h == 6) Fft96::stage1_first<C::XF>(sX + r, sT + r, sWa);
+                else if (h == 7) Fft96::stage1_last<C::XF>(sX + r, sT + r, sWa);
+            }
+            __syncthreads();
+            // stage 2: thread = (row, k): 8 consecutive lanes write 8 consecutive longitudes
+            if (tid < 128) {
+                const int r = tid >> 3, k3 = tid & 7;
+                double y[12];
+                Fft96::stage2<C::XF>(sT + r, sWa, k3, y);
+                double* orow = out + (size_t)row_lat(r) * C::IX + k3;
+#pragma unroll
+                for (int t = 0; t < 12; t++) {
+                    double v = y[t];
+                    if (sc) v *= cg[0];
+                    if (ad) v += cf[0];
+                    orow[8 * (t & 3) + 32 * (t >> 2)] = v;
+                }
+            }
+        } else {
         // ---- dense backward Fourier operator on the FP64 tensor pipe:
         //   grid[i][r] = sum_c finv[i][c] * X[c][r],  M = IX, N = NR, K = KP
-        double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : f) * C::IX * C::IL;
         const int i = 8 * w + g;
 #pragma unroll
         for (int nt = 0; nt < C::NR / 8; nt++) {
@@ -429,6 +479,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             if (ad) { c0 += cf[2 * nt]; c1 += cf[2 * nt + 1]; }
             out[(size_t)ja * C::IX + i] = c0;
             out[(size_t)jb * C::IX + i] = c1;
+        }
         }
         KSTAMP(4 * (f - f0) + 3);
         // the next field's Legendre stage rewrites sX only after the next __syncthreads pair
@@ -582,12 +633,14 @@ void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K2_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_to_spec<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K2_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM_FFT));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM_FFT));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM_BATCH));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM_BATCH));
 }
@@ -605,15 +658,27 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
                               double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
     using C = SCfg<TRUNC>;
     // one SM is left to the closing CTA when a step is to be closed
-    static int occ = 0;       // resident CTAs per SM of this kernel (2 at T30, 1 at T47)
-    if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false>, C::K1_THREADS, C::K1_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
+    // T30: the Fourier stage is the regrouped FFTPACK FFT (fft96.cuh); otherwise the dense operator on the FP64 tensor pipe
+    constexpr bool HF = C::HAS_FFT;
+    const bool fft = HF && ctx->fft_inverse;
+    const size_t smem = fft ? C::K1_SMEM_FFT : C::K1_SMEM;
+    static int occ_tab[2] = {0, 0};       // resident CTAs per SM (2 at T30, 1 at T47), per variant
+    int& occ = occ_tab[fft ? 1 : 0];
+    if (!occ) {
+        if (fft) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false, HF>, C::K1_THREADS, smem));
+        else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false, false>, C::K1_THREADS, smem));
+        if (occ < 1) occ = 1;
+        if (occ > 2) occ = 2;
+    }
     const int nchunk = stream_chunks(ctx, C::LG, nmembers, nbatch, cl.clk ? 1 : 0, occ);
     dim3 grid(nchunk * C::LG + (cl.clk ? 1 : 0), nmembers);
+    const bool pdl = ctx->dv.trace == nullptr || ctx->trace_pdl;
     // chunks of >= 3 fields (ensemble batches) take the throughput-oriented variant, the single-member step the latency-oriented one
-    if ((nbatch + nchunk - 1) / nchunk >= 3)
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_stream<TRUNC, true>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
-    else
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_stream<TRUNC, false>, grid, dim3(C::K1_THREADS), C::K1_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl));
+    const bool batch = (nbatch + nchunk - 1) / nchunk >= 3;
+#define S2G_LAUNCH(B, F) CUDA_CHECK(launch_pdl(pdl, k_s2g_stream<TRUNC, B, F>, grid, dim3(C::K1_THREADS), smem, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, cl))
+    if (fft) { if (batch) S2G_LAUNCH(true, HF); else S2G_LAUNCH(false, HF); }
+    else { if (batch) S2G_LAUNCH(true, false); else S2G_LAUNCH(false, false); }
+#undef S2G_LAUNCH
 }
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
