@@ -20,11 +20,9 @@ __device__ __forceinline__ cd operator-(cd a, cd b) { return cd{a.re - b.re, a.i
 __device__ __forceinline__ cd neg(cd a) { return cd{-a.re, -a.im}; }
 __device__ __forceinline__ cd times_i(cd a) { return cd{-a.im, a.re}; }
 
-// uvspec  spectral.f90:173-196
-__device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vor, const double* div, int m, int n, cd& uc, cd& vc) {
-    const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
-    const size_t q = m + (size_t)mx * n;
-    const double dx = tv.uvdx[q], dym = tv.uvdym[q], dyp = tv.uvdyp[q];   // loaded ahead of the branches: one round trip
+// uvspec  spectral.f90:173-196; the _t forms take the three operator-table entries of (m,n) from the caller
+__device__ __forceinline__ void dev_uvspec_t(int mx, int nx, int tr, const double* vor, const double* div, int m, int n,
+                                             double dx, double dym, double dyp, cd& uc, cd& vc) {
     const cd zp = times_i(dx * ld(vor, mx, m, n));
     const cd zc = times_i(dx * ld(div, mx, m, n));
     if (n == 0) {
@@ -38,16 +36,23 @@ __device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vo
         uc = (dym * ld(vor, mx, m, n - 1) - dyp * ld(vor, mx, m, n + 1)) + zc;
     }
 }
+__device__ __forceinline__ void dev_uvspec(const DevTables& tv, const double* vor, const double* div, int m, int n, cd& uc, cd& vc) {
+    const size_t q = m + (size_t)tv.mx * n;
+    const double dx = tv.uvdx[q], dym = tv.uvdym[q], dyp = tv.uvdyp[q];   // loaded ahead of the branches: one round trip
+    dev_uvspec_t(tv.mx, tv.nx, tv.trunc, vor, div, m, n, dx, dym, dyp, uc, vc);
+}
 
 // grad  spectral.f90:124-144
-__device__ __forceinline__ void dev_grad(const DevTables& tv, const double* psi, int m, int n, cd& dx, cd& dy) {
-    const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;
-    const size_t q = m + (size_t)mx * n;
-    const double gx = tv.gradx[m], gym = tv.gradym[q], gyp = tv.gradyp[q];
+__device__ __forceinline__ void dev_grad_t(int mx, int nx, int tr, const double* psi, int m, int n, double gx, double gym, double gyp, cd& dx, cd& dy) {
     dx = times_i(gx * ld(psi, mx, m, n));
     if (n == 0) dy = gyp * ld(psi, mx, m, 1);
     else if (n == nx - 1) dy = neg(gym * ld(psi, mx, m, tr));
     else dy = neg(gym * ld(psi, mx, m, n - 1)) + gyp * ld(psi, mx, m, n + 1);
+}
+__device__ __forceinline__ void dev_grad(const DevTables& tv, const double* psi, int m, int n, cd& dx, cd& dy) {
+    const size_t q = m + (size_t)tv.mx * n;
+    const double gx = tv.gradx[m], gym = tv.gradym[q], gyp = tv.gradyp[q];
+    dev_grad_t(tv.mx, tv.nx, tv.trunc, psi, m, n, gx, gym, gyp, dx, dy);
 }
 
 // vds  spectral.f90:146-171

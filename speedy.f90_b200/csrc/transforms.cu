@@ -356,10 +356,30 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             cf[2 * nt] = tv.coriol[ja]; cf[2 * nt + 1] = tv.coriol[jb];
         }
     }
+    // FFT variant (registers to spare): the operator-table entries of the FIRST field's derived input (uvspec / grad) are
+    // fetched here, ahead of the wait — they are constants, and on the single-member step a CTA has one field
+    constexpr int NE = (C::MX * C::NX + C::K1_THREADS - 1) / C::K1_THREADS;
+    constexpr bool PRE = FFT && !BATCH;
+    double pre[PRE ? NE : 1][3];
+    if constexpr (PRE) {
+        const int op0 = (f0 < f1) ? desc[f0].op : 0;
+#pragma unroll
+        for (int u = 0; u < NE; u++) {
+            const int t = tid + u * C::K1_THREADS;
+            pre[u][0] = pre[u][1] = pre[u][2] = 0.0;
+            if (op0 != 0 && t < C::MX * C::NX) {
+                const int m = t % C::MX;
+                pre[u][0] = (op0 <= 2) ? tv.uvdx[t] : tv.gradx[m];
+                pre[u][1] = (op0 <= 2) ? tv.uvdym[t] : tv.gradym[t];
+                pre[u][2] = (op0 <= 2) ? tv.uvdyp[t] : tv.gradyp[t];
+            }
+        }
+    }
     pdl_wait();                                        // the spectral fields of the previous kernel are complete
     pdl_trigger();
     const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
-#define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 96 && blockIdx.y == 0) tv.trace[48 + (i)] += gtimer() - tk0; } while (0)   // block 96: a derived (uvspec) field at T30
+    // block 96: a derived (uvspec) field at T30; batch variant: block 4, third and fourth field of its chunk (steady state)
+#define KSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == (BATCH ? 4 : 96) && blockIdx.y == 0) { const int si_ = (i) - (BATCH ? 8 : 0); if (si_ >= 0 && si_ < 8) tv.trace[48 + si_] += gtimer() - tk0; } } while (0)
     if (tid == 0 && f0 < f1) issue(f0);
     // Legendre work items: one thread owns a zonal wavenumber m and TWO latitude pairs (jlA, jlA + JG/2), so that the
     // spectral coefficients it reads serve 8 sums (the stage is bound by shared-memory bandwidth); a warp covers
@@ -384,15 +404,18 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         } else {
             // derived input: 1 ucos, 2 vcos = uvspec(vor, div) (spectral.f90:173-196); 3 d/dx, 4 d/dy = grad(ps) (:124-144)
             // fixed trip count, fully unrolled: the operator-table loads of all of a thread's coefficients are in flight together
-            constexpr int NE = (C::MX * C::NX + C::K1_THREADS - 1) / C::K1_THREADS;
 #pragma unroll
             for (int u = 0; u < NE; u++) {
                 const int t = tid + u * C::K1_THREADS;
                 if (t < C::MX * C::NX) {
                     const int n = t / C::MX, m = t - n * C::MX;
                     cd r0, r1;
-                    if (dsc.op <= 2) dev_uvspec(tv, sA, sB, m, n, r0, r1);
-                    else dev_grad(tv, sA, m, n, r0, r1);
+                    double t0, t1, t2;
+                    if (PRE && f == f0) { t0 = pre[u][0]; t1 = pre[u][1]; t2 = pre[u][2]; }
+                    else if (dsc.op <= 2) { t0 = tv.uvdx[t]; t1 = tv.uvdym[t]; t2 = tv.uvdyp[t]; }
+                    else { t0 = tv.gradx[m]; t1 = tv.gradym[t]; t2 = tv.gradyp[t]; }
+                    if (dsc.op <= 2) dev_uvspec_t(C::MX, C::NX, TRUNC, sA, sB, m, n, t0, t1, t2, r0, r1);
+                    else dev_grad_t(C::MX, C::NX, TRUNC, sA, m, n, t0, t1, t2, r0, r1);
                     cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
                     if (m + n > C::MX) r = cd{0.0, 0.0};
                     st(sIn, C::MX, m, n, r);
