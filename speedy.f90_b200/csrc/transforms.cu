@@ -291,7 +291,7 @@ struct SCfg : TCfg<TRUNC> {
 };
 
 template <int TRUNC, bool BATCH, bool FFT>
-__global__ void __maxnreg__(TRUNC == 30 ? 80 : 112)    // T30: <= 80 registers, two CTAs per SM (their Legendre and Fourier phases overlap); T47: one CTA of 576 threads
+__global__ void __maxnreg__(TRUNC == 30 ? 80 : 96)    // T30: <= 80 registers, two CTAs per SM (their Legendre and Fourier phases overlap); T47: one CTA of 576 threads
 k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, CloseArgs cl) {
     using C = SCfg<TRUNC>;

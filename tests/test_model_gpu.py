@@ -185,6 +185,36 @@ def test_one_year_integration(pkg):
     c.close()
 
 
+def test_one_year_climate_is_physical(pkg):
+    """Oracle-independent check of the whole path: area-weighted global means over the last 360 days of a one-year run
+    (sampled every 5 days) against what an atmosphere — and SPEEDY's published climate — looks like: outgoing long-wave
+    and absorbed solar radiation near 235 W/m2 and in near balance, 2.5-3 mm/day of precipitation, a 285 K lowest level,
+    dry mass conserved.  (Measured: OLR 229.2, TSR 236.2, precipitation 2.60 mm/day, T 285.1 K, ps 987.47 -> 987.61 hPa;
+    tools/climate_check.py, profiles/r1m_climate_check.json.)"""
+    c = pkg.Speedy(trunc=30)
+    c.model_init(BC)
+    wt = pkg.host_table(30, "wt")
+    w = np.concatenate([wt, wt[::-1]]) / 2.0
+    gm = lambda f: float((np.asarray(f, np.float64).mean(axis=-1) * w).sum())
+    ps0 = gm(c.output_fields()["ps"]) / 100.0
+    acc = dict(olr=0.0, tsr=0.0, prec=0.0, tlow=0.0, ps=0.0)
+    n = 0
+    for d in range(365):
+        assert c.run_steps(36) == 0
+        if d >= 5 and d % 5 == 0:
+            o = c.output_fields()
+            acc["olr"] += gm(c.get_field("olr")); acc["tsr"] += gm(c.get_field("tsr"))
+            acc["prec"] += gm(c.get_field("precnv") + c.get_field("precls")) * 86.4      # g/(m2 s) -> mm/day
+            acc["tlow"] += gm(o["t"][-1]); acc["ps"] += gm(o["ps"]) / 100.0
+            n += 1
+    m = {k: v / n for k, v in acc.items()}
+    assert 220.0 < m["olr"] < 250.0 and 225.0 < m["tsr"] < 250.0 and abs(m["tsr"] - m["olr"]) < 15.0
+    assert 2.0 < m["prec"] < 3.5
+    assert 280.0 < m["tlow"] < 290.0
+    assert abs(m["ps"] - ps0) < 1.0
+    c.close()
+
+
 def test_t47_at_72_steps_per_day(pkg, oracle47_n72):
     """params.f90:30 nsteps is a run-time setting here (speedy_cfg.nsteps).  T47 at 72 steps/day (delt = 1200 s):
     48 h parity against the oracle built with the same setting, then two months without leaving the
