@@ -82,7 +82,7 @@ struct speedy_ctx {
     int sppt_on = 0;
     unsigned long long seed = 0;
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
-    bool fft_inverse = true; // T30 spec->grid: regrouped FFTPACK FFT (fft96.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
+    bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
     int num_sms = 148;
     spd::DevBuf<unsigned long long> trace;

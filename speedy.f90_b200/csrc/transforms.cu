@@ -21,6 +21,7 @@
 #include "spectral_ops.cuh"
 #include "tma.cuh"
 #include "fft96.cuh"
+#include "fft144.cuh"
 #include "close_step.cuh"
 
 namespace spd {
@@ -267,10 +268,10 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int MP = (B::MX + 31) / 32 * 32;             // m padded to whole warps
     static constexpr int K1_THREADS = B::IX / 8 * 32;
     static constexpr size_t K1_SMEM = sizeof(double) * (PT + 3 * B::NSPEC2 + B::KP * XS) + 2 * sizeof(uint64_t);
-    // FFT variant of the Fourier stage (fft96.cuh, T30 only): half-complex rows + the buffer between its two stages, position-major
-    // with an odd row stride (the Legendre stage's scattered writes and the FFT's 16-row reads are both conflict-free), + twiddles
-    static constexpr int XF = 17;
-    static constexpr bool HAS_FFT = (B::IX == 96 && NR == 16);
+    // FFT variant of the Fourier stage (fft96.cuh / fft144.cuh): half-complex rows + the buffer between its two stages,
+    // position-major with an odd row stride (the Legendre stage's scattered writes and the FFT's row-wise reads spread over the banks), + twiddles
+    static constexpr int XF = NR + 1;
+    static constexpr bool HAS_FFT = (B::IX == 96 && NR == 16) || (B::IX == 144 && NR == 8);
     static constexpr size_t K1_SMEM_FFT = sizeof(double) * (PT + 3 * B::NSPEC2 + 2 * B::IX * XF + B::IX) + 2 * sizeof(uint64_t);
     // K2: groups of 16 Fourier rows = 8 zonal wavenumbers
     static constexpr int RG = 16, CG = B::KP / RG, MG = RG / 2;
@@ -287,7 +288,7 @@ struct SCfg : TCfg<TRUNC> {
     static_assert(2 * RG * ES + 2 <= B::IL * GS, "fold buffers fit in the grid buffer");
     static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && 32 % (JG / 2) == 0 && JG * MP <= K1_THREADS, "K1 tiling");
     static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && PS % 16 == 8 && PS >= TR + B::MX && (TR * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
-    static_assert(K1_SMEM <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
+    static_assert(K1_SMEM <= 232448 && K1_SMEM_FFT <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
 };
 
 template <int TRUNC, bool BATCH, bool FFT>
@@ -342,7 +343,7 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         // half-complex rows hold positions 0..2*trunc (fourier.f90:40-45); the zero padding up to ix is written once
         for (int t = tid; t < (C::IX - (C::K2 - 1)) * C::XF; t += nthr) sX[(C::K2 - 1) * C::XF + t] = 0.0;
         for (int t = tid; t < C::IX; t += nthr) sWa[t] = tv.fftwa[t];
-        const int jr = row_lat((tid >> 3) & (C::NR - 1));      // stage 2: thread = (row, k of the third pass)
+        const int jr = row_lat((tid >> (C::IX == 96 ? 3 : 4)) & (C::NR - 1));      // stage 2: thread = (row, k of the third pass)
         cg[0] = tv.cosgr[jr]; cf[0] = tv.coriol[jr];
     } else {
         const double* A = tv.finv + (size_t)(8 * w + g) * C::KP + q;
@@ -464,27 +465,52 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         KSTAMP(4 * (f - f0) + 2);
         double* out = out_base + (size_t)e * out_ms + (size_t)(dsc.oslot1 ? dsc.oslot1 - 1 : f) * C::IX * C::IL;
         if constexpr (FFT) {
-            // ---- backward FFT per latitude row, FFTPACK's passes regrouped into two register-resident stages (fft96.cuh).
-            // stage 1: half-warp = one closed input set x the 16 rows
-            if (tid < 128) {
-                const int h = tid >> 4, r = tid & 15;
-                if (h < 5) Fft96::stage1_general<C::XF>(sX + r, sT + r, sWa, 3 + 2 * h);
-                else if (h == 6) Fft96::stage1_first<C::XF>(sX + r, sT + r, sWa);
-                else if (h == 7) Fft96::stage1_last<C::XF>(sX + r, sT + r, sWa);
-            }
-            __syncthreads();
-            // stage 2: thread = (row, k): 8 consecutive lanes write 8 consecutive longitudes
-            if (tid < 128) {
-                const int r = tid >> 3, k3 = tid & 7;
-                double y[12];
-                Fft96::stage2<C::XF>(sT + r, sWa, k3, y);
-                double* orow = out + (size_t)row_lat(r) * C::IX + k3;
+            // ---- backward FFT per latitude row, FFTPACK's passes regrouped into two register-resident stages
+            // (fft96.cuh at T30: 16 rows per CTA; fft144.cuh at T47: 8 rows per CTA)
+            if constexpr (C::IX == 96) {
+                // stage 1: half-warp = one closed input set x the 16 rows
+                if (tid < 128) {
+                    const int h = tid >> 4, r = tid & 15;
+                    if (h < 5) Fft96::stage1_general<C::XF>(sX + r, sT + r, sWa, 3 + 2 * h);
+                    else if (h == 6) Fft96::stage1_first<C::XF>(sX + r, sT + r, sWa);
+                    else if (h == 7) Fft96::stage1_last<C::XF>(sX + r, sT + r, sWa);
+                }
+                __syncthreads();
+                // stage 2: thread = (row, k): 8 consecutive lanes write 8 consecutive longitudes
+                if (tid < 128) {
+                    const int r = tid >> 3, k3 = tid & 7;
+                    double y[12];
+                    Fft96::stage2<C::XF>(sT + r, sWa, k3, y);
+                    double* orow = out + (size_t)row_lat(r) * C::IX + k3;
 #pragma unroll
-                for (int t = 0; t < 12; t++) {
-                    double v = y[t];
-                    if (sc) v *= cg[0];
-                    if (ad) v += cf[0];
-                    orow[8 * (t & 3) + 32 * (t >> 2)] = v;
+                    for (int t = 0; t < 12; t++) {
+                        double v = y[t];
+                        if (sc) v *= cg[0];
+                        if (ad) v += cf[0];
+                        orow[8 * (t & 3) + 32 * (t >> 2)] = v;
+                    }
+                }
+            } else {
+                // stage 1: quarter-warp = one (input set, k pair) x the 8 rows; warp 0: k = 1,2, warp 1: k = 3,4, warp 2: the i = 1 sets
+                if (tid < 80) {
+                    const int role = tid >> 3, r = tid & 7;
+                    if (role < 8) Fft144::stage1_general<C::XF>(sX + r, sT + r, sWa, 3 + 2 * (role & 3), role >> 2);
+                    else Fft144::stage1_first<C::XF>(sX + r, sT + r, sWa, role - 8);
+                }
+                __syncthreads();
+                // stage 2: thread = (row, k): 16 consecutive lanes write 16 consecutive longitudes
+                if (tid < 128) {
+                    const int r = tid >> 4, k3 = tid & 15;
+                    double y[9];
+                    Fft144::stage2<C::XF>(sT + r, sWa, k3, y);
+                    double* orow = out + (size_t)row_lat(r) * C::IX + k3;
+#pragma unroll
+                    for (int t = 0; t < 9; t++) {
+                        double v = y[t];
+                        if (sc) v *= cg[0];
+                        if (ad) v += cf[0];
+                        orow[16 * (t % 3) + 48 * (t / 3)] = v;
+                    }
                 }
             }
         } else {
@@ -664,6 +690,8 @@ void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM_FFT));
     CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<30, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K1_SMEM_FFT));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM_FFT));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM_FFT));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM_BATCH));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM_BATCH));
 }
@@ -681,7 +709,7 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
                               double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
     using C = SCfg<TRUNC>;
     // one SM is left to the closing CTA when a step is to be closed
-    // T30: the Fourier stage is the regrouped FFTPACK FFT (fft96.cuh); otherwise the dense operator on the FP64 tensor pipe
+    // the Fourier stage is the regrouped FFTPACK FFT (fft96.cuh / fft144.cuh) unless SPEEDY_DENSE_INVERSE asks for the dense operator on the FP64 tensor pipe
     constexpr bool HF = C::HAS_FFT;
     const bool fft = HF && ctx->fft_inverse;
     const size_t smem = fft ? C::K1_SMEM_FFT : C::K1_SMEM;

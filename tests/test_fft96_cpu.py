@@ -1,4 +1,4 @@
-"""csrc/fft96.cuh — FFTPACK's backward passes regrouped into two register-resident stages (K1's Fourier stage at T30).
+"""csrc/fft96.cuh, csrc/fft144.cuh — FFTPACK's backward passes regrouped into two register-resident stages (K1's Fourier stage).
 The header is built for the host (device qualifiers compiled away) and must reproduce the oracle's pass-by-pass rfftb1
 (fftpack.f90:69-134) bit for bit: same butterflies, same twiddle table, only the order of independent work differs."""
 import ctypes
@@ -26,4 +26,23 @@ def test_regrouped_backward_fft_is_fftpack_bit_for_bit(oracle, tmp_path):
         oracle.L.orc_rfftb(P(ref))
         out = np.zeros(96)
         L.fft96_backward(P(c), P(wa), P(out))
+        assert np.array_equal(out, ref)
+
+
+def test_regrouped_backward_fft_t47(oracle47, tmp_path):
+    so = tmp_path / "fft144_host.so"
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", str(so),
+                           os.path.join(ROOT, "tests", "helpers", "fft144_host.cpp")])
+    L = ctypes.CDLL(str(so))
+    wa = np.ascontiguousarray(load_pkg().host_table(47, "fft_work"))
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.default_rng(8)
+    for trial in range(40):
+        c = rng.standard_normal(144) * 10.0 ** rng.integers(-3, 4)
+        if trial % 2:
+            c[95:] = 0.0
+        ref = c.copy()
+        oracle47.L.orc_rfftb(P(ref))
+        out = np.zeros(144)
+        L.fft144_backward(P(c), P(wa), P(out))
         assert np.array_equal(out, ref)
