@@ -20,6 +20,7 @@
 #include "ctx.h"
 #include "spectral_ops.cuh"
 #include "tma.cuh"
+#include <type_traits>
 #include "fft96.cuh"
 #include "fft144.cuh"
 #include "close_step.cuh"
@@ -262,6 +263,8 @@ struct SCfg : TCfg<TRUNC> {
     // A read past the end of a row meets the next row (finite) times a masked-out coefficient (zero).
     __host__ __device__ static constexpr int tri_cnt(int n) { return (B::MX - n + 1 < B::MX) ? (B::MX - n + 1) : B::MX; }
     __host__ __device__ static constexpr int tri_off(int n) { int o = 0; for (int i = 0; i < n; i++) o += tri_cnt(i); return o; }
+    // terms of the inverse Legendre sum that can be non-zero for wavenumbers m >= mw * w (m + n <= MX)
+    __host__ __device__ static constexpr int leg_terms(int w, int mw) { int t = B::MX + 1 - mw * w; return t > B::NX ? B::NX : (t < 1 ? 1 : t); }
     static constexpr int TR = (tri_off(B::NX) + 1) / 2 * 2;       // doubles per latitude in the packed table (even: 16-byte rows)
     static constexpr int PS = TR + B::MX + (24 - (TR + B::MX) % 16) % 16;   // shared row: >= MX zeroed pad, stride = 8 mod 16 (alternating bank halves)
     static constexpr int PT = JG * PS;                            // P tile, doubles
@@ -433,16 +436,24 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             const double* PA = sP + (size_t)jlA * C::PS + m2;
             const double* PB = sP + (size_t)jlB * C::PS + m2;
             const double2* X = reinterpret_cast<const double2*>(sIn) + m2;
+            // the wavenumbers of warp w start at MW*w: their coefficients vanish for n > MX - MW*w (triangular truncation), so
+            // the higher warps leave the sum early.  One instruction stream for all warps: blocks of 8 terms, fully unrolled,
+            // with a warp-uniform exit between blocks; each accumulator still adds its terms in ascending n.
             double ear = 0.0, eai = 0.0, oar = 0.0, oai = 0.0, ebr = 0.0, ebi = 0.0, obr = 0.0, obi = 0.0;
+            const int nmax = C::leg_terms(w, MW);
 #pragma unroll
-            for (int n = 0; n < C::NX; n += 2) {
-                const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
-                ear += x.x * pa; eai += x.y * pa; ebr += x.x * pb; ebi += x.y * pb;
-            }
+            for (int nb = 0; nb < C::NX; nb += 8) {
+                if (nb >= nmax) break;
 #pragma unroll
-            for (int n = 1; n < C::NX; n += 2) {
-                const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
-                oar += x.x * pa; oai += x.y * pa; obr += x.x * pb; obi += x.y * pb;
+                for (int n = nb; n < nb + 8 && n < C::NX; n += 2) {
+                    const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
+                    ear += x.x * pa; eai += x.y * pa; ebr += x.x * pb; ebi += x.y * pb;
+                }
+#pragma unroll
+                for (int n = nb + 1; n < nb + 8 && n < C::NX; n += 2) {
+                    const double2 x = X[n * C::MX]; const double pa = PA[C::tri_off(n)], pb = PB[C::tri_off(n)];
+                    oar += x.x * pa; oai += x.y * pa; obr += x.x * pb; obi += x.y * pb;
+                }
             }
             if constexpr (FFT) {
                 // FFTPACK's half-complex order (fourier.f90:40-45): a0, then (re, im) of m = 1..; the imaginary part of m = 0 is dropped
