@@ -198,11 +198,11 @@ void model_create(speedy_ctx* ctx) {
         for (int f = 0; f < GO_N; f++) {
             const int r = f % GO_PER;
             const bool cosgr = f < GO_PSDT && (r == 0 || r == 1 || r == 3 || r == 4 || r == 6 || r == 7);   // vdspec(.,.,2): spectral.f90:208-213
-            g[f] = XDesc{L.gout + f * NG, cosgr ? 1 : 0, 0};
+            g[f] = XDesc{f * NG, cosgr ? 1 : 0, 0};      // relative to the gout region (whole rows of the K2 input tensor map)
         }
         g[GO_QCORH].flags = 4;      // gated on the device clock's do_forcing
         M.desc_dir.upload(g);
-        std::vector<XDesc> one(1, XDesc{L.qcorh_g, 0, 0});
+        std::vector<XDesc> one(1, XDesc{(long long)GO_QCORH * NG, 0, 0});
         M.desc_one_dir.upload(one);
     }
 }
@@ -236,13 +236,13 @@ static void xform_output(speedy_ctx* ctx) {
 }
 static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
-    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
+    launch_grid_to_spec(ctx, M.mem.p + M.L.gout, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
                         ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
 }
 static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     Model& M = *ctx->model;
     (void)gated;
-    launch_grid_to_spec(ctx, M.mem.p, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0, nullptr);
+    launch_grid_to_spec(ctx, M.mem.p + M.L.gout, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0, nullptr);
 }
 
 // get_tendencies up to (and including) the direct transforms

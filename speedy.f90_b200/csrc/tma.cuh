@@ -44,6 +44,9 @@ __device__ __forceinline__ void tensor_g2s_3d(void* dst_smem, const void* tmap, 
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+// order earlier generic-proxy accesses to shared memory before later async-proxy (TMA) writes to the same locations
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // named barriers (ids 1..15; 0 is __syncthreads): producer/consumer hand-off between warp roles
 __device__ __forceinline__ void named_arrive(int id, int nthreads) {
     __threadfence_block();   // the arriving side's shared/global writes are ordered before the arrival

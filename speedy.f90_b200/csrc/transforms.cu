@@ -20,6 +20,10 @@
 #include "ctx.h"
 #include "spectral_ops.cuh"
 #include "tma.cuh"
+#include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <type_traits>
 #include "fft96.cuh"
 #include "fft144.cuh"
@@ -286,9 +290,12 @@ struct SCfg : TCfg<TRUNC> {
     static constexpr int OOFF = RG * ES + 1;                      // sO behind sE, shifted one bank
     // latency variant: the even/odd folds alias the grid buffer (dead after the Fourier stage), 107 KB at T30: two CTAs per SM;
     // batch variant: separate fold buffers (the next field is already streaming into the grid buffer) + the raw field buffer
-    static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * GS + RG * FS + RG * YS + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
-    static constexpr size_t K2_SMEM_BATCH = K2_SMEM + sizeof(double) * (2 * RG * ES + 2 + B::IL * B::IX);
-    static_assert(2 * RG * ES + 2 <= B::IL * GS, "fold buffers fit in the grid buffer");
+    // the grid field arrives as IX/16 tensor-map boxes of [16 longitudes x IL latitudes] (128-byte rows, SWIZZLE_128B): the B
+    // fragments of the DMMA read it conflict-free without row padding, and no re-layout pass is needed
+    static constexpr int NBOX = B::IX / 16, BOX = 16 * B::IL;
+    static constexpr size_t K2_SMEM = sizeof(double) * (B::IL * B::IX + RG * FS + RG * YS + (P_SMEM ? PD : 0)) + 2 * sizeof(uint64_t);
+    static constexpr size_t K2_SMEM_BATCH = K2_SMEM + sizeof(double) * (2 * RG * ES + 2);
+    static_assert(2 * RG * ES + 2 <= B::IL * B::IX && B::IX % 16 == 0 && (BOX * 8) % 1024 == 0, "fold buffers fit in the grid buffer; whole swizzle atoms");
     static_assert(B::IY % LG == 0 && NR % 8 == 0 && JG % 4 == 0 && 32 % (JG / 2) == 0 && JG * MP <= K1_THREADS, "K1 tiling");
     static_assert(B::KP % RG == 0 && (PS * 8) % 16 == 0 && PS % 16 == 8 && PS >= TR + B::MX && (TR * 8) % 16 == 0 && (B::NSPEC2 * 8) % 16 == 0 && (PD * 8) % 16 == 0, "K2 tiling / bulk-copy sizes");
     static_assert(K1_SMEM <= 232448 && K1_SMEM_FFT <= 232448 && K2_SMEM_BATCH <= 232448, "shared memory budget");
@@ -549,40 +556,41 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
 }
 
 template <int TRUNC, bool BATCH>
-__global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, (!BATCH && TRUNC == 30) ? 2 : 1)
-k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int nchunk,
+__global__ void __launch_bounds__(SCfg<TRUNC>::K2_THREADS, TRUNC == 30 ? 2 : 1)
+k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int nchunk,
              double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
     using C = SCfg<TRUNC>;
-    extern __shared__ __align__(16) double smem[];
-    double* sG = smem;                                  // [IL][GS] grid field, rows padded for conflict-free B fragments
-    double* sF = sG + C::IL * C::GS;                    // [RG][FS] rows of the dense forward Fourier operator
+    extern __shared__ __align__(1024) double smem[];
+    double* sG = smem;                                  // [NBOX][IL][16] grid field, 16-byte chunks of a row XOR-swizzled with the row index (TMA SWIZZLE_128B)
+    double* sF = sG + C::IL * C::IX;                    // [RG][FS] rows of the dense forward Fourier operator
     double* sY = sF + C::RG * C::FS;                    // [RG][YS] Fourier coefficients of this group
     double* sPd = sY + C::RG * C::YS;                   // [IY][NX][MG]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sPd + (C::P_SMEM ? C::PD : 0));   // [0] operator + P tiles, [1] grid field
     double* sE = BATCH ? reinterpret_cast<double*>(bars + 2) : sG;   // even / odd folds (latency variant: in the dead grid buffer)
     double* sO = sE + C::OOFF;
-    double* sRaw = sE + 2 * C::RG * C::ES + 2;          // BATCH only: [IL][IX] grid field as it arrives (one bulk copy)
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) trace_begin(tv.trace, 2);
     const int grp = blockIdx.x % C::CG, chunk = blockIdx.x / C::CG, e = blockIdx.y;
     const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
-    const double* mbase = in_base + (size_t)e * in_ms;
     const int c0row = grp * C::RG;
     int gate_open = 1;
     auto live = [&](int f) { return gate_open || !(desc[f].flags & 4); };
     auto next_live = [&](int f) { while (f < f1 && !live(f)) f++; return f; };
     const uint32_t rowb = C::IX * sizeof(double);
-    // Two ways to bring a field in.  Long chunks (ensemble batches): ONE bulk copy into the raw buffer, then a re-layout
-    // pass to padded rows — 48 row copies take ~1 us to drain through the TMA unit, the single copy half of that, and the
-    // next copy overlaps the whole field.  Short chunks (1-2 fields per CTA, the single-member step): row copies straight
-    // into the padded buffer, no extra pass on the critical path.
-    constexpr bool one_copy = BATCH;
+    // a field = NBOX tensor-map boxes issued by one thread (48 row copies took ~1 us to drain through the TMA unit); the map is
+    // [longitude][row of IX doubles][member], a field at element offset `off` starts at row off / IX
     auto issue = [&](int f) {
-        const double* src = mbase + desc[f].off;
-        if (tid == 0) mbar_expect_tx(&bars[1], C::IL * rowb);
-        if (one_copy) { if (tid == 0) bulk_g2s(sRaw, src, C::IL * rowb, &bars[1]); }
-        else if (tid < C::IL) bulk_g2s(sG + tid * C::GS, src + (size_t)tid * C::IX, rowb, &bars[1]);
+        if (tid == 0) {
+            const long long off = desc[f].off;
+            const int row0 = (int)(off / C::IX);
+            if (off != (long long)row0 * C::IX) __trap();   // fields must start on whole rows of the input map
+            fence_proxy_async();                        // the folds of the previous field (generic writes) alias this buffer
+            mbar_expect_tx(&bars[1], C::IL * rowb);
+#pragma unroll
+            for (int b = 0; b < C::NBOX; b++) tensor_g2s_3d(sG + b * C::BOX, &gmap, 16 * b, row0, e, &bars[1]);
+        }
     };
+    if (tid == 0 && (smem_u32(sG) & 1023u)) __trap();   // the swizzle pattern is a function of the address: the boxes must start on 1 KB
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
     // prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
@@ -602,36 +610,30 @@ k_g2s_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
         if (it == 0) mbar_wait(&bars[0], 0);
         mbar_wait(&bars[1], it & 1);
         const int fn = next_live(f + 1);
-        if (one_copy) {
-            // ---- re-layout to padded rows with the cosgr / cosgr2 pre-scale of vdspec (spectral.f90:208-222)
-            for (int t = tid; t < C::IL * C::IX / 2; t += nthr) {
-                const int j = (2 * t) / C::IX, i = 2 * t - j * C::IX;
-                double2 v = *reinterpret_cast<const double2*>(sRaw + 2 * t);
-                if (scl) { const double sj = scl[j]; v.x *= sj; v.y *= sj; }
-                *reinterpret_cast<double2*>(sG + j * C::GS + i) = v;
-            }
-            __syncthreads();                            // sG complete, raw buffer free
-            if (fn < f1) issue(fn);
-            scl = nullptr;
-        }
-        // ---- dense forward Fourier operator for this CTA's rows (fourier.f90:56-82):
-        //   Y[c][j] = sum_i ffwd[c][i] * (g[i][j] * scl[j]),  M = RG, N = IL, K = IX
+        // ---- dense forward Fourier operator for this CTA's rows (fourier.f90:56-82), with the cosgr / cosgr2 pre-scale of
+        // vdspec (spectral.f90:208-222):  Y[c][j] = sum_i ffwd[c][i] * (g[i][j] * scl[j]),  M = RG, N = IL, K = IX.
+        // B fragment of lane (g, q) at k-step ks: latitude 8 nt + g, longitude 4 ks + q = box ks / 4, 16-byte chunk
+        // 2 (ks % 4) + q / 2 of the row, XORed with the row index mod 8 (= g)
+        int swz[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) swz[kk] = (((2 * kk + (q >> 1)) ^ g) << 1) + (q & 1);
         for (int tile = w; tile < C::MT * C::NT; tile += nw) {
             const int mt = tile / C::NT, nt = tile - mt * C::NT;
             const double* A = sF + (8 * mt + g) * C::FS + q;
-            const double* Bf = sG + (8 * nt + g) * C::GS + q;
+            const double* Bf = sG + (8 * nt + g) * 16;
             double c0 = 0.0, c1 = 0.0;
             if (scl) {
                 const double sj = scl[8 * nt + g];
 #pragma unroll
-                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks] * sj);
+                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[(ks >> 2) * C::BOX + swz[ks & 3]] * sj);
             } else {
 #pragma unroll
-                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[4 * ks]);
+                for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[(ks >> 2) * C::BOX + swz[ks & 3]]);
             }
             *reinterpret_cast<double2*>(sY + (8 * mt + g) * C::YS + 8 * nt + 2 * q) = make_double2(c0, c1);
         }
-        __syncthreads();                                // sY complete, padded grid buffer free
+        __syncthreads();                                // sY complete, grid buffer free
+        if (BATCH && fn < f1) issue(fn);                // batch variant: separate fold buffers, the next field streams in now
         // Gaussian-weighted even/odd fold (legendre.f90:127-133)
         for (int t = tid; t < C::RG * C::IY; t += nthr) {
             const int cl = t / C::IY, jh = t - cl * C::IY;
@@ -742,19 +744,54 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
     else { if (batch) S2G_LAUNCH(true, false); else S2G_LAUNCH(false, false); }
 #undef S2G_LAUNCH
 }
+// tensor map of K2's input: [longitude][row of IX doubles][member] over the caller's buffer, boxes of 16 longitudes x IL rows,
+// SWIZZLE_128B.  A field at element offset `off` (a multiple of IX) starts at row off / IX.  Maps are cached per buffer.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static const CUtensorMap& grid_field_map(const double* d_in, long long in_ms, int nmembers, int ix, int il) {
+    static std::map<std::tuple<const void*, long long, int, int>, CUtensorMap> cache;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const auto key = std::make_tuple((const void*)d_in, in_ms, nmembers, ix);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) throw std::runtime_error("cuTensorMapEncodeTiled is not available in this driver");
+        enc = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    if ((reinterpret_cast<uintptr_t>(d_in) & 15) || (nmembers > 1 && (in_ms * sizeof(double)) % 16)) throw std::runtime_error("grid_to_spec: input buffer must be 16-byte aligned");
+    // rows: everything a member's descriptors may address; the extent is a clipping bound, not an allocation size
+    const cuuint64_t rows = (nmembers > 1 && in_ms > 0) ? (cuuint64_t)(in_ms / ix) : (cuuint64_t)1 << 22;
+    const cuuint64_t dims[3] = {(cuuint64_t)ix, rows, (cuuint64_t)nmembers};
+    const cuuint64_t strides[2] = {(cuuint64_t)ix * sizeof(double), (nmembers > 1 ? (cuuint64_t)in_ms : rows * (cuuint64_t)ix) * sizeof(double)};
+    const cuuint32_t box[3] = {16u, (cuuint32_t)il, 1u};
+    const cuuint32_t es[3] = {1u, 1u, 1u};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(d_in), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed for the grid_to_spec input (" + std::to_string((int)r) + ")");
+    return cache.emplace(key, m).first->second;
+}
+
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                               double* d_out, long long out_ms, int nmembers, const int* gate) {
     using C = SCfg<TRUNC>;
-    static int occ = 0;       // resident CTAs per SM of the latency variant (2 at T30, 1 at T47)
+    static int occ = 0, occ_b = 0;       // resident CTAs per SM of the latency / batch variant
     if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2s_stream<TRUNC, false>, C::K2_THREADS, C::K2_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
+    if (!occ_b) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_g2s_stream<TRUNC, true>, C::K2_THREADS, C::K2_SMEM_BATCH)); if (occ_b < 1) occ_b = 1; if (occ_b > 2) occ_b = 2; }
     int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ);
-    if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch);   // batch variant: one CTA per SM
+    if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ_b);   // batch variant
     dim3 grid(nchunk * C::CG, nmembers);
+    const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if ((nbatch + nchunk - 1) / nchunk >= 3)
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, gmap, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
     else
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, false>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, d_in, in_ms, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, false>, grid, dim3(C::K2_THREADS), C::K2_SMEM, ctx->stream, gmap, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
 }
 
 // layout of the per-wavenumber-group P tiles of the streaming direct transform: [grp][jh][n][mloc]
