@@ -55,6 +55,27 @@ __device__ __forceinline__ void dev_grad(const DevTables& tv, const double* psi,
     dev_grad_t(tv.mx, tv.nx, tv.trunc, psi, m, n, gx, gym, gyp, dx, dy);
 }
 
+// one component of uvspec / grad at (m,n): the K1 input stage builds ONE derived field per transform, so it evaluates (and
+// loads the stencil of) that component only.  Same expressions as above.
+__device__ __forceinline__ cd dev_ucos_t(int mx, int nx, int tr, const double* vor, const double* div, int m, int n, double dx, double dym, double dyp) {
+    const cd zc = times_i(dx * ld(div, mx, m, n));
+    if (n == 0) return zc - dyp * ld(vor, mx, m, 1);
+    if (n == nx - 1) return dym * ld(vor, mx, m, tr);
+    return (dym * ld(vor, mx, m, n - 1) - dyp * ld(vor, mx, m, n + 1)) + zc;
+}
+__device__ __forceinline__ cd dev_vcos_t(int mx, int nx, int tr, const double* vor, const double* div, int m, int n, double dx, double dym, double dyp) {
+    const cd zp = times_i(dx * ld(vor, mx, m, n));
+    if (n == 0) return zp + dyp * ld(div, mx, m, 1);
+    if (n == nx - 1) return neg(dym * ld(div, mx, m, tr));
+    return (neg(dym * ld(div, mx, m, n - 1)) + dyp * ld(div, mx, m, n + 1)) + zp;
+}
+__device__ __forceinline__ cd dev_gradx_t(int mx, const double* psi, int m, int n, double gx) { return times_i(gx * ld(psi, mx, m, n)); }
+__device__ __forceinline__ cd dev_grady_t(int mx, int nx, int tr, const double* psi, int m, int n, double gym, double gyp) {
+    if (n == 0) return gyp * ld(psi, mx, m, 1);
+    if (n == nx - 1) return neg(gym * ld(psi, mx, m, tr));
+    return neg(gym * ld(psi, mx, m, n - 1)) + gyp * ld(psi, mx, m, n + 1);
+}
+
 // vds  spectral.f90:146-171
 __device__ __forceinline__ void dev_vds(const DevTables& tv, const double* uc, const double* vc, int m, int n, cd& vor, cd& div) {
     const int mx = tv.mx, nx = tv.nx, tr = tv.trunc;

@@ -414,22 +414,56 @@ k_s2g_stream(const double* __restrict__ in_base, long long in_ms, const XDesc* _
             }
         } else {
             // derived input: 1 ucos, 2 vcos = uvspec(vor, div) (spectral.f90:173-196); 3 d/dx, 4 d/dy = grad(ps) (:124-144)
-            // fixed trip count, fully unrolled: the operator-table loads of all of a thread's coefficients are in flight together
+            // fixed trip count, fully unrolled: the operator-table loads of all of a thread's coefficients are in flight together;
+            // one instantiation per component, each reading only its own stencil (half the shared-memory loads of a full uvspec)
+            // (the single-member T30 variant keeps ONE instruction stream that evaluates both components: its code runs once per
+            // CTA, and four specialised copies measured 0.1 us slower per step there, against -1.5 % at 8 members and -5 % at T47)
+            constexpr bool SPLIT = BATCH || TRUNC != 30;
+            if constexpr (!SPLIT) {
 #pragma unroll
-            for (int u = 0; u < NE; u++) {
-                const int t = tid + u * C::K1_THREADS;
-                if (t < C::MX * C::NX) {
-                    const int n = t / C::MX, m = t - n * C::MX;
-                    cd r0, r1;
-                    double t0, t1, t2;
-                    if (PRE && f == f0) { t0 = pre[u][0]; t1 = pre[u][1]; t2 = pre[u][2]; }
-                    else if (dsc.op <= 2) { t0 = tv.uvdx[t]; t1 = tv.uvdym[t]; t2 = tv.uvdyp[t]; }
-                    else { t0 = tv.gradx[m]; t1 = tv.gradym[t]; t2 = tv.gradyp[t]; }
-                    if (dsc.op <= 2) dev_uvspec_t(C::MX, C::NX, TRUNC, sA, sB, m, n, t0, t1, t2, r0, r1);
-                    else dev_grad_t(C::MX, C::NX, TRUNC, sA, m, n, t0, t1, t2, r0, r1);
-                    cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
-                    if (m + n > C::MX) r = cd{0.0, 0.0};
-                    st(sIn, C::MX, m, n, r);
+                for (int u = 0; u < NE; u++) {
+                    const int t = tid + u * C::K1_THREADS;
+                    if (t < C::MX * C::NX) {
+                        const int n = t / C::MX, m = t - n * C::MX;
+                        cd r0, r1;
+                        double t0, t1, t2;
+                        if (PRE && f == f0) { t0 = pre[u][0]; t1 = pre[u][1]; t2 = pre[u][2]; }
+                        else if (dsc.op <= 2) { t0 = tv.uvdx[t]; t1 = tv.uvdym[t]; t2 = tv.uvdyp[t]; }
+                        else { t0 = tv.gradx[m]; t1 = tv.gradym[t]; t2 = tv.gradyp[t]; }
+                        if (dsc.op <= 2) dev_uvspec_t(C::MX, C::NX, TRUNC, sA, sB, m, n, t0, t1, t2, r0, r1);
+                        else dev_grad_t(C::MX, C::NX, TRUNC, sA, m, n, t0, t1, t2, r0, r1);
+                        cd r = (dsc.op == 1 || dsc.op == 3) ? r0 : r1;
+                        if (m + n > C::MX) r = cd{0.0, 0.0};
+                        st(sIn, C::MX, m, n, r);
+                    }
+                }
+            } else {
+                auto derived = [&](auto opc) {
+                    constexpr int OP = decltype(opc)::value;
+#pragma unroll
+                    for (int u = 0; u < NE; u++) {
+                        const int t = tid + u * C::K1_THREADS;
+                        if (t < C::MX * C::NX) {
+                            const int n = t / C::MX, m = t - n * C::MX;
+                            double t0, t1, t2;
+                            if (PRE && f == f0) { t0 = pre[u][0]; t1 = pre[u][1]; t2 = pre[u][2]; }
+                            else if (OP <= 2) { t0 = tv.uvdx[t]; t1 = tv.uvdym[t]; t2 = tv.uvdyp[t]; }
+                            else { t0 = tv.gradx[m]; t1 = tv.gradym[t]; t2 = tv.gradyp[t]; }
+                            cd r;
+                            if constexpr (OP == 1) r = dev_ucos_t(C::MX, C::NX, TRUNC, sA, sB, m, n, t0, t1, t2);
+                            else if constexpr (OP == 2) r = dev_vcos_t(C::MX, C::NX, TRUNC, sA, sB, m, n, t0, t1, t2);
+                            else if constexpr (OP == 3) r = dev_gradx_t(C::MX, sA, m, n, t0);
+                            else r = dev_grady_t(C::MX, C::NX, TRUNC, sA, m, n, t1, t2);
+                            if (m + n > C::MX) r = cd{0.0, 0.0};
+                            st(sIn, C::MX, m, n, r);
+                        }
+                    }
+                };
+                switch (dsc.op) {
+                    case 1: derived(std::integral_constant<int, 1>{}); break;
+                    case 2: derived(std::integral_constant<int, 2>{}); break;
+                    case 3: derived(std::integral_constant<int, 3>{}); break;
+                    default: derived(std::integral_constant<int, 4>{}); break;
                 }
             }
         }
