@@ -136,15 +136,25 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
     cd vordt, divdt, tdt, trdt, psdt = zero;
     {
         const int f = GO_PER * k;
-        cd vo, di, dum;
-        dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 0), sfield(mb, a.L.sout, nsp, f + 1), m, n, vo, di);
-        vordt = vo;
+        // all stencil operands of the three vds calls are loaded unconditionally (neighbour index clamped at the edges, where the
+        // value is not used) ahead of the n-dependent branches: one round trip instead of one per call
+        const int nm = n > 0 ? n - 1 : 0, np = n < nx - 1 ? n + 1 : nx - 1;
+        const double gx = tv.gradx[m], dym = tv.vddym[q], dyp = tv.vddyp[q];
+        const double* F0 = sfield(mb, a.L.sout, nsp, f + 0); const double* F1 = sfield(mb, a.L.sout, nsp, f + 1);
+        const double* F4 = sfield(mb, a.L.sout, nsp, f + 4); const double* F7 = sfield(mb, a.L.sout, nsp, f + 7);
+        const cd um = ld(F0, mx, m, nm), u0 = ld(F0, mx, m, n), up = ld(F0, mx, m, np);
+        const cd vm = ld(F1, mx, m, nm), v0 = ld(F1, mx, m, n), vp = ld(F1, mx, m, np);
         const cd ke = ld(sfield(mb, a.L.sout, nsp, f + 2), mx, m, n);
+        const cd ut0 = ld(sfield(mb, a.L.sout, nsp, f + 3), mx, m, n), vtm = ld(F4, mx, m, nm), vtp = ld(F4, mx, m, np);
+        const cd tt = ld(sfield(mb, a.L.sout, nsp, f + 5), mx, m, n);
+        const cd uq0 = ld(sfield(mb, a.L.sout, nsp, f + 6), mx, m, n), vqm = ld(F7, mx, m, nm), vqp = ld(F7, mx, m, np);
+        const cd qt = ld(sfield(mb, a.L.sout, nsp, f + 8), mx, m, n);
+        cd vo, di;
+        dev_vds_r(nx, n, gx, dym, dyp, um, u0, up, vm, v0, vp, vo, di);
+        vordt = vo;
         divdt = di - neg(el2 * ke);                                      // - laplacian(KE)
-        dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 3), sfield(mb, a.L.sout, nsp, f + 4), m, n, dum, di);
-        tdt = di + ld(sfield(mb, a.L.sout, nsp, f + 5), mx, m, n);
-        dev_vds(tv, sfield(mb, a.L.sout, nsp, f + 6), sfield(mb, a.L.sout, nsp, f + 7), m, n, dum, di);
-        trdt = di + ld(sfield(mb, a.L.sout, nsp, f + 8), mx, m, n);
+        tdt = dev_vds_div_r(nx, n, gx, dym, dyp, ut0, vtm, vtp) + tt;
+        trdt = dev_vds_div_r(nx, n, gx, dym, dyp, uq0, vqm, vqp) + qt;
     }
     // time level 1 of the prognostics (all linear terms use it, alph = 0.5: tendencies.f90:32)
     const cd vor1 = ld(sfield(mb, a.L.vor, nsp, k), mx, m, n);

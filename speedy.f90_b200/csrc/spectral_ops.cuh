@@ -94,4 +94,29 @@ __device__ __forceinline__ void dev_vds(const DevTables& tv, const double* uc, c
     }
 }
 
+// vds on operands already in registers (um/u0/up, vm/v0/vp: ucos, vcos at n-1, n, n+1 with the neighbour index clamped at the
+// edges, where it is not used): the caller loads them and the three table entries unconditionally, all at once, so that
+// the stencil branches do not serialise the global-memory round trips.  Same expressions as dev_vds.
+__device__ __forceinline__ void dev_vds_r(int nx, int n, double gx, double dym, double dyp, cd um, cd u0, cd up, cd vm, cd v0, cd vp, cd& vor, cd& div) {
+    const cd zp = times_i(gx * u0);
+    const cd zc = times_i(gx * v0);
+    if (n == 0) {
+        vor = zc - dyp * up;
+        div = zp + dyp * vp;
+    } else if (n == nx - 1) {
+        vor = dym * um;
+        div = neg(dym * vm);
+    } else {
+        vor = (dym * um - dyp * up) + zc;
+        div = (neg(dym * vm) + dyp * vp) + zp;
+    }
+}
+// the divergence half alone (spectral.f90:160-168)
+__device__ __forceinline__ cd dev_vds_div_r(int nx, int n, double gx, double dym, double dyp, cd u0, cd vm, cd vp) {
+    const cd zp = times_i(gx * u0);
+    if (n == 0) return zp + dyp * vp;
+    if (n == nx - 1) return neg(dym * vm);
+    return (neg(dym * vm) + dyp * vp) + zp;
+}
+
 }  // namespace spd
