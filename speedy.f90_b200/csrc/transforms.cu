@@ -613,9 +613,8 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
     const uint32_t rowb = C::IX * sizeof(double);
     // a field = NBOX tensor-map boxes issued by one thread (48 row copies took ~1 us to drain through the TMA unit); the map is
     // [longitude][row of IX doubles][member], a field at element offset `off` starts at row off / IX
-    auto issue = [&](int f) {
+    auto issue_off = [&](long long off) {
         if (tid == 0) {
-            const long long off = desc[f].off;
             const int row0 = (int)(off / C::IX);
             if (off != (long long)row0 * C::IX) __trap();   // fields must start on whole rows of the input map
             fence_proxy_async();                        // the folds of the previous field (generic writes) alias this buffer
@@ -624,6 +623,7 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
             for (int b = 0; b < C::NBOX; b++) tensor_g2s_3d(sG + b * C::BOX, &gmap, 16 * b, row0, e, &bars[1]);
         }
     };
+    auto issue = [&](int f) { if (tid == 0) issue_off(desc[f].off); };
     if (tid == 0 && (smem_u32(sG) & 1023u)) __trap();   // the swizzle pattern is a function of the address: the boxes must start on 1 KB
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
     __syncthreads();
@@ -631,16 +631,31 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
     if (tid == 0) mbar_expect_tx(&bars[0], C::RG * rowb + (C::P_SMEM ? C::PD * sizeof(double) : 0));
     if (tid < C::RG) bulk_g2s(sF + tid * C::FS, tv.ffwd + (size_t)(c0row + tid) * C::IX, rowb, &bars[0]);
     if (C::P_SMEM && tid == C::RG) bulk_g2s(sPd, tv.polyd + (size_t)grp * C::PD, C::PD * sizeof(double), &bars[0]);
+    // constants this thread needs later are fetched here too, ahead of the dependency wait: the first field's descriptor, the
+    // latitude factors of this warp's DMMA tile (one tile per warp) and this thread's Gaussian weight of the fold — each would
+    // otherwise cost an L2 round trip on the critical path of a CTA that handles a single field
+    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, nw = nthr >> 5;
+    static_assert(C::MT * C::NT * 32 == C::K2_THREADS && C::RG * C::IY == C::K2_THREADS, "one DMMA tile per warp, one fold element per thread");
+    const XDesc d0 = (f0 < f1) ? desc[f0] : XDesc{0, 0, 0, 0, 0};
+    const int nt_w = w % C::NT;
+    const double sj_cosgr = tv.cosgr[8 * nt_w + g], sj_cosgr2 = tv.cosgr2[8 * nt_w + g];
+    const double wgt_t = tv.wt[tid % C::IY];
     pdl_wait();                                        // the grid fields of the previous kernel are complete
     pdl_trigger();
-    gate_open = gate ? *gate : 1;                       // in-graph conditional work (the daily forcing transform)
-    int f = next_live(f0);
-    if (f < f1) issue(f);
-    const int w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3, nw = nthr >> 5;
+    int f = f0;
+    if (f0 < f1 && !(d0.flags & 4)) {                   // not a gated field: its copy does not wait for the gate
+        issue_off(d0.off);
+        gate_open = gate ? *gate : 1;
+    } else {
+        gate_open = gate ? *gate : 1;                   // in-graph conditional work (the daily forcing transform)
+        f = next_live(f0);
+        if (f < f1) issue(f);
+    }
     int it = 0;
     for (; f < f1; it++) {
-        const XDesc dsc = desc[f];
-        const double* scl = (dsc.flags & 1) ? tv.cosgr : ((dsc.flags & 2) ? tv.cosgr2 : nullptr);
+        const XDesc dsc = (f == f0) ? d0 : desc[f];
+        const bool scl = (dsc.flags & 3) != 0;
+        const double sj = (dsc.flags & 1) ? sj_cosgr : sj_cosgr2;
         if (it == 0) mbar_wait(&bars[0], 0);
         mbar_wait(&bars[1], it & 1);
         const int fn = next_live(f + 1);
@@ -657,7 +672,6 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
             const double* Bf = sG + (8 * nt + g) * 16;
             double c0 = 0.0, c1 = 0.0;
             if (scl) {
-                const double sj = scl[8 * nt + g];
 #pragma unroll
                 for (int ks = 0; ks < C::IX / 4; ks++) dmma884(c0, c1, A[4 * ks], Bf[(ks >> 2) * C::BOX + swz[ks & 3]] * sj);
             } else {
@@ -672,7 +686,7 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
         for (int t = tid; t < C::RG * C::IY; t += nthr) {
             const int cl = t / C::IY, jh = t - cl * C::IY;
             const double south = sY[cl * C::YS + jh], north = sY[cl * C::YS + (C::IL - 1 - jh)];
-            const double wgt = tv.wt[jh];
+            const double wgt = wgt_t;
             sE[cl * C::ES + jh] = (north + south) * wgt;
             sO[cl * C::ES + jh] = (north - south) * wgt;
         }
