@@ -287,7 +287,7 @@ def run_b200(args):
         return {"batch": nb, "us": 1e6 * t, "GBps": by / t / 1e9, "frac_hbm": by / t / 1e9 / hbm, "transforms_per_s": nb / t}
     try:
         legendre_batched = {"spec_to_grid": _transform_batch(True, 5824), "grid_to_spec": _transform_batch(False, 4672),
-                            "note": "algorithmic bytes per transform over the measured HBM copy bandwidth; at this batch the dense-operator transforms are FP64-pipe-bound (~40 % of the 36 TFLOP/s FP64 peak, profiles/r1l_transform_microbench_t30.json), not HBM-bound"}
+                            "note": "algorithmic bytes per transform over the measured HBM copy bandwidth; at this batch the transforms are bound by shared-memory wavefronts of the Legendre stages and, in grid->spec, by the dense DFT on the FP64 tensor pipe (profiles/README.md, r1n), not by HBM"}
     except Exception as ex:
         legendre_batched = {"error": str(ex)}
     tot = sum(kt_warm.values())
