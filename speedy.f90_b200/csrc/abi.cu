@@ -153,6 +153,8 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
         setup_transform_kernels();
         upload_tables(ctx);
         model_create(ctx);
@@ -168,6 +170,8 @@ int speedy_destroy(speedy_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     model_destroy(ctx);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->copy_event) cudaEventDestroy(ctx->copy_event);
     delete ctx;
     API_END
 }

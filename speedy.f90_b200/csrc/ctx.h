@@ -88,6 +88,8 @@ struct speedy_ctx {
     spd::DevBuf<unsigned long long> trace;
     int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host copy of the state, overlapped with the output conversions (speedy_run_steps_host)
+    cudaEvent_t copy_event = nullptr;
     long long launches = 0;
     bool use_graphs = true;
     // device tables

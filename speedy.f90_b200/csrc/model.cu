@@ -701,13 +701,18 @@ int speedy_run_steps_host(speedy_ctx* ctx, double* state, size_t n, int nsteps, 
     for (int e = 0; e < ctx->nmembers; e++)
         CUDA_CHECK(cudaMemcpyAsync(M.mem.p + (size_t)e * M.L.stride + M.L.vor, state + (size_t)e * len, len * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     run_steps_core(ctx, nsteps);
+    // the state goes home on a second stream while the output() transforms and conversions (which only read it) run
+    CUDA_CHECK(cudaEventRecord(ctx->copy_event, ctx->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
     for (int e = 0; e < ctx->nmembers; e++)
-        CUDA_CHECK(cudaMemcpyAsync(state + (size_t)e * len, M.mem.p + (size_t)e * M.L.stride + M.L.vor, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaMemcpyAsync(state + (size_t)e * len, M.mem.p + (size_t)e * M.L.stride + M.L.vor, len * sizeof(double), cudaMemcpyDeviceToHost, ctx->copy_stream));
     if (out) {
         float* d = enqueue_output(ctx, 0);
         CUDA_CHECK(cudaMemcpyAsync(out, d, speedy_output_len(ctx) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    if (finish_run(ctx)) return 1;
+    const int rc = finish_run(ctx);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
+    if (rc) return 1;
     API_END
 }
 
