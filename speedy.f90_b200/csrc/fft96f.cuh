@@ -1,0 +1,164 @@
+// Forward real FFT of length 96 — FFTPACK's passes (fftpack.f90:136-202 rfftf1 with rffti1's factor list 2,4,4,3 taken
+// backwards: :774 radf3, :844 radf4 twice, :722 radf2), regrouped like fft96.cuh (its transpose) so that a thread keeps its
+// data in registers across two passes:
+//   stage A = radf3 (ido 1, l1 32) + radf4 (ido 3, l1 8): eight closed sets of 12 reals — grid points k + 8 j + 32 jj in,
+//             12 contiguous reals out;
+//   stage B = radf4 (ido 12, l1 2) + radf2 (ido 48, l1 1): five closed sets of 16 reals (radf4's general butterflies
+//             i = 3,5,..,11 for both k, and the four radf2 butterflies they feed) and two of 8 (radf4's i = 1 and i = ido).
+// Butterflies, constants and twiddles are the reference's, expression by expression.  NOT YET USED BY A KERNEL: K2 applies
+// the dense operator; this header is the validated building block of a K2 that owns whole fields
+// (tests/test_fft96_cpu.py checks a host build bit for bit against the oracle's pass-by-pass rfftf1).
+// Data layout as in fft96.cuh: element p of row r at X[p * XS + r]; wa is rffti1's table, 0-based.
+#pragma once
+
+namespace spd {
+
+struct Fft96F {
+    // stage A for radf4's k = k3 + 1 (k3 = 0..7): x[4*jj + j] = grid point k3 + 8 j + 32 jj in, T[12 k3 .. 12 k3 + 11] out
+    template <int XS>
+    static __device__ __forceinline__ void stageA(const double (&x)[12], double* T, const double* wa, int k3) {
+        const double taur = -.5;
+        const double taui = (double)(.5f * sqrtf(3.f));    // .5*sqrt(3.) in real32 (fftpack.f90:787)
+        double c[3][4];                                    // radf4's cc(i,k,j) = radf3's ch(1,i,k + 8 (j-1))
+#pragma unroll
+        for (int j = 0; j < 4; j++) {                      // radf3, ido = 1 (fftpack.f90:789-794)
+            const double a1 = x[j], a2 = x[4 + j], a3 = x[8 + j];
+            const double cr2 = a2 + a3;
+            c[0][j] = a1 + cr2;
+            c[2][j] = taui * (a3 - a2);
+            c[1][j] = a1 + taur * cr2;
+        }
+        double* o = T + (size_t)(12 * k3) * XS;            // ch(i,j,k) at (i-1) + 3 (j-1)
+        {   // i = 1 (fftpack.f90:859-866)
+            const double tr1 = c[0][1] + c[0][3];
+            const double tr2 = c[0][0] + c[0][2];
+            o[0 * XS] = tr1 + tr2;                         // ch(1,1,k)
+            o[11 * XS] = tr2 - tr1;                        // ch(3,4,k)
+            o[5 * XS] = c[0][0] - c[0][2];                 // ch(3,2,k)
+            o[6 * XS] = c[0][3] - c[0][1];                 // ch(1,3,k)
+        }
+        {   // i = 3, ic = 2 (fftpack.f90:872-905); twiddles wa(85 + ..)
+            const double w1r = wa[84], w1i = wa[85], w2r = wa[87], w2i = wa[88], w3r = wa[90], w3i = wa[91];
+            const double cr2 = w1r * c[1][1] + w1i * c[2][1];
+            const double ci2 = w1r * c[2][1] - w1i * c[1][1];
+            const double cr3 = w2r * c[1][2] + w2i * c[2][2];
+            const double ci3 = w2r * c[2][2] - w2i * c[1][2];
+            const double cr4 = w3r * c[1][3] + w3i * c[2][3];
+            const double ci4 = w3r * c[2][3] - w3i * c[1][3];
+            const double tr1 = cr2 + cr4;
+            const double tr4 = cr4 - cr2;
+            const double ti1 = ci2 + ci4;
+            const double ti4 = ci2 - ci4;
+            const double ti2 = c[2][0] + ci3;
+            const double ti3 = c[2][0] - ci3;
+            const double tr2 = c[1][0] + cr3;
+            const double tr3 = c[1][0] - cr3;
+            o[1 * XS] = tr1 + tr2;                         // ch(2,1,k)
+            o[9 * XS] = tr2 - tr1;                         // ch(1,4,k)
+            o[2 * XS] = ti1 + ti2;                         // ch(3,1,k)
+            o[10 * XS] = ti1 - ti2;                        // ch(2,4,k)
+            o[7 * XS] = ti4 + tr3;                         // ch(2,3,k)
+            o[3 * XS] = tr3 - ti4;                         // ch(1,2,k)
+            o[8 * XS] = tr4 + ti3;                         // ch(3,3,k)
+            o[4 * XS] = tr4 - ti3;                         // ch(2,2,k)
+        }
+    }
+
+    // one radf2 butterfly (fftpack.f90:741-752) at i1 (ic = 50 - i1) on radf4's outputs of both k: (ar, ai) = ch(i1-1, ., 1),
+    // ch(i1, ., 1) of radf4 (k = 1), (br, bi) the same for k = 2; writes the half-complex result
+    template <int XS>
+    static __device__ __forceinline__ void radf2_at(double* Y, const double* wa, int i1, double ar, double ai, double br, double bi) {
+        const int ic = 50 - i1;
+        const double wr = wa[i1 - 3], wi = wa[i1 - 2];
+        const double tr2 = wr * br + wi * bi;
+        const double ti2 = wr * bi - wi * br;
+        Y[(i1 - 1) * XS] = ai + ti2;                       // ch(i,1,k)
+        Y[(47 + ic) * XS] = ti2 - ai;                      // ch(ic,2,k)
+        Y[(i1 - 2) * XS] = ar + tr2;                       // ch(i-1,1,k)
+        Y[(46 + ic) * XS] = ar - tr2;                      // ch(ic-1,2,k)
+    }
+
+    // stage B, general set of radf4's butterfly i (3,5,..,11), both k
+    template <int XS>
+    static __device__ __forceinline__ void stageB_general(const double* T, double* Y, const double* wa, int i) {
+        const double w1r = wa[45 + i], w1i = wa[46 + i], w2r = wa[57 + i], w2i = wa[58 + i], w3r = wa[69 + i], w3i = wa[70 + i];
+        // radf4 outputs of k = 1, 2 at the four radf2 positions: [0] i (j 1), [1] i+24 (j 3), [2] 26-i (ic, j 2), [3] 50-i (ic, j 4)
+        double pr[2][4], pi[2][4];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double* c = T + (size_t)((i - 2) + 12 * k) * XS;      // cc(i-1,k,1); cc(.,k,j) 24 (j-1) further
+            const double c1r = c[0], c1i = c[XS], c2r = c[24 * XS], c2i = c[25 * XS], c3r = c[48 * XS], c3i = c[49 * XS], c4r = c[72 * XS], c4i = c[73 * XS];
+            const double cr2 = w1r * c2r + w1i * c2i;
+            const double ci2 = w1r * c2i - w1i * c2r;
+            const double cr3 = w2r * c3r + w2i * c3i;
+            const double ci3 = w2r * c3i - w2i * c3r;
+            const double cr4 = w3r * c4r + w3i * c4i;
+            const double ci4 = w3r * c4i - w3i * c4r;
+            const double tr1 = cr2 + cr4;
+            const double tr4 = cr4 - cr2;
+            const double ti1 = ci2 + ci4;
+            const double ti4 = ci2 - ci4;
+            const double ti2 = c1i + ci3;
+            const double ti3 = c1i - ci3;
+            const double tr2 = c1r + cr3;
+            const double tr3 = c1r - cr3;
+            pr[k][0] = tr1 + tr2;                          // ch(i-1,1,k)
+            pr[k][3] = tr2 - tr1;                          // ch(ic-1,4,k)
+            pi[k][0] = ti1 + ti2;                          // ch(i,1,k)
+            pi[k][3] = ti1 - ti2;                          // ch(ic,4,k)
+            pr[k][1] = ti4 + tr3;                          // ch(i-1,3,k)
+            pr[k][2] = tr3 - ti4;                          // ch(ic-1,2,k)
+            pi[k][1] = tr4 + ti3;                          // ch(i,3,k)
+            pi[k][2] = tr4 - ti3;                          // ch(ic,2,k)
+        }
+        radf2_at<XS>(Y, wa, i, pr[0][0], pi[0][0], pr[1][0], pi[1][0]);
+        radf2_at<XS>(Y, wa, i + 24, pr[0][1], pi[0][1], pr[1][1], pi[1][1]);
+        radf2_at<XS>(Y, wa, 26 - i, pr[0][2], pi[0][2], pr[1][2], pi[1][2]);
+        radf2_at<XS>(Y, wa, 50 - i, pr[0][3], pi[0][3], pr[1][3], pi[1][3]);
+    }
+
+    // stage B, radf4's i = 1 case (fftpack.f90:859-866) for both k, feeding radf2's i = 1 (:729-732) and i = ido (:757-760)
+    // cases and its butterfly 25
+    template <int XS>
+    static __device__ __forceinline__ void stageB_first(const double* T, double* Y, const double* wa) {
+        double a[2], d[2], yr[2], yi[2];                   // ch(1,1,k), ch(12,4,k), ch(12,2,k), ch(1,3,k)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double* c = T + (size_t)(12 * k) * XS;
+            const double c1 = c[0], c2 = c[24 * XS], c3 = c[48 * XS], c4 = c[72 * XS];
+            const double tr1 = c2 + c4;
+            const double tr2 = c1 + c3;
+            a[k] = tr1 + tr2;
+            d[k] = tr2 - tr1;
+            yr[k] = c1 - c3;
+            yi[k] = c4 - c2;
+        }
+        Y[0] = a[0] + a[1];                                // radf2: ch(1,1,1)
+        Y[95 * XS] = a[0] - a[1];                          // ch(48,2,1)
+        Y[48 * XS] = -d[1];                                // ch(1,2,1) = -cc(48,1,2)
+        Y[47 * XS] = d[0];                                 // ch(48,1,1) =  cc(48,1,1)
+        radf2_at<XS>(Y, wa, 25, yr[0], yi[0], yr[1], yi[1]);
+    }
+
+    // stage B, radf4's i = ido case (fftpack.f90:911-920) for both k, feeding radf2's butterflies 13 and 37
+    template <int XS>
+    static __device__ __forceinline__ void stageB_last(const double* T, double* Y, const double* wa) {
+        const double hsqt2 = (double)(.5f * sqrtf(2.f));   // .5*sqrt(2.) in real32 (fftpack.f90:857)
+        double pr[2], pi[2], qr[2], qi[2];                 // ch(12,1,k), ch(1,2,k) -> positions 11, 12; ch(12,3,k), ch(1,4,k) -> 35, 36
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double* c = T + (size_t)(11 + 12 * k) * XS;
+            const double c1 = c[0], c2 = c[24 * XS], c3 = c[48 * XS], c4 = c[72 * XS];
+            const double ti1 = -hsqt2 * (c2 + c4);
+            const double tr1 = hsqt2 * (c2 - c4);
+            pr[k] = tr1 + c1;
+            qr[k] = c1 - tr1;
+            pi[k] = ti1 - c3;
+            qi[k] = ti1 + c3;
+        }
+        radf2_at<XS>(Y, wa, 13, pr[0], pi[0], pr[1], pi[1]);
+        radf2_at<XS>(Y, wa, 37, qr[0], qi[0], qr[1], qi[1]);
+    }
+};
+
+}  // namespace spd
