@@ -81,7 +81,8 @@ int speedy_legendre_dir(speedy_ctx* ctx, const double* in, int nbatch, double* o
 int speedy_fourier_inv(speedy_ctx* ctx, const double* in, int nbatch, const int* kcos, double* out);
 /* fourier_dir   fourier.f90:56-82: real(ix,il) -> real(2*mx,il) */
 int speedy_fourier_dir(speedy_ctx* ctx, const double* in, int nbatch, double* out);
-/* device-pointer variants (enqueue only; kcos stays a HOST array, NULL = all 1) */
+/* device-pointer variants (enqueue only; kcos stays a HOST array, NULL = all 1).  The buffers must be 16-byte aligned
+ * (cudaMalloc pointers are): the fields are fetched with bulk / tensor-map copies */
 int speedy_spec_to_grid_dev(speedy_ctx* ctx, const double* d_spec, int nbatch, const int* kcos, double* d_grid);
 int speedy_grid_to_spec_dev(speedy_ctx* ctx, const double* d_grid, int nbatch, double* d_spec);
 
