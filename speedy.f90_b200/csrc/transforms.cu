@@ -21,12 +21,14 @@
 #include "spectral_ops.cuh"
 #include "tma.cuh"
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <type_traits>
 #include "fft96.cuh"
 #include "fft144.cuh"
+#include "fft96f.cuh"
 #include "close_step.cuh"
 
 namespace spd {
@@ -738,6 +740,157 @@ k_g2s_stream(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__
     if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 2); }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// EXPERIMENTAL (SPEEDY_K2_FIELD=1, T30 ensemble batches only; written at the end of round 1 without GPU time left — it has NOT
+// run on a device yet and is off by default): grid->spec with one CTA per WHOLE field instead of four wavenumber-group CTAs.
+// The field is read once, the zonal transform is FFTPACK's forward FFT regrouped into two register-resident stages
+// (fft96f.cuh, bit-identical to rfftf1 on the host) instead of the dense operator, and the direct Legendre sums of all
+// wavenumbers read the triangle-packed P table staged once per CTA.  Estimated shared-memory wavefronts per field: ~3 000
+// against ~10 000 for the four-CTA form.
+//   sG  [NBOX][IL][16]  grid field, tensor-map boxes with the 128-byte swizzle (as k_g2s_stream)
+//   sT  [IX][XP]        between the FFT stages, position-major; afterwards the even/odd folds EO[parity][jh][64]
+//   sY  [IX][XP]        half-complex rows, position-major
+//   sP  [IY][TR]        P table, per latitude the triangle m + n <= trunc + 1 packed row by row (polyt)
+template <int TRUNC>
+struct FieldCfg : SCfg<TRUNC> {
+    using C = SCfg<TRUNC>;
+    static constexpr int XP = C::IL + 1;                                   // odd row stride: conflict-free for consecutive rows
+    static constexpr int THREADS = 8 * C::IL;                              // stage A: one thread per (row, k of radf4)
+    static constexpr int EOW = 2 * ((C::MX + 1) / 2 * 2);                  // doubles per latitude of a fold row (re, im per m)
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)C::IL * C::IX + 2 * (size_t)C::IX * XP + (size_t)C::IY * C::TR) + 2 * sizeof(uint64_t);
+    static_assert(TRUNC == 30 && C::IX == 96, "whole-field kernel: T30 only (fft96f.cuh)");
+    static_assert(2 * C::IY * EOW <= C::IX * XP && SMEM <= 232448 && ((size_t)C::IY * C::TR * 8) % 16 == 0, "fold buffer fits in sT; shared memory budget");
+};
+
+template <int TRUNC>
+__global__ void __launch_bounds__(FieldCfg<TRUNC>::THREADS, 1)
+k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int nchunk,
+            double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
+    using C = FieldCfg<TRUNC>;
+    extern __shared__ __align__(1024) double smem[];
+    double* sG = smem;
+    double* sT = sG + C::IL * C::IX;
+    double* sY = sT + C::IX * C::XP;
+    double* sP = sY + C::IX * C::XP;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (size_t)C::IY * C::TR);   // [0] P table, [1] grid field
+    double* sEO = sT;                                                      // [2][IY][EOW], after the FFT
+    __shared__ double sWa[C::IX];
+    __shared__ int sTri[C::NX + 1];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int chunk = blockIdx.x, e = blockIdx.y;
+    const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
+    int gate_open = 1;
+    auto live = [&](int f) { return gate_open || !(desc[f].flags & 4); };
+    auto next_live = [&](int f) { while (f < f1 && !live(f)) f++; return f; };
+    auto issue = [&](int f) {
+        if (tid == 0) {
+            const long long off = desc[f].off;
+            const int row0 = (int)(off / C::IX);
+            if (off != (long long)row0 * C::IX) __trap();
+            fence_proxy_async();
+            mbar_expect_tx(&bars[1], C::IL * C::IX * sizeof(double));
+#pragma unroll
+            for (int b = 0; b < C::NBOX; b++) tensor_g2s_3d(sG + b * C::BOX, &gmap, 16 * b, row0, e, &bars[1]);
+        }
+    };
+    if (tid == 0 && (smem_u32(sG) & 1023u)) __trap();
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    // prologue on constant tables only
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], (uint32_t)((size_t)C::IY * C::TR * sizeof(double)));
+        bulk_g2s(sP, tv.polyt, (uint32_t)((size_t)C::IY * C::TR * sizeof(double)), &bars[0]);
+    }
+    for (int t = tid; t < C::IX; t += nthr) sWa[t] = tv.fftwa[t];
+    for (int t = tid; t <= C::NX; t += nthr) sTri[t] = C::tri_off(t);
+    const double scale = (double)(1.0f / (float)C::IX);                    // fourier.f90:72
+    // stage A mapping: k fastest (8 consecutive lanes read 8 consecutive longitudes of a row)
+    const int rA = tid >> 3, k3 = tid & 7;
+    const double sjA1 = tv.cosgr[rA], sjA2 = tv.cosgr2[rA];
+    pdl_wait();
+    pdl_trigger();
+    gate_open = gate ? *gate : 1;
+    int f = next_live(f0);
+    if (f < f1) issue(f);
+    __syncthreads();                                                       // sWa, sTri
+    int it = 0;
+    for (; f < f1; it++) {
+        const XDesc dsc = desc[f];
+        const int fn = next_live(f + 1);
+        if (it == 0) mbar_wait(&bars[0], 0);
+        mbar_wait(&bars[1], it & 1);
+        // ---- forward FFT, stage A (radf3 + radf4): grid points k3 + 8 j + 32 jj of row rA, with the cosgr / cosgr2 pre-scale
+        // of vdspec (spectral.f90:208-222).  Element (lat, lon): box lon / 16, 16-byte chunk ((lon % 16) / 2) ^ (lat % 8).
+        {
+            double x[12];
+            const double sj = (dsc.flags & 1) ? sjA1 : ((dsc.flags & 2) ? sjA2 : 1.0);
+            const bool scl = (dsc.flags & 3) != 0;
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int lon = k3 + 8 * j + 32 * jj;                   // box 2 jj + j / 2, in-box longitude k3 + 8 (j % 2)
+                    const int chunkc = ((k3 >> 1) + 4 * (j & 1)) ^ (rA & 7);
+                    const double v = sG[(2 * jj + (j >> 1)) * C::BOX + rA * 16 + (chunkc << 1) + (lon & 1)];
+                    x[4 * jj + j] = scl ? v * sj : v;
+                }
+            Fft96F::stageA<C::XP>(x, sT + rA, sWa, k3);
+        }
+        __syncthreads();                                                   // sT complete, grid buffer free
+        if (fn < f1) issue(fn);
+        // ---- stage B (radf4 + radf2): consecutive lanes = consecutive rows; sets 0..4 general (i = 3 + 2 set), 5 first, 6 last
+        if (tid < 7 * C::IL) {
+            const int set = tid / C::IL, r = tid - set * C::IL;
+            if (set < 5) Fft96F::stageB_general<C::XP>(sT + r, sY + r, sWa, 3 + 2 * set);
+            else if (set == 5) Fft96F::stageB_first<C::XP>(sT + r, sY + r, sWa);
+            else Fft96F::stageB_last<C::XP>(sT + r, sY + r, sWa);
+        }
+        __syncthreads();                                                   // sY complete, sT free for the folds
+        // ---- fourier_dir's 1/ix (fourier.f90:72-80) and the Gaussian-weighted even/odd fold (legendre.f90:127-133):
+        // coefficient row c = 2 m (re), 2 m + 1 (im) <-> half-complex position 0 / 2 m - 1, 2 m; Im(m = 0) = 0
+        for (int t = tid; t < C::K2 * C::IY; t += nthr) {
+            const int c = t / C::IY, jh = t - c * C::IY;
+            double ev = 0.0, od = 0.0;
+            if (c != 1) {
+                const int pos = (c == 0) ? 0 : c - 1;
+                const double south = sY[pos * C::XP + jh] * scale, north = sY[pos * C::XP + (C::IL - 1 - jh)] * scale;
+                const double wgt = tv.wt[jh];
+                ev = (north + south) * wgt;
+                od = (north - south) * wgt;
+            }
+            sEO[(size_t)jh * C::EOW + c] = ev;
+            sEO[(size_t)(C::IY + jh) * C::EOW + c] = od;
+        }
+        __syncthreads();
+        // ---- direct Legendre (legendre.f90:142-154) for all wavenumbers: one thread per (m, two n of equal parity)
+        double* out = out_base + (size_t)e * out_ms + (size_t)f * C::K2 * C::NX;
+        constexpr int NP = 2 * ((C::NX + 3) / 4);
+        for (int t = tid; t < NP * C::MX; t += nthr) {
+            const int np = t / C::MX, m = t - np * C::MX;
+            const int nA = 4 * (np >> 1) + (np & 1), nB = nA + 2;
+            const bool vA = nA < C::NX, vB = nB < C::NX;
+            const bool cA = vA && nA <= TRUNC && m + nA <= C::MX, cB = vB && nB <= TRUNC && m + nB <= C::MX;
+            double ar = 0.0, ai = 0.0, br = 0.0, bi = 0.0;
+            if (cA) {
+                const double2* F = reinterpret_cast<const double2*>(sEO + (size_t)((np & 1) ? C::IY : 0) * C::EOW) + m;
+                const double* PA = sP + sTri[nA] + m;
+                const double* PB = sP + sTri[cB ? nB : nA] + m;
+#pragma unroll
+                for (int jh = 0; jh < C::IY; jh++) {
+                    const double2 fv = F[(size_t)jh * (C::EOW / 2)];
+                    const double pa = PA[(size_t)jh * C::TR], pb = PB[(size_t)jh * C::TR];
+                    ar += pa * fv.x; ai += pa * fv.y; br += pb * fv.x; bi += pb * fv.y;
+                }
+                if (!cB) { br = 0.0; bi = 0.0; }
+            }
+            if (vA) *reinterpret_cast<double2*>(out + nA * C::K2 + 2 * m) = make_double2(ar, ai);
+            if (vB) *reinterpret_cast<double2*>(out + nB * C::K2 + 2 * m) = make_double2(br, bi);
+        }
+        __syncthreads();                                                   // the folds (in sT) are free for the next field
+        f = fn;
+    }
+}
+
 void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K1_SMEM));
@@ -834,8 +987,20 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     if (!occ_b) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_g2s_stream<TRUNC, true>, C::K2_THREADS, C::K2_SMEM_BATCH)); if (occ_b < 1) occ_b = 1; if (occ_b > 2) occ_b = 2; }
     int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ);
     if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ_b);   // batch variant
-    dim3 grid(nchunk * C::CG, nmembers);
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
+    if constexpr (TRUNC == 30) {
+        // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
+        static const bool field_mode = getenv("SPEEDY_K2_FIELD") != nullptr;
+        if (field_mode && (nbatch + nchunk - 1) / nchunk >= 3) {
+            using F = FieldCfg<TRUNC>;
+            static bool attr = false;
+            if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_g2s_field<TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM)); attr = true; }
+            const int nch = stream_chunks(ctx, 1, nmembers, nbatch);
+            CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_field<TRUNC>, dim3(nch, nmembers), dim3(F::THREADS), F::SMEM, ctx->stream, gmap, d_desc, nbatch, nch, d_out, out_ms, ctx->dv, gate));
+            return;
+        }
+    }
+    dim3 grid(nchunk * C::CG, nmembers);
     if ((nbatch + nchunk - 1) / nchunk >= 3)
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_stream<TRUNC, true>, grid, dim3(C::K2_THREADS), C::K2_SMEM_BATCH, ctx->stream, gmap, d_desc, nbatch, nchunk, d_out, out_ms, ctx->dv, gate));
     else
