@@ -849,7 +849,7 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
         // ---- fourier_dir's 1/ix (fourier.f90:72-80) and the Gaussian-weighted even/odd fold (legendre.f90:127-133):
         // coefficient row c = 2 m (re), 2 m + 1 (im) <-> half-complex position 0 / 2 m - 1, 2 m; Im(m = 0) = 0
         for (int t = tid; t < C::K2 * C::IY; t += nthr) {
-            const int c = t / C::IY, jh = t - c * C::IY;
+            const int jh = t / C::K2, c = t - jh * C::K2;                 // c fastest: the fold rows are written contiguously
             double ev = 0.0, od = 0.0;
             if (c != 1) {
                 const int pos = (c == 0) ? 0 : c - 1;
