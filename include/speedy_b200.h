@@ -182,6 +182,10 @@ long long speedy_launch_count(const speedy_ctx* ctx);
 void* speedy_stream(const speedy_ctx* ctx);
 /* use CUDA graphs for speedy_run_steps (1, default) or plain launches (0) */
 int speedy_set_graphs(speedy_ctx* ctx, int on);
+/* kernel-selection switches (no counterpart in the reference; used by the A/B tools and by the parity tests of the alternative
+ * kernels): "k2_field" (grid->spec batches through the whole-field FFT kernel), "dense_inverse" (spec->grid Fourier stage as the
+ * dense FFTPACK operator), "graphs".  Returns <0 for an unknown name. */
+int speedy_set_option(speedy_ctx* ctx, const char* name, int value);
 
 
 /* bench/profiling: mean CUDA-event duration (ms) of each kernel of the main-loop body over

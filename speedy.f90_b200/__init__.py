@@ -52,6 +52,7 @@ def lib():
         _lib.speedy_write_output_file.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6
         _lib.speedy_save_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_load_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        _lib.speedy_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
     return _lib
 
 
@@ -377,6 +378,10 @@ class Speedy:
     def set_sppt_draw(self, on):
         """sppt.f90:45-99 — draw eta on the device (default) or read it from the `sppt_eta` field"""
         _chk(self.L.speedy_set_sppt_draw(self.h, int(bool(on))))
+
+    def set_option(self, name, value):
+        """kernel-selection switch of the context (speedy_set_option): "k2_field", "dense_inverse", "graphs"."""
+        _chk(self.L.speedy_set_option(self.h, name.encode(), int(value)))
 
     def set_graphs(self, on):
         _chk(self.L.speedy_set_graphs(self.h, int(bool(on))))

@@ -910,6 +910,24 @@ int speedy_set_sppt_draw(speedy_ctx* ctx, int on) {
     API_END
 }
 
+// Kernel-selection switches of a context (A/B measurements and the parity tests of the alternative kernels):
+//   "k2_field"      1: grid->spec of ensemble batches through the whole-field FFT kernel (default from SPEEDY_K2_FIELD)
+//   "dense_inverse" 1: spec->grid Fourier stage as the dense FFTPACK operator on the FP64 tensor pipe (default from SPEEDY_DENSE_INVERSE)
+//   "graphs"        as speedy_set_graphs
+int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
+    API_BEGIN
+    check_ready(ctx);
+    if (!name) throw std::runtime_error("null option name");
+    const std::string n(name);
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (n == "k2_field") ctx->k2_field = value != 0;
+    else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
+    else if (n == "graphs") ctx->use_graphs = value != 0;
+    else throw std::runtime_error("unknown option " + n);
+    drop_graph(*ctx->model);   // the kernel choice is baked into a captured graph
+    API_END
+}
+
 // In-graph timeline of the main-loop kernels (debug aid): on != 0 makes every kernel stamp the GPU's global
 // timer; speedy_trace_read returns, in microseconds per step, the duration of each of the four kernels
 // (order of speedy_kernel_names) and the idle gap in front of each, then the number of steps traced.

@@ -757,7 +757,7 @@ struct FieldCfg : SCfg<TRUNC> {
     static constexpr int XP = C::IL + 1;                                   // odd row stride: conflict-free for consecutive rows
     static constexpr int THREADS = 8 * C::IL;                              // stage A: one thread per (row, k of radf4)
     static constexpr int EOW = 2 * ((C::MX + 1) / 2 * 2);                  // doubles per latitude of a fold row (re, im per m)
-    static constexpr size_t SMEM = sizeof(double) * ((size_t)C::IL * C::IX + 2 * (size_t)C::IX * XP + (size_t)C::IY * C::TR) + 2 * sizeof(uint64_t);
+    static constexpr size_t SMEM = sizeof(double) * ((size_t)C::IL * C::IX + 2 * (size_t)C::IX * XP + (size_t)C::IY * C::TR + C::IX) + 2 * sizeof(uint64_t) + sizeof(int) * (C::NX + 2);
     static_assert(TRUNC == 30 && C::IX == 96, "whole-field kernel: T30 only (fft96f.cuh)");
     static_assert(2 * C::IY * EOW <= C::IX * XP && SMEM <= 232448 && ((size_t)C::IY * C::TR * 8) % 16 == 0, "fold buffer fits in sT; shared memory budget");
 };
@@ -774,8 +774,9 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
     double* sP = sY + C::IX * C::XP;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + (size_t)C::IY * C::TR);   // [0] P table, [1] grid field
     double* sEO = sT;                                                      // [2][IY][EOW], after the FFT
-    __shared__ double sWa[C::IX];
-    __shared__ int sTri[C::NX + 1];
+    // no static shared arrays here: the dynamic buffer must start on the 1 KB boundary the swizzle pattern is tied to
+    double* sWa = reinterpret_cast<double*>(bars + 2);                     // [IX]
+    int* sTri = reinterpret_cast<int*>(sWa + C::IX);                       // [NX + 1]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int chunk = blockIdx.x, e = blockIdx.y;
     const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
@@ -990,8 +991,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if constexpr (TRUNC == 30) {
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
-        static const bool field_mode = getenv("SPEEDY_K2_FIELD") != nullptr;
-        if (field_mode && (nbatch + nchunk - 1) / nchunk >= 3) {
+        if (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3) {
             using F = FieldCfg<TRUNC>;
             static bool attr = false;
             if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_g2s_field<TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM)); attr = true; }

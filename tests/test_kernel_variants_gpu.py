@@ -1,0 +1,65 @@
+"""Parity of the alternative transform kernels a context can be switched to (speedy_set_option):
+the whole-field FFT grid->spec kernel of ensemble batches ("k2_field") and the dense-operator
+Fourier stage of spec->grid ("dense_inverse").  Same oracle, same tolerances as the default kernels:
+1e-12 relative RMS per transform call, 1e-10 on the prognostic coefficients after 48 h."""
+import os
+import numpy as np
+import pytest
+from conftest import ROOT, random_spec, rel_rms
+
+pytestmark = pytest.mark.gpu
+BC = os.path.join(ROOT, "data", "bc_t30.bin")
+PROG = ("vor", "div", "t", "tr", "ps")
+
+
+@pytest.mark.parametrize("nb", [584, 1201])
+def test_grid_to_spec_whole_field(pkg, oracle, nb):
+    o = oracle
+    c = pkg.Speedy(trunc=30)
+    c.set_option("k2_field", 1)
+    rng = np.random.default_rng(99)
+    g = rng.uniform(-1, 1, size=(nb, o.il, o.ix))
+    got = c.grid_to_spec(g)
+    c.set_option("k2_field", 0)
+    base = c.grid_to_spec(g)
+    idx = np.r_[0:8, nb // 2:nb // 2 + 8, nb - 8:nb]
+    ref = o.grid_to_spec(g[idx])
+    assert rel_rms(got[idx], ref) < 1e-12
+    assert rel_rms(got, base) < 1e-12
+    n = np.arange(o.nx)[:, None]; m = np.arange(o.mx)[None, :]
+    dead = ((m + n) > o.trunc + 1) | (n > o.trunc)
+    assert np.all(got[:, dead] == 0)
+    assert np.all(got[:, :, 0].imag == 0)
+    c.close()
+
+
+@pytest.mark.parametrize("nb", [8, 91])
+def test_spec_to_grid_dense_inverse(pkg, oracle, nb):
+    o = oracle
+    c = pkg.Speedy(trunc=30)
+    c.set_option("dense_inverse", 1)
+    rng = np.random.default_rng(98)
+    s = random_spec(rng, (nb,), o.nx, o.mx, o.trunc)
+    kcos = np.where(np.arange(nb) % 2 == 0, 1, 2).astype(np.int32)
+    assert rel_rms(c.spec_to_grid(s, kcos), o.spec_to_grid(s, kcos)) < 1e-12
+    c.close()
+
+
+@pytest.mark.parametrize("opt", ["k2_field", "dense_inverse"])
+def test_48h_run_variant(pkg, oracle, opt):
+    """four identical members (the batch variants of the kernels) for 48 h against the oracle"""
+    oracle.model_init(BC)
+    assert oracle.run(72) == 0
+    c = pkg.Speedy(trunc=30, nmembers=4)
+    c.set_option(opt, 1)
+    c.model_init(BC)
+    assert c.run_steps(72) == 0
+    ref = oracle.state()
+    for n in PROG:
+        f = c.get_field(n, all_members=True)
+        assert np.array_equal(f[0], f[3]), n
+        e = rel_rms(f[0], ref[n])
+        assert e < 1e-10, (n, e)
+    for n in ("iptop", "icnv", "icltop"):
+        assert np.array_equal(c.get_field(n), oracle.ifield(n)), n
+    c.close()

@@ -60,7 +60,9 @@ def main():
             print(json.dumps(res[-1]))
     out = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out, exist_ok=True)
-    json.dump({"trunc": trunc, "hbm_gbs_peak": hbm, "results": res}, open(os.path.join(out, f"bench_transforms_t{trunc}.json"), "w"), indent=1)
+    tag = sys.argv[2] if len(sys.argv) > 2 else ""
+    json.dump({"trunc": trunc, "hbm_gbs_peak": hbm, "env": {k: v for k, v in os.environ.items() if k.startswith("SPEEDY_")}, "results": res},
+              open(os.path.join(out, f"bench_transforms_t{trunc}{tag}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
