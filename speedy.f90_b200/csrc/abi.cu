@@ -60,6 +60,13 @@ void upload_tables(speedy_ctx* ctx) {
         }
         v.polyt = up(ctx, "polyt", pt);
     }
+    if (t.d.trunc == 30) {   // quad kernels (transforms_quad.cu)
+        std::vector<int> tiles; std::vector<double> pq;
+        build_quad_tables(t, tiles, pq);
+        v.polyq = up(ctx, "polyq", pq);
+        ctx->d_qtile.upload(tiles);
+        v.qtile = ctx->d_qtile.p;
+    }
     v.finv = up(ctx, "finv", t.finv);
     v.ffwd = up(ctx, "ffwd", t.ffwd);
     v.fftwa = up(ctx, "fftwa", t.fft_work);
@@ -150,6 +157,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->trace_pdl = getenv("SPEEDY_TRACE_PDL") != nullptr;
         ctx->fft_inverse = getenv("SPEEDY_DENSE_INVERSE") == nullptr;
         ctx->k2_field = getenv("SPEEDY_K2_FIELD") != nullptr;
+        ctx->k2_quad = getenv("SPEEDY_K2_QUAD") != nullptr;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -157,6 +165,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
         setup_transform_kernels();
+        setup_quad_kernels();
         upload_tables(ctx);
         model_create(ctx);
     } catch (...) { delete ctx; throw; }

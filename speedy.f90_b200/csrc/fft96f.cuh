@@ -5,9 +5,9 @@
 //             12 contiguous reals out;
 //   stage B = radf4 (ido 12, l1 2) + radf2 (ido 48, l1 1): five closed sets of 16 reals (radf4's general butterflies
 //             i = 3,5,..,11 for both k, and the four radf2 butterflies they feed) and two of 8 (radf4's i = 1 and i = ido).
-// Butterflies, constants and twiddles are the reference's, expression by expression.  NOT YET USED BY A KERNEL: K2 applies
-// the dense operator; this header is the validated building block of a K2 that owns whole fields
-// (tests/test_fft96_cpu.py checks a host build bit for bit against the oracle's pass-by-pass rfftf1).
+// Butterflies, constants and twiddles are the reference's, expression by expression.  Used by the whole-field grid->spec kernels
+// (k_g2s_field in transforms.cu, k_g2s_quad in transforms_quad.cu); tests/test_fft96_cpu.py checks a host build bit for bit
+// against the oracle's pass-by-pass rfftf1.
 // Data layout as in fft96.cuh: element p of row r at X[p * XS + r]; wa is rffti1's table, 0-based.
 #pragma once
 
@@ -66,21 +66,30 @@ struct Fft96F {
 
     // one radf2 butterfly (fftpack.f90:741-752) at i1 (ic = 50 - i1) on radf4's outputs of both k: (ar, ai) = ch(i1-1, ., 1),
     // ch(i1, ., 1) of radf4 (k = 1), (br, bi) the same for k = 2; writes the half-complex result
+    // `St` is a store functor st(pos, value) for half-complex position pos (the pointer forms below store to Y[pos * XS]; the
+    // quad kernel maps the position to a coefficient row and drops the positions above the truncation)
     template <int XS>
-    static __device__ __forceinline__ void radf2_at(double* Y, const double* wa, int i1, double ar, double ai, double br, double bi) {
+    struct StoreY {
+        double* Y;
+        __device__ __forceinline__ void operator()(int pos, double v) const { Y[pos * XS] = v; }
+    };
+    template <class St>
+    static __device__ __forceinline__ void radf2_at_f(const St& st, const double* wa, int i1, double ar, double ai, double br, double bi) {
         const int ic = 50 - i1;
         const double wr = wa[i1 - 3], wi = wa[i1 - 2];
         const double tr2 = wr * br + wi * bi;
         const double ti2 = wr * bi - wi * br;
-        Y[(i1 - 1) * XS] = ai + ti2;                       // ch(i,1,k)
-        Y[(47 + ic) * XS] = ti2 - ai;                      // ch(ic,2,k)
-        Y[(i1 - 2) * XS] = ar + tr2;                       // ch(i-1,1,k)
-        Y[(46 + ic) * XS] = ar - tr2;                      // ch(ic-1,2,k)
+        st(i1 - 1, ai + ti2);                              // ch(i,1,k)
+        st(47 + ic, ti2 - ai);                             // ch(ic,2,k)
+        st(i1 - 2, ar + tr2);                              // ch(i-1,1,k)
+        st(46 + ic, ar - tr2);                             // ch(ic-1,2,k)
     }
 
     // stage B, general set of radf4's butterfly i (3,5,..,11), both k
     template <int XS>
-    static __device__ __forceinline__ void stageB_general(const double* T, double* Y, const double* wa, int i) {
+    static __device__ __forceinline__ void stageB_general(const double* T, double* Y, const double* wa, int i) { stageB_general_f<XS>(T, StoreY<XS>{Y}, wa, i); }
+    template <int XS, class St>
+    static __device__ __forceinline__ void stageB_general_f(const double* T, const St& st, const double* wa, int i) {
         const double w1r = wa[45 + i], w1i = wa[46 + i], w2r = wa[57 + i], w2i = wa[58 + i], w3r = wa[69 + i], w3i = wa[70 + i];
         // radf4 outputs of k = 1, 2 at the four radf2 positions: [0] i (j 1), [1] i+24 (j 3), [2] 26-i (ic, j 2), [3] 50-i (ic, j 4)
         double pr[2][4], pi[2][4];
@@ -111,16 +120,18 @@ struct Fft96F {
             pi[k][1] = tr4 + ti3;                          // ch(i,3,k)
             pi[k][2] = tr4 - ti3;                          // ch(ic,2,k)
         }
-        radf2_at<XS>(Y, wa, i, pr[0][0], pi[0][0], pr[1][0], pi[1][0]);
-        radf2_at<XS>(Y, wa, i + 24, pr[0][1], pi[0][1], pr[1][1], pi[1][1]);
-        radf2_at<XS>(Y, wa, 26 - i, pr[0][2], pi[0][2], pr[1][2], pi[1][2]);
-        radf2_at<XS>(Y, wa, 50 - i, pr[0][3], pi[0][3], pr[1][3], pi[1][3]);
+        radf2_at_f(st, wa, i, pr[0][0], pi[0][0], pr[1][0], pi[1][0]);
+        radf2_at_f(st, wa, i + 24, pr[0][1], pi[0][1], pr[1][1], pi[1][1]);
+        radf2_at_f(st, wa, 26 - i, pr[0][2], pi[0][2], pr[1][2], pi[1][2]);
+        radf2_at_f(st, wa, 50 - i, pr[0][3], pi[0][3], pr[1][3], pi[1][3]);
     }
 
     // stage B, radf4's i = 1 case (fftpack.f90:859-866) for both k, feeding radf2's i = 1 (:729-732) and i = ido (:757-760)
     // cases and its butterfly 25
     template <int XS>
-    static __device__ __forceinline__ void stageB_first(const double* T, double* Y, const double* wa) {
+    static __device__ __forceinline__ void stageB_first(const double* T, double* Y, const double* wa) { stageB_first_f<XS>(T, StoreY<XS>{Y}, wa); }
+    template <int XS, class St>
+    static __device__ __forceinline__ void stageB_first_f(const double* T, const St& st, const double* wa) {
         double a[2], d[2], yr[2], yi[2];                   // ch(1,1,k), ch(12,4,k), ch(12,2,k), ch(1,3,k)
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -133,16 +144,18 @@ struct Fft96F {
             yr[k] = c1 - c3;
             yi[k] = c4 - c2;
         }
-        Y[0] = a[0] + a[1];                                // radf2: ch(1,1,1)
-        Y[95 * XS] = a[0] - a[1];                          // ch(48,2,1)
-        Y[48 * XS] = -d[1];                                // ch(1,2,1) = -cc(48,1,2)
-        Y[47 * XS] = d[0];                                 // ch(48,1,1) =  cc(48,1,1)
-        radf2_at<XS>(Y, wa, 25, yr[0], yi[0], yr[1], yi[1]);
+        st(0, a[0] + a[1]);                                // radf2: ch(1,1,1)
+        st(95, a[0] - a[1]);                               // ch(48,2,1)
+        st(48, -d[1]);                                     // ch(1,2,1) = -cc(48,1,2)
+        st(47, d[0]);                                      // ch(48,1,1) =  cc(48,1,1)
+        radf2_at_f(st, wa, 25, yr[0], yi[0], yr[1], yi[1]);
     }
 
     // stage B, radf4's i = ido case (fftpack.f90:911-920) for both k, feeding radf2's butterflies 13 and 37
     template <int XS>
-    static __device__ __forceinline__ void stageB_last(const double* T, double* Y, const double* wa) {
+    static __device__ __forceinline__ void stageB_last(const double* T, double* Y, const double* wa) { stageB_last_f<XS>(T, StoreY<XS>{Y}, wa); }
+    template <int XS, class St>
+    static __device__ __forceinline__ void stageB_last_f(const double* T, const St& st, const double* wa) {
         const double hsqt2 = (double)(.5f * sqrtf(2.f));   // .5*sqrt(2.) in real32 (fftpack.f90:857)
         double pr[2], pi[2], qr[2], qi[2];                 // ch(12,1,k), ch(1,2,k) -> positions 11, 12; ch(12,3,k), ch(1,4,k) -> 35, 36
 #pragma unroll
@@ -156,8 +169,8 @@ struct Fft96F {
             pi[k] = ti1 - c3;
             qi[k] = ti1 + c3;
         }
-        radf2_at<XS>(Y, wa, 13, pr[0], pi[0], pr[1], pi[1]);
-        radf2_at<XS>(Y, wa, 37, qr[0], qi[0], qr[1], qi[1]);
+        radf2_at_f(st, wa, 13, pr[0], pi[0], pr[1], pi[1]);
+        radf2_at_f(st, wa, 37, qr[0], qi[0], qr[1], qi[1]);
     }
 };
 

@@ -921,6 +921,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     const std::string n(name);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (n == "k2_field") ctx->k2_field = value != 0;
+    else if (n == "k2_quad") ctx->k2_quad = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

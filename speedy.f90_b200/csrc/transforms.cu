@@ -892,6 +892,8 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
     }
 }
 
+void launch_g2s_quad(speedy_ctx* ctx, const CUtensorMap& gmap, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
+
 void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K1_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<47>::K1_SMEM));
@@ -990,6 +992,10 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ_b);   // batch variant
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if constexpr (TRUNC == 30) {
+        if (ctx->k2_quad && (nbatch + nchunk - 1) / nchunk >= 3) {     // four fields at a time: FFT + DMMA Legendre (transforms_quad.cu)
+            launch_g2s_quad(ctx, gmap, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+            return;
+        }
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
         if (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3) {
             using F = FieldCfg<TRUNC>;

@@ -12,15 +12,16 @@ BC = os.path.join(ROOT, "data", "bc_t30.bin")
 PROG = ("vor", "div", "t", "tr", "ps")
 
 
+@pytest.mark.parametrize("opt", ["k2_field", "k2_quad"])
 @pytest.mark.parametrize("nb", [584, 1201])
-def test_grid_to_spec_whole_field(pkg, oracle, nb):
+def test_grid_to_spec_whole_field(pkg, oracle, nb, opt):
     o = oracle
     c = pkg.Speedy(trunc=30)
-    c.set_option("k2_field", 1)
+    c.set_option(opt, 1)
     rng = np.random.default_rng(99)
     g = rng.uniform(-1, 1, size=(nb, o.il, o.ix))
     got = c.grid_to_spec(g)
-    c.set_option("k2_field", 0)
+    c.set_option(opt, 0)
     base = c.grid_to_spec(g)
     idx = np.r_[0:8, nb // 2:nb // 2 + 8, nb - 8:nb]
     ref = o.grid_to_spec(g[idx])
@@ -45,7 +46,7 @@ def test_spec_to_grid_dense_inverse(pkg, oracle, nb):
     c.close()
 
 
-@pytest.mark.parametrize("opt", ["k2_field", "dense_inverse"])
+@pytest.mark.parametrize("opt", ["k2_field", "k2_quad", "dense_inverse"])
 def test_48h_run_variant(pkg, oracle, opt):
     """four identical members (the batch variants of the kernels) for 48 h against the oracle"""
     oracle.model_init(BC)
