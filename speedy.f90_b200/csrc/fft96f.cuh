@@ -89,14 +89,23 @@ struct Fft96F {
     template <int XS>
     static __device__ __forceinline__ void stageB_general(const double* T, double* Y, const double* wa, int i) { stageB_general_f<XS>(T, StoreY<XS>{Y}, wa, i); }
     template <int XS, class St>
-    static __device__ __forceinline__ void stageB_general_f(const double* T, const St& st, const double* wa, int i) {
+    static __device__ __forceinline__ void stageB_general_f(const double* T, const St& st, const double* wa, int i) { stageB_general_g(LoadT<XS>{T}, st, wa, i); }
+    // `Ld` is a load functor ld(blk, off) for stage A's output at position 12 blk + off (blk = k + 2 j of radf4's cc(., k, j))
+    template <int XS>
+    struct LoadT {
+        const double* T;
+        __device__ __forceinline__ double operator()(int blk, int off) const { return T[(12 * blk + off) * XS]; }
+    };
+    template <class Ld, class St>
+    static __device__ __forceinline__ void stageB_general_g(const Ld& ld, const St& st, const double* wa, int i) {
         const double w1r = wa[45 + i], w1i = wa[46 + i], w2r = wa[57 + i], w2i = wa[58 + i], w3r = wa[69 + i], w3i = wa[70 + i];
         // radf4 outputs of k = 1, 2 at the four radf2 positions: [0] i (j 1), [1] i+24 (j 3), [2] 26-i (ic, j 2), [3] 50-i (ic, j 4)
         double pr[2][4], pi[2][4];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const double* c = T + (size_t)((i - 2) + 12 * k) * XS;      // cc(i-1,k,1); cc(.,k,j) 24 (j-1) further
-            const double c1r = c[0], c1i = c[XS], c2r = c[24 * XS], c2i = c[25 * XS], c3r = c[48 * XS], c3i = c[49 * XS], c4r = c[72 * XS], c4i = c[73 * XS];
+            // cc(i-1,k,j), cc(i,k,j): position (i - 2) + 12 k + 24 (j - 1) and the next
+            const double c1r = ld(k, i - 2), c1i = ld(k, i - 1), c2r = ld(k + 2, i - 2), c2i = ld(k + 2, i - 1), c3r = ld(k + 4, i - 2), c3i = ld(k + 4, i - 1),
+                         c4r = ld(k + 6, i - 2), c4i = ld(k + 6, i - 1);
             const double cr2 = w1r * c2r + w1i * c2i;
             const double ci2 = w1r * c2i - w1i * c2r;
             const double cr3 = w2r * c3r + w2i * c3i;
@@ -131,12 +140,13 @@ struct Fft96F {
     template <int XS>
     static __device__ __forceinline__ void stageB_first(const double* T, double* Y, const double* wa) { stageB_first_f<XS>(T, StoreY<XS>{Y}, wa); }
     template <int XS, class St>
-    static __device__ __forceinline__ void stageB_first_f(const double* T, const St& st, const double* wa) {
+    static __device__ __forceinline__ void stageB_first_f(const double* T, const St& st, const double* wa) { stageB_first_g(LoadT<XS>{T}, st, wa); }
+    template <class Ld, class St>
+    static __device__ __forceinline__ void stageB_first_g(const Ld& ld, const St& st, const double* wa) {
         double a[2], d[2], yr[2], yi[2];                   // ch(1,1,k), ch(12,4,k), ch(12,2,k), ch(1,3,k)
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const double* c = T + (size_t)(12 * k) * XS;
-            const double c1 = c[0], c2 = c[24 * XS], c3 = c[48 * XS], c4 = c[72 * XS];
+            const double c1 = ld(k, 0), c2 = ld(k + 2, 0), c3 = ld(k + 4, 0), c4 = ld(k + 6, 0);
             const double tr1 = c2 + c4;
             const double tr2 = c1 + c3;
             a[k] = tr1 + tr2;
@@ -155,13 +165,14 @@ struct Fft96F {
     template <int XS>
     static __device__ __forceinline__ void stageB_last(const double* T, double* Y, const double* wa) { stageB_last_f<XS>(T, StoreY<XS>{Y}, wa); }
     template <int XS, class St>
-    static __device__ __forceinline__ void stageB_last_f(const double* T, const St& st, const double* wa) {
+    static __device__ __forceinline__ void stageB_last_f(const double* T, const St& st, const double* wa) { stageB_last_g(LoadT<XS>{T}, st, wa); }
+    template <class Ld, class St>
+    static __device__ __forceinline__ void stageB_last_g(const Ld& ld, const St& st, const double* wa) {
         const double hsqt2 = (double)(.5f * sqrtf(2.f));   // .5*sqrt(2.) in real32 (fftpack.f90:857)
         double pr[2], pi[2], qr[2], qi[2];                 // ch(12,1,k), ch(1,2,k) -> positions 11, 12; ch(12,3,k), ch(1,4,k) -> 35, 36
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const double* c = T + (size_t)(11 + 12 * k) * XS;
-            const double c1 = c[0], c2 = c[24 * XS], c3 = c[48 * XS], c4 = c[72 * XS];
+            const double c1 = ld(k, 11), c2 = ld(k + 2, 11), c3 = ld(k + 4, 11), c4 = ld(k + 6, 11);
             const double ti1 = -hsqt2 * (c2 + c4);
             const double tr1 = hsqt2 * (c2 - c4);
             pr[k] = tr1 + c1;

@@ -892,7 +892,7 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
     }
 }
 
-void launch_g2s_quad(speedy_ctx* ctx, const CUtensorMap& gmap, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
+void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
 
 void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K1_SMEM));
@@ -952,11 +952,11 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
 // SWIZZLE_128B.  A field at element offset `off` (a multiple of IX) starts at row off / IX.  Maps are cached per buffer.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static const CUtensorMap& grid_field_map(const double* d_in, long long in_ms, int nmembers, int ix, int il) {
-    static std::map<std::tuple<const void*, long long, int, int>, CUtensorMap> cache;
+static const CUtensorMap& grid_field_map(const double* d_in, long long in_ms, int nmembers, int ix, int il) {   // il: latitudes per box
+    static std::map<std::tuple<const void*, long long, int, int, int>, CUtensorMap> cache;
     static std::mutex mu;
     std::lock_guard<std::mutex> lock(mu);
-    const auto key = std::make_tuple((const void*)d_in, in_ms, nmembers, ix);
+    const auto key = std::make_tuple((const void*)d_in, in_ms, nmembers, ix, il);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     static EncodeTiledFn enc = nullptr;
@@ -993,7 +993,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if constexpr (TRUNC == 30) {
         if (ctx->k2_quad && (nbatch + nchunk - 1) / nchunk >= 3) {     // four fields at a time: FFT + DMMA Legendre (transforms_quad.cu)
-            launch_g2s_quad(ctx, gmap, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+            launch_g2s_quad(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
             return;
         }
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
