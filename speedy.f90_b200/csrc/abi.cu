@@ -157,7 +157,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->trace_pdl = getenv("SPEEDY_TRACE_PDL") != nullptr;
         ctx->fft_inverse = getenv("SPEEDY_DENSE_INVERSE") == nullptr;
         ctx->k2_field = getenv("SPEEDY_K2_FIELD") != nullptr;
-        ctx->k2_quad = getenv("SPEEDY_K2_QUAD") != nullptr;
+        if (const char* v = getenv("SPEEDY_K2_QUAD")) ctx->k2_quad = atoi(v) != 0;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));

@@ -34,21 +34,26 @@ __device__ __forceinline__ void dmma884q(double& c0, double& c1, double a, doubl
 
 struct QCfg {
     static constexpr int TRUNC = 30, MX = 31, NX = 32, IX = 96, IL = 48, IY = 24, K2 = 2 * MX, NSPEC2 = NX * K2;
-    static constexpr int WARPS = 12, THREADS = 32 * WARPS;
-    static constexpr int NG = 3, GT = 128;           // latitude bands = warpgroups; threads per group
+    static constexpr int WARPS = 24, THREADS = 32 * WARPS;
+    static constexpr int NG = 3, GT = 128;           // latitude bands; threads per FFT group (a warpgroup)
+    static constexpr int NPH = 2;                    // fields in the FFT stages at a time: group (band, phase) takes every NPH-th field
     static constexpr int RING = 3;                   // band buffers per group: one being transformed, two in flight
     static constexpr int NBOX = IX / 16;             // tensor-map boxes of [16 longitudes x 8 latitudes] = one 1 KB swizzle atom
     static constexpr int BAND = 2 * NBOX * 128;      // doubles per band buffer: [hemisphere][box][8 rows][16 longitudes]
     static constexpr int CS = 52, FS = K2 * CS;      // EO[field][c][slot]; CS = 4 mod 16 and FS = 8 mod 16: conflict-free B fragments
-    static constexpr int SLOTS = 8, KS = IY / 4;     // tiles per warp, k-steps per tile
+    static constexpr int SLOTS = 4, KS = IY / 4;     // tiles per warp, k-steps per tile
+    static constexpr int TCOLS = 2 * SLOTS * KS;     // 32-bit TMEM columns of a warp's P fragments
+    static constexpr int NBAR = RING * NPH;          // "band landed" barriers per band: field seq uses buffer seq % RING and barrier seq % NBAR, so
+                                                     // that each barrier has ONE waiting group (phase parity is only safe for a waiter that cannot fall behind)
     static constexpr int NLIVE = 93, NTILE = 124;    // live / all (m, parity, n-tile) tiles
     static constexpr int LCAP = 128;                 // fields per CTA and launch (the host splits larger batches)
-    static constexpr int RSTG = 68, FSTG = NX * RSTG + 2;   // output staging [field][n][RSTG]: row = 2 mod 4 and field = 1 mod 8 sixteen-byte slots
-    static constexpr size_t SMEM_G2S = sizeof(double) * (NG * RING * BAND + 4 * FS + IX) + sizeof(uint64_t) * (NG * RING + 1) + sizeof(int) * NTILE +
+    static constexpr int RSTG = K2, FSTG = NX * RSTG + 2;   // output staging [field][n][K2]: a field is one contiguous run (one bulk store); field stride = 1 mod 8 sixteen-byte slots
+    static constexpr size_t SMEM_G2S = sizeof(double) * (NG * RING * BAND + 4 * FS + IX) + sizeof(uint64_t) * (NG * NBAR + 2) + sizeof(int) * NTILE +
                                        LCAP * (3 * sizeof(int) + sizeof(long long));
+    static_assert(NG * NPH * GT == THREADS && (WARPS / 4) * TCOLS <= 512 && TCOLS % 16 == 0, "FFT groups; tensor-memory columns");
     static_assert(FS % 16 == 8 && CS % 16 == 4 && (BAND * 8) % 1024 == 0 && BAND == IX * 16 && SMEM_G2S <= 232448, "layout");
-    static_assert(WARPS * SLOTS >= NLIVE && NG * 8 == IY && NG * GT == THREADS && SLOTS % 4 == 0, "tiling");
-    static_assert((RSTG / 2) % 4 == 2 && (FSTG / 2) % 8 == 1 && RSTG >= K2 && 4 * FSTG <= 4 * FS, "staging layout");
+    static_assert(WARPS * SLOTS >= NLIVE && NG * 8 == IY && SLOTS % 4 == 0, "tiling");
+    static_assert((FSTG / 2) % 8 == 1 && RSTG == K2 && 4 * FSTG <= 4 * FS && (NSPEC2 * 8) % 16 == 0, "staging layout");
 };
 
 
@@ -97,6 +102,25 @@ void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<dou
 // of the grid array (16 longitudes | 6 blocks of 16 | row | member): 128-byte segments, hardware 128-byte swizzle.
 // The spectral coefficients leave through shared memory: the tile results are staged over the (dead) EO buffer in the output
 // layout and written as whole 128-byte lines (a lane's own result is 16 bytes at a 496-byte stride: 32 sectors per store).
+// tensor memory as a scratchpad for the P fragments: 32x32b shape, thread i of warp w owns TMEM lane 32 (w % 4) + i
+__device__ __forceinline__ void tmem_st16(uint32_t addr, const double* v) {     // 8 doubles -> 16 columns
+    uint32_t r[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { r[2 * i] = (uint32_t)__double2loint(v[i]); r[2 * i + 1] = (uint32_t)__double2hiint(v[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+                    "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t addr, double* v) {           // issue only: tmem_ld_wait() before the values are used
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+                   "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
+}
+
 __global__ void __launch_bounds__(QCfg::THREADS, 1)
 k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end,
            double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
@@ -105,12 +129,14 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     double* sRing = smem;                               // [NG][RING][BAND]
     double* sEO = sRing + C::NG * C::RING * C::BAND;    // [4][K2][CS]; after the tile sums: output staging [4][NX][RSTG]
     double* sWa = sEO + 4 * C::FS;                      // [IX] twiddles
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sWa + C::IX);     // [NG][RING] band buffers
-    long long* sOut = reinterpret_cast<long long*>(bars + C::NG * C::RING + 1);   // [LCAP] output offset of the field
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sWa + C::IX);     // [NG][NBAR] "band landed", then "EO free"; the last slot holds the TMEM base address
+    uint64_t* eo_free = bars + C::NG * C::NBAR;
+    long long* sOut = reinterpret_cast<long long*>(bars + C::NG * C::NBAR + 2);   // [LCAP] output offset of the field
     int* sRow0 = reinterpret_cast<int*>(sOut + C::LCAP);           // [LCAP] first row of the field in the tensor map
     int* sE = sRow0 + C::LCAP;                                      // [LCAP] member
     int* sFl = sE + C::LCAP;                                        // [LCAP] descriptor flags
     int* sTile = sFl + C::LCAP;
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + C::NG * C::NBAR + 1);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid == 0) trace_begin(tv.trace, 2);
     // this CTA's quads of the flattened (member, field) list
@@ -119,15 +145,14 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     const int i0 = idx_base + 4 * q0, cnt = min(idx_base + 4 * q1, idx_end) - i0;
     if (tid == 0 && ((smem_u32(sRing) & 1023u) || cnt > C::LCAP)) __trap();
     if (tid == 0) {
-        for (int k = 0; k < C::NG * C::RING; k++) mbar_init(&bars[k], 1);
+        for (int k = 0; k < C::NG * C::NBAR + 1; k++) mbar_init(&bars[k], 1);
         mbar_fence_init();
     }
+    if (w == 0) {                                       // all 512 columns of the SM's tensor memory (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
     // ---- prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
-    double a[C::SLOTS][C::KS];                          // P fragments of this warp's tiles, resident for the whole kernel
-#pragma unroll
-    for (int i = 0; i < C::SLOTS; i++)
-#pragma unroll
-        for (int ks = 0; ks < C::KS; ks++) a[i][ks] = tv.polyq[(((size_t)w * C::SLOTS + i) * C::KS + ks) * 32 + lane];
     for (int t = tid; t < 2 * C::FS; t += C::THREADS) reinterpret_cast<double2*>(sEO)[t] = make_double2(0.0, 0.0);   // row c = 1 (Im m = 0, fourier.f90:76) stays zero
     for (int t = tid; t < C::IX; t += C::THREADS) sWa[t] = tv.fftwa[t];
     for (int t = tid; t < C::NTILE; t += C::THREADS) sTile[t] = tv.qtile[t];
@@ -138,8 +163,22 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
         if (d.off != (long long)row0 * C::IX) __trap();
         sRow0[t] = row0; sE[t] = e; sFl[t] = d.flags; sOut[t] = (long long)e * out_ms + (long long)f * C::NSPEC2;
     }
-    // roles: group = latitude band; stage A thread = (parity, latitude pair of the band, k of radf4); stage B thread = (set, slot)
-    const int b = w >> 2, wl = w & 3, par = wl >> 1, ha = wl & 1;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // P fragments of this warp's tiles: parked in tensor memory for the whole kernel (they would take 48 registers per thread of
+    // a 768-thread CTA), fetched back at the start of every Legendre phase
+    const uint32_t taddr = *sTmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(C::TCOLS * (w >> 2));
+    {
+        double a[C::SLOTS * C::KS];
+#pragma unroll
+        for (int j = 0; j < C::SLOTS * C::KS; j++) a[j] = tv.polyq[((size_t)w * C::SLOTS * C::KS + j) * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < C::TCOLS / 16; c++) tmem_st16(taddr + 16 * c, a + 8 * c);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // roles: FFT group = (latitude band, field phase); stage A thread = (parity, latitude pair of the band, k of radf4); stage B thread = (set, slot)
+    const int gi = w >> 2, b = gi % C::NG, ph = gi / C::NG, wl = w & 3, par = wl >> 1, ha = wl & 1;
     const int k3 = (lane & 3) + 4 * (lane >> 4), rsel = (lane >> 2) & 3;
     const int jl = 4 * ha + rsel, jh = 8 * b + jl;      // a warp reads 4 consecutive rows: distinct swizzle phases, conflict-free
     const int s16A = (8 * par + jl) ^ (4 * (k3 & 3));
@@ -156,25 +195,26 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     const int t128 = tid & 127, setB = t128 >> 4, s16B = t128 & 15;
     const int slotB = 24 * (s16B >> 3) + 8 * b + (s16B & 7);
     double* ring = sRing + b * C::RING * C::BAND;
-    uint64_t* gbar = bars + b * C::RING;
-    __syncthreads();
+    uint64_t* gbar = bars + b * C::NBAR;
     pdl_wait();                                         // the grid fields of the previous kernel are complete
     pdl_trigger();
     const int gate_open = gate ? *gate : 1;
     auto skip = [&](int t) { return !gate_open && (sFl[t] & 4); };
     auto next_live = [&](int t) { while (t < cnt && skip(t)) t++; return t; };
-    auto issue = [&](int t, int k) {                    // one thread of the group: the two boxes of field t's band into ring buffer k
+    auto issue = [&](int t, int sq) {                   // one thread of the group: the two boxes of list entry t's band = live field number sq
         const int row0 = sRow0[t], e = sE[t];
-        double* dst = ring + k * C::BAND;
+        double* dst = ring + (sq % C::RING) * C::BAND;
+        uint64_t* br = &gbar[sq % C::NBAR];
         fence_proxy_async();
-        mbar_expect_tx(&gbar[k], C::BAND * sizeof(double));
-        tensor_g2s_4d(dst, &gmap, 0, 0, row0 + 8 * b, e, &gbar[k]);
-        tensor_g2s_4d(dst + C::BAND / 2, &gmap, 0, 0, row0 + C::IL - 8 - 8 * b, e, &gbar[k]);
+        mbar_expect_tx(br, C::BAND * sizeof(double));
+        tensor_g2s_4d(dst, &gmap, 0, 0, row0 + 8 * b, e, br);
+        tensor_g2s_4d(dst + C::BAND / 2, &gmap, 0, 0, row0 + C::IL - 8 - 8 * b, e, br);
     };
-    int tl = next_live(0);                              // next field to load
-    for (int k = 0; k < C::RING; k++)
-        if (tl < cnt) { if (wl == 0 && lane == 0) issue(tl, k); tl = next_live(tl + 1); }
-    int n = 0;                                          // fields consumed by this group
+    if (ph == 0 && wl == 0 && lane == 0) {              // the first RING fields of the band
+        int tl = next_live(0);
+        for (int k = 0; k < C::RING && tl < cnt; k++) { issue(tl, k); tl = next_live(tl + 1); }
+    }
+    int n = 0;                                          // live fields met so far (the same count in every thread)
     // phase stamps of CTA 0 (speedy_trace + SPEEDY_TRACE_STAMPS): cycles in [FFT of the quad, wait, tile sums, wait, staging, wait + copy-out, wait]
     long long tq = 0;
 #define QSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[24 + (i)] += (unsigned long long)(t_ - tq); tq = t_; } } while (0)
@@ -185,9 +225,15 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
             const int t = t0 + fs;
             if (skip(t)) continue;
             present |= 1u << fs;
-            const int k = n % C::RING, fl = sFl[t];
+            const int seq = n++;
+            if (seq % C::NPH != ph) continue;           // the other group of this band takes it
+            const int k = seq % C::RING, fl = sFl[t];
             double* G = ring + k * C::BAND;
-            mbar_wait(&gbar[k], (n / C::RING) & 1);
+            long long tf = 0;
+#define FSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[32 + (i)] += (unsigned long long)(t_ - tf); tf = t_; } } while (0)
+            if (tv.trace) tf = clock64();
+            mbar_wait(&gbar[seq % C::NBAR], (seq / C::NBAR) & 1);
+            FSTAMP(0);
             // ---- fold of the two hemispheres (legendre.f90:127-133, taken before the linear FFT; its Gaussian weight is in the P
             // fragments) with the cosgr / cosgr2 pre-scale of vdspec (spectral.f90:208-222)
             double x[12];
@@ -203,35 +249,41 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
 #pragma unroll
                 for (int u = 0; u < 12; u++) x[u] *= sc;
             }
-            named_sync(1 + b, C::GT);                   // every row of the band is in registers: the buffer may be overwritten
+            FSTAMP(1);
+            named_sync(1 + gi, C::GT);                  // every row of the band is in registers: the buffer may be overwritten
+            FSTAMP(2);
             // ---- stage A: radf3 + radf4 (fftpack.f90:774,844), in place
             Fft96F::stageA<16>(x, G + s16A, sWa, k3);
-            named_sync(1 + b, C::GT);                   // T complete
+            FSTAMP(3);
+            named_sync(1 + gi, C::GT);                  // T complete
+            FSTAMP(4);
             // ---- stage B: radf4 + radf2 (fftpack.f90:844,722); half-complex position -> coefficient row, truncated at m = trunc
+            if (t0 > 0) mbar_wait(eo_free, ((t0 >> 2) - 1) & 1);        // the previous quad's coefficients have left the buffer (bulk store)
             if (setB < 7) {
                 double* E = sEO + fs * C::FS + slotB;
                 auto st = [E](int pos, double v) { if (pos <= 2 * C::TRUNC) E[(pos + (pos > 0)) * C::CS] = v; };
                 auto ld = [G, s16B](int blk, int off) { return G[(12 * blk + off) * 16 + (s16B ^ (4 * (blk & 3)))]; };
-                switch (setB) {                           // one instantiation per set: every position, twiddle index and truncation test is an immediate
-                    case 0: Fft96F::stageB_general_g(ld, st, sWa, 3); break;
-                    case 1: Fft96F::stageB_general_g(ld, st, sWa, 5); break;
-                    case 2: Fft96F::stageB_general_g(ld, st, sWa, 7); break;
-                    case 3: Fft96F::stageB_general_g(ld, st, sWa, 9); break;
-                    case 4: Fft96F::stageB_general_g(ld, st, sWa, 11); break;
-                    case 5: Fft96F::stageB_first_g(ld, st, sWa); break;
-                    default: Fft96F::stageB_last_g(ld, st, sWa); break;
-                }
+                // the five general sets share one instruction stream (the butterfly index is a run-time value): the two half-warps of
+                // a warp work on different sets, and specialised copies would run one after the other
+                if (setB < 5) Fft96F::stageB_general_g(ld, st, sWa, 3 + 2 * setB);
+                else if (setB == 5) { Fft96F::stageB_first_g(ld, st, sWa); E[C::CS] = 0.0; }      // row c = 1: Im(m = 0) = 0 (fourier.f90:76)
+                else Fft96F::stageB_last_g(ld, st, sWa);
             }
-            // the buffer goes back to the TMA once the whole group has read T: only the issuing warp waits (bar.sync / bar.arrive
-            // are warp-aligned instructions: the roles must be whole warps)
+            FSTAMP(5);
+            // the buffer goes back to the TMA (for the field RING places ahead) once the whole group has read T: only the issuing warp
+            // waits (bar.sync / bar.arrive are warp-aligned instructions: the roles must be whole warps)
             if (wl == 0) {
-                named_sync(4 + b, C::GT);
-                if (lane == 0 && tl < cnt) issue(tl, k);
+                named_sync(7 + gi, C::GT);
+                if (lane == 0) {
+                    int t3 = t;
+                    for (int u = 0; u < C::RING; u++) t3 = next_live(t3 + 1);
+                    if (t3 < cnt) issue(t3, seq + C::RING);
+                }
             } else {
-                named_arrive(4 + b, C::GT);
+                named_arrive(7 + gi, C::GT);
             }
-            if (tl < cnt) tl = next_live(tl + 1);
-            n++;
+            FSTAMP(6);
+#undef FSTAMP
         }
         QSTAMP(0);
         __syncthreads();                                // EO of the quad complete
@@ -240,21 +292,23 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
         const double* Bq = sEO + (g >> 1) * C::FS + (g & 1) * C::CS + q;
         int tt[C::SLOTS];
         double c0[C::SLOTS], c1[C::SLOTS];
+        {
+            double a[C::SLOTS * C::KS];
 #pragma unroll
-        for (int i = 0; i < C::SLOTS; i += 4) {
-            const double* Bp[4];
+            for (int c = 0; c < C::TCOLS / 16; c++) tmem_ld16(taddr + 16 * c, a + 8 * c);
+            const double* Bp[C::SLOTS];
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                const int L = (i + u) * C::WARPS + w;
-                tt[i + u] = (L < C::NLIVE) ? sTile[L] : -1;
-                const int tv_ = tt[i + u] < 0 ? 0 : tt[i + u];
+            for (int u = 0; u < C::SLOTS; u++) {
+                const int L = u * C::WARPS + w;
+                tt[u] = (L < C::NLIVE) ? sTile[L] : -1;
+                const int tv_ = tt[u] < 0 ? 0 : tt[u];
                 Bp[u] = Bq + 2 * (tv_ & 255) * C::CS + 24 * ((tv_ >> 8) & 1);
-                c0[i + u] = 0.0; c1[i + u] = 0.0;
+                c0[u] = 0.0; c1[u] = 0.0;
             }
 #pragma unroll
             for (int ks = 0; ks < C::KS; ks++)
 #pragma unroll
-                for (int u = 0; u < 4; u++) dmma884q(c0[i + u], c1[i + u], a[i + u][ks], Bp[u][4 * ks]);
+                for (int u = 0; u < C::SLOTS; u++) dmma884q(c0[u], c1[u], a[u * C::KS + ks], Bp[u][4 * ks]);
         }
         QSTAMP(2);
         __syncthreads();                                // every tile has read EO: the buffer becomes the output staging area
@@ -273,24 +327,24 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
             }
         }
         QSTAMP(4);
+        fence_proxy_async();                            // the staged coefficients (generic stores) become visible to the bulk-copy engine
         __syncthreads();
-        // whole 128-byte lines to global memory: a field's 32 x 31 complex coefficients are contiguous
-        for (int fs = 0; fs < 4; fs++) {
-            if (!((present >> fs) & 1)) continue;
-            double2* outp = reinterpret_cast<double2*>(out_base + sOut[t0 + fs]);
-            const double2* src = reinterpret_cast<const double2*>(sEO + fs * C::FSTG);
-            for (int s2 = tid; s2 < C::NX * C::MX; s2 += C::THREADS) {
-                const int nn = s2 / C::MX, mm = s2 - nn * C::MX;
-                outp[s2] = src[nn * (C::RSTG / 2) + mm];
-            }
+        // a field's 32 x 31 complex coefficients are one contiguous run: one bulk store each (TMA, SASS UBLKCP), asynchronous — the
+        // next quad's FFT runs meanwhile; its stage B waits on `eo_free` before it writes the buffer again
+        if (w == C::WARPS - 1 && lane == 0) {
+            for (int fs = 0; fs < 4; fs++)
+                if ((present >> fs) & 1) bulk_s2g(out_base + sOut[t0 + fs], sEO + fs * C::FSTG, C::NSPEC2 * sizeof(double));
+            bulk_commit_wait_read();
+            mbar_arrive(eo_free);
         }
         QSTAMP(5);
-        __syncthreads();                                // staging read: the buffer is EO again
-        QSTAMP(6);
-        for (int t = tid; t < 4 * C::IL; t += C::THREADS) sEO[(t / C::IL) * C::FS + C::CS + (t % C::IL)] = 0.0;   // restore row c = 1
     }
 #undef QSTAMP
-    if (tv.trace) { __syncthreads(); if (tid == 0) trace_end(tv.trace, 2); }
+    if (w == C::WARPS - 1 && lane == 0) bulk_wait_all();      // the last stores have left the SM's shared memory and are committed
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*sTmem), "r"(512u) : "memory");
+    if (tv.trace && tid == 0) trace_end(tv.trace, 2);
 }
 
 void setup_quad_kernels() {

@@ -1,6 +1,7 @@
-"""Parity of the alternative transform kernels a context can be switched to (speedy_set_option):
-the whole-field FFT grid->spec kernel of ensemble batches ("k2_field") and the dense-operator
-Fourier stage of spec->grid ("dense_inverse").  Same oracle, same tolerances as the default kernels:
+"""Parity of every transform kernel a context can be switched to (speedy_set_option): grid->spec of
+ensemble batches through the quad kernel (default: FFT + DMMA Legendre, four fields at a time), the
+whole-field FFT kernel ("k2_field") and the streaming kernel with the dense operator ("k2_quad" = 0);
+spec->grid with the dense-operator Fourier stage ("dense_inverse").  Same oracle, same tolerances as the default kernels:
 1e-12 relative RMS per transform call, 1e-10 on the prognostic coefficients after 48 h."""
 import os
 import numpy as np
@@ -12,16 +13,24 @@ BC = os.path.join(ROOT, "data", "bc_t30.bin")
 PROG = ("vor", "div", "t", "tr", "ps")
 
 
-@pytest.mark.parametrize("opt", ["k2_field", "k2_quad"])
-@pytest.mark.parametrize("nb", [584, 1201])
-def test_grid_to_spec_whole_field(pkg, oracle, nb, opt):
+VARIANTS = {"quad": {"k2_quad": 1}, "field": {"k2_quad": 0, "k2_field": 1}, "stream": {"k2_quad": 0, "k2_field": 0}}
+
+
+def _select(c, variant):
+    for k, v in VARIANTS[variant].items():
+        c.set_option(k, v)
+
+
+@pytest.mark.parametrize("variant", ["quad", "field"])
+@pytest.mark.parametrize("nb", [584, 1201, 1202, 1203])
+def test_grid_to_spec_whole_field(pkg, oracle, nb, variant):
     o = oracle
     c = pkg.Speedy(trunc=30)
-    c.set_option(opt, 1)
+    _select(c, variant)
     rng = np.random.default_rng(99)
     g = rng.uniform(-1, 1, size=(nb, o.il, o.ix))
     got = c.grid_to_spec(g)
-    c.set_option(opt, 0)
+    _select(c, "stream")
     base = c.grid_to_spec(g)
     idx = np.r_[0:8, nb // 2:nb // 2 + 8, nb - 8:nb]
     ref = o.grid_to_spec(g[idx])
@@ -46,13 +55,16 @@ def test_spec_to_grid_dense_inverse(pkg, oracle, nb):
     c.close()
 
 
-@pytest.mark.parametrize("opt", ["k2_field", "k2_quad", "dense_inverse"])
-def test_48h_run_variant(pkg, oracle, opt):
+@pytest.mark.parametrize("variant", ["quad", "field", "stream", "dense_inverse"])
+def test_48h_run_variant(pkg, oracle, variant):
     """four identical members (the batch variants of the kernels) for 48 h against the oracle"""
     oracle.model_init(BC)
     assert oracle.run(72) == 0
     c = pkg.Speedy(trunc=30, nmembers=4)
-    c.set_option(opt, 1)
+    if variant == "dense_inverse":
+        c.set_option("dense_inverse", 1)
+    else:
+        _select(c, variant)
     c.model_init(BC)
     assert c.run_steps(72) == 0
     ref = oracle.state()

@@ -10,6 +10,7 @@ nb = int(sys.argv[2]) if len(sys.argv) > 2 else 584
 c = pkg.Speedy(trunc=30)
 rng = np.random.default_rng(99)
 g = rng.uniform(-1, 1, size=(nb, c.il, c.ix))
+c.set_option("k2_quad", 0)
 base = c.grid_to_spec(g)
 c.set_option(opt, 1)
 got = c.grid_to_spec(g)
