@@ -9,9 +9,11 @@ land/sea slabs) for every ensemble member resident on this rank's GPU, replayed 
 
 N > 1 (torchrun, one rank per GPU): members shard across ranks with no data-path collective
  -> weak scaling; the only collective is the timing max/barrier.
-`--impl reference` times the reference's CPU algorithm (the oracle restatement built -Ofast:
-no Fortran compiler exists in this image) on the host, one core (the
-reference is serial), rank 0 only.
+For every N the same run also measures BASELINE configs[2] at that N (8 SPPT members per GPU, the
+ensemble-moment all-reduce over NCCL once per simulated day): key `ensemble_sppt_8_per_gpu`.
+`--impl reference` times the reference's CPU algorithm — the C++ PORT in oracle/ built -Ofast (no
+Fortran compiler exists in this image; cpu_baseline.kind = "port") — on the host,
+one core (the reference is serial), rank 0 only.
 """
 import argparse
 import ctypes
@@ -38,6 +40,7 @@ def _args():
     ap.add_argument("--members", type=int, default=1, help="ensemble members per GPU (1 = BASELINE configs[1])")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ensemble", action="store_true", help="skip the BASELINE configs[2] leg (8 SPPT members per GPU + daily moment all-reduce)")
     return ap.parse_args()
 
 
@@ -47,7 +50,8 @@ def _config(args):
             "members_per_gpu": args.members, "total_members": args.members * args.gpus,
             "model_steps_per_bench_step": NSTEPS_PER_DAY, "start_date": "1982-01-01",
             "parallelism": f"ensemble members sharded {args.members}/GPU x {args.gpus} GPU(s), no data-path collective",
-            "l2": "256 MiB buffer overwritten between timed steps (L2 flush); within a simulated day the 15 MB state is L2-resident by construction",
+            "l2": "256 MiB buffer overwritten between timed steps (L2 flush, enqueued on the same stream, untimed); within a simulated day the 15 MB state is L2-resident by construction",
+            "host_sync": "none inside the timed region: all timed days are enqueued (CUDA graph replays), the range guard is polled once after the last day",
             "output_cadence": "none inside the timed region (nsteps_out > run length)"}
 
 
@@ -154,6 +158,18 @@ def _ncu_traffic(kernel, members):
     return None, "no ncu summary committed"
 
 
+def _pin_rank_to_cores(local, nlocal):
+    """one disjoint block of host cores per rank: the per-day launch work of N processes must not share cores"""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cores) // max(nlocal, 1))
+        mine = cores[local * per:(local + 1) * per] or cores
+        os.sched_setaffinity(0, mine)
+        return len(mine)
+    except Exception:
+        return None
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -165,13 +181,15 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the hot path has no CPU fallback")
+    ncores = _pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
     pkg = _load_pkg()
     c = pkg.Speedy(trunc=30, nmembers=args.members, device=local)
     c.model_init(BC)
-    stream = torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local))
+    stream = torch.cuda.ExternalStream(c.stream, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -180,7 +198,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---------------- device-resident throughput (`value`) ----------------
+    # every timed day is ENQUEUED (graph replay) behind an untimed L2 flush on the same stream, bracketed by CUDA events on that
+    # stream; the host synchronises once, after the last day (the range guard is polled there): no host round trip per day
     for _ in range(max(args.warmup, 3)):
         assert c.run_steps(NSTEPS_PER_DAY) == 0
     c.synchronize()
@@ -189,22 +215,19 @@ def run_b200(args):
     sampler = ClockSampler(local) if rank == 0 else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.fill_(k & 0xFF)               # L2 flush between timed steps (untimed)
-        torch.cuda.synchronize()
-        ev[k][0].record(stream)
-        rc = c.run_steps(NSTEPS_PER_DAY)    # one simulated day; returns after the stream drained (diagnostics guard read back)
-        ev[k][1].record(stream)
-        assert rc == 0, "check_diagnostics: model variables out of accepted range"
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            flush.fill_(k & 0xFF)               # L2 flush between timed steps (untimed, same stream)
+            ev[k][0].record(stream)
+            c.enqueue_steps(NSTEPS_PER_DAY)     # one simulated day
+            ev[k][1].record(stream)
+    rc = c.finish()
+    assert rc == 0, "check_diagnostics: model variables out of accepted range"
     barrier()
     t_wall = time.perf_counter() - t_wall0
     clocks = sampler.stop() if sampler else None
-    dev_s = sum(a.elapsed_time(b) for a, b in ev) * 1e-3
+    dev_s = rank_max(sum(a.elapsed_time(b) for a, b in ev) * 1e-3)
     launches = c.launch_count - launches0
-    tt = torch.tensor([dev_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_s = float(tt.item())
     total_days = args.steps * args.members * world
     value = total_days / dev_s
 
@@ -226,11 +249,15 @@ def run_b200(args):
     for k in range(e2e_days):
         assert c.run_steps_host(s_np, NSTEPS_PER_DAY, o_np) == 0
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t2 = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_days * args.members * world / float(t2.item())
+    e2e_value = e2e_days * args.members * world / rank_max(time.perf_counter() - t0)
+
+    # ---------------- BASELINE configs[2] at this N: 8 SPPT members per GPU, ensemble-moment all-reduce once per simulated day ----------------
+    ens_line = None
+    if args.members == 1 and not args.no_ensemble:
+        try:
+            ens_line = _ensemble_leg(pkg, torch, dist, world, rank, local, dev, barrier, rank_max)
+        except Exception as ex:
+            ens_line = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
@@ -248,62 +275,46 @@ def run_b200(args):
     kt_cold = c.time_kernels(NSTEPS_PER_DAY, flush_l2=True)
     kt_warm = c.time_kernels(NSTEPS_PER_DAY, flush_l2=False)
     # the same kernels on the GPU's own nanosecond timer inside the replayed graph (first CTA start -> last CTA end,
-    # programmatic dependent launch off so that the kernels do not overlap): no event / launch overhead in these
+    # programmatic dependent launch off so that the kernels do not overlap): no event / launch overhead in these.
+    # ONE timer for the roofline: the kernel ranking and achieved / frac both come from these durations.
     c.trace(True)
     c.run_steps(3 * NSTEPS_PER_DAY)
     timeline = c.trace_read()
     c.trace(False)
     M = args.members
-    nact = sum(2 * min(c.mx, c.trunc + 2 - n) for n in range(c.nx))      # 1054 active reals (legendre.f90:33-41)
-    NG = c.ix * c.il
-    alg = {  # algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)
-        "spec_to_grid": M * 77 * (8 * nact + 8 * NG),                   # 91 of the reference minus the 14 level-1 wind fields nobody reads
-        "grid_to_spec": M * 73 * (8 * NG + 8 * (nact - 2)),
-        "grid_columns": M * NG * 8 * (77 + 73 + 45 + 8 + 32 + 2),       # 77 fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
-        "spec_step": M * c.mx * c.nx * 16 * 165,
-    }
-    # BASELINE metric (2), "Legendre GB/s vs roofline": the two transform kernels alone on a large device-resident batch
-    # (5824 = 91 fields x 8 levels x 8 members), CUDA events on the library stream, L2 flushed between reps
-    def _transform_batch(inverse, nb):
-        spec = torch.rand((nb, c.nx, c.mx, 2), dtype=torch.float64, device="cuda") * 2 - 1
-        grid = torch.rand((nb, c.il, c.ix), dtype=torch.float64, device="cuda") * 2 - 1
-        times = []
-        for rep in range(6):
-            flush.fill_(rep)
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            if inverse:
-                rc = c.L.speedy_spec_to_grid_dev(c.h, ctypes.c_void_p(spec.data_ptr()), nb, None, ctypes.c_void_p(grid.data_ptr()))
-            else:
-                rc = c.L.speedy_grid_to_spec_dev(c.h, ctypes.c_void_p(grid.data_ptr()), nb, ctypes.c_void_p(spec.data_ptr()))
-            assert rc == 0
-            e1.record(stream)
-            e1.synchronize()
-            if rep >= 2:
-                times.append(e0.elapsed_time(e1) * 1e-3)
-        t = sorted(times)[len(times) // 2]
-        by = nb * ((8 * nact + 8 * NG) if inverse else (8 * NG + 8 * (nact - 2)))
-        return {"batch": nb, "us": 1e6 * t, "GBps": by / t / 1e9, "frac_hbm": by / t / 1e9 / hbm, "transforms_per_s": nb / t}
+    alg = _algorithmic_bytes(c, M)
     try:
-        legendre_batched = {"spec_to_grid": _transform_batch(True, 5824), "grid_to_spec": _transform_batch(False, 4672),
-                            "note": "algorithmic bytes per transform over the measured HBM copy bandwidth; at this batch the transforms are bound by shared-memory wavefronts of the Legendre stages and, in grid->spec, by the dense DFT on the FP64 tensor pipe (profiles/README.md, r1n), not by HBM"}
+        legendre_batched = {"spec_to_grid": _transform_batch(c, torch, stream, flush, True, 5824, hbm),
+                            "grid_to_spec": _transform_batch(c, torch, stream, flush, False, 4672, hbm),
+                            "note": "BASELINE metric (2): algorithmic bytes per transform over the measured HBM copy bandwidth, device-resident random fields, L2 flushed "
+                                    "between repetitions; grid->spec runs the quad kernel (FFTPACK FFT + DMMA Legendre tiles, P fragments in tensor memory), spec->grid "
+                                    "the streaming kernel (FFT + scalar Legendre sums); both are bound by shared-memory wavefronts and the FP64 pipe before HBM (profiles/README.md r2)"}
     except Exception as ex:
         legendre_batched = {"error": str(ex)}
-    tot = sum(kt_warm.values())
     dom = max(alg, key=lambda k: timeline["us"][k])     # the longest kernel of the step on the GPU's own timer
-    ach = alg[dom] / (kt_cold[dom] * 1e-3) / 1e9
+    dom_us = timeline["us"][dom]
+    ach = alg[dom] / (dom_us * 1e-6) / 1e9
     traffic, traffic_src = _ncu_traffic(dom, M)
+    step_us = 1e6 * dev_s / (args.steps * NSTEPS_PER_DAY)
+    whole_step = {f"members_{M}": {"algorithmic_bytes_per_step": sum(alg.values()), "us_per_step": step_us,
+                                   "GBps": sum(alg.values()) / (step_us * 1e-6) / 1e9, "frac_hbm": sum(alg.values()) / (step_us * 1e-6) / 1e9 / hbm}}
+    if ens_line and "us_per_step" in ens_line:
+        a8 = sum(_algorithmic_bytes(c, ens_line["members_per_gpu"], sppt=True).values())
+        whole_step[f"members_{ens_line['members_per_gpu']}_sppt"] = {"algorithmic_bytes_per_step": a8, "us_per_step": ens_line["us_per_step"],
+                                                                      "GBps": a8 / (ens_line["us_per_step"] * 1e-6) / 1e9,
+                                                                      "frac_hbm": a8 / (ens_line["us_per_step"] * 1e-6) / 1e9 / hbm}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic,
                 "traffic_source": traffic_src, "algorithmic_bytes_per_launch": alg[dom],
-                "peak_source": peak_src, "timing": "CUDA events on the library stream around each launch, L2 flushed before each launch, mean of 36 steps",
-                "achieved_warm_l2": alg[dom] / (kt_warm[dom] * 1e-3) / 1e9,
-                "share_of_step": kt_warm[dom] / tot,
-                "kernel_ms_cold": kt_cold, "kernel_ms_warm": kt_warm,
+                "peak_source": peak_src,
+                "timing": "in-graph duration of the kernel on %globaltimer (first CTA start -> last CTA end), mean over 108 replayed steps, programmatic dependent launch off; "
+                          "the kernel ranking uses the same timer",
                 "kernel_us_gpu_timer": timeline["us"], "gap_before_us_gpu_timer": timeline["gap_before_us"],
-                "gpu_timer_note": "in-graph durations on %globaltimer with programmatic dependent launch disabled; the CUDA-event figures above carry ~5 us of event+launch overhead per kernel",
-                "legendre": {k: {"GBps_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9, "frac_hbm_cold": alg[k] / (kt_cold[k] * 1e-3) / 1e9 / hbm,
-                                 "GBps_warm": alg[k] / (kt_warm[k] * 1e-3) / 1e9} for k in ("spec_to_grid", "grid_to_spec")},
+                "share_of_step": dom_us / sum(timeline["us"].values()),
+                "frac_by_kernel": {k: alg[k] / (timeline["us"][k] * 1e-6) / 1e9 / hbm for k in alg},
+                "cuda_event_timing": {"note": "secondary: CUDA events around each plain launch carry ~5 us of event + launch overhead per kernel",
+                                      "kernel_ms_cold_l2": kt_cold, "kernel_ms_warm_l2": kt_warm,
+                                      "achieved_cold_l2": alg[dom] / (kt_cold[dom] * 1e-3) / 1e9},
+                "whole_step": whole_step,
                 "legendre_batched": legendre_batched,
                 "note": "single-member T30 is latency-bound (SURVEY.md F12): one step moves ~19 MB (3 us of HBM time); each kernel is a chain of dependent FP64 operations (DFMA 8.7 cycles, exp 160 cycles dependent issue on B200, tools/dmma_probe.cu)"}
 
@@ -314,26 +325,10 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "speedy_run_steps_host(ctx, state, n, 36, out): pinned host state -> device, 36 steps, state + output() fields -> host, per simulated day; wall clock",
                     "days": e2e_days},
-            "gpu_launches": int(launches), "us_per_model_step": 1e6 * dev_s / (args.steps * NSTEPS_PER_DAY),
-            "wall_s_timed_region": t_wall, "roofline": roofline}
-    if world == 1 and args.members == 1:
-        # BASELINE configs[2] in passing (not the headline): 8 SPPT members resident on this GPU, 5 simulated days
-        try:
-            c8 = pkg.Speedy(trunc=30, nmembers=8, device=local, sppt_on=1, seed=1)
-            c8.model_init(BC)
-            for _ in range(2):
-                assert c8.run_steps(NSTEPS_PER_DAY) == 0
-            c8.synchronize()
-            t0 = time.perf_counter()
-            for _ in range(5):
-                assert c8.run_steps(NSTEPS_PER_DAY) == 0
-            c8.synchronize()
-            dt8 = time.perf_counter() - t0
-            line["ensemble_8_members_per_gpu"] = {"member_days_per_s": 8 * 5 / dt8, "us_per_step": 1e6 * dt8 / (5 * NSTEPS_PER_DAY),
-                                                  "note": "SPPT on, wall clock, device-resident; per-GPU figure of the 64-member / 8-GPU config"}
-            c8.close()
-        except Exception as ex:
-            line["ensemble_8_members_per_gpu"] = {"error": str(ex)}
+            "gpu_launches": int(launches), "us_per_model_step": step_us,
+            "wall_s_timed_region": t_wall, "host_cores_per_rank": ncores, "roofline": roofline}
+    if ens_line is not None:
+        line["ensemble_sppt_8_per_gpu"] = ens_line
     if not args.no_cpu_baseline and world == 1:
         try:
             L = _oracle_fast()
@@ -341,12 +336,103 @@ def run_b200(args):
             v, dt = _cpu_days_per_sec(L, 25)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"25 simulated days (900 time steps, {dt:.1f} s) after 2 warm-up days, single member",
-                                    "note": "C++ restatement of speedy.f90 built -Ofast -march=native (no Fortran compiler in this image); the reference is serial"}
+                                    "note": "C++ PORT of speedy.f90 (oracle/, g++ -Ofast -march=native), not a gfortran build of the reference: no Fortran compiler in this image; the reference is serial"}
         except Exception as ex:  # the baseline leg must not hide the GPU number
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"failed: {ex}"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _algorithmic_bytes(c, M, sppt=False):
+    """algorithmic bytes per launch (SURVEY.md §8d per-unit figures x units per launch)"""
+    nact = sum(2 * min(c.mx, c.trunc + 2 - n) for n in range(c.nx))      # 1054 active reals (legendre.f90:33-41)
+    NG = c.ix * c.il
+    ninv = 77 + (8 if sppt else 0)                                        # 91 of the reference minus the 14 level-1 wind fields nobody reads (+8 SPPT)
+    return {"spec_to_grid": M * ninv * (8 * nact + 8 * NG),
+            "grid_to_spec": M * 73 * (8 * NG + 8 * (nact - 2)),
+            "grid_columns": M * NG * 8 * (ninv + 73 + 45 + 8 + 32 + 2),   # fields in, 73 out, ~45 2-D surface/slab state, tt_rsw, tau2, stratc
+            "spec_step": M * c.mx * c.nx * 16 * 165}
+
+
+def _transform_batch(c, torch, stream, flush, inverse, nb, hbm):
+    """BASELINE metric (2), "Legendre GB/s vs roofline": a transform kernel alone on a large device-resident batch
+    (5824 = 91 fields x 8 levels x 8 members), CUDA events on the library stream, L2 flushed between reps"""
+    nact = sum(2 * min(c.mx, c.trunc + 2 - n) for n in range(c.nx))
+    NG = c.ix * c.il
+    spec = torch.rand((nb, c.nx, c.mx, 2), dtype=torch.float64, device="cuda") * 2 - 1
+    grid = torch.rand((nb, c.il, c.ix), dtype=torch.float64, device="cuda") * 2 - 1
+    times = []
+    for rep in range(6):
+        flush.fill_(rep)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        if inverse:
+            rc = c.L.speedy_spec_to_grid_dev(c.h, ctypes.c_void_p(spec.data_ptr()), nb, None, ctypes.c_void_p(grid.data_ptr()))
+        else:
+            rc = c.L.speedy_grid_to_spec_dev(c.h, ctypes.c_void_p(grid.data_ptr()), nb, ctypes.c_void_p(spec.data_ptr()))
+        assert rc == 0
+        e1.record(stream)
+        e1.synchronize()
+        if rep >= 2:
+            times.append(e0.elapsed_time(e1) * 1e-3)
+    t = sorted(times)[len(times) // 2]
+    by = nb * ((8 * nact + 8 * NG) if inverse else (8 * NG + 8 * (nact - 2)))
+    return {"batch": nb, "us": 1e6 * t, "GBps": by / t / 1e9, "frac_hbm": by / t / 1e9 / hbm, "transforms_per_s": nb / t}
+
+
+def _ensemble_leg(pkg, torch, dist, world, rank, local, dev, barrier, rank_max, members=8, days=8):
+    """BASELINE configs[2] at N GPUs: `members` SPPT members per GPU (global member index = rank * members + e keys the noise),
+    the whole ensemble advanced `days` simulated days; once per simulated day the sum / sum of squares of the 41 output levels over
+    the resident members (speedy_ensemble_sums_dev) is all-reduced over the ranks (NCCL, one flat fp64 buffer: the ensemble
+    mean / spread diagnostic).  Everything is enqueued; one host synchronisation at the end."""
+    ce = pkg.Speedy(trunc=30, nmembers=members, device=local, sppt_on=1, seed=1, member_offset=rank * members)
+    ce.model_init(BC)
+    es = torch.cuda.ExternalStream(ce.stream, device=dev)
+    n41 = 41 * ce.il * ce.ix
+    flat = torch.zeros(2 * n41 + 1, dtype=torch.float64, device=dev)
+    comm_seen = dist.get_world_size() if world > 1 else 1
+
+    def one_day():
+        ce.enqueue_steps(NSTEPS_PER_DAY)
+        rc = ce.L.speedy_ensemble_sums_dev(ce.h, ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(flat.data_ptr() + 8 * n41))
+        assert rc == 0
+        flat[-1] = float(members)
+        if world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    with torch.cuda.stream(es):
+        for _ in range(2):
+            one_day()
+    assert ce.finish() == 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(es):
+        e0.record(es)
+        for _ in range(days):
+            one_day()
+        e1.record(es)
+    assert ce.finish() == 0
+    barrier()
+    dt = rank_max(e0.elapsed_time(e1) * 1e-3)
+    total = int(round(float(flat[-1].item())))
+    # steady-state cost of the collective alone
+    ar_us = None
+    if world > 1:
+        with torch.cuda.stream(es):
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(es)
+            for _ in range(20):
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            a1.record(es)
+        torch.cuda.synchronize()
+        ar_us = rank_max(a0.elapsed_time(a1) * 1e3 / 20)
+    ce.close()
+    return {"config": "BASELINE configs[2]: T30/L8 SPPT ensemble, 8 members per GPU", "members_per_gpu": members, "total_members": members * world,
+            "members_counted_by_allreduce": total, "comm_nranks_seen": comm_seen, "days": days,
+            "member_days_per_s": members * world * days / dt, "us_per_step": 1e6 * dt / (days * NSTEPS_PER_DAY),
+            "allreduce_us_steady_state": ar_us, "allreduce_bytes": int(flat.numel() * 8),
+            "timing": "CUDA events on the library stream around all days (incl. the daily moment reduction and all-reduce), max over ranks; weak scaling"}
 
 
 def main():

@@ -135,6 +135,10 @@ int speedy_check_diagnostics(speedy_ctx* ctx, int time_level, double* diag);
  * `model_step` is the 1-based step counter of the reference (speedy.f90:21).
  * Daily host-side inputs are pulled through the callback-free "env" below. */
 int speedy_run_steps(speedy_ctx* ctx, int nsteps);
+/* the same loop in two halves: speedy_enqueue_steps only enqueues the work on the ctx stream (no host synchronisation: many
+ * days can be queued back to back), speedy_finish drains the stream and returns 1 if check_diagnostics tripped at any step */
+int speedy_enqueue_steps(speedy_ctx* ctx, int nsteps);
+int speedy_finish(speedy_ctx* ctx);
 
 /* ---- model environment: boundaries.f90, forcing.f90, date.f90, land/sea init -------- */
 /* initialize (initialization.f90:12-82) from a boundary-condition source:

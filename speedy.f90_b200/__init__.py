@@ -301,6 +301,14 @@ class Speedy:
         """speedy.f90:27-54 main-loop body, nsteps times; returns 1 if check_diagnostics tripped."""
         return _chk(self.L.speedy_run_steps(self.h, int(nsteps)))
 
+    def enqueue_steps(self, nsteps):
+        """main-loop body nsteps times, enqueue only (no host synchronisation); pair with finish()"""
+        _chk(self.L.speedy_enqueue_steps(self.h, int(nsteps)))
+
+    def finish(self):
+        """drain the stream; returns 1 if check_diagnostics tripped since the last finish / run_steps"""
+        return _chk(self.L.speedy_finish(self.h))
+
     def couple_sea_land(self, day):
         _chk(self.L.speedy_couple_sea_land(self.h, int(day)))
 

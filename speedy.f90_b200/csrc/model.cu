@@ -678,6 +678,22 @@ int speedy_run_steps(speedy_ctx* ctx, int nsteps) {
     API_END
 }
 
+// The same loop without the host round trip: speedy_enqueue_steps only enqueues (graph replays + tail steps) and returns;
+// speedy_finish drains the stream and reports the range guard like speedy_run_steps.  A caller that integrates many days back
+// to back (bench.py, ensemble drivers) enqueues them all and polls once.
+int speedy_enqueue_steps(speedy_ctx* ctx, int nsteps) {
+    API_BEGIN
+    check_ready(ctx, true);
+    run_steps_core(ctx, nsteps);
+    API_END
+}
+int speedy_finish(speedy_ctx* ctx) {
+    API_BEGIN
+    check_ready(ctx, true);
+    if (finish_run(ctx)) return 1;
+    API_END
+}
+
 // enqueue the output() conversions of one member into the context's device buffer
 static float* enqueue_output(speedy_ctx* ctx, int member) {
     Model& M = *ctx->model;
