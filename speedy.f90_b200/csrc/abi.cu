@@ -66,6 +66,10 @@ void upload_tables(speedy_ctx* ctx) {
         v.polyq = up(ctx, "polyq", pq);
         ctx->d_qtile.upload(tiles);
         v.qtile = ctx->d_qtile.p;
+        build_quad_inverse_tables(t, tiles, pq);
+        v.polyi = up(ctx, "polyi", pq);
+        ctx->d_qtile_inv.upload(tiles);
+        v.qtile_inv = ctx->d_qtile_inv.p;
     }
     v.finv = up(ctx, "finv", t.finv);
     v.ffwd = up(ctx, "ffwd", t.ffwd);
@@ -158,6 +162,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->fft_inverse = getenv("SPEEDY_DENSE_INVERSE") == nullptr;
         ctx->k2_field = getenv("SPEEDY_K2_FIELD") != nullptr;
         if (const char* v = getenv("SPEEDY_K2_QUAD")) ctx->k2_quad = atoi(v) != 0;
+        if (const char* v = getenv("SPEEDY_K1_QUAD")) ctx->k1_quad = atoi(v) != 0;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));
@@ -260,7 +265,7 @@ static int xform_host(speedy_ctx* ctx, bool inverse, int mode, const double* in,
     ctx->ensure_scratch(ctx->scratch_b, out_len * nbatch);
     const XDesc* dd = make_desc(ctx, nbatch, in_len, kcos, 0, true);
     h2d(ctx, ctx->scratch_a.p, in, in_len * nbatch);
-    if (inverse) launch_spec_to_grid(ctx, ctx->scratch_a.p, 0, dd, nbatch, ctx->scratch_b.p, 0, 1, mode);
+    if (inverse) launch_spec_to_grid(ctx, ctx->scratch_a.p, 0, dd, nbatch, ctx->scratch_b.p, 0, 1, mode, nullptr, true);
     else launch_grid_to_spec(ctx, ctx->scratch_a.p, 0, dd, nbatch, ctx->scratch_b.p, 0, 1, mode);
     d2h(ctx, out, ctx->scratch_b.p, out_len * nbatch);
     API_END
@@ -288,7 +293,7 @@ int speedy_fourier_dir(speedy_ctx* ctx, const double* in, int nbatch, double* ou
 int speedy_spec_to_grid_dev(speedy_ctx* ctx, const double* d_spec, int nbatch, const int* kcos, double* d_grid) {
     API_BEGIN
     const XDesc* dd = make_desc(ctx, nbatch, (size_t)2 * ctx->d.nspec(), kcos, 0, true);
-    launch_spec_to_grid(ctx, d_spec, 0, dd, nbatch, d_grid, 0, 1, 0);
+    launch_spec_to_grid(ctx, d_spec, 0, dd, nbatch, d_grid, 0, 1, 0, nullptr, true);
     API_END
 }
 int speedy_grid_to_spec_dev(speedy_ctx* ctx, const double* d_grid, int nbatch, double* d_spec) {

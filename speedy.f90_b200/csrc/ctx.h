@@ -34,6 +34,8 @@ struct DevTables {
     const double* fband;                 // (301,4)
     const double* polyq;                 // T30: P fragments of the quad kernels' DMMA tiles, (warp, tile slot, k-step, lane) order (transforms_quad.cu)
     const int* qtile;                    // T30: (m, parity, n-tile) of every tile of the direct quad transform
+    const double* polyi;                 // T30: P fragments of the inverse quad transform, (warp, tile slot, fragment, lane)
+    const int* qtile_inv;                // T30: (m, band, even / odd k-steps) per (warp, tile slot) of the inverse quad transform
     unsigned long long* trace;           // nullptr, or the in-graph timeline buffer (speedy_trace)
 };
 
@@ -85,6 +87,7 @@ struct speedy_ctx {
     unsigned long long seed = 0;
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
+    bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
     bool k2_field = false;   // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator
     int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
@@ -98,7 +101,7 @@ struct speedy_ctx {
     bool use_graphs = true;
     // device tables
     std::map<std::string, spd::DevBuf<double>> dtab;
-    spd::DevBuf<int> d_qtile;
+    spd::DevBuf<int> d_qtile, d_qtile_inv;
     spd::DevTables dv{};
     // scratch for host-pointer API calls
     spd::DevBuf<double> scratch_a, scratch_b, scratch_c, scratch_d;
@@ -117,7 +120,7 @@ void upload_level_consts(speedy_ctx* ctx);      // consts in dynamics.cu
 struct CloseArgs;   // close_step.cuh
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
-                         int nmembers, int mode, const CloseArgs* close = nullptr);
+                         int nmembers, int mode, const CloseArgs* close = nullptr, bool quad_ok = false);   // quad_ok: derived fields (op != 0) come as aligned pairs
 // mode: 0 full grid->spec, 1 fourier_dir only (out = (2mx,il)), 2 legendre_dir only (in = (2mx,il))
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
@@ -126,6 +129,7 @@ void setup_transform_kernels();
 // transforms_quad.cu (T30 ensemble batches)
 void setup_quad_kernels();
 void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyq);
+void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyi);
 // transforms_f32.cu (precision = 1)
 void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers);
 void launch_grid_to_spec_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);

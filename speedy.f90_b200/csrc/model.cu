@@ -177,16 +177,27 @@ void model_create(speedy_ctx* ctx) {
         // per-step list: the physics uses the level-1 wind at the lowest level only (surface fluxes), so the
         // uvspec + transform of u,v at levels 1..kx-1 (physics.f90:95-96) is dead work and is not enqueued
         {
+            // order: the derived fields first, as PAIRS sharing their sources — (ucos, vcos) of a level, (d/dx, d/dy) of ps — so that the
+            // quad kernel finds a pair in slots (0, 1) or (2, 3) of a quad and evaluates it in place; then the plain fields
             std::vector<XDesc> cs;
             const int nf = ctx->sppt_on ? GI_N : GI_NBASE;
-            for (int j2 = 1; j2 <= 2; j2++)
+            for (int j2 = 1; j2 <= 2; j2++) {
+                std::vector<int> order;
+                for (int k = 0; k < KXc; k++) { order.push_back(GI_U + k); order.push_back(GI_V + k); }
+                order.push_back(GI_PX); order.push_back(GI_PY);
+                order.push_back(GI_U1 + KXc - 1); order.push_back(GI_V1 + KXc - 1);
+                std::vector<char> used(GI_N, 0);
+                for (int f : order) used[f] = 1;
                 for (int f = 0; f < nf; f++) {
                     const bool dead = (f >= GI_U1 && f < GI_U1 + KXc - 1) || (f >= GI_V1 && f < GI_V1 + KXc - 1);
-                    if (dead) continue;
+                    if (!dead && !used[f]) order.push_back(f);
+                }
+                for (int f : order) {
                     XDesc x = h[(size_t)(j2 - 1) * GI_N + f];
                     x.oslot1 = f + 1;
                     cs.push_back(x);
                 }
+            }
             M.nstep_fields = (int)cs.size() / 2;
             M.desc_step.upload(cs);
         }
@@ -228,7 +239,7 @@ static void xform_step(speedy_ctx* ctx, int j2, bool with_close = false) {
     Model& M = *ctx->model;
     const CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + 31) / 32), ctx->nmembers, nullptr};
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_step.p + (size_t)(j2 - 1) * M.nstep_fields, M.nstep_fields,
-                        M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0, with_close ? &cl : nullptr);
+                        M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0, with_close ? &cl : nullptr, true);
 }
 static void xform_output(speedy_ctx* ctx) {
     Model& M = *ctx->model;
@@ -938,6 +949,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (n == "k2_field") ctx->k2_field = value != 0;
     else if (n == "k2_quad") ctx->k2_quad = value != 0;
+    else if (n == "k1_quad") ctx->k1_quad = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

@@ -53,6 +53,13 @@ __device__ __forceinline__ void tensor_g2s_4d(void* dst_smem, const void* tmap, 
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
+// shared -> global TILE store through a tensor map (cp.async.bulk.tensor, SASS UTMASTG), bulk-group completion
+__device__ __forceinline__ void tensor_s2g_4d(const void* tmap, int c0, int c1, int c2, int c3, const void* src_smem) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // close the bulk group and wait until its copies have finished READING shared memory (the buffer may be reused)
 __device__ __forceinline__ void bulk_commit_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");

@@ -921,10 +921,21 @@ static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch, 
     return nchunk;
 }
 
+void launch_s2g_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers,
+                     const CloseArgs& cl);
+
 template <int TRUNC>
 static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                              double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
+                              double* d_out, long long out_ms, int nmembers, const CloseArgs& cl, bool quad_ok) {
     using C = SCfg<TRUNC>;
+    if constexpr (TRUNC == 30) {
+        // ensemble batches: four fields at a time, FFT + DMMA Legendre (transforms_quad.cu); the list must hold derived fields as
+        // aligned pairs (quad_ok), and three or more fields per SM must be there to fill the quads
+        if (quad_ok && ctx->k1_quad && ctx->fft_inverse && (long long)nbatch * nmembers >= 3ll * ctx->num_sms) {
+            launch_s2g_quad(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
+            return;
+        }
+    }
     // one SM is left to the closing CTA when a step is to be closed
     // the Fourier stage is the regrouped FFTPACK FFT (fft96.cuh / fft144.cuh) unless SPEEDY_DENSE_INVERSE asks for the dense operator on the FP64 tensor pipe
     constexpr bool HF = C::HAS_FFT;
@@ -1019,14 +1030,14 @@ int polyd_mg(int trunc) { return trunc == 30 ? SCfg<30>::MG : SCfg<47>::MG; }
 int polyt_row(int trunc) { return trunc == 30 ? SCfg<30>::TR : SCfg<47>::TR; }
 
 void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                         double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close) {
+                         double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close, bool quad_ok) {
     if (nbatch <= 0) return;
     if (mode == 0 && ctx->precision == 1) {
         launch_spec_to_grid_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);   // the caller closes the step separately
     } else if (mode == 0) {
         const CloseArgs cl = close ? *close : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
-        if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
-        else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
+        if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl, quad_ok);
+        else launch_s2g_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl, false);
     } else if (ctx->d.trunc == 30) {
         dim3 grid(nbatch * TCfg<30>::LG, nmembers);
         k_spec_to_grid<30><<<grid, TCfg<30>::K1_THREADS, TCfg<30>::K1_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode);

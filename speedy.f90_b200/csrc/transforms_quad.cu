@@ -24,6 +24,10 @@
 #include <mutex>
 #include <tuple>
 #include "fft96f.cuh"
+#include "fft96.cuh"
+#include "spectral_ops.cuh"
+#include "close_step.cuh"
+#include <algorithm>
 
 namespace spd {
 
@@ -347,8 +351,339 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     if (tv.trace && tid == 0) trace_end(tv.trace, 2);
 }
 
+// ==========================================================================================================================
+// k_s2g_quad  spec->grid = legendre_inv (legendre.f90:74-111) + fourier_inv (fourier.f90:23-53), incl. the uvspec / grad input
+// stage (spectral.f90:124-196), the cosgr scale of fourier_inv (kcos /= 1) and the Coriolis add (tendencies.f90:103).  The mirror
+// of k_g2s_quad: per quad of four fields
+//   P0  the four spectral fields (or the source fields of derived PAIRS: ucos / vcos from (vor, div), d/dx / d/dy from ps)
+//       arrive by bulk copies, one quad ahead;
+//   P1  derived pairs are evaluated in registers and written back over their sources; coefficients outside the triangle
+//       m + n <= trunc + 1 are zeroed (the reference never reads them, legendre.f90:38);
+//   P2  inverse Legendre as DMMA tiles  X(j, (field, re/im)) = sum_n P(m, n, j) * S(n, (field, re/im))  per (m, latitude band),
+//       even and odd n in two accumulators: row j (southern) = even - odd, row il+1-j (northern) = even + odd
+//       (legendre.f90:105-109); the P fragments live in tensor memory; the half-complex rows (fourier.f90:33-45) go to
+//       X[field][band][position][16 rows];
+//   P3  six FFT groups (band x two fields at a time) run FFTPACK's backward FFT in place: stage 1 (radb2 + radb4) over X,
+//       stage 2 (radb4 + radb3) into the band's grid rows in the swizzled layout of a tensor-map box, which leaves the SM
+//       as two asynchronous tensor stores (southern and northern rows).
+struct QICfg {
+    static constexpr int TRUNC = 30, MX = 31, NX = 32, IX = 96, IL = 48, IY = 24, K2 = 2 * MX, NSPEC2 = NX * K2;
+#ifndef SPD_K1Q_WARPS
+#define SPD_K1Q_WARPS 12
+#endif
+    // 12 warps (three FFT groups, one per band, every field of the quad in turn; up to 168 registers per thread: the in-place stage 1
+    // keeps a set's 16 inputs live across a barrier) or 24 warps (two fields at a time per band; 80 registers: spills)
+    static constexpr int WARPS = SPD_K1Q_WARPS, THREADS = 32 * WARPS, NG = 3, GT = 128, NBOX = IX / 16, NPH = WARPS / 12;
+    static constexpr int BAND = IX * 16;             // doubles per (field, band) buffer: X / T [96 positions][16 rows], then [2 hemispheres][8 rows][96]
+    static constexpr int FSI = NSPEC2 + 2;           // spectral field stride in sIn: = 2 mod 16, conflict-free B fragments
+    static constexpr int TSLOTS = 96 / WARPS, TCOLS = 16 * TSLOTS;   // tiles per warp; TMEM columns per warp (a tile = 8 fragments = 16 columns)
+    static constexpr int NTILES = MX * NG;           // (m, band)
+    static constexpr int LCAP = 128;                 // fields per CTA and launch
+    static constexpr size_t SMEM = sizeof(double) * (4 * NG * BAND + 4 * FSI + IX) + sizeof(uint64_t) * 4 + sizeof(int) * WARPS * TSLOTS +
+                                   LCAP * (2 * sizeof(long long) + 3 * sizeof(int));
+    static_assert(FSI % 16 == 2 && (BAND * 8) % 1024 == 0 && SMEM <= 232448 && (WARPS / 4) * TCOLS <= 512, "layout");
+};
+
+// host: tiles (m, band) balanced over the warps by their k-step counts, P fragments per (warp, tile slot, fragment, lane):
+// fragments 0..3 = even-n k-steps, 4..7 = odd-n k-steps of the tile; A(row = latitude pair of the band, k = n)
+void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyi) {
+    using C = QICfg;
+    struct Tl { int cost, m, b, ke, ko; };
+    std::vector<Tl> all;
+    for (int m = 0; m < C::MX; m++) {
+        const int cnt = C::NX - m, ne = (cnt + 1) / 2, no = cnt / 2;     // n = 0..trunc+1-m (legendre.f90:38)
+        for (int b = 0; b < C::NG; b++) all.push_back(Tl{(ne + 3) / 4 + (no + 3) / 4, m, b, (ne + 3) / 4, (no + 3) / 4});
+    }
+    std::stable_sort(all.begin(), all.end(), [](const Tl& x, const Tl& y) { return x.cost > y.cost; });
+    std::vector<int> load(C::WARPS, 0), cnt(C::WARPS, 0);
+    tiles.assign((size_t)C::WARPS * C::TSLOTS, -1);
+    polyi.assign((size_t)C::WARPS * C::TSLOTS * 8 * 32, 0.0);
+    for (const Tl& tl : all) {
+        int w = 0;
+        for (int i = 1; i < C::WARPS; i++) if (load[i] < load[w] || (load[i] == load[w] && cnt[i] < cnt[w])) w = i;
+        if (cnt[w] >= C::TSLOTS) throw std::runtime_error("quad inverse tile balance");
+        const int slot = cnt[w]++;
+        load[w] += tl.cost;
+        tiles[(size_t)w * C::TSLOTS + slot] = tl.m | (tl.b << 8) | (tl.ke << 12) | (tl.ko << 16);
+        for (int fr = 0; fr < 8; fr++)
+            for (int lane = 0; lane < 32; lane++) {
+                const int g = lane >> 2, q = lane & 3, p = fr >> 2, ks = fr & 3;
+                const int n = p + 2 * (4 * ks + q), jh = 8 * tl.b + g;
+                const bool valid = n < C::NX && tl.m + n <= C::MX;
+                polyi[(((size_t)w * C::TSLOTS + slot) * 8 + fr) * 32 + lane] = valid ? t.poly[((size_t)jh * C::NX + n) * C::MX + tl.m] : 0.0;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(QICfg::THREADS, 1)
+k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc, int nbatch, int q_base, int q_end, int nwork,
+           const __grid_constant__ CUtensorMap omap, DevTables tv, CloseArgs cl) {
+    using C = QICfg;
+    if (blockIdx.x == (unsigned)nwork) {                // the extra CTA: closes the previous step, off the critical path
+        pdl_wait();
+        pdl_trigger();
+        close_step_cta(cl, threadIdx.x);
+        return;
+    }
+    extern __shared__ __align__(1024) double smem[];
+    double* sX = smem;                                  // [4 fields][NG bands][BAND]
+    double* sIn = sX + 4 * C::NG * C::BAND;             // [4][FSI] spectral coefficients of the quad, reference layout (m fastest)
+    double* sWa = sIn + 4 * C::FSI;                     // [IX] twiddles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sWa + C::IX);     // [0] quad sources landed; [3] holds the TMEM base address
+    long long* sOff = reinterpret_cast<long long*>(bars + 4);      // [LCAP] source offset (first source of a derived pair: `off`)
+    long long* sOff2 = sOff + C::LCAP;                              // [LCAP] second source (`off2` of a uvspec pair)
+    int* sOp = reinterpret_cast<int*>(sOff2 + C::LCAP);             // [LCAP] op | flags << 8 | member << 16
+    int* sOrow = sOp + C::LCAP;                                      // [LCAP] first row of the output field in the output tensor map
+    int* sTile = sOrow + C::LCAP;                                    // [WARPS][TSLOTS]
+    uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + 3);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    if (tid == 0) trace_begin(tv.trace, 0);
+    // this CTA's quads: quad Q = (member e, quad qm of the member's field list)
+    const int qpm = (nbatch + 3) >> 2;
+    const int nq = q_end - q_base;
+    const int c0 = q_base + (int)((long long)blockIdx.x * nq / nwork), c1 = q_base + (int)((long long)(blockIdx.x + 1) * nq / nwork);
+    const int ncq = c1 - c0;
+    if (tid == 0 && ((smem_u32(sX) & 1023u) || 4 * ncq > C::LCAP)) __trap();
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_fence_init(); }
+    if (w == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // ---- prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
+    for (int t = tid; t < C::IX; t += C::THREADS) sWa[t] = tv.fftwa[t];
+    for (int t = tid; t < C::WARPS * C::TSLOTS; t += C::THREADS) sTile[t] = tv.qtile_inv[t];
+    for (int t = tid; t < 4 * ncq; t += C::THREADS) {
+        const int Q = c0 + (t >> 2), e = Q / qpm, f = 4 * (Q - e * qpm) + (t & 3);
+        if (f < nbatch) {
+            const XDesc d = desc[f];
+            sOff[t] = (long long)e * in_ms + d.off; sOff2[t] = (long long)e * in_ms + d.off2;
+            sOp[t] = d.op | (d.flags << 8) | (e << 16);
+            sOrow[t] = (d.oslot1 ? d.oslot1 - 1 : f) * C::IL;
+        } else {
+            sOp[t] = -1;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t taddr = *sTmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(C::TCOLS * (w >> 2));
+    {
+        double a[8];
+#pragma unroll
+        for (int i = 0; i < C::TSLOTS; i++) {
+#pragma unroll
+            for (int fr = 0; fr < 8; fr++) a[fr] = tv.polyi[(((size_t)w * C::TSLOTS + i) * 8 + fr) * 32 + lane];
+            tmem_st16(taddr + 16 * i, a);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    // FFT roles: group = (band, field phase); stage 1 thread = (set, row); stage 2 thread = (row, k of radb4's third pass)
+    const int gi = w >> 2, b = gi % C::NG, ph = gi / C::NG, wl = w & 3, t128 = tid & 127;
+    static_assert(C::NPH == 1 || C::NPH == 2, "one or two fields at a time per band");
+    const int set1 = t128 >> 4, row1 = t128 & 15;
+    const int k3 = (lane & 3) + 4 * (lane >> 4), rsel = (lane >> 2) & 3;
+    const int row2 = 4 * wl + rsel, hem = row2 >> 3, r8 = row2 & 7;          // a warp of stage 2 = 4 consecutive rows of one hemisphere block
+    const int lat2 = hem ? (C::IL - 8 - 8 * b + r8) : (8 * b + r8);
+    const double cg = tv.cosgr[lat2], cf = tv.coriol[lat2];
+    int oG[C::NBOX];                                     // swizzled position of (row2, longitude 16 bx + k3) in the output box (as the input boxes of k_g2s_quad)
+#pragma unroll
+    for (int bx = 0; bx < C::NBOX; bx++) {
+        const int sg = 6 * r8 + bx;
+        oG[bx] = hem * (C::BAND / 2) + sg * 16 + (((k3 >> 1) ^ (sg & 7)) << 1) + (k3 & 1);
+    }
+    pdl_wait();                                         // the spectral fields of the previous kernel are complete
+    pdl_trigger();
+    auto issue_quad = [&](int cq) {                     // one thread: the sources of local quad cq
+        uint32_t bytes = 0;
+        for (int fs = 0; fs < 4; fs++) {
+            const int t = 4 * cq + fs, op = sOp[t];
+            if (op < 0) continue;
+            const int o = op & 255;
+            if (o == 0 || o == 1 || o == 3) bytes += C::NSPEC2 * sizeof(double);         // the field itself / first source of a pair
+            else if (o == 2) bytes += C::NSPEC2 * sizeof(double);                        // second source of a uvspec pair
+        }
+        mbar_expect_tx(&bars[0], bytes);
+        for (int fs = 0; fs < 4; fs++) {
+            const int t = 4 * cq + fs, op = sOp[t];
+            if (op < 0) continue;
+            const int o = op & 255;
+            if (o == 0 || o == 1 || o == 3) bulk_g2s(sIn + fs * C::FSI, in_base + sOff[t], C::NSPEC2 * sizeof(double), &bars[0]);
+            else if (o == 2) bulk_g2s(sIn + fs * C::FSI, in_base + sOff2[t], C::NSPEC2 * sizeof(double), &bars[0]);
+        }
+    };
+    if (tid == 0 && ncq > 0) issue_quad(0);
+    // phase stamps of CTA 0 (speedy_trace + SPEEDY_TRACE_STAMPS): cycles in [sources + derived pairs, mask, wait, Legendre tiles, wait, FFT + stores, wait]
+    long long tq = 0;
+#define ISTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[48 + (i)] += (unsigned long long)(t_ - tq); tq = t_; } } while (0)
+    if (tv.trace) tq = clock64();
+    for (int cq = 0; cq < ncq; cq++) {
+        const int t0 = 4 * cq;
+        // ---- P1: derived pairs in registers, then back over their sources; triangle mask
+        bool waited = false;
+#pragma unroll 1
+        for (int pp = 0; pp < 2; pp++) {
+            const int o = sOp[t0 + 2 * pp] < 0 ? 0 : (sOp[t0 + 2 * pp] & 255);
+            if (o != 1 && o != 3) continue;             // (ucos, vcos) = uvspec(vor, div) / (d/dx, d/dy) = grad(ps) in slots 2 pp, 2 pp + 1
+            constexpr int NU = (C::MX * C::NX + C::THREADS - 1) / C::THREADS;
+            double pre[NU][3];                           // operator-table entries of this thread's two (m, n), fetched ahead of the wait
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const int t = tid + u * C::THREADS;
+                pre[u][0] = pre[u][1] = pre[u][2] = 0.0;
+                if (t < C::MX * C::NX) {
+                    const int m = t % C::MX;
+                    pre[u][0] = (o == 1) ? tv.uvdx[t] : tv.gradx[m];
+                    pre[u][1] = (o == 1) ? tv.uvdym[t] : tv.gradym[t];
+                    pre[u][2] = (o == 1) ? tv.uvdyp[t] : tv.gradyp[t];
+                }
+            }
+            if (!waited) { mbar_wait(&bars[0], cq & 1); waited = true; }
+            double* A = sIn + (2 * pp) * C::FSI;
+            double* B = sIn + (2 * pp + 1) * C::FSI;
+            cd res[NU][2];
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const int t = tid + u * C::THREADS;
+                if (t < C::MX * C::NX) {
+                    const int n = t / C::MX, m = t - n * C::MX;
+                    if (o == 1) dev_uvspec_t(C::MX, C::NX, C::TRUNC, A, B, m, n, pre[u][0], pre[u][1], pre[u][2], res[u][0], res[u][1]);
+                    else dev_grad_t(C::MX, C::NX, C::TRUNC, A, m, n, pre[u][0], pre[u][1], pre[u][2], res[u][0], res[u][1]);
+                }
+            }
+            __syncthreads();                            // every stencil read is done: the sources may be overwritten
+#pragma unroll
+            for (int u = 0; u < NU; u++) {
+                const int t = tid + u * C::THREADS;
+                if (t < C::MX * C::NX) {
+                    const int n = t / C::MX, m = t - n * C::MX;
+                    st(A, C::MX, m, n, res[u][0]);
+                    st(B, C::MX, m, n, res[u][1]);
+                }
+            }
+        }
+        if (!waited) mbar_wait(&bars[0], cq & 1);
+        ISTAMP(0);
+        for (int t = tid; t < 4 * C::MX * C::NX; t += C::THREADS) {      // outside the triangle: zero (a finite product with the zero P entries)
+            const int fs = t / (C::MX * C::NX), r = t - fs * (C::MX * C::NX), n = r / C::MX, m = r - n * C::MX;
+            if (m + n > C::MX) st(sIn + fs * C::FSI, C::MX, m, n, cd{0.0, 0.0});
+        }
+        ISTAMP(1);
+        __syncthreads();                                // sIn complete; X free (the previous quad's stores have read it: wait below)
+        ISTAMP(2);
+        // ---- P2: inverse Legendre, DMMA tiles (m, band), even and odd n
+        {
+            const double* Bq = sIn + (g >> 1) * C::FSI + (g & 1) + (2 * q) * C::K2;       // column = (field, re/im), k = n = parity + 2 (4 ks + q)
+            double* Xq = sX + q * (C::NG * C::BAND);
+            const int swx = 8 * (q & 1);
+#pragma unroll
+            for (int i = 0; i < C::TSLOTS; i += 2) {
+                double a[2][8];
+                tmem_ld16(taddr + 16 * i, a[0]);
+                tmem_ld16(taddr + 16 * (i + 1), a[1]);
+                int tl[2];
+                double ce0[2], ce1[2], co0[2], co1[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) { tl[u] = sTile[w * C::TSLOTS + i + u]; ce0[u] = ce1[u] = co0[u] = co1[u] = 0.0; }
+                // one warp-uniform trip count for the pair of tiles (their k-step counts differ by at most one: the tiles are dealt in
+                // order of cost) and no branch around a DMMA: fragments beyond a tile's own count are zero
+                const int tva = tl[0] < 0 ? 0 : tl[0], tvb = tl[1] < 0 ? 0 : tl[1];
+                const int kmax = max(max((tva >> 12) & 15, (tva >> 16) & 15), max((tvb >> 12) & 15, (tvb >> 16) & 15));
+                const double* Bpa = Bq + 2 * (tva & 255);
+                const double* Bpb = Bq + 2 * (tvb & 255);
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {
+                    if (ks < kmax) {
+                        dmma884q(ce0[0], ce1[0], a[0][ks], Bpa[ks * (8 * C::K2)]);
+                        dmma884q(co0[0], co1[0], a[0][4 + ks], Bpa[ks * (8 * C::K2) + C::K2]);
+                        dmma884q(ce0[1], ce1[1], a[1][ks], Bpb[ks * (8 * C::K2)]);
+                        dmma884q(co0[1], co1[1], a[1][4 + ks], Bpb[ks * (8 * C::K2) + C::K2]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (tl[u] < 0) continue;
+                    const int m = tl[u] & 255, bb = (tl[u] >> 8) & 15;
+                    double* Xb = Xq + bb * C::BAND;
+                    const int rs = g ^ swx, rn = (15 - g) ^ swx;           // southern row jl, northern row in ascending-latitude order
+                    const int pr = m ? 2 * m - 1 : 0;                      // FFTPACK's half-complex order (fourier.f90:40-45); Im(m = 0) is dropped
+                    Xb[pr * 16 + rs] = ce0[u] - co0[u];
+                    Xb[pr * 16 + rn] = ce0[u] + co0[u];
+                    if (m) {
+                        Xb[(pr + 1) * 16 + rs] = ce1[u] - co1[u];
+                        Xb[(pr + 1) * 16 + rn] = ce1[u] + co1[u];
+                    }
+                }
+            }
+        }
+        ISTAMP(3);
+        __syncthreads();                                // X of the quad complete; sIn free
+        ISTAMP(4);
+        if (tid == 0 && cq + 1 < ncq) issue_quad(cq + 1);
+        // ---- P3: backward FFT per (field, band), fields ph and ph + 2 of the quad
+#pragma unroll 1
+        for (int fs = ph; fs < 4; fs += C::NPH) {
+            const int op = sOp[t0 + fs];
+            if (op < 0) continue;
+            const int fl = (op >> 8) & 255;
+            double* Xb = sX + (fs * C::NG + b) * C::BAND;
+            // stage 1: radb2 + radb4 (fftpack.f90:204,328), in place: every input of the set into registers, group barrier (at a point
+            // where the warps converge: bar.sync is warp-aligned and the two half-warps of a warp work on different sets), then the stores
+            {
+                const int rx = row1 ^ (8 * (fs & 1));
+                auto ld = [Xb, rx](int pos) { return pos <= 2 * C::TRUNC ? Xb[pos * 16 + rx] : 0.0; };       // zero padding above the truncation (fourier.f90:34-41)
+                auto stt = [Xb, row1](int blk, int off, double v) { Xb[(12 * blk + off) * 16 + (row1 ^ (4 * (blk & 3)))] = v; };
+                double v[16];
+                if (set1 < 5) Fft96::stage1_general_ld(ld, 3 + 2 * set1, v);
+                else if (set1 == 5) Fft96::stage1_first_ld(ld, v);
+                else if (set1 == 6) Fft96::stage1_last_ld(ld, v);
+                named_sync(1 + gi, C::GT);
+                if (set1 < 5) Fft96::stage1_general_st(v, stt, sWa, 3 + 2 * set1);
+                else if (set1 == 5) Fft96::stage1_first_st(v, stt, sWa);
+                else if (set1 == 6) Fft96::stage1_last_st(v, stt, sWa);
+            }
+            named_sync(1 + gi, C::GT);                  // T complete
+            // stage 2: radb4 + radb3 (fftpack.f90:328,256), then fourier_inv's cosgr scale and the Coriolis add
+            double y[12];
+            Fft96::stage2<16>(Xb + (row2 ^ (4 * (k3 & 3))), sWa, k3, y);
+            named_sync(1 + gi, C::GT);                  // every T value is in registers: the buffer becomes the grid rows of the band
+#pragma unroll
+            for (int jj = 0; jj < 3; jj++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    double v = y[4 * jj + j];
+                    if (fl & 1) v *= cg;
+                    if (fl & 2) v += cf;
+                    Xb[oG[2 * jj + (j >> 1)] ^ (8 * (j & 1))] = v;
+                }
+            fence_proxy_async();
+            if (wl == 0) {
+                named_sync(7 + gi, C::GT);
+                if (lane == 0) {
+                    const int e = op >> 16, row0 = sOrow[t0 + fs];
+                    tensor_s2g_4d(&omap, 0, 0, row0 + 8 * b, e, Xb);
+                    tensor_s2g_4d(&omap, 0, 0, row0 + C::IL - 8 - 8 * b, e, Xb + C::BAND / 2);
+                    bulk_commit();
+                }
+            } else {
+                named_arrive(7 + gi, C::GT);
+            }
+        }
+        if (wl == 0 && lane == 0) bulk_wait_read_all(); // this group's stores have read their buffers
+        ISTAMP(5);
+        __syncthreads();
+        ISTAMP(6);
+    }
+#undef ISTAMP
+    if (wl == 0 && lane == 0) bulk_wait_all();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*sTmem), "r"(512u) : "memory");
+    if (tv.trace && tid == 0) trace_end(tv.trace, 0);
+}
+
 void setup_quad_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCfg::SMEM_G2S));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QICfg::SMEM));
 }
 
 // 4-D view of a batch of grid fields for the band loads: [16 longitudes][IX/16 blocks][row of IX doubles][member], box = one
@@ -394,6 +729,24 @@ void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
         const int ncta = nquad < ctx->num_sms ? nquad : ctx->num_sms;
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end,
                               d_out, out_ms, ctx->dv, gate));
+    }
+}
+
+void launch_s2g_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers,
+                     const CloseArgs& cl) {
+    using C = QICfg;
+    const CUtensorMap& omap = grid_band_map(d_out, out_ms, nmembers);
+    const int qpm = (nbatch + 3) / 4, nq = qpm * nmembers;
+    const int reserve = cl.clk ? 1 : 0;                                   // one SM is left to the closing CTA when a step is to be closed
+    const int per = (C::LCAP / 4) * (ctx->num_sms - reserve);             // quads per launch: at most LCAP / 4 per CTA
+    bool first = true;
+    for (int base = 0; base < nq; base += per) {
+        const int end = base + per < nq ? base + per : nq;
+        const int nwork = (end - base) < ctx->num_sms - reserve ? (end - base) : ctx->num_sms - reserve;
+        const CloseArgs c = first ? cl : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_quad, dim3(nwork + (c.clk ? 1 : 0)), dim3(C::THREADS), C::SMEM, ctx->stream, d_in, in_ms, d_desc,
+                              nbatch, base, end, nwork, omap, ctx->dv, c));
+        first = false;
     }
 }
 
