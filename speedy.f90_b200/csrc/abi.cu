@@ -160,7 +160,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         ctx->precision = cfg->precision;
         ctx->trace_pdl = getenv("SPEEDY_TRACE_PDL") != nullptr;
         ctx->fft_inverse = getenv("SPEEDY_DENSE_INVERSE") == nullptr;
-        ctx->k2_field = getenv("SPEEDY_K2_FIELD") != nullptr;
+        if (const char* v = getenv("SPEEDY_K2_FIELD")) ctx->k2_field = atoi(v) > 0 ? atoi(v) : 1;
         if (const char* v = getenv("SPEEDY_K2_QUAD")) ctx->k2_quad = atoi(v) != 0;
         if (const char* v = getenv("SPEEDY_K1_QUAD")) ctx->k1_quad = atoi(v) != 0;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");

@@ -89,7 +89,7 @@ struct speedy_ctx {
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
-    bool k2_field = false;   // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator
+    int k2_field = 0;        // 1: ensemble batches, 2: every launch incl. the single-member step (one CTA per field)      // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator
     int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
     int num_sms = 148;
     spd::DevBuf<unsigned long long> trace;

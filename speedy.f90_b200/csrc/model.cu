@@ -947,7 +947,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     if (!name) throw std::runtime_error("null option name");
     const std::string n(name);
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    if (n == "k2_field") ctx->k2_field = value != 0;
+    if (n == "k2_field") ctx->k2_field = value;
     else if (n == "k2_quad") ctx->k2_quad = value != 0;
     else if (n == "k1_quad") ctx->k1_quad = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;

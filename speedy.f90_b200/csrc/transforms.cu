@@ -778,6 +778,7 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
     double* sWa = reinterpret_cast<double*>(bars + 2);                     // [IX]
     int* sTri = reinterpret_cast<int*>(sWa + C::IX);                       // [NX + 1]
     const int tid = threadIdx.x, nthr = blockDim.x;
+    if (tid == 0) trace_begin(tv.trace, 2);
     const int chunk = blockIdx.x, e = blockIdx.y;
     const int f0 = (int)((long long)chunk * nbatch / nchunk), f1 = (int)((long long)(chunk + 1) * nbatch / nchunk);
     int gate_open = 1;
@@ -890,6 +891,7 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
         __syncthreads();                                                   // the folds (in sT) are free for the next field
         f = fn;
     }
+    if (tv.trace && tid == 0) trace_end(tv.trace, 2);
 }
 
 void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
@@ -1008,7 +1010,7 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
             return;
         }
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
-        if (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3) {
+        if (ctx->k2_field == 2 || (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3)) {
             using F = FieldCfg<TRUNC>;
             static bool attr = false;
             if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_g2s_field<TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM)); attr = true; }

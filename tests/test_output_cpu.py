@@ -68,3 +68,16 @@ def test_output_file_errors(tmp_path):
     f3, ps = fields(8, 48, 96, 2)
     with pytest.raises(S.SpeedyError):
         S.write_output_file(tmp_path / "no_such_dir" / "a.nc", *f3, ps)
+
+
+def test_reference_run_comparison_harness(tmp_path):
+    """tools/compare_reference_run.py end to end on files in the reference's output format (written by the library's host-side writer
+    from the oracle's fields): the harness that pins the oracle to a gfortran run once one exists must read the files, step the oracle
+    to each file's time and report a zero difference here"""
+    import subprocess, sys, json, os
+    from conftest import ROOT
+    out = tmp_path / "cmp.json"
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "compare_reference_run.py"), "--self-test", str(tmp_path / "run"), "--json", str(out)])
+    res = json.load(open(out))
+    assert len(res["files"]) == 4 and [r["step"] for r in res["files"]] == [0, 1, 2, 3]
+    assert res["worst"]["oracle"] == 0.0
