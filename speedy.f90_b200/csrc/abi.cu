@@ -171,6 +171,9 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         CUDA_CHECK(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
         setup_transform_kernels();
         setup_quad_kernels();
+        setup_f32_kernels();
+        setup_column_kernels();
+        setup_spec_step_kernels();
         upload_tables(ctx);
         model_create(ctx);
     } catch (...) { delete ctx; throw; }

@@ -92,6 +92,7 @@ struct speedy_ctx {
     int k2_field = 0;        // 1: ensemble batches, 2: every launch incl. the single-member step (one CTA per field)      // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator
     int precision = 0;       // 0 fp64 everywhere; 1 real32 spherical-harmonic transforms (transforms_f32.cu), fp64 elsewhere
     int num_sms = 148;
+    int occ_k1[2] = {0, 0}, occ_k2 = 0, occ_k2b = 0;   // occupancy of the streaming transform kernels on this context's device (filled on first use)
     spd::DevBuf<unsigned long long> trace;
     int member_offset = 0;   // global index of member 0 of this context (SPPT stream id of a sharded ensemble)
     cudaStream_t stream = nullptr;
@@ -126,6 +127,9 @@ void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_membe
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
                          int nmembers, int mode, const int* gate = nullptr);
 void setup_transform_kernels();
+void setup_f32_kernels();          // transforms_f32.cu
+void setup_column_kernels();       // physics.cu
+void setup_spec_step_kernels();    // dynamics.cu
 // transforms_quad.cu (T30 ensemble batches)
 void setup_quad_kernels();
 void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyq);

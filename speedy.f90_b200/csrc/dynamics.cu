@@ -499,16 +499,16 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
     if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }
     const size_t smem = spec_step_smem(ctx->d.mx, ctx->d.nx);
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
-    }
     if (ctx->nmembers >= 4) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_spec_step<true>, grid, dim3(SC, KX), smem, ctx->stream, a));
     else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_spec_step<false>, grid, dim3(SC, KX), smem, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
+}
+
+// per device (speedy_create calls it after cudaSetDevice): the shared-memory opt-in is a per-device function attribute
+void setup_spec_step_kernels() {
+    CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 }
 
 void launch_close_step(speedy_ctx* ctx) {

@@ -737,7 +737,8 @@ int speedy_run_steps_host(speedy_ctx* ctx, double* state, size_t n, int nsteps, 
         float* d = enqueue_output(ctx, 0);
         CUDA_CHECK(cudaMemcpyAsync(out, d, speedy_output_len(ctx) * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    const int rc = finish_run(ctx);
+    int rc = 0;
+    try { rc = finish_run(ctx); } catch (...) { cudaStreamSynchronize(ctx->copy_stream); throw; }   // the caller's buffer must not be in flight when an error is reported
     CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
     if (rc) return 1;
     API_END
@@ -852,6 +853,7 @@ struct RestartHeader {
     int phi_next_valid;
     double implicit_dt;
     DevClock clock;
+    int precision, sppt_draw;    // version 2: the arithmetic mode and the noise source continue as they were
 };
 const char kRestartMagic[8] = {'S', 'P', 'D', 'B', '2', '0', '0', 'R'};
 }  // namespace
@@ -866,7 +868,7 @@ int speedy_save_restart(speedy_ctx* ctx, const char* path) {
     RestartHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, kRestartMagic, 8);
-    h.version = 1; h.trunc = ctx->d.trunc; h.nmembers = ctx->nmembers; h.nsteps = ctx->tab.c.nsteps; h.sppt_on = ctx->sppt_on;
+    h.version = 2; h.precision = ctx->precision; h.sppt_draw = M.sppt_draw ? 1 : 0; h.trunc = ctx->d.trunc; h.nmembers = ctx->nmembers; h.nsteps = ctx->tab.c.nsteps; h.sppt_on = ctx->sppt_on;
     h.member_offset = ctx->member_offset; h.stride = (long long)M.L.stride; h.istride = (long long)M.L.istride; h.seed = ctx->seed;
     memcpy(h.start, M.start, sizeof h.start);
     h.phi_next_valid = M.phi_next_valid ? 1 : 0;
@@ -901,10 +903,15 @@ int speedy_load_restart(speedy_ctx* ctx, const char* path) {
     std::vector<double> mem;
     std::vector<int> imem, sppt;
     std::string err;
-    if (fread(&h, sizeof h, 1, f) != 1 || fread(cnt, sizeof cnt, 1, f) != 1 || memcmp(h.magic, kRestartMagic, 8) != 0 || h.version != 1) err = "not a restart file of this library";
+    if (fread(&h, sizeof h, 1, f) != 1 || fread(cnt, sizeof cnt, 1, f) != 1 || memcmp(h.magic, kRestartMagic, 8) != 0 || h.version != 2) err = "not a restart file of this library (version 2)";
     else if (h.trunc != ctx->d.trunc || h.nmembers != ctx->nmembers || h.nsteps != ctx->tab.c.nsteps || h.sppt_on != ctx->sppt_on ||
              h.stride != (long long)M.L.stride || h.istride != (long long)M.L.istride || cnt[0] != M.mem.n || cnt[1] != M.imem.n || cnt[2] != M.sppt_state.n)
         err = "restart file was written by a context of another configuration (trunc / nmembers / nsteps / sppt_on)";
+    // a bit-identical continuation needs the same SPPT stream and arithmetic: refuse a silent change of either
+    else if (ctx->sppt_on && (h.seed != ctx->seed || h.member_offset != ctx->member_offset))
+        err = "restart file was written with another SPPT seed / member_offset (create the context with the file's values)";
+    else if (h.precision != ctx->precision || (ctx->sppt_on && h.sppt_draw != (M.sppt_draw ? 1 : 0)))
+        err = "restart file was written with another precision mode / SPPT noise source";
     else {
         mem.resize(cnt[0]); imem.resize(cnt[1]); sppt.resize(cnt[2]);
         if (fread(mem.data(), sizeof(double), mem.size(), f) != mem.size() || fread(imem.data(), sizeof(int), imem.size(), f) != imem.size() ||

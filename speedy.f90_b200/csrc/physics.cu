@@ -1163,6 +1163,12 @@ static const ColMaps& column_maps(speedy_ctx* ctx) {
 
 void free_column_maps(Model& M) { delete static_cast<ColMaps*>(M.colmaps); M.colmaps = nullptr; }
 
+// per device (speedy_create calls it after cudaSetDevice): the shared-memory opt-in is a per-device function attribute
+void setup_column_kernels() {
+    CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
+}
+
 // ---- launchers ------------------------------------------------------------------------------
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged) {
     Model& M = *ctx->model;
@@ -1177,12 +1183,6 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     }
     const int N = ctx->d.ngrid();
     if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
-        attr_set = true;
-    }
     dim3 grid(N / TC, ctx->nmembers);
     // more tiles than SMs (ensemble batches, T47): the two-CTAs-per-SM variant; otherwise the uncapped one
     if ((long long)grid.x * grid.y > ctx->num_sms) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_grid_columns<true>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));

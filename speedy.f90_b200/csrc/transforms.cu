@@ -913,6 +913,7 @@ void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_s2g_stream<47, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K1_SMEM_FFT));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<30, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<30>::K2_SMEM_BATCH));
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_stream<47, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCfg<47>::K2_SMEM_BATCH));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_field<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FieldCfg<30>::SMEM));
 }
 
 // fields per persistent CTA: spread (slices x members x chunks) over the SMs, one CTA each
@@ -943,8 +944,7 @@ static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_
     constexpr bool HF = C::HAS_FFT;
     const bool fft = HF && ctx->fft_inverse;
     const size_t smem = fft ? C::K1_SMEM_FFT : C::K1_SMEM;
-    static int occ_tab[2] = {0, 0};       // resident CTAs per SM (2 at T30, 1 at T47), per variant
-    int& occ = occ_tab[fft ? 1 : 0];
+    int& occ = ctx->occ_k1[fft ? 1 : 0];   // resident CTAs per SM (2 at T30, 1 at T47), per variant; cached per context (= per device)
     if (!occ) {
         if (fft) CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false, HF>, C::K1_THREADS, smem));
         else CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_s2g_stream<TRUNC, false, false>, C::K1_THREADS, smem));
@@ -998,7 +998,7 @@ template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                               double* d_out, long long out_ms, int nmembers, const int* gate) {
     using C = SCfg<TRUNC>;
-    static int occ = 0, occ_b = 0;       // resident CTAs per SM of the latency / batch variant
+    int &occ = ctx->occ_k2, &occ_b = ctx->occ_k2b;       // resident CTAs per SM of the latency / batch variant; cached per context (= per device)
     if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2s_stream<TRUNC, false>, C::K2_THREADS, C::K2_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
     if (!occ_b) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_g2s_stream<TRUNC, true>, C::K2_THREADS, C::K2_SMEM_BATCH)); if (occ_b < 1) occ_b = 1; if (occ_b > 2) occ_b = 2; }
     int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ);
@@ -1012,8 +1012,6 @@ static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
         if (ctx->k2_field == 2 || (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3)) {
             using F = FieldCfg<TRUNC>;
-            static bool attr = false;
-            if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(k_g2s_field<TRUNC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F::SMEM)); attr = true; }
             const int nch = stream_chunks(ctx, 1, nmembers, nbatch);
             CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_field<TRUNC>, dim3(nch, nmembers), dim3(F::THREADS), F::SMEM, ctx->stream, gmap, d_desc, nbatch, nch, d_out, out_ms, ctx->dv, gate));
             return;

@@ -172,16 +172,17 @@ k_g2s_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __re
     }
 }
 
+// per device (speedy_create calls it after cudaSetDevice); every real32 kernel, whichever launcher runs first (at T47 the direct
+// transform needs more than the default 48 KB and is the FIRST transform of speedy_model_init)
+void setup_f32_kernels() {
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::S2G_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::S2G_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::G2S_SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::G2S_SMEM));
+}
+
 void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                              double* d_out, long long out_ms, int nmembers) {
-    static bool attr = false;
-    if (!attr) {
-        CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::S2G_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(k_s2g_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::S2G_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<30>::G2S_SMEM));
-        CUDA_CHECK(cudaFuncSetAttribute(k_g2s_f32<47>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FCfg<47>::G2S_SMEM));
-        attr = true;
-    }
     if (ctx->d.trunc == 30) k_s2g_f32<30><<<dim3(nbatch * FCfg<30>::LG, nmembers), FCfg<30>::THREADS, FCfg<30>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv);
     else k_s2g_f32<47><<<dim3(nbatch * FCfg<47>::LG, nmembers), FCfg<47>::THREADS, FCfg<47>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv);
     CUDA_CHECK(cudaGetLastError());

@@ -556,16 +556,17 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
                 const int t = tid + u * C::THREADS;
                 if (t < C::MX * C::NX) {
                     const int n = t / C::MX, m = t - n * C::MX;
-                    st(A, C::MX, m, n, res[u][0]);
-                    st(B, C::MX, m, n, res[u][1]);
+                    const bool in = m + n <= C::MX;                  // outside the triangle: zero (legendre.f90:38)
+                    st(A, C::MX, m, n, in ? res[u][0] : cd{0.0, 0.0});
+                    st(B, C::MX, m, n, in ? res[u][1] : cd{0.0, 0.0});
                 }
             }
         }
         if (!waited) mbar_wait(&bars[0], cq & 1);
         ISTAMP(0);
-        for (int t = tid; t < 4 * C::MX * C::NX; t += C::THREADS) {      // outside the triangle: zero (a finite product with the zero P entries)
+        for (int t = tid; t < 4 * C::MX * C::NX; t += C::THREADS) {      // plain fields: zero outside the triangle (a finite product with the zero P entries)
             const int fs = t / (C::MX * C::NX), r = t - fs * (C::MX * C::NX), n = r / C::MX, m = r - n * C::MX;
-            if (m + n > C::MX) st(sIn + fs * C::FSI, C::MX, m, n, cd{0.0, 0.0});
+            if (m + n > C::MX && (sOp[t0 + fs] & 255) == 0) st(sIn + fs * C::FSI, C::MX, m, n, cd{0.0, 0.0});
         }
         ISTAMP(1);
         __syncthreads();                                // sIn complete; X free (the previous quad's stores have read it: wait below)

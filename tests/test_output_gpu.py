@@ -64,5 +64,26 @@ def test_restart_continues_bit_for_bit(pkg, tmp_path, sppt):
     c.model_init(BC)
     with pytest.raises(pkg.SpeedyError):
         c.load_restart(rst)
-    for s in (a, b, c):
+    others = [c]
+    if sppt:
+        # ... and so is another SPPT stream (seed / member_offset) or noise source: the continuation would silently differ
+        for kw2, draw in ((dict(kw, seed=6), True), (dict(kw, member_offset=2), True), (kw, False)):
+            d = pkg.Speedy(**kw2)
+            d.model_init(BC)
+            d.set_sppt_draw(draw)
+            with pytest.raises(pkg.SpeedyError):
+                d.load_restart(rst)
+            others.append(d)
+    for s in [a, b] + others:
         s.close()
+
+
+def test_real32_transform_mode_initialises_at_t47(pkg):
+    """precision = 1 at T47: the first transform of model_init is the real32 grid->spec kernel, whose shared-memory opt-in
+    (50.7 KB > the 48 KB default) must be in place whichever launcher runs first"""
+    from conftest import bc_t47
+    c = pkg.Speedy(trunc=47, precision=1)
+    c.model_init(bc_t47())
+    assert c.run_steps(4) == 0
+    assert np.isfinite(c.get_field("vor")).all()
+    c.close()

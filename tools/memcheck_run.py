@@ -1,11 +1,11 @@
 """Short run of each configuration for compute-sanitizer (memcheck / racecheck): plain launches, 4 steps.
-usage: compute-sanitizer --tool memcheck python tools/memcheck_run.py [t30|t30x4|t47]"""
+usage: compute-sanitizer --tool memcheck python tools/memcheck_run.py [t30|t30x4|t30x8|t47]   (t30x8: the quad transform kernels)"""
 import sys, os
 sys.path.insert(0, os.getcwd())
 from __graft_entry__ import _load_pkg
 pkg = _load_pkg()
 sel = sys.argv[1] if len(sys.argv) > 1 else "all"
-for name, trunc, members in (("t30", 30, 1), ("t30x4", 30, 4), ("t47", 47, 1)):
+for name, trunc, members in (("t30", 30, 1), ("t30x4", 30, 4), ("t30x8", 30, 8), ("t47", 47, 1)):
     if sel not in ("all", name):
         continue
     bc = pkg.BC_T30
