@@ -141,9 +141,11 @@ int speedy_enqueue_steps(speedy_ctx* ctx, int nsteps);
 int speedy_finish(speedy_ctx* ctx);
 
 /* ---- model environment: boundaries.f90, forcing.f90, date.f90, land/sea init -------- */
-/* initialize (initialization.f90:12-82) from a boundary-condition source:
- * `bc_path` is either a directory holding the reference's data/bc/t30 tree or a packed
- * .bin produced by tools/pack_boundary.py.  Start date as in namelist.nml. */
+/* initialize (initialization.f90:12-82) from a boundary-condition source: `bc_path` is the packed
+ * .bin that tools/pack_boundary.py makes from the reference's data/bc/t30 tree (the float32 variables of the
+ * NetCDF-4 files copied verbatim; the flip / missing-value / forchk logic runs in the loader).  The pack holds a
+ * window of the SST-anomaly record (72 months from 1979-01 as shipped; `--months` of the packer widens it): a run
+ * that leaves it fails with an error instead of reading past it.  Start date as in namelist.nml. */
 int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month, int day, int hour, int minute);
 /* current model date (date.f90:20) and step counter */
 int speedy_model_date(const speedy_ctx* ctx, int* ymdhm, long long* model_step);

@@ -11,7 +11,8 @@ handling): flipping and missing-value logic stay in the loaders (input_output.f9
 Dataset byte offsets were found by walking the HDF5 object headers and are
 guarded by file size + sha256 prefix.  `ssta` is cut to the first NSSTA months (1979-01 ...).
 
-usage: python tools/pack_boundary.py [/root/reference/data/bc/t30] [out.bin]
+usage: python tools/pack_boundary.py [/root/reference/data/bc/t30] [out.bin] [--months N]
+       --months N   SST-anomaly records to keep (default 72 = 1979-01 .. 1984-12, the shipped data/bc_t30.bin; the file holds 420)
 """
 import hashlib
 import os
@@ -34,6 +35,13 @@ FILES = {
 
 
 def main():
+    global NSSTA
+    if "--months" in sys.argv:
+        i = sys.argv.index("--months")
+        NSSTA = int(sys.argv[i + 1])
+        del sys.argv[i:i + 2]
+        assert 1 <= NSSTA <= 420
+        FILES["anom/sea_surface_temperature_anomaly.nc"][2][0] = ("ssta", 6454, NSSTA)
     src = sys.argv[1] if len(sys.argv) > 1 else "/root/reference/data/bc/t30"
     out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "bc_t30.bin")
     fields = []
