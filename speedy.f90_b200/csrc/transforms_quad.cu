@@ -91,7 +91,9 @@ void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<dou
                     const int n = p + 2 * (8 * tt + g), jh = 4 * ks + q;
                     const bool valid = n <= C::TRUNC && m + n <= C::MX;
                     // the Gaussian weight of the fold (legendre.f90:131-132) and fourier_dir's 1/ix ride in the P fragment
-                    polyq[(((size_t)w * C::SLOTS + i) * C::KS + ks) * 32 + lane] = valid ? t.poly[((size_t)jh * C::NX + n) * C::MX + m] * (t.wt[jh] * scale) : 0.0;
+                    // fragments are stored in pairs (j, j + 1) per lane: one 16-byte load per lane, 512 contiguous bytes per warp
+                    const int j = i * C::KS + ks;
+                    polyq[((((size_t)w * C::SLOTS * C::KS) / 2 + j / 2) * 32 + lane) * 2 + (j & 1)] = valid ? t.poly[((size_t)jh * C::NX + n) * C::MX + m] * (t.wt[jh] * scale) : 0.0;
                 }
         }
 }
@@ -176,7 +178,10 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     {
         double a[C::SLOTS * C::KS];
 #pragma unroll
-        for (int j = 0; j < C::SLOTS * C::KS; j++) a[j] = tv.polyq[((size_t)w * C::SLOTS * C::KS + j) * 32 + lane];
+        for (int j = 0; j < C::SLOTS * C::KS; j += 2) {
+            const double2 v = reinterpret_cast<const double2*>(tv.polyq)[((size_t)w * (C::SLOTS * C::KS / 2) + j / 2) * 32 + lane];
+            a[j] = v.x; a[j + 1] = v.y;
+        }
 #pragma unroll
         for (int c = 0; c < C::TCOLS / 16; c++) tmem_st16(taddr + 16 * c, a + 8 * c);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
@@ -410,7 +415,7 @@ void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::ve
                 const int g = lane >> 2, q = lane & 3, p = fr >> 2, ks = fr & 3;
                 const int n = p + 2 * (4 * ks + q), jh = 8 * tl.b + g;
                 const bool valid = n < C::NX && tl.m + n <= C::MX;
-                polyi[(((size_t)w * C::TSLOTS + slot) * 8 + fr) * 32 + lane] = valid ? t.poly[((size_t)jh * C::NX + n) * C::MX + tl.m] : 0.0;
+                polyi[((((size_t)w * C::TSLOTS + slot) * 4 + fr / 2) * 32 + lane) * 2 + (fr & 1)] = valid ? t.poly[((size_t)jh * C::NX + n) * C::MX + tl.m] : 0.0;   // pairs per lane: 16-byte loads
             }
     }
 }
@@ -472,7 +477,10 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
 #pragma unroll
         for (int i = 0; i < C::TSLOTS; i++) {
 #pragma unroll
-            for (int fr = 0; fr < 8; fr++) a[fr] = tv.polyi[(((size_t)w * C::TSLOTS + i) * 8 + fr) * 32 + lane];
+            for (int fr = 0; fr < 8; fr += 2) {
+                const double2 v = reinterpret_cast<const double2*>(tv.polyi)[(((size_t)w * C::TSLOTS + i) * 4 + fr / 2) * 32 + lane];
+                a[fr] = v.x; a[fr + 1] = v.y;
+            }
             tmem_st16(taddr + 16 * i, a);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
