@@ -107,7 +107,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -225,7 +225,6 @@ def run_b200(args):
     assert rc == 0, "check_diagnostics: model variables out of accepted range"
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop() if sampler else None
     dev_s = rank_max(sum(a.elapsed_time(b) for a, b in ev) * 1e-3)
     launches = c.launch_count - launches0
     total_days = args.steps * args.members * world
@@ -258,6 +257,9 @@ def run_b200(args):
             ens_line = _ensemble_leg(pkg, torch, dist, world, rank, local, dev, barrier, rank_max)
         except Exception as ex:
             ens_line = {"error": repr(ex)}
+    # clocks / throttle reasons sampled through ALL the timed regions (device-resident days, host-buffer days, the ensemble leg): the
+    # first alone lasts ~20 ms at the driver's --steps 20
+    clocks = sampler.stop() if sampler else None
 
     if rank != 0:
         if world > 1:

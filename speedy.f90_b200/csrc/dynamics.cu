@@ -414,6 +414,7 @@ __global__ void k_ensemble_sums(const double* __restrict__ base, long long strid
 struct SpptArgs {
     double* base; long long stride; Layout L; DevTables tv;
     unsigned long long seed; int* state; int member0; int draw; int nsteps; double rearth;   // state[0] = updates done so far, state[1] = block ticket
+    double phi, f0;          // sppt.f90:32 and :76-80, evaluated once on the host (thirty exp() per thread otherwise)
 };
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -423,6 +424,9 @@ __device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
 }
 __device__ __forceinline__ double u01(unsigned long long h) { return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
 __global__ void k_sppt_update(SpptArgs a) {
+    // nothing here reads what the previous kernel (the spectral step) writes: dependents may launch at once and the work runs under
+    // the spectral step's tail; the wait at the END keeps the chain transitive (spec->grid's wait on this kernel implies the step)
+    pdl_trigger();
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t < KX * nsp;
@@ -434,12 +438,8 @@ __global__ void k_sppt_update(SpptArgs a) {
     const int counter = a.state[0];
     const bool first = counter == 0;
     double* mb = a.base + (size_t)e * a.stride;
-    const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
-    const double phi = exp(-(24 / (double)a.nsteps) / time_decorr);   // sppt.f90:32
-    double f0 = 0.0;
-    const double rr = len_decorr / a.rearth;
-    for (int nn = 1; nn <= a.tv.trunc; nn++) f0 = f0 + (2 * nn + 1) * exp(-0.5 * (rr * rr) * nn * (nn + 1));
-    f0 = sqrt(((stddev * stddev) * (1 - phi * phi)) / (2 * f0));
+    const double len_decorr = 500000.0;
+    const double phi = a.phi, f0 = a.f0;
     const double sigma = f0 * exp(-0.25 * (len_decorr * len_decorr) * a.tv.el2[r]);
     cd eta;
     if (a.draw) {
@@ -471,6 +471,7 @@ __global__ void k_sppt_update(SpptArgs a) {
         const int nblk = gridDim.x * gridDim.y;
         if (atomicAdd(&a.state[1], 1) == nblk - 1) { a.state[0] = counter + 1; a.state[1] = 0; __threadfence(); }
     }
+    pdl_wait();
 }
 
 // ---- launchers -------------------------------------------------------------------------------
@@ -541,9 +542,17 @@ void launch_sppt_update(speedy_ctx* ctx) {
     SpptArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv;
     a.seed = ctx->seed; a.state = M.sppt_state.p; a.member0 = ctx->member_offset; a.draw = M.sppt_draw ? 1 : 0; a.nsteps = ctx->tab.c.nsteps; a.rearth = ctx->tab.c.rearth;
+    {   // sppt.f90:32,76-80 in the reference's order of operations
+        const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
+        a.phi = exp(-(24 / (double)a.nsteps) / time_decorr);
+        double f0 = 0.0;
+        const double rr = len_decorr / a.rearth;
+        for (int nn = 1; nn <= ctx->d.trunc; nn++) f0 = f0 + (2 * nn + 1) * exp(-0.5 * (rr * rr) * nn * (nn + 1));
+        a.f0 = sqrt(((stddev * stddev) * (1 - a.phi * a.phi)) / (2 * f0));
+    }
     const int total = KX * ctx->d.nspec();
     dim3 grid((total + 127) / 128, ctx->nmembers);
-    k_sppt_update<<<grid, 128, 0, ctx->stream>>>(a);
+    CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_sppt_update, grid, dim3(128), 0, ctx->stream, a));
     ctx->launches++;
     CUDA_CHECK(cudaGetLastError());
 }
