@@ -87,7 +87,6 @@ struct speedy_ctx {
     unsigned long long seed = 0;
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
-    bool col_split = false;   // ensemble batches: the column work as k_col_levels (thread per column and level) + k_col_serial (thread per column); 0: the level-parallel tile kernel
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
     int k2_field = 0;        // 1: ensemble batches, 2: every launch incl. the single-member step (one CTA per field)      // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator

@@ -126,7 +126,6 @@ void model_create(speedy_ctx* ctx) {
     reg("hfluxn", L.hfluxn, 3 * NG);
     reg("ts", L.ts, NG); reg("tskin", L.tskin, NG); reg("u0", L.u0, NG); reg("v0", L.v0, NG); reg("t0", L.t0, NG);
     reg("qcloud", L.qcloud, NG); reg("cloudc", L.cloudc, NG); reg("clstr", L.clstr, NG);
-    reg("colscr", L.colscr, (long long)COLSCR_ROWS * NG);
     L.qcorh_g = L.gout + (long long)GO_QCORH * NG;     // the daily humidity-correction field is the 74th K2 input
     M.fields["qcorh_g"] = FieldInfo{L.qcorh_g, (size_t)NG, false};
     L.stride = (off + 15) / 16 * 16;
@@ -958,7 +957,6 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     if (n == "k2_field") ctx->k2_field = value;
     else if (n == "k2_quad") ctx->k2_quad = value != 0;
     else if (n == "k1_quad") ctx->k1_quad = value != 0;
-    else if (n == "col_split") ctx->col_split = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

@@ -38,7 +38,6 @@ enum {
     GI_SPPT = 91, GI_N = 99, GI_NBASE = 91
 };
 // K2 input fields: per level 9 (utend, vtend, KE, -uT', -vT', ttend, -uq, -vq, qtend) + psdt
-constexpr int COLSCR_ROWS = 97;   // se, qsat, rh, qg, dtlsc, dqlsc, two long-wave source terms (8 levels each), psg, 4 band radiances x 8 levels
 enum { GO_PER = 9, GO_PSDT = 72, GO_QCORH = 73, GO_N = 74 };   // slot 73: daily humidity-correction field (forcing.f90:98)
 
 // offsets (in doubles) inside a member region
@@ -58,7 +57,6 @@ struct Layout {
     long long precnv, precls, cbmf, slrd, slr, olr, slru, ustr, vstr, shf, evap, hfluxn, ts, tskin, u0, v0, t0;
     long long qcloud, cloudc, clstr;
     long long qcorh_g;   // grid-point humidity correction before its transform (forcing.f90:98)
-    long long colscr;    // COLSCR_ROWS grid rows: level-local results handed from k_col_levels to k_col_serial (ensemble batches)
     // int fields, offsets in ints inside the member's int region
     long long istride, iptop, icltop, icnv;
 };

@@ -1163,20 +1163,11 @@ static const ColMaps& column_maps(speedy_ctx* ctx) {
 
 void free_column_maps(Model& M) { delete static_cast<ColMaps*>(M.colmaps); M.colmaps = nullptr; }
 
-}  // namespace spd
-#pragma push_macro("exp")
-#undef exp      // the batch kernels run one instruction stream per warp: exp() inlined, so that independent calls overlap
-#include "physics_batch.cuh"
-#pragma pop_macro("exp")
-namespace spd {
-
 // per device (speedy_create calls it after cudaSetDevice): the shared-memory opt-in is a per-device function attribute
 void setup_column_kernels() {
-    CUDA_CHECK(cudaFuncSetAttribute(k_col_serial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SER_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
     CUDA_CHECK(cudaFuncSetAttribute(k_grid_columns<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COL_SMEM));
 }
-
 
 // ---- launchers ------------------------------------------------------------------------------
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged) {
@@ -1193,18 +1184,7 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     const int N = ctx->d.ngrid();
     if (N % TC) throw std::runtime_error("grid size must be a multiple of the column tile");
     dim3 grid(N / TC, ctx->nmembers);
-    const bool pdl = ctx->dv.trace == nullptr || ctx->trace_pdl;
-    // ensemble batches (three or more tiles per SM): level-local work with a thread per (column, level), then the column-serial
-    // sweeps with a thread per column (physics_batch.cuh)
-    if (ctx->col_split && (long long)grid.x * grid.y >= 3ll * ctx->num_sms) {
-        CUDA_CHECK(launch_pdl(pdl, k_col_levels, grid, dim3(KX * 32), 0, ctx->stream, a));
-        if (N % (SER_WARPS * TC)) throw std::runtime_error("grid size must be a multiple of the serial kernel's block of tiles");
-        CUDA_CHECK(launch_pdl(pdl, k_col_serial, dim3(N / (SER_WARPS * TC), ctx->nmembers), dim3(SER_WARPS * 32), SER_SMEM, ctx->stream, a));
-        ctx->launches += 2;
-        CUDA_CHECK(cudaGetLastError());
-        return;
-    }
-    // more tiles than SMs (T47, two members): the two-CTAs-per-SM variant; otherwise the uncapped one
+    // more tiles than SMs (ensemble batches, T47): the two-CTAs-per-SM variant; otherwise the uncapped one
     if ((long long)grid.x * grid.y > ctx->num_sms) CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_grid_columns<true>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     else CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_grid_columns<false>, grid, dim3(COL_THREADS), COL_SMEM, ctx->stream, a));
     ctx->launches++;
