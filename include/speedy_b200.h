@@ -190,7 +190,9 @@ void* speedy_stream(const speedy_ctx* ctx);
 int speedy_set_graphs(speedy_ctx* ctx, int on);
 /* kernel-selection switches (no counterpart in the reference; used by the A/B tools and by the parity tests of the alternative
  * kernels): "k2_field" (grid->spec batches through the whole-field FFT kernel), "dense_inverse" (spec->grid Fourier stage as the
- * dense FFTPACK operator), "graphs".  Returns <0 for an unknown name. */
+ * dense FFTPACK operator), "k1_quad" / "k2_quad" (ensemble batches through the four-field FFT + DMMA kernels, default 1),
+ * "member_ready" (default 1: in the main-loop step the column tiles of a member start when that member's grid fields are stored,
+ * 0: when the whole spec->grid launch is complete), "graphs".  Returns <0 for an unknown name. */
 int speedy_set_option(speedy_ctx* ctx, const char* name, int value);
 
 

@@ -14,6 +14,7 @@ struct CloseArgs {
     const double* partial;    // [member][block][kx][2] + [member][kx]: partial sums written by k_spec_step
     int nb, ne;               // spectral-step blocks per member, members
     unsigned long long* trace; // in-graph timeline buffer (stand-alone closer in trace mode), else nullptr
+    unsigned* ready;          // [member] completion counts of the spec->grid kernel that carries this closer (member_ready.cuh), or nullptr
 };
 
 // threads 0..255 of the calling CTA (warp w <-> (member, level) pairs w, w+8, ...; lanes take blocks in a fixed order)
@@ -23,20 +24,37 @@ __device__ __forceinline__ void close_step_cta(const CloseArgs& a, int tid) {
     const int c = tid & 31, k = tid >> 5;
     if (!a.clk->close_pending) return;
     const int nb = a.nb, ne = a.ne;
-    for (int idx = k; idx < ne * KXL; idx += KXL) {
-        const int e = idx / KXL, kk = idx - e * KXL;
-        double d1 = 0.0, d2 = 0.0;
-        for (int b = c; b < nb; b += 32) {
-            const double* part = a.partial + ((size_t)e * nb + b) * (2 * KXL);
-            d1 += __ldcg(part + kk); d2 += __ldcg(part + KXL + kk);
+    // warp k = level k; four members at a time, their loads issued together (one L2 round trip per four members)
+    const int kk = k;
+    for (int e0 = 0; e0 < ne; e0 += 4) {
+        double d1[4], d2[4], d3[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int e = e0 + u;
+            d1[u] = 0.0; d2[u] = 0.0; d3[u] = 0.0;
+            if (e < ne) {
+                for (int b = c; b < nb; b += 32) {
+                    const double* part = a.partial + ((size_t)e * nb + b) * (2 * KXL);
+                    d1[u] += __ldcg(part + kk); d2[u] += __ldcg(part + KXL + kk);
+                }
+                if (c == 0) d3[u] = __ldcg(a.partial + (size_t)ne * nb * 2 * KXL + (size_t)e * KXL + kk);
+            }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { d1 += __shfl_xor_sync(0xffffffffu, d1, o); d2 += __shfl_xor_sync(0xffffffffu, d2, o); }
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { d1[u] += __shfl_xor_sync(0xffffffffu, d1[u], o); d2[u] += __shfl_xor_sync(0xffffffffu, d2[u], o); }
+        }
         if (c == 0) {
-            const double d3 = (double)sqrtf(0.5f) * __ldcg(a.partial + (size_t)ne * nb * 2 * KXL + (size_t)e * KXL + kk);
-            if (e == 0) { a.clk->diag[kk] = d1; a.clk->diag[KXL + kk] = d2; a.clk->diag[2 * KXL + kk] = d3; }
-            const bool bad = !(d1 <= 500.0) || !(d2 <= 500.0) || !(d3 >= 180.0) || !(d3 <= 320.0);
-            if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int e = e0 + u;
+                if (e >= ne) break;
+                const double t3 = (double)sqrtf(0.5f) * d3[u];
+                if (e == 0) { a.clk->diag[kk] = d1[u]; a.clk->diag[KXL + kk] = d2[u]; a.clk->diag[2 * KXL + kk] = t3; }
+                const bool bad = !(d1[u] <= 500.0) || !(d2[u] <= 500.0) || !(t3 >= 180.0) || !(t3 <= 320.0);
+                if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
+            }
         }
     }
     // all 256 threads of the closing group (named barrier: the rest of the CTA may be elsewhere)

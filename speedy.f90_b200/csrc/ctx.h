@@ -87,6 +87,7 @@ struct speedy_ctx {
     unsigned long long seed = 0;
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
+    bool member_ready = true; // main-loop step on the quad transforms: the column tiles of a member start when that member's grid fields are stored (member_ready.cuh); 0: when the whole transform is
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
     int k2_field = 0;        // 1: ensemble batches, 2: every launch incl. the single-member step (one CTA per field)      // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator
@@ -132,6 +133,8 @@ void setup_column_kernels();       // physics.cu
 void setup_spec_step_kernels();    // dynamics.cu
 // transforms_quad.cu (T30 ensemble batches)
 void setup_quad_kernels();
+bool s2g_quad_selected(const speedy_ctx* ctx, int nbatch, int nmembers, bool quad_ok);   // transforms.cu: would this spec->grid launch take the quad kernel
+unsigned s2g_quad_ready_counts(int nbatch);                                             // member_ready.cuh: counts per member of one launch
 void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyq);
 void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyi);
 // transforms_f32.cu (precision = 1)

@@ -29,6 +29,7 @@ struct SpecArgs {
     double dt;
     int flag;
     double* partial;
+    unsigned* ready_reset;   // main-loop step: the per-member completion counts of this step's spec->grid kernel, zeroed here for the next step
 };
 
 __device__ __forceinline__ const double* sfield(const double* mb, long long off, int nsp, int f) { return mb + off + (size_t)f * nsp * 2; }
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
     const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
     pdl_wait();                 // everything above reads constant tables only; the fields below come from the previous kernel
     pdl_trigger();
+    if (a.ready_reset && blockIdx.x == 0 && tid == 0) a.ready_reset[blockIdx.y] = 0u;   // every column tile of the step has passed its wait
     const unsigned long long tk0 = tv.trace ? gtimer() : 0ull;
 #define SSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 5 && blockIdx.y == 0) tv.trace[56 + (i)] += gtimer() - tk0; } while (0)
     const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
@@ -479,7 +481,7 @@ static SpecArgs spec_args(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpecArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv; a.lc = M.lc.p; a.clk = M.clock.p;
-    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p;
+    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p; a.ready_reset = nullptr;
     return a;
 }
 
@@ -496,6 +498,7 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     Model& M = *ctx->model;
     SpecArgs a = spec_args(ctx);
     a.j1 = j1; a.j2 = j2; a.dt = dt; a.flag = (store_tend_only ? 1 : 0) | (close_step ? 2 : 0);
+    if (close_step && M.ready_target) a.ready_reset = M.ready.p;
     dim3 grid((ctx->d.nspec() + SC - 1) / SC, ctx->nmembers);
     const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
     if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }

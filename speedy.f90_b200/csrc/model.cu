@@ -1,3 +1,4 @@
+#include <algorithm>
 // Model-level entry points of the C ABI: device-resident state, start-up
 // (initialization.f90:12-82), the time step (time_stepping.f90:12-122), the main-loop body
 // (speedy.f90:27-54) replayed as a CUDA graph, the surface slabs, diagnostics and output.
@@ -146,6 +147,7 @@ void model_create(speedy_ctx* ctx) {
     {
         const size_t nb = (d.nspec() + 31) / 32;
         M.diag_partial.alloc(nb * ctx->nmembers * 2 * KXc + (size_t)ctx->nmembers * KXc);
+        M.ready.alloc(ctx->nmembers);
     }
 
     // transform descriptors --------------------------------------------------------------
@@ -237,7 +239,12 @@ static void xform_inverse(speedy_ctx* ctx, int j2, int first, int count) {
 // with_close: an extra CTA of the kernel closes the previous main-loop step if one is pending (close_step.cuh)
 static void xform_step(speedy_ctx* ctx, int j2, bool with_close = false) {
     Model& M = *ctx->model;
-    const CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + 31) / 32), ctx->nmembers, nullptr};
+    CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + 31) / 32), ctx->nmembers, nullptr, nullptr};
+    M.ready_target = 0;
+    if (with_close && ctx->member_ready && s2g_quad_selected(ctx, M.nstep_fields, ctx->nmembers, true)) {
+        cl.ready = M.ready.p;
+        M.ready_target = s2g_quad_ready_counts(M.nstep_fields) + 1;     // + the closing CTA
+    }
     launch_spec_to_grid(ctx, M.mem.p, M.L.stride, M.desc_step.p + (size_t)(j2 - 1) * M.nstep_fields, M.nstep_fields,
                         M.mem.p + M.L.gin, M.L.stride, ctx->nmembers, 0, with_close ? &cl : nullptr, true);
 }
@@ -284,6 +291,7 @@ static void enqueue_main_loop_step(speedy_ctx* ctx) {
     launch_grid_columns(ctx, 0, -1, 1);
     xform_direct(ctx, true);
     launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1);
+    ctx->model->ready_target = 0;
     if (tracing) launch_close_step(ctx);
 }
 // the coupler call of the last step (speedy.f90:53) when no further step follows in this call
@@ -957,6 +965,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     if (n == "k2_field") ctx->k2_field = value;
     else if (n == "k2_quad") ctx->k2_quad = value != 0;
     else if (n == "k1_quad") ctx->k1_quad = value != 0;
+    else if (n == "member_ready") ctx->member_ready = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);
@@ -973,7 +982,7 @@ int speedy_trace(speedy_ctx* ctx, int on) {
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     drop_graph(*ctx->model);
     if (on) {
-        std::vector<unsigned long long> h(64, 0ull);
+        std::vector<unsigned long long> h(64 + 2 * 640, 0ull);   // + per-CTA timelines of the two quad transforms (transforms_quad.cu CSTAMP)
         for (int i = 0; i < 4; i++) h[i] = ~0ull;
         ctx->trace.upload(h);
         ctx->dv.trace = ctx->trace.p;
@@ -1004,6 +1013,20 @@ int speedy_trace_read(speedy_ctx* ctx, double* out9) {
             CUDA_CHECK(cudaMemcpy(k2, ctx->trace.p + 24, sizeof(k2), cudaMemcpyDeviceToHost));
             fprintf(stderr, "\nK2 stamps (us) [wait,dft,fold,legendre] per field:");
             for (int i = 0; i < 8; i++) fprintf(stderr, " %.2f", 1e-3 * (double)k2[i] / n);
+        }
+        for (int kq = 0; kq < 2; kq++) {     // per-CTA timeline of the last launch of the quad kernels: min / median / max over the CTAs, us after the first start
+            std::vector<unsigned long long> c(640);
+            CUDA_CHECK(cudaMemcpy(c.data(), ctx->trace.p + 64 + 640 * kq, 640 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            unsigned long long t0 = ~0ull; int nc = 0;
+            for (int i = 0; i < 160; i++) if (c[4 * i]) { t0 = std::min(t0, c[4 * i]); nc++; }
+            if (!nc) continue;
+            fprintf(stderr, "\n%s quad CTAs (%d) [start, first quad, after quads, end] min/med/max us:", kq ? "K2" : "K1", nc);
+            for (int sidx = 0; sidx < 4; sidx++) {
+                std::vector<double> v;
+                for (int i = 0; i < 160; i++) if (c[4 * i] && c[4 * i + sidx]) v.push_back(1e-3 * (double)(c[4 * i + sidx] - t0));
+                std::sort(v.begin(), v.end());
+                if (!v.empty()) fprintf(stderr, " %.2f/%.2f/%.2f", v.front(), v[v.size() / 2], v.back());
+            }
         }
         fprintf(stderr, "\nspec_step stamps (us) [operands, spectral tendencies, implicit, leapfrog, geopotential, end]:");
         for (int i = 24; i < 30; i++) fprintf(stderr, " %.2f", 1e-3 * (double)st[i] / n);

@@ -14,6 +14,7 @@
 #include "model.h"
 #include "calendar.h"
 #include "tma.cuh"
+#include "member_ready.cuh"
 #include <cuda.h>   // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace spd {
@@ -63,6 +64,8 @@ struct ColumnArgs {
     int csw_override;        // -1: take compute_shortwave from the device clock
     int sppt_on;
     unsigned long long* trace;
+    const unsigned* ready;   // main-loop step behind the quad transform: per-member completion counts (member_ready.cuh), else nullptr
+    unsigned ready_target;
     // [member][row][column] tensor maps: box = rows x 32 columns, one TMA instruction per tile
     CUtensorMap m_dyn, m_phys, m_tau2, m_stratc, m_rsw;
 };
@@ -161,7 +164,12 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         bulk_g2s(sFband, a.fband, NFBAND * 8, &bars[0]);
         bulk_g2s(sLc, a.lc, (uint32_t)sizeof(LevelConsts), &bars[0]);
     }
-    pdl_wait();                                        // the grid fields of the previous kernel are complete
+    if (a.ready) {                                     // this member's grid fields are complete (the transform may still be storing later members)
+        if (tid == 0) ready_wait(a.ready + e, a.ready_target);
+        __syncthreads();
+    } else {
+        pdl_wait();                                    // the grid fields of the previous kernel are complete
+    }
     pdl_trigger();
     if (a.trace) tk0 = gtimer();
     if (tid == 0) {     // five tile copies (UTMALDG) instead of ~140 row copies: small bulk copies drain slowly through the TMA unit
@@ -1176,6 +1184,7 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.sh = M.sh; a.merged = merged;
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
+    a.ready = M.ready_target ? M.ready.p : nullptr; a.ready_target = M.ready_target;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on; a.trace = ctx->dv.trace;
     {
         const ColMaps& cm = column_maps(ctx);

@@ -927,14 +927,18 @@ static int stream_chunks(speedy_ctx* ctx, int slices, int nmembers, int nbatch, 
 void launch_s2g_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers,
                      const CloseArgs& cl);
 
+// ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (transforms_quad.cu); the list must hold derived fields as
+// aligned pairs (quad_ok), and three or more fields per SM must be there to fill the quads
+bool s2g_quad_selected(const speedy_ctx* ctx, int nbatch, int nmembers, bool quad_ok) {
+    return ctx->d.trunc == 30 && ctx->precision == 0 && quad_ok && ctx->k1_quad && ctx->fft_inverse && (long long)nbatch * nmembers >= 3ll * ctx->num_sms;
+}
+
 template <int TRUNC>
 static void launch_s2g_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                               double* d_out, long long out_ms, int nmembers, const CloseArgs& cl, bool quad_ok) {
     using C = SCfg<TRUNC>;
     if constexpr (TRUNC == 30) {
-        // ensemble batches: four fields at a time, FFT + DMMA Legendre (transforms_quad.cu); the list must hold derived fields as
-        // aligned pairs (quad_ok), and three or more fields per SM must be there to fill the quads
-        if (quad_ok && ctx->k1_quad && ctx->fft_inverse && (long long)nbatch * nmembers >= 3ll * ctx->num_sms) {
+        if (s2g_quad_selected(ctx, nbatch, nmembers, quad_ok)) {
             launch_s2g_quad(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
             return;
         }

@@ -19,6 +19,7 @@
 //   the reference order to ~1e-15 relative (tests: 1e-12 per call, 1e-10 after 48 h).
 #include "ctx.h"
 #include "tma.cuh"
+#include "member_ready.cuh"
 #include <cuda.h>
 #include <map>
 #include <mutex>
@@ -127,6 +128,9 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, double* v) {           
     for (int i = 0; i < 8; i++) v[i] = __hiloint2double((int)r[2 * i + 1], (int)r[2 * i]);
 }
 
+// per-CTA timeline of the last traced launch (speedy_trace + SPEEDY_TRACE_STAMPS): %globaltimer at [start, first quad, after the quads, end]
+#define CSTAMP(kslot, i) do { if (tv.trace && tid == 0 && blockIdx.x < 160) tv.trace[64 + 640 * (kslot) + 4 * blockIdx.x + (i)] = gtimer(); } while (0)
+
 __global__ void __launch_bounds__(QCfg::THREADS, 1)
 k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end,
            double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
@@ -145,6 +149,7 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + C::NG * C::NBAR + 1);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid == 0) trace_begin(tv.trace, 2);
+    CSTAMP(1, 0);
     // this CTA's quads of the flattened (member, field) list
     const int nquad = (idx_end - idx_base + 3) >> 2;
     const int q0 = (int)((long long)blockIdx.x * nquad / gridDim.x), q1 = (int)((long long)(blockIdx.x + 1) * nquad / gridDim.x);
@@ -228,6 +233,7 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     long long tq = 0;
 #define QSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[24 + (i)] += (unsigned long long)(t_ - tq); tq = t_; } } while (0)
     if (tv.trace) tq = clock64();
+    CSTAMP(1, 1);
     for (int t0 = 0; t0 < cnt; t0 += 4) {
         unsigned present = 0;
         for (int fs = 0; fs < 4 && t0 + fs < cnt; fs++) {
@@ -349,11 +355,13 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
         QSTAMP(5);
     }
 #undef QSTAMP
+    CSTAMP(1, 2);
     if (w == C::WARPS - 1 && lane == 0) bulk_wait_all();      // the last stores have left the SM's shared memory and are committed
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*sTmem), "r"(512u) : "memory");
     if (tv.trace && tid == 0) trace_end(tv.trace, 2);
+    CSTAMP(1, 3);
 }
 
 // ==========================================================================================================================
@@ -428,6 +436,10 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
         pdl_wait();
         pdl_trigger();
         close_step_cta(cl, threadIdx.x);
+        if (cl.ready) {                                 // the calendar is advanced: one count per member (member_ready.cuh)
+            __syncthreads();
+            for (int e = threadIdx.x; e < cl.ne; e += blockDim.x) ready_signal(cl.ready + e);
+        }
         return;
     }
     extern __shared__ __align__(1024) double smem[];
@@ -443,11 +455,13 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid == 0) trace_begin(tv.trace, 0);
+    CSTAMP(0, 0);
     // this CTA's quads: quad Q = (member e, quad qm of the member's field list)
     const int qpm = (nbatch + 3) >> 2;
     const int nq = q_end - q_base;
-    const int c0 = q_base + (int)((long long)blockIdx.x * nq / nwork), c1 = q_base + (int)((long long)(blockIdx.x + 1) * nq / nwork);
-    const int ncq = c1 - c0;
+    // quads are dealt out round robin: local quad cq = quad q_base + blockIdx.x + cq nwork, so the members complete in order
+    const int ncq = (int)blockIdx.x < nq ? (nq - 1 - (int)blockIdx.x) / nwork + 1 : 0;
+    auto quad_of = [&](int cq) { return q_base + (int)blockIdx.x + cq * nwork; };
     if (tid == 0 && ((smem_u32(sX) & 1023u) || 4 * ncq > C::LCAP)) __trap();
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_fence_init(); }
     if (w == 0) {
@@ -458,7 +472,7 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     for (int t = tid; t < C::IX; t += C::THREADS) sWa[t] = tv.fftwa[t];
     for (int t = tid; t < C::WARPS * C::TSLOTS; t += C::THREADS) sTile[t] = tv.qtile_inv[t];
     for (int t = tid; t < 4 * ncq; t += C::THREADS) {
-        const int Q = c0 + (t >> 2), e = Q / qpm, f = 4 * (Q - e * qpm) + (t & 3);
+        const int Q = quad_of(t >> 2), e = Q / qpm, f = 4 * (Q - e * qpm) + (t & 3);
         if (f < nbatch) {
             const XDesc d = desc[f];
             sOff[t] = (long long)e * in_ms + d.off; sOff2[t] = (long long)e * in_ms + d.off2;
@@ -524,6 +538,7 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     long long tq = 0;
 #define ISTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[48 + (i)] += (unsigned long long)(t_ - tq); tq = t_; } } while (0)
     if (tv.trace) tq = clock64();
+    CSTAMP(0, 1);
     for (int cq = 0; cq < ncq; cq++) {
         const int t0 = 4 * cq;
         // ---- P1: derived pairs in registers, then back over their sources; triangle mask
@@ -628,6 +643,8 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
         __syncthreads();                                // X of the quad complete; sIn free
         ISTAMP(4);
         if (tid == 0 && cq + 1 < ncq) issue_quad(cq + 1);
+        // the previous quad's stores of this band group were issued a Legendre phase ago: complete by now, so its member can be told
+        if (cl.ready && cq > 0 && wl == 0 && lane == 0) { bulk_wait_all(); ready_signal(cl.ready + quad_of(cq - 1) / qpm); }
         // ---- P3: backward FFT per (field, band), fields ph and ph + 2 of the quad
 #pragma unroll 1
         for (int fs = ph; fs < 4; fs += C::NPH) {
@@ -683,12 +700,20 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
         ISTAMP(6);
     }
 #undef ISTAMP
-    if (wl == 0 && lane == 0) bulk_wait_all();
+    CSTAMP(0, 2);
+    if (wl == 0 && lane == 0) {
+        bulk_wait_all();
+        if (cl.ready && ncq > 0) ready_signal(cl.ready + quad_of(ncq - 1) / qpm);
+    }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (w == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(*sTmem), "r"(512u) : "memory");
     if (tv.trace && tid == 0) trace_end(tv.trace, 0);
+    CSTAMP(0, 3);
 }
+
+// completion counts one member's fields add to its ready counter (member_ready.cuh): one per band group and quad
+unsigned s2g_quad_ready_counts(int nbatch) { return (unsigned)(QICfg::NG * QICfg::NPH * ((nbatch + 3) / 4)); }
 
 void setup_quad_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_g2s_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)QCfg::SMEM_G2S));
@@ -752,7 +777,8 @@ void launch_s2g_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
     for (int base = 0; base < nq; base += per) {
         const int end = base + per < nq ? base + per : nq;
         const int nwork = (end - base) < ctx->num_sms - reserve ? (end - base) : ctx->num_sms - reserve;
-        const CloseArgs c = first ? cl : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
+        CloseArgs c = first ? cl : CloseArgs{nullptr, nullptr, 0, 0, nullptr, nullptr};
+        c.ready = cl.ready;
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_s2g_quad, dim3(nwork + (c.clk ? 1 : 0)), dim3(C::THREADS), C::SMEM, ctx->stream, d_in, in_ms, d_desc,
                               nbatch, base, end, nwork, omap, ctx->dv, c));
         first = false;
