@@ -96,3 +96,24 @@ def test_48h_run_variant(pkg, oracle, variant):
     for n in ("iptop", "icnv", "icltop"):
         assert np.array_equal(c.get_field(n), oracle.ifield(n)), n
     c.close()
+
+
+@pytest.mark.parametrize("sppt", [0, 1])
+def test_member_ready_handoff_is_bitwise_neutral(pkg, sppt):
+    """the per-member hand-off between the quad spec->grid kernel and the column kernel (member_ready.cuh) only changes WHEN a column
+    tile starts: 72 steps of 8 members (SPPT members differ from each other) with and without it give the same bits, graphs and plain launches"""
+    out = {}
+    for ready, graphs in ((1, 1), (0, 1), (1, 0)):
+        c = pkg.Speedy(trunc=30, nmembers=8, sppt_on=sppt, seed=11)
+        c.set_option("member_ready", ready)
+        c.set_option("graphs", graphs)
+        c.model_init(BC)
+        assert c.run_steps(72) == 0
+        out[(ready, graphs)] = {n: c.get_field(n, all_members=True) for n in PROG + ("sst_om", "tau2")}
+        c.close()
+    base = out[(0, 1)]
+    if sppt:
+        assert not np.array_equal(base["t"][0], base["t"][7])
+    for key in ((1, 1), (1, 0)):
+        for n, v in base.items():
+            assert np.array_equal(out[key][n], v), (key, n)
