@@ -982,7 +982,7 @@ int speedy_trace(speedy_ctx* ctx, int on) {
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     drop_graph(*ctx->model);
     if (on) {
-        std::vector<unsigned long long> h(64 + 2 * 640, 0ull);   // + per-CTA timelines of the two quad transforms (transforms_quad.cu CSTAMP)
+        std::vector<unsigned long long> h(64 + 2 * 640 + 16, 0ull);   // + per-CTA timelines of the two quad transforms (transforms_quad.cu CSTAMP)
         for (int i = 0; i < 4; i++) h[i] = ~0ull;
         ctx->trace.upload(h);
         ctx->dv.trace = ctx->trace.p;
@@ -1027,6 +1027,12 @@ int speedy_trace_read(speedy_ctx* ctx, double* out9) {
                 std::sort(v.begin(), v.end());
                 if (!v.empty()) fprintf(stderr, " %.2f/%.2f/%.2f", v.front(), v[v.size() / 2], v.back());
             }
+        }
+        {
+            unsigned long long f2[8];
+            CUDA_CHECK(cudaMemcpy(f2, ctx->trace.p + 1344, sizeof(f2), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "\nK2 per-field stamps of CTA 0 (kcycles) [band wait, fold, stage A, sync, stage B wait, stage B, sync]:");
+            for (int i = 0; i < 7; i++) fprintf(stderr, " %.2f", 1e-3 * (double)f2[i] / n);
         }
         fprintf(stderr, "\nspec_step stamps (us) [operands, spectral tendencies, implicit, leapfrog, geopotential, end]:");
         for (int i = 24; i < 30; i++) fprintf(stderr, " %.2f", 1e-3 * (double)st[i] / n);

@@ -132,7 +132,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, double* v) {           
 #define CSTAMP(kslot, i) do { if (tv.trace && tid == 0 && blockIdx.x < 160) tv.trace[64 + 640 * (kslot) + 4 * blockIdx.x + (i)] = gtimer(); } while (0)
 
 __global__ void __launch_bounds__(QCfg::THREADS, 1)
-k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end,
+k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end, int unit,
            double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
     using C = QCfg;
     extern __shared__ __align__(1024) double smem[];
@@ -150,10 +150,10 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid == 0) trace_begin(tv.trace, 2);
     CSTAMP(1, 0);
-    // this CTA's quads of the flattened (member, field) list
-    const int nquad = (idx_end - idx_base + 3) >> 2;
-    const int q0 = (int)((long long)blockIdx.x * nquad / gridDim.x), q1 = (int)((long long)(blockIdx.x + 1) * nquad / gridDim.x);
-    const int i0 = idx_base + 4 * q0, cnt = min(idx_base + 4 * q1, idx_end) - i0;
+    // this CTA's run of the flattened (member, field) list, in units of four fields (quads) — of two when there are fewer quads than SMs
+    const int nunit = (idx_end - idx_base + unit - 1) / unit;
+    const int q0 = (int)((long long)blockIdx.x * nunit / gridDim.x), q1 = (int)((long long)(blockIdx.x + 1) * nunit / gridDim.x);
+    const int i0 = idx_base + unit * q0, cnt = min(idx_base + unit * q1, idx_end) - i0;
     if (tid == 0 && ((smem_u32(sRing) & 1023u) || cnt > C::LCAP)) __trap();
     if (tid == 0) {
         for (int k = 0; k < C::NG * C::NBAR + 1; k++) mbar_init(&bars[k], 1);
@@ -245,7 +245,7 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
             const int k = seq % C::RING, fl = sFl[t];
             double* G = ring + k * C::BAND;
             long long tf = 0;
-#define FSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[32 + (i)] += (unsigned long long)(t_ - tf); tf = t_; } } while (0)
+#define FSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[1344 + (i)] += (unsigned long long)(t_ - tf); tf = t_; } } while (0)
             if (tv.trace) tf = clock64();
             mbar_wait(&gbar[seq % C::NBAR], (seq / C::NBAR) & 1);
             FSTAMP(0);
@@ -392,8 +392,9 @@ struct QICfg {
     static constexpr int TSLOTS = 96 / WARPS, TCOLS = 16 * TSLOTS;   // tiles per warp; TMEM columns per warp (a tile = 8 fragments = 16 columns)
     static constexpr int NTILES = MX * NG;           // (m, band)
     static constexpr int LCAP = 128;                 // fields per CTA and launch
+    static constexpr int NDEAD = (NX - 1) * (NX - 2) / 2;   // (m, n) of the mx x nx rectangle outside the triangle m + n <= mx (legendre.f90:38): n - 1 in row n
     static constexpr size_t SMEM = sizeof(double) * (4 * NG * BAND + 4 * FSI + IX) + sizeof(uint64_t) * 4 + sizeof(int) * WARPS * TSLOTS +
-                                   LCAP * (2 * sizeof(long long) + 3 * sizeof(int));
+                                   LCAP * (2 * sizeof(long long) + 3 * sizeof(int)) + sizeof(unsigned short) * (NDEAD + 3);
     static_assert(FSI % 16 == 2 && (BAND * 8) % 1024 == 0 && SMEM <= 232448 && (WARPS / 4) * TCOLS <= 512, "layout");
 };
 
@@ -452,6 +453,7 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     int* sOp = reinterpret_cast<int*>(sOff2 + C::LCAP);             // [LCAP] op | flags << 8 | member << 16
     int* sOrow = sOp + C::LCAP;                                      // [LCAP] first row of the output field in the output tensor map
     int* sTile = sOrow + C::LCAP;                                    // [WARPS][TSLOTS]
+    unsigned short* sDead = reinterpret_cast<unsigned short*>(sTile + C::WARPS * C::TSLOTS);   // [NDEAD] (n << 8 | m) outside the triangle
     uint32_t* sTmem = reinterpret_cast<uint32_t*>(bars + 3);
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     if (tid == 0) trace_begin(tv.trace, 0);
@@ -471,6 +473,10 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     // ---- prologue on constant tables only (may overlap the tail of the previous kernel: PDL)
     for (int t = tid; t < C::IX; t += C::THREADS) sWa[t] = tv.fftwa[t];
     for (int t = tid; t < C::WARPS * C::TSLOTS; t += C::THREADS) sTile[t] = tv.qtile_inv[t];
+    for (int t = tid; t < C::MX * C::NX; t += C::THREADS) {
+        const int n = t / C::MX, m = t - n * C::MX;
+        if (m + n > C::MX) sDead[(n - 1) * (n - 2) / 2 + (m - (C::MX - n + 1))] = (unsigned short)((n << 8) | m);
+    }
     for (int t = tid; t < 4 * ncq; t += C::THREADS) {
         const int Q = quad_of(t >> 2), e = Q / qpm, f = 4 * (Q - e * qpm) + (t & 3);
         if (f < nbatch) {
@@ -486,13 +492,16 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t taddr = *sTmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(C::TCOLS * (w >> 2));
+    // P fragments of this warp's tiles: parked in tensor memory for the whole kernel.  (Reading them from L2 inside the tile loop when a
+    // CTA has only one or two quads was measured: the 196 KB per CTA take as long there as here — 8-member step 95.3 against 94.0 us.)
+    const double2* pfrag = reinterpret_cast<const double2*>(tv.polyi) + (size_t)w * C::TSLOTS * 4 * 32 + lane;
     {
         double a[8];
 #pragma unroll
         for (int i = 0; i < C::TSLOTS; i++) {
 #pragma unroll
             for (int fr = 0; fr < 8; fr += 2) {
-                const double2 v = reinterpret_cast<const double2*>(tv.polyi)[(((size_t)w * C::TSLOTS + i) * 4 + fr / 2) * 32 + lane];
+                const double2 v = pfrag[(i * 4 + fr / 2) * 32];
                 a[fr] = v.x; a[fr + 1] = v.y;
             }
             tmem_st16(taddr + 16 * i, a);
@@ -587,9 +596,9 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
         }
         if (!waited) mbar_wait(&bars[0], cq & 1);
         ISTAMP(0);
-        for (int t = tid; t < 4 * C::MX * C::NX; t += C::THREADS) {      // plain fields: zero outside the triangle (a finite product with the zero P entries)
-            const int fs = t / (C::MX * C::NX), r = t - fs * (C::MX * C::NX), n = r / C::MX, m = r - n * C::MX;
-            if (m + n > C::MX && (sOp[t0 + fs] & 255) == 0) st(sIn + fs * C::FSI, C::MX, m, n, cd{0.0, 0.0});
+        for (int t = tid; t < 4 * C::NDEAD; t += C::THREADS) {           // plain fields: zero outside the triangle (a finite product with the zero P entries)
+            const int fs = t / C::NDEAD, mn = sDead[t - fs * C::NDEAD];
+            if ((sOp[t0 + fs] & 255) == 0) st(sIn + fs * C::FSI, C::MX, mn & 255, mn >> 8, cd{0.0, 0.0});
         }
         ISTAMP(1);
         __syncthreads();                                // sIn complete; X free (the previous quad's stores have read it: wait below)
@@ -759,9 +768,11 @@ void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
     const int nf = nbatch * nmembers, per = C::LCAP * ctx->num_sms;      // fields per launch: at most LCAP per CTA
     for (int base = 0; base < nf; base += per) {
         const int end = base + per < nf ? base + per : nf;
-        const int nquad = (end - base + 3) / 4;
-        const int ncta = nquad < ctx->num_sms ? nquad : ctx->num_sms;
-        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end,
+        // fewer quads than SMs (8 members of the model step: 70): hand out pairs instead, the FFT phase of a CTA halves
+        const int nquad = (end - base + 3) / 4, unit = nquad < ctx->num_sms ? 2 : 4;
+        const int nunit = (end - base + unit - 1) / unit;
+        const int ncta = nunit < ctx->num_sms ? nunit : ctx->num_sms;
+        CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end, unit,
                               d_out, out_ms, ctx->dv, gate));
     }
 }
