@@ -494,14 +494,18 @@ k_s2g_quad(const double* __restrict__ in_base, long long in_ms, const XDesc* __r
     const uint32_t taddr = *sTmem + ((uint32_t)(32 * (w & 3)) << 16) + (uint32_t)(C::TCOLS * (w >> 2));
     // P fragments of this warp's tiles: parked in tensor memory for the whole kernel.  (Reading them from L2 inside the tile loop when a
     // CTA has only one or two quads was measured: the 196 KB per CTA take as long there as here — 8-member step 95.3 against 94.0 us.)
+    // Only the k-steps a tile uses are fetched (high wavenumbers have few n: 43 % of the fragments are padding, and the fetch is
+    // what the prologue costs — 148 CTAs pull the table out of L2 at once).
     const double2* pfrag = reinterpret_cast<const double2*>(tv.polyi) + (size_t)w * C::TSLOTS * 4 * 32 + lane;
     {
         double a[8];
 #pragma unroll
         for (int i = 0; i < C::TSLOTS; i++) {
+            const int tw = sTile[w * C::TSLOTS + i], ke = tw < 0 ? 0 : (tw >> 12) & 15, ko = tw < 0 ? 0 : (tw >> 16) & 15;
 #pragma unroll
             for (int fr = 0; fr < 8; fr += 2) {
-                const double2 v = pfrag[(i * 4 + fr / 2) * 32];
+                const bool used = (fr < 4 ? fr : fr - 4) < (fr < 4 ? ke : ko);      // fragments fr, fr + 1 = k-steps of the even (0..3) / odd (4..7) n
+                const double2 v = used ? pfrag[(i * 4 + fr / 2) * 32] : make_double2(0.0, 0.0);
                 a[fr] = v.x; a[fr + 1] = v.y;
             }
             tmem_st16(taddr + 16 * i, a);
