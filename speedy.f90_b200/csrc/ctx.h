@@ -88,6 +88,8 @@ struct speedy_ctx {
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     bool member_ready = true; // main-loop step on the quad transforms: the column tiles of a member start when that member's grid fields are stored (member_ready.cuh); 0: when the whole transform is
+    bool input_is_transient = false;   // set by the main-loop step around its grid->spec launch: the input fields are dead once read (the next step rewrites them)
+    bool l2_discard = true;  // ensemble steps: transient grid fields are dropped from L2 after their only read (discard.global.L2) instead of being written back
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
     int k2_field = 0;        // 1: ensemble batches, 2: every launch incl. the single-member step (one CTA per field)      // grid->spec ensemble batches: whole-field FFT kernel (k_g2s_field) instead of the four wavenumber-group CTAs with the dense operator

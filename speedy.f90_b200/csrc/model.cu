@@ -254,8 +254,10 @@ static void xform_output(speedy_ctx* ctx) {
 }
 static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
+    ctx->input_is_transient = with_daily_qcorh;     // main-loop step: the column kernel's output is read here and nowhere else
     launch_grid_to_spec(ctx, M.mem.p + M.L.gout, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
                         ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
+    ctx->input_is_transient = false;
 }
 static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     Model& M = *ctx->model;
@@ -966,6 +968,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     else if (n == "k2_quad") ctx->k2_quad = value != 0;
     else if (n == "k1_quad") ctx->k1_quad = value != 0;
     else if (n == "member_ready") ctx->member_ready = value != 0;
+    else if (n == "l2_discard") ctx->l2_discard = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

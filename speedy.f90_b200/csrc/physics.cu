@@ -64,6 +64,7 @@ struct ColumnArgs {
     int csw_override;        // -1: take compute_shortwave from the device clock
     int sppt_on;
     unsigned long long* trace;
+    int discard_gin;         // main-loop step: the grid fields are dead once the tile is staged (the next step's transform rewrites them): their L2 lines are dropped, not written back
     const unsigned* ready;   // main-loop step behind the quad transform: per-member completion counts (member_ready.cuh), else nullptr
     unsigned ready_target;
     // [member][row][column] tensor maps: box = rows x 32 columns, one TMA instruction per tile
@@ -149,6 +150,8 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
 #define GOUT(f) gout[(size_t)(f) * N + col]
 #define G2(off) mb[(off) + col]
 #define G3(off, k) mb[(off) + (size_t)((k)-1) * N + col]
+// diagnostics nobody on the device reads again (the reference's module variables for output / inspection): streaming stores, first out of L2
+#define DIAG2(off, v) __stcs(&mb[(off) + col], (v))
 #define TAU2W(k, b, v) do { const double v_ = (v); mb[a.L.tau2 + ((size_t)((b)-1) * KX + ((k)-1)) * N + col] = v_; STAU2(k, b) = v_; } while (0)
 
     // ---- stage the tile: one bulk copy per field row, spread over the threads -------------------
@@ -203,6 +206,15 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         mbar_wait(&bars[0], 0);
 #pragma unroll
         for (int k = 1; k <= KX; k++) phig[k] = SG(GI_PHI + k - 1);
+        if (a.discard_gin) {
+            // an ensemble's transient fields (spec->grid output, read once here) are most of what streams through L2 in a step; left
+            // alone they are written back to HBM when evicted and push the live state out (profiles/r2c_l2_*.csv)
+            if (want_dyn) mbar_wait(&bars[1], 0);
+            const char* g0 = reinterpret_cast<const char*>(mb + a.L.gin + col0);
+            const int nrow = want_dyn ? ngin : ngin - GI_U1, row0 = want_dyn ? 0 : GI_U1;
+            for (int t = lane; t < 2 * nrow; t += 32)      // a tile row = TC doubles = two lines
+                l2_discard_line(g0 + (size_t)(row0 + (t >> 1)) * N * sizeof(double) + (t & 1) * 128);
+        }
         named_sync(BAR_MID, COL_THREADS);      // thermodynamic prep (level warps) and icnv (convection) are in shared memory
 #pragma unroll
         for (int k = 1; k <= KX; k++) { se[k] = SE(k); qsat[k] = QSAT(k); rh[k] = RH(k); qg[k] = QG(k); }
@@ -449,7 +461,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             LWS(2, KX) = LWS(2, KX) - corlw;
             fsfcd = fsfcd + corlw;
             slrd = fsfcd;
-            G2(a.L.slrd) = slrd;
+            DIAG2(a.L.slrd, slrd);
             SC(S_SLRD) = slrd;
             SC(S_FLX1) = flux[1]; SC(S_FLX2) = flux[2]; SC(S_FLX3) = flux[3]; SC(S_FLX4) = flux[4];
         }
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             }
             precls = precls * psg;
         }
-        G2(a.L.precnv) = precnv; G2(a.L.precls) = precls; G2(a.L.cbmf) = cbmf;
+        DIAG2(a.L.precnv, precnv); DIAG2(a.L.precls, precls); DIAG2(a.L.cbmf, cbmf);
         ib[a.L.iptop + col] = iptop;
         STAMP(2);
     }
@@ -613,7 +625,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 clstr = clstr + fm * (clstrl - clstr);
             }
             ib[a.L.icltop + col] = icltop;
-            G2(a.L.qcloud) = qcloud; G2(a.L.cloudc) = cloudc; G2(a.L.clstr) = clstr;
+            DIAG2(a.L.qcloud, qcloud); DIAG2(a.L.cloudc, cloudc); DIAG2(a.L.clstr, clstr);
             SC(S_CLOUDC) = cloudc; SC(S_QCLOUD) = qcloud; SI(I_ICLTOP) = icltop;
         }
         named_sync(BAR_LEV, LEV_THREADS);
@@ -702,7 +714,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 flux1 = flux1 + tau3[kk];
             }
             ftop = ftop - flux1;
-            G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; G2(a.L.ssr) = fsfc; G2(a.L.tsr) = ftop;
+            G2(a.L.ssrd) = fsfcd; SURF(SF_SSRD) = fsfcd; DIAG2(a.L.ssr, fsfc); DIAG2(a.L.tsr, ftop);
 #pragma unroll
             for (int kk = 1; kk <= KX; kk++) { const double v = dfabs[kk] * rps * lc.grdscp[kk - 1]; G3(a.L.tt_rsw, kk) = v; RSW(kk) = v; }   // physics.f90:160-162
             const double eps1 = lc.eps1;
@@ -810,20 +822,20 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             ts = tsea + fmask * (stl_am - tsea);
             tskin = tsea + fmask * (tskin - tsea);
             const double t0 = t1_2 + fmask * (t1_1 - t1_2);
-            mb[a.L.ustr + col] = ustr1; mb[a.L.ustr + N + col] = ustr2; mb[a.L.ustr + 2 * N + col] = ustr3;
-            mb[a.L.vstr + col] = vstr1; mb[a.L.vstr + N + col] = vstr2; mb[a.L.vstr + 2 * N + col] = vstr3;
-            mb[a.L.shf + col] = shf1; mb[a.L.shf + N + col] = shf2; mb[a.L.shf + 2 * N + col] = shf3;
-            mb[a.L.evap + col] = evap1; mb[a.L.evap + N + col] = evap2; mb[a.L.evap + 2 * N + col] = evap3;
-            mb[a.L.slru + col] = slru1; mb[a.L.slru + N + col] = slru2; mb[a.L.slru + 2 * N + col] = slru3;
+            DIAG2(a.L.ustr, ustr1); DIAG2(a.L.ustr + N, ustr2); DIAG2(a.L.ustr + 2 * N, ustr3);
+            DIAG2(a.L.vstr, vstr1); DIAG2(a.L.vstr + N, vstr2); DIAG2(a.L.vstr + 2 * N, vstr3);
+            DIAG2(a.L.shf, shf1); mb[a.L.shf + N + col] = shf2; DIAG2(a.L.shf + 2 * N, shf3);        // (:,2) of shf / evap: read by the sea model of the next step
+            DIAG2(a.L.evap, evap1); mb[a.L.evap + N + col] = evap2; DIAG2(a.L.evap + 2 * N, evap3);
+            DIAG2(a.L.slru, slru1); DIAG2(a.L.slru + N, slru2); DIAG2(a.L.slru + 2 * N, slru3);
             mb[a.L.hfluxn + col] = hfluxn1; mb[a.L.hfluxn + N + col] = hfluxn2;
-            G2(a.L.ts) = ts; G2(a.L.tskin) = tskin; G2(a.L.u0) = u0; G2(a.L.v0) = v0; G2(a.L.t0) = t0;
+            DIAG2(a.L.ts, ts); DIAG2(a.L.tskin, tskin); DIAG2(a.L.u0, u0); DIAG2(a.L.v0, v0); DIAG2(a.L.t0, t0);
         }
         STAMP(5);
         // ------------------- upward longwave  longwave_radiation.f90:120-194 -------------------
         {
             const double refsfc = 1.0 - emisfc;
             const double fsfcu = slru3;
-            G2(a.L.slr) = fsfcu - slrd;
+            DIAG2(a.L.slr, fsfcu - slrd);
             const int nts = band_row(ts);
             for (int jb = 1; jb <= 4; jb++) flux[jb] = sFband[nts + 301 * (jb - 1)] * fsfcu + refsfc * flux[jb];
             LWS(2, KX) = LWS(2, KX) + epslw * fsfcu;
@@ -871,7 +883,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             tt_rlw[2] = tt_rlw[2] - corlw2;
             double ftop = corlw1 + corlw2;
             for (int jb = 1; jb <= 4; jb++) ftop = ftop + flux[jb];
-            G2(a.L.olr) = ftop;
+            DIAG2(a.L.olr, ftop);
 #pragma unroll
             for (int k = 1; k <= KX; k++) tt_rlw[k] = tt_rlw[k] * rps * lc.grdscp[k - 1];   // physics.f90:182-186, added in the closing stage
         }
@@ -1185,6 +1197,7 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
     a.ready = M.ready_target ? M.ready.p : nullptr; a.ready_target = M.ready_target;
+    a.discard_gin = merged && ctx->l2_discard && mode == 0 && (long long)(ctx->d.ngrid() / TC) * ctx->nmembers > ctx->num_sms;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on; a.trace = ctx->dv.trace;
     {
         const ColMaps& cm = column_maps(ctx);

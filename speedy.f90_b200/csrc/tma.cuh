@@ -92,6 +92,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // ---- in-graph timeline (debug aid, speedy_trace): per kernel slot the earliest CTA start and the latest
 // CTA end on the GPU's global nanosecond timer.  trace == nullptr in production launches.
 __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// The 128-byte line at p (aligned) holds data nobody will read again before it is rewritten: L2 may drop it without writing it back.
+__device__ __forceinline__ void l2_discard_line(const void* p) { asm volatile("discard.global.L2 [%0], 128;" :: "l"(p) : "memory"); }
+
 __device__ __forceinline__ void trace_begin(unsigned long long* trace, int slot) { if (trace) atomicMin(&trace[slot], gtimer()); }
 __device__ __forceinline__ void trace_end(unsigned long long* trace, int slot) { if (trace) atomicMax(&trace[4 + slot], gtimer()); }
 

@@ -133,7 +133,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, double* v) {           
 
 __global__ void __launch_bounds__(QCfg::THREADS, 1)
 k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end, int unit,
-           double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate) {
+           double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate, const double* __restrict__ dead_in, long long in_ms) {
     using C = QCfg;
     extern __shared__ __align__(1024) double smem[];
     double* sRing = smem;                               // [NG][RING][BAND]
@@ -248,6 +248,13 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
 #define FSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 0) { const long long t_ = clock64(); tv.trace[1344 + (i)] += (unsigned long long)(t_ - tf); tf = t_; } } while (0)
             if (tv.trace) tf = clock64();
             mbar_wait(&gbar[seq % C::NBAR], (seq / C::NBAR) & 1);
+            if (dead_in && t128 < 96) {
+                // the band is in shared memory and nobody reads its source again (main-loop step): drop the 2 x 8 rows x 6 lines from L2
+                // instead of letting them be written back to HBM on eviction
+                const int hem = t128 / 48, r = (t128 - 48 * hem) / 6, l = t128 % 6;
+                const int row = sRow0[t] + (hem ? C::IL - 8 - 8 * b : 8 * b) + r;
+                l2_discard_line(reinterpret_cast<const char*>(dead_in + (size_t)sE[t] * in_ms + (size_t)row * C::IX) + l * 128);
+            }
             FSTAMP(0);
             // ---- fold of the two hemispheres (legendre.f90:127-133, taken before the linear FFT; its Gaussian weight is in the P
             // fragments) with the cosgr / cosgr2 pre-scale of vdspec (spectral.f90:208-222)
@@ -777,7 +784,7 @@ void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
         const int nunit = (end - base + unit - 1) / unit;
         const int ncta = nunit < ctx->num_sms ? nunit : ctx->num_sms;
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end, unit,
-                              d_out, out_ms, ctx->dv, gate));
+                              d_out, out_ms, ctx->dv, gate, (ctx->input_is_transient && ctx->l2_discard) ? d_in : (const double*)nullptr, in_ms));
     }
 }
 
