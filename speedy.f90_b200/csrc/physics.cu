@@ -202,10 +202,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
     }
 
     if (warp == W_VDIF) {
-        double se[KX + 1], rh[KX + 1], qsat[KX + 1], qg[KX + 1], phig[KX + 1];
         mbar_wait(&bars[0], 0);
-#pragma unroll
-        for (int k = 1; k <= KX; k++) phig[k] = SG(GI_PHI + k - 1);
         if (a.discard_gin) {
             // an ensemble's transient fields (spec->grid output, read once here) are most of what streams through L2 in a step; left
             // alone they are written back to HBM when evicted and push the live state out (profiles/r2c_l2_*.csv)
@@ -216,8 +213,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 l2_discard_line(g0 + (size_t)(row0 + (t >> 1)) * N * sizeof(double) + (t & 1) * 128);
         }
         named_sync(BAR_MID, COL_THREADS);      // thermodynamic prep (level warps) and icnv (convection) are in shared memory
-#pragma unroll
-        for (int k = 1; k <= KX; k++) { se[k] = SE(k); qsat[k] = QSAT(k); rh[k] = RH(k); qg[k] = QG(k); }
+        // the column's rows are read in place (shared memory): private copies of five 8-level arrays do not fit the 96 registers of the batch kernel
         // ------------------- vertical_diffusion.f90:30-143 -------------------
         {
             const double trshc = 6.0, trvdi = 24.0, trvds = 6.0, redshc = 0.5, rhgrad = 0.5, segrad = F32(0.1);
@@ -235,8 +231,8 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             double drh0 = rhgrad * (lc.fsg[KX - 1] - lc.fsg[nl1 - 1]);
             double fvdiq2 = fvdiq * lc.sigh[nl1];
             {
-                const double dmse = se[KX] - se[nl1] + lc.alhc * (qg[KX] - qsat[nl1]);
-                const double drh = rh[KX] - rh[nl1];
+                const double dmse = SE(KX) - SE(nl1) + lc.alhc * (QG(KX) - QSAT(nl1));
+                const double drh = RH(KX) - RH(nl1);
                 double fcnv = 1.0;
                 if (dmse >= 0.0) {
                     if (SI(I_ICNV) > 0) fcnv = redshc;
@@ -244,33 +240,36 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                     ttenvd[nl1] = fluxse * rsig[nl1];
                     ttenvd[KX] = -fluxse * rsig[KX];
                     if (drh >= 0.0) {
-                        const double fluxq = fcnv * fshcq * qsat[KX] * drh;
+                        const double fluxq = fcnv * fshcq * QSAT(KX) * drh;
                         qtenvd[nl1] = fluxq * rsig[nl1];
                         qtenvd[KX] = -fluxq * rsig[KX];
                     }
                 } else if (drh > drh0) {
-                    const double fluxq = fvdiq2 * qsat[nl1] * drh;
+                    const double fluxq = fvdiq2 * QSAT(nl1) * drh;
                     qtenvd[nl1] = fluxq * rsig[nl1];
                     qtenvd[KX] = -fluxq * rsig[KX];
                 }
             }
+#pragma unroll
             for (int k = 3; k <= KX - 2; k++) {
                 if (lc.sigh[k] > 0.5) {
                     drh0 = rhgrad * (lc.fsg[k] - lc.fsg[k - 1]);
                     fvdiq2 = fvdiq * lc.sigh[k];
-                    const double drh = rh[k + 1] - rh[k];
+                    const double drh = RH(k + 1) - RH(k);
                     if (drh >= drh0) {
-                        const double fluxq = fvdiq2 * qsat[k] * drh;
+                        const double fluxq = fvdiq2 * QSAT(k) * drh;
                         qtenvd[k] = qtenvd[k] + fluxq * rsig[k];
                         qtenvd[k + 1] = qtenvd[k + 1] - fluxq * rsig[k + 1];
                     }
                 }
             }
-            for (int k = 1; k <= nl1; k++) {
-                const double se0 = se[k + 1] + segrad * (phig[k] - phig[k + 1]);
-                if (se[k] < se0) {
-                    const double fluxse = fvdise * (se0 - se[k]);
+#pragma unroll
+            for (int k = 1; k <= nl1; k++) {               // unrolled: static indices keep the column's arrays in registers
+                const double se0 = SE(k + 1) + segrad * (SG(GI_PHI + (k) - 1) - SG(GI_PHI + (k + 1) - 1));
+                if (SE(k) < se0) {
+                    const double fluxse = fvdise * (se0 - SE(k));
                     ttenvd[k] = ttenvd[k] + fluxse * rsig[k];
+#pragma unroll
                     for (int k1 = k + 1; k1 <= KX; k1++) ttenvd[k1] = ttenvd[k1] - fluxse * rsig1[k];
                 }
             }
@@ -474,102 +473,92 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
     // ---------------- phase B (level warp 1): convection.f90:27-245 + the LSC reductions ----------------
     int iptop = 0, icltop = 0;
     double cloudc = 0.0, clstr = 0.0, qcloud = 0.0, precnv = 0.0, precls = 0.0;
-    double se[KX + 1], qg[KX + 1], qsat[KX + 1], rh[KX + 1], tg[KX + 1], phig[KX + 1];
-    const double wvi2[KX + 1] = {0, lc.wvi[8], lc.wvi[9], lc.wvi[10], lc.wvi[11], lc.wvi[12], lc.wvi[13], lc.wvi[14], lc.wvi[15]};
+    // the sweeps index their columns with run-time levels: they read the shared rows in place (private copies would be local-memory
+    // arrays, and local memory is written through to L2: 41 MB per launch of an 8-member step before this, profiles/r2_prof_m8)
     if (k == 1) {
-#pragma unroll
-        for (int kk = 1; kk <= KX; kk++) {
-            se[kk] = SE(kk); qg[kk] = QG(kk); qsat[kk] = QSAT(kk); rh[kk] = RH(kk); tg[kk] = SG(GI_T1 + kk - 1); phig[kk] = SG(GI_PHI + kk - 1);
-        }
         double cbmf = 0.0;
         {
             const double psmin = F32(0.8), trcnv = 6.0, rhbl = F32(0.9), rhil = F32(0.7), entmax = 0.5, smf = F32(0.8);
             const int nl1 = KX - 1, nlp = KX + 1;
-            double dfse[KX + 1], dfqa[KX + 1];
 #pragma unroll
-            for (int k = 1; k <= KX; k++) { dfse[k] = 0.0; dfqa[k] = 0.0; }
+            for (int k = 1; k <= KX; k++) { DFSE(k) = 0.0; DFQA(k) = 0.0; }
             // diagnose_convection :170-245
             int itop = nlp;
             double qdif = 0.0;
             if (psg > psmin) {
-                const double mse0 = se[KX] + lc.alhc * qg[KX];
-                double mse1 = se[nl1] + lc.alhc * qg[nl1];
+                const double mse0 = SE(KX) + lc.alhc * QG(KX);
+                double mse1 = SE(nl1) + lc.alhc * QG(nl1);
                 mse1 = dmin(mse0, mse1);
-                const double mss0 = dmax(mse0, se[KX] + lc.alhc * qsat[KX]);
+                const double mss0 = dmax(mse0, SE(KX) + lc.alhc * QSAT(KX));
                 int ktop1 = KX, ktop2 = KX;
                 double msthr = 0.0;
                 for (int k = KX - 3; k >= 3; k--) {
-                    const double mssk = se[k] + lc.alhc * qsat[k], mssk1 = se[k + 1] + lc.alhc * qsat[k + 1];
-                    const double mss2 = mssk + wvi2[k] * (mssk1 - mssk);
+                    const double mssk = SE(k) + lc.alhc * QSAT(k), mssk1 = SE(k + 1) + lc.alhc * QSAT(k + 1);
+                    const double mss2 = mssk + lc.wvi[(k) + 7] * (mssk1 - mssk);
                     if (mss0 > mss2) ktop1 = k;
                     if (mse1 > mss2) { ktop2 = k; msthr = mss2; }
                 }
                 if (ktop1 < KX) {
-                    const double qthr0 = rhbl * qsat[KX], qthr1 = rhbl * qsat[nl1];
-                    const bool lqthr = (qg[KX] > qthr0 && qg[nl1] > qthr1);
+                    const double qthr0 = rhbl * QSAT(KX), qthr1 = rhbl * QSAT(nl1);
+                    const bool lqthr = (QG(KX) > qthr0 && QG(nl1) > qthr1);
                     if (ktop2 < KX) {
                         itop = ktop1;
-                        qdif = dmax(qg[KX] - qthr0, (mse0 - msthr) * lc.ralhc);
+                        qdif = dmax(QG(KX) - qthr0, (mse0 - msthr) * lc.ralhc);
                     } else if (lqthr) {
                         itop = ktop1;
-                        qdif = qg[KX] - qthr0;
+                        qdif = QG(KX) - qthr0;
                     }
                 }
             }
             if (itop != nlp) {
                 const double fqmax = 5.0;
                 const double fm0 = lc.fm0, rdps = lc.rdps;          // p0*dhs(kx)/(grav*trcnv*3600), 2/(1-psmin): host-evaluated
-                double entr[KX + 1];
-#pragma unroll
-                for (int k = 2; k <= nl1; k++) entr[k] = lc.entr[k - 1]; // convection.f90:118-131, host-evaluated
                 int k = KX, k1 = k - 1;
-                const double qmax = dmax(F32(1.01) * qg[k], qsat[k]);
-                double sb = se[k1] + wvi2[k1] * (se[k] - se[k1]);
-                double qb = qg[k1] + wvi2[k1] * (qg[k] - qg[k1]);
-                qb = dmin(qb, qg[k]);
+                const double qmax = dmax(F32(1.01) * QG(k), QSAT(k));
+                double sb = SE(k1) + lc.wvi[(k1) + 7] * (SE(k) - SE(k1));
+                double qb = QG(k1) + lc.wvi[(k1) + 7] * (QG(k) - QG(k1));
+                qb = dmin(qb, QG(k));
                 const double fpsa = psg * dmin(1.0, (psg - psmin) * rdps);
                 double fmass = fm0 * fpsa * dmin(fqmax, qdif / (qmax - qb));
                 cbmf = fmass;
-                double fus = fmass * se[k], fuq = fmass * qmax;
+                double fus = fmass * SE(k), fuq = fmass * qmax;
                 double fds = fmass * sb, fdq = fmass * qb;
-                dfse[k] = fds - fus;
-                dfqa[k] = fdq - fuq;
+                DFSE(k) = fds - fus;
+                DFQA(k) = fdq - fuq;
                 for (k = KX - 1; k >= itop + 1; k--) {
                     k1 = k - 1;
-                    dfse[k] = fus - fds;
-                    dfqa[k] = fuq - fdq;
-                    const double enmass = entr[k] * psg * cbmf;
+                    DFSE(k) = fus - fds;
+                    DFQA(k) = fuq - fdq;
+                    const double enmass = lc.entr[k - 1] * psg * cbmf;     // convection.f90:118-131, host-evaluated
                     fmass = fmass + enmass;
-                    fus = fus + enmass * se[k];
-                    fuq = fuq + enmass * qg[k];
-                    sb = se[k1] + wvi2[k1] * (se[k] - se[k1]);
-                    qb = qg[k1] + wvi2[k1] * (qg[k] - qg[k1]);
+                    fus = fus + enmass * SE(k);
+                    fuq = fuq + enmass * QG(k);
+                    sb = SE(k1) + lc.wvi[(k1) + 7] * (SE(k) - SE(k1));
+                    qb = QG(k1) + lc.wvi[(k1) + 7] * (QG(k) - QG(k1));
                     fds = fmass * sb;
                     fdq = fmass * qb;
-                    dfse[k] = dfse[k] + fds - fus;
-                    dfqa[k] = dfqa[k] + fdq - fuq;
-                    const double delq = rhil * qsat[k] - qg[k];
+                    DFSE(k) = DFSE(k) + fds - fus;
+                    DFQA(k) = DFQA(k) + fdq - fuq;
+                    const double delq = rhil * QSAT(k) - QG(k);
                     if (delq > 0.0) {
                         const double fsq = smf * cbmf * delq;
-                        dfqa[k] = dfqa[k] + fsq;
-                        dfqa[KX] = dfqa[KX] - fsq;
+                        DFQA(k) = DFQA(k) + fsq;
+                        DFQA(KX) = DFQA(KX) - fsq;
                     }
                 }
                 k = itop;
-                const double qsatb = qsat[k] + wvi2[k] * (qsat[k + 1] - qsat[k]);
+                const double qsatb = QSAT(k) + lc.wvi[(k) + 7] * (QSAT(k + 1) - QSAT(k));
                 precnv = dmax(fuq - fmass * qsatb, 0.0);
-                dfse[k] = fus - fds + lc.alhc * precnv;
-                dfqa[k] = fuq - fdq - precnv;
+                DFSE(k) = fus - fds + lc.alhc * precnv;
+                DFQA(k) = fuq - fdq - precnv;
             }
             iptop = itop;
             // physics.f90:127-138 (level 1 is not rescaled)
 #pragma unroll
             for (int k = 2; k <= KX; k++) {
-                dfse[k] = dfse[k] * rps * lc.grdscp[k - 1];
-                dfqa[k] = dfqa[k] * rps * lc.grdsig[k - 1];
+                DFSE(k) = DFSE(k) * rps * lc.grdscp[k - 1];
+                DFQA(k) = DFQA(k) * rps * lc.grdsig[k - 1];
             }
-#pragma unroll
-            for (int k = 1; k <= KX; k++) { DFSE(k) = dfse[k]; DFQA(k) = dfqa[k]; }
         }
         const int icnv_ = KX - iptop;   // physics.f90:132, before LSC lowers iptop
         ib[a.L.icnv + col] = icnv_;
@@ -601,13 +590,13 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             // clouds  shortwave_radiation.f90:332-410
             const double rhcl1 = F32(0.30), rhcl2 = 1.00, qacl = F32(0.20), wpcl = F32(0.2), pmaxcl = 10.0;
             const double clsmax = F32(0.60), clsminl = F32(0.15), gse_s0 = 0.25, gse_s1 = F32(0.40);
-            const double gse = (se[KX - 1] - se[KX]) / (phig[KX - 1] - phig[KX]);   // physics.f90:147
+            const double gse = (SE(KX - 1) - SE(KX)) / (SG(GI_PHI + (KX - 1) - 1) - SG(GI_PHI + (KX) - 1));   // physics.f90:147
             const double rrcl = 1. / (rhcl2 - rhcl1);
-            if (rh[nl1] > rhcl1) { cloudc = rh[nl1] - rhcl1; icltop = nl1; }
+            if (RH(nl1) > rhcl1) { cloudc = RH(nl1) - rhcl1; icltop = nl1; }
             else { cloudc = 0.0; icltop = nlp; }
             for (int kk = 3; kk <= KX - 2; kk++) {
-                const double drh = rh[kk] - rhcl1;
-                if (drh > cloudc && qg[kk] > qacl) { cloudc = drh; icltop = kk; }
+                const double drh = RH(kk) - rhcl1;
+                if (drh > cloudc && QG(kk) > qacl) { cloudc = drh; icltop = kk; }
             }
             {
                 const double pr1 = dmin(pmaxcl, F32(86.4) * (precnv + precls));
@@ -615,12 +604,12 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 cloudc = dmin(1.0, wpcl * sqrt(pr1) + cc * cc);
                 icltop = min(iptop, icltop);
             }
-            qcloud = qg[nl1];
+            qcloud = QG(nl1);
             {
                 const double clfact = F32(1.2), rgse = 1.0 / (gse_s1 - gse_s0);
                 const double fstab = dmax(0.0, dmin(1.0, rgse * (gse - gse_s0)));
                 clstr = fstab * dmax(clsmax - clfact * cloudc, 0.0);
-                const double clstrl = dmax(clstr, clsminl) * rh[KX];
+                const double clstrl = dmax(clstr, clsminl) * RH(KX);
                 const double fm = SURF(SF_FMASK);
                 clstr = clstr + fm * (clstrl - clstr);
             }
@@ -681,8 +670,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             const double fband2 = F32(0.05), fband1 = 1.0 - fband2;
             double tau1[KX + 1], tau2_[KX + 1], tau3[KX + 1], dfabs[KX + 1];
 #pragma unroll
-            for (int kk = 1; kk <= KX; kk++) { tau1[kk] = TAU1(kk); tau2_[kk] = TAU2S(kk); tau3[kk] = 0.0; }
-            if (icltop <= KX) tau3[icltop] = albcl * cloudc;
+            for (int kk = 1; kk <= KX; kk++) { tau1[kk] = TAU1(kk); tau2_[kk] = TAU2S(kk); tau3[kk] = (kk == icltop) ? albcl * cloudc : 0.0; }   // static indices: registers
             tau3[KX] = albcls * clstr;
             double ftop = fsol;
             double flux1 = fsol * fband1, flux2 = fsol * fband2;
@@ -692,6 +680,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             dfabs[2] = flux1;
             flux1 = tau1[2] * (flux1 - ozone * psg);
             dfabs[2] = dfabs[2] - flux1;
+#pragma unroll
             for (int kk = 3; kk <= KX; kk++) {
                 tau3[kk] = flux1 * tau3[kk];
                 flux1 = flux1 - tau3[kk];
@@ -699,6 +688,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 flux1 = tau1[kk] * flux1;
                 dfabs[kk] = dfabs[kk] - flux1;
             }
+#pragma unroll
             for (int kk = 2; kk <= KX; kk++) {
                 dfabs[kk] = dfabs[kk] + flux2;
                 flux2 = tau2_[kk] * flux2;
@@ -707,6 +697,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             const double fsfcd = flux1 + flux2;
             flux1 = flux1 * albsfc;
             const double fsfc = fsfcd - flux1;
+#pragma unroll
             for (int kk = KX; kk >= 1; kk--) {
                 dfabs[kk] = dfabs[kk] + flux1;
                 flux1 = tau1[kk] * flux1;
@@ -791,7 +782,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             const double ustr1 = -cdldv * ug8, vstr1 = -cdldv * vg8;
             const double chlcp = chl * lc.cp;
             double shf1 = chlcp * denvvs1 * (tskin - t1_1);
-            const double q1_1 = qg[KX];
+            const double q1_1 = QG(KX);
             const double qsat0_1 = qsat_pt(tskin, psg);
             double evap1 = chl * denvvs1 * dmax(0.0, soilw_am * qsat0_1 - q1_1);
             const double tsk3 = (tskin * tskin) * tskin;
@@ -862,7 +853,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
                 flux[1] = f1; flux[2] = f2; flux[3] = f3; flux[4] = f4;
             }
             {
-                const int nt1 = band_row(tg[1]);
+                const int nt1 = band_row(SG(GI_T1 + (1) - 1));
                 double t = LWS(2, 1);
                 for (int jb = 1; jb <= 2; jb++) {
                     const double tau = STAU2(1, jb);
