@@ -88,6 +88,10 @@ struct speedy_ctx {
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     bool member_ready = true; // main-loop step on the quad transforms: the column tiles of a member start when that member's grid fields are stored (member_ready.cuh); 0: when the whole transform is
+    bool transient_alias = true;       // ensemble main-loop step on the quad transforms: one buffer per member carries the step's transient fields — the column
+                                       // kernel writes its grid tendencies over the grid fields it has staged, grid->spec writes each field's coefficients over
+                                       // that field's own grid rows — so a step allocates a third of the L2 lines ("one transient buffer")
+    long long g2s_out_field_stride = 0; // set by the main-loop step around its grid->spec launch: doubles between consecutive output fields (0: packed, 2*nspec)
     bool input_is_transient = false;   // set by the main-loop step around its grid->spec launch: the input fields are dead once read (the next step rewrites them)
     bool l2_discard = true;  // ensemble steps: transient grid fields are dropped from L2 after their only read (discard.global.L2) instead of being written back
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
@@ -135,7 +139,8 @@ void setup_column_kernels();       // physics.cu
 void setup_spec_step_kernels();    // dynamics.cu
 // transforms_quad.cu (T30 ensemble batches)
 void setup_quad_kernels();
-bool s2g_quad_selected(const speedy_ctx* ctx, int nbatch, int nmembers, bool quad_ok);   // transforms.cu: would this spec->grid launch take the quad kernel
+bool s2g_quad_selected(const speedy_ctx* ctx, int nbatch, int nmembers, bool quad_ok);
+bool g2s_quad_selected(speedy_ctx* ctx, int nbatch, int nmembers);                       // transforms.cu: would this grid->spec launch take the quad kernel   // transforms.cu: would this spec->grid launch take the quad kernel
 unsigned s2g_quad_ready_counts(int nbatch);                                             // member_ready.cuh: counts per member of one launch
 void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyq);
 void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyi);

@@ -29,6 +29,7 @@ struct SpecArgs {
     double dt;
     int flag;
     double* partial;
+    long long sout_off, sout_fs;   // the grid->spec output of the step: offset in the member block and doubles between fields (packed, or in place over the grid rows)
     unsigned* ready_reset;   // main-loop step: the per-member completion counts of this step's spec->grid kernel, zeroed here for the next step
 };
 
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
 #define SSTAMP(i) do { if (tv.trace && tid == 0 && blockIdx.x == 5 && blockIdx.y == 0) tv.trace[56 + (i)] += gtimer() - tk0; } while (0)
     const cd tcorh = ld(mb + a.L.tcorh, mx, m, n);
     const cd qcorh_old = ld(mb + a.L.qcorh, mx, m, n);
-    const cd qcorh_new = (a.flag & 2) ? ld(sfield(mb, a.L.sout, nsp, GO_QCORH), mx, m, n) : zero;
+    const cd qcorh_new = (a.flag & 2) ? ld((mb + a.sout_off + (size_t)(GO_QCORH) * a.sout_fs), mx, m, n) : zero;
     const int do_forcing = (a.flag & 2) ? a.clk->do_forcing : 0;
-    const cd psdt_in = ld(sfield(mb, a.L.sout, nsp, GO_PSDT), mx, m, n);
+    const cd psdt_in = ld((mb + a.sout_off + (size_t)(GO_PSDT) * a.sout_fs), mx, m, n);
     const cd phis_q = ld(mb + a.L.phis, mx, m, n);
     // time level j1 of the prognostics for the filter (time_stepping.f90:163-166); j1 == 1 re-uses level 1
     cd vorj = zero, divj = zero, tj = zero, trj = zero, psj = zero;
@@ -142,15 +143,15 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
         // value is not used) ahead of the n-dependent branches: one round trip instead of one per call
         const int nm = n > 0 ? n - 1 : 0, np = n < nx - 1 ? n + 1 : nx - 1;
         const double gx = tv.gradx[m], dym = tv.vddym[q], dyp = tv.vddyp[q];
-        const double* F0 = sfield(mb, a.L.sout, nsp, f + 0); const double* F1 = sfield(mb, a.L.sout, nsp, f + 1);
-        const double* F4 = sfield(mb, a.L.sout, nsp, f + 4); const double* F7 = sfield(mb, a.L.sout, nsp, f + 7);
+        const double* F0 = (mb + a.sout_off + (size_t)(f + 0) * a.sout_fs); const double* F1 = (mb + a.sout_off + (size_t)(f + 1) * a.sout_fs);
+        const double* F4 = (mb + a.sout_off + (size_t)(f + 4) * a.sout_fs); const double* F7 = (mb + a.sout_off + (size_t)(f + 7) * a.sout_fs);
         const cd um = ld(F0, mx, m, nm), u0 = ld(F0, mx, m, n), up = ld(F0, mx, m, np);
         const cd vm = ld(F1, mx, m, nm), v0 = ld(F1, mx, m, n), vp = ld(F1, mx, m, np);
-        const cd ke = ld(sfield(mb, a.L.sout, nsp, f + 2), mx, m, n);
-        const cd ut0 = ld(sfield(mb, a.L.sout, nsp, f + 3), mx, m, n), vtm = ld(F4, mx, m, nm), vtp = ld(F4, mx, m, np);
-        const cd tt = ld(sfield(mb, a.L.sout, nsp, f + 5), mx, m, n);
-        const cd uq0 = ld(sfield(mb, a.L.sout, nsp, f + 6), mx, m, n), vqm = ld(F7, mx, m, nm), vqp = ld(F7, mx, m, np);
-        const cd qt = ld(sfield(mb, a.L.sout, nsp, f + 8), mx, m, n);
+        const cd ke = ld((mb + a.sout_off + (size_t)(f + 2) * a.sout_fs), mx, m, n);
+        const cd ut0 = ld((mb + a.sout_off + (size_t)(f + 3) * a.sout_fs), mx, m, n), vtm = ld(F4, mx, m, nm), vtp = ld(F4, mx, m, np);
+        const cd tt = ld((mb + a.sout_off + (size_t)(f + 5) * a.sout_fs), mx, m, n);
+        const cd uq0 = ld((mb + a.sout_off + (size_t)(f + 6) * a.sout_fs), mx, m, n), vqm = ld(F7, mx, m, nm), vqp = ld(F7, mx, m, np);
+        const cd qt = ld((mb + a.sout_off + (size_t)(f + 8) * a.sout_fs), mx, m, n);
         cd vo, di;
         dev_vds_r(nx, n, gx, dym, dyp, um, u0, up, vm, v0, vp, vo, di);
         vordt = vo;
@@ -482,6 +483,7 @@ static SpecArgs spec_args(speedy_ctx* ctx) {
     SpecArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv; a.lc = M.lc.p; a.clk = M.clock.p;
     a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p; a.ready_reset = nullptr;
+    a.sout_off = M.L.sout; a.sout_fs = 2LL * ctx->d.nspec();
     return a;
 }
 
@@ -499,6 +501,7 @@ void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend
     SpecArgs a = spec_args(ctx);
     a.j1 = j1; a.j2 = j2; a.dt = dt; a.flag = (store_tend_only ? 1 : 0) | (close_step ? 2 : 0);
     if (close_step && M.ready_target) a.ready_reset = M.ready.p;
+    if (close_step && M.alias_active) { a.sout_off = M.L.gin; a.sout_fs = ctx->d.ngrid(); }
     dim3 grid((ctx->d.nspec() + SC - 1) / SC, ctx->nmembers);
     const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
     if (M.diag_partial.n < need) { M.diag_partial.alloc(need); a.partial = M.diag_partial.p; }

@@ -255,9 +255,12 @@ static void xform_output(speedy_ctx* ctx) {
 static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
     ctx->input_is_transient = with_daily_qcorh;     // main-loop step: the column kernel's output is read here and nowhere else
-    launch_grid_to_spec(ctx, M.mem.p + M.L.gout, M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH, M.mem.p + M.L.sout, M.L.stride,
-                        ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
+    const bool alias = with_daily_qcorh && M.alias_active;
+    ctx->g2s_out_field_stride = alias ? ctx->d.ngrid() : 0;
+    launch_grid_to_spec(ctx, M.mem.p + (alias ? M.L.gin : M.L.gout), M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH,
+                        M.mem.p + (alias ? M.L.gin : M.L.sout), M.L.stride, ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
     ctx->input_is_transient = false;
+    ctx->g2s_out_field_stride = 0;
 }
 static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     Model& M = *ctx->model;
@@ -289,11 +292,14 @@ static void enqueue_main_loop_step(speedy_ctx* ctx) {
     // with the stand-alone kernel
     const bool tracing = ctx->dv.trace != nullptr || ctx->precision != 0;
     if (ctx->sppt_on) launch_sppt_update(ctx);
+    ctx->model->alias_active = ctx->transient_alias && ctx->l2_discard && g2s_quad_selected(ctx, GO_N, ctx->nmembers) &&
+                               s2g_quad_selected(ctx, ctx->model->nstep_fields, ctx->nmembers, true);
     xform_step(ctx, 2, !tracing);
     launch_grid_columns(ctx, 0, -1, 1);
     xform_direct(ctx, true);
     launch_spec_step(ctx, 2, 2, 2 * delt, 0, 1);
     ctx->model->ready_target = 0;
+    ctx->model->alias_active = false;
     if (tracing) launch_close_step(ctx);
 }
 // the coupler call of the last step (speedy.f90:53) when no further step follows in this call
@@ -969,6 +975,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     else if (n == "k1_quad") ctx->k1_quad = value != 0;
     else if (n == "member_ready") ctx->member_ready = value != 0;
     else if (n == "l2_discard") ctx->l2_discard = value != 0;
+    else if (n == "transient_alias") ctx->transient_alias = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

@@ -82,6 +82,7 @@ struct Model {
     DevBuf<LevelConsts> lc;
     DevBuf<float> outbuf;          // output() staging (input_output.f90:201-206)
     DevBuf<unsigned> ready;        // [member] completion counts of the step's spec->grid kernel (member_ready.cuh)
+    bool alias_active = false;     // while a main-loop step is being enqueued: gout and sout live in the gin rows (speedy_ctx::transient_alias)
     unsigned ready_target = 0;     // while a main-loop step is being enqueued: the count at which a member's grid fields are complete; 0: hand-off by kernel boundary
     DevBuf<double> diag_partial;   // [member][block][kx][2] + [member][kx] partial sums of check_diagnostics
     DevBuf<XDesc> desc_step;       // compact per-step list (two time levels): the fields the column kernel actually reads

@@ -64,6 +64,7 @@ struct ColumnArgs {
     int csw_override;        // -1: take compute_shortwave from the device clock
     int sppt_on;
     unsigned long long* trace;
+    int discard_row0;        // first grid-field row to drop (the rows below it are overwritten by this kernel's own output when the transient buffer is shared)
     int discard_gin;         // main-loop step: the grid fields are dead once the tile is staged (the next step's transform rewrites them): their L2 lines are dropped, not written back
     const unsigned* ready;   // main-loop step behind the quad transform: per-member completion counts (member_ready.cuh), else nullptr
     unsigned ready_target;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             // alone they are written back to HBM when evicted and push the live state out (profiles/r2c_l2_*.csv)
             if (want_dyn) mbar_wait(&bars[1], 0);
             const char* g0 = reinterpret_cast<const char*>(mb + a.L.gin + col0);
-            const int nrow = want_dyn ? ngin : ngin - GI_U1, row0 = want_dyn ? 0 : GI_U1;
+            const int rfirst = want_dyn ? 0 : GI_U1, row0 = rfirst > a.discard_row0 ? rfirst : a.discard_row0, nrow = ngin - row0;
             for (int t = lane; t < 2 * nrow; t += 32)      // a tile row = TC doubles = two lines
                 l2_discard_line(g0 + (size_t)(row0 + (t >> 1)) * N * sizeof(double) + (t & 1) * 128);
         }
@@ -1188,6 +1189,12 @@ void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged
     a.base = M.mem.p; a.stride = M.L.stride; a.ibase = M.imem.p; a.L = M.L; a.lc = M.lc.p; a.clk = M.clock.p;
     a.fband = ctx->dv.fband; a.coriol = ctx->dv.coriol; a.coa = ctx->dv.coa;
     a.ready = M.ready_target ? M.ready.p : nullptr; a.ready_target = M.ready_target;
+    a.discard_row0 = 0;
+    if (merged && mode == 0 && M.alias_active) {      // the K2 inputs go over the grid fields this tile has staged (rows 0..GO_N-1 of the same columns)
+        a.L.gout = M.L.gin;
+        a.L.qcorh_g = M.L.gin + (long long)GO_QCORH * ctx->d.ngrid();
+        a.discard_row0 = GO_N;
+    }
     a.discard_gin = merged && ctx->l2_discard && mode == 0 && (long long)(ctx->d.ngrid() / TC) * ctx->nmembers > ctx->num_sms;
     a.ix = ctx->d.ix; a.il = ctx->d.il; a.mode = mode; a.csw_override = csw_override; a.sppt_on = ctx->sppt_on; a.trace = ctx->dv.trace;
     {

@@ -998,15 +998,28 @@ static const CUtensorMap& grid_field_map(const double* d_in, long long in_ms, in
     return cache.emplace(key, m).first->second;
 }
 
+// field chunks per member of the streaming grid->spec kernel (three or more fields per chunk: its batch variant, and the quad kernel at T30)
 template <int TRUNC>
-static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                              double* d_out, long long out_ms, int nmembers, const int* gate) {
+static int g2s_chunks(speedy_ctx* ctx, int nbatch, int nmembers) {
     using C = SCfg<TRUNC>;
     int &occ = ctx->occ_k2, &occ_b = ctx->occ_k2b;       // resident CTAs per SM of the latency / batch variant; cached per context (= per device)
     if (!occ) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2s_stream<TRUNC, false>, C::K2_THREADS, C::K2_SMEM)); if (occ < 1) occ = 1; if (occ > 2) occ = 2; }
     if (!occ_b) { CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, k_g2s_stream<TRUNC, true>, C::K2_THREADS, C::K2_SMEM_BATCH)); if (occ_b < 1) occ_b = 1; if (occ_b > 2) occ_b = 2; }
     int nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ);
     if ((nbatch + nchunk - 1) / nchunk >= 3) nchunk = stream_chunks(ctx, C::CG, nmembers, nbatch, 0, occ_b);   // batch variant
+    return nchunk;
+}
+bool g2s_quad_selected(speedy_ctx* ctx, int nbatch, int nmembers) {
+    if (ctx->d.trunc != 30 || ctx->precision != 0 || !ctx->k2_quad || nbatch <= 0) return false;
+    const int nchunk = g2s_chunks<30>(ctx, nbatch, nmembers);
+    return (nbatch + nchunk - 1) / nchunk >= 3;
+}
+
+template <int TRUNC>
+static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
+                              double* d_out, long long out_ms, int nmembers, const int* gate) {
+    using C = SCfg<TRUNC>;
+    const int nchunk = g2s_chunks<TRUNC>(ctx, nbatch, nmembers);
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if constexpr (TRUNC == 30) {
         if (ctx->k2_quad && (nbatch + nchunk - 1) / nchunk >= 3) {     // four fields at a time: FFT + DMMA Legendre (transforms_quad.cu)

@@ -133,7 +133,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t addr, double* v) {           
 
 __global__ void __launch_bounds__(QCfg::THREADS, 1)
 k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ desc, int nbatch, int idx_base, int idx_end, int unit,
-           double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate, const double* __restrict__ dead_in, long long in_ms) {
+           double* __restrict__ out_base, long long out_ms, DevTables tv, const int* __restrict__ gate, const double* __restrict__ dead_in, long long in_ms, long long out_fs) {
     using C = QCfg;
     extern __shared__ __align__(1024) double smem[];
     double* sRing = smem;                               // [NG][RING][BAND]
@@ -172,7 +172,7 @@ k_g2s_quad(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ d
         const XDesc d = desc[f];
         const int row0 = (int)(d.off / C::IX);
         if (d.off != (long long)row0 * C::IX) __trap();
-        sRow0[t] = row0; sE[t] = e; sFl[t] = d.flags; sOut[t] = (long long)e * out_ms + (long long)f * C::NSPEC2;
+        sRow0[t] = row0; sE[t] = e; sFl[t] = d.flags; sOut[t] = (long long)e * out_ms + (long long)f * out_fs;     // out_fs > 2 nspec: each field's coefficients over its own (consumed) grid rows
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -784,7 +784,8 @@ void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
         const int nunit = (end - base + unit - 1) / unit;
         const int ncta = nunit < ctx->num_sms ? nunit : ctx->num_sms;
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end, unit,
-                              d_out, out_ms, ctx->dv, gate, (ctx->input_is_transient && ctx->l2_discard) ? d_in : (const double*)nullptr, in_ms));
+                              d_out, out_ms, ctx->dv, gate, (ctx->input_is_transient && ctx->l2_discard) ? d_in : (const double*)nullptr, in_ms,
+                              ctx->g2s_out_field_stride ? ctx->g2s_out_field_stride : (long long)C::NSPEC2));
     }
 }
 

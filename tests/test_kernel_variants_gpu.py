@@ -99,21 +99,28 @@ def test_48h_run_variant(pkg, oracle, variant):
 
 
 @pytest.mark.parametrize("sppt", [0, 1])
-def test_member_ready_handoff_is_bitwise_neutral(pkg, sppt):
-    """the per-member hand-off between the quad spec->grid kernel and the column kernel (member_ready.cuh) only changes WHEN a column
-    tile starts: 72 steps of 8 members (SPPT members differ from each other) with and without it give the same bits, graphs and plain launches"""
+def test_step_plumbing_is_bitwise_neutral(pkg, sppt):
+    """what only changes WHEN or WHERE the ensemble step moves its data must not change a bit: the per-member hand-off between the quad
+    spec->grid kernel and the column kernel (member_ready.cuh), the L2 discards of the transient grid fields, the shared transient buffer
+    (grid tendencies over the staged grid fields, coefficients over their own grid rows), CUDA graphs vs plain launches.
+    72 steps of 8 members (SPPT members differ from each other)."""
     out = {}
-    for ready, graphs in ((1, 1), (0, 1), (1, 0)):
+    cases = {"plain": dict(member_ready=0, l2_discard=0, transient_alias=0, graphs=1),
+             "all": dict(member_ready=1, l2_discard=1, transient_alias=1, graphs=1),
+             "all, no graphs": dict(member_ready=1, l2_discard=1, transient_alias=1, graphs=0),
+             "no alias": dict(member_ready=1, l2_discard=1, transient_alias=0, graphs=1),
+             "no hand-off": dict(member_ready=0, l2_discard=1, transient_alias=1, graphs=1)}
+    for name, opts in cases.items():
         c = pkg.Speedy(trunc=30, nmembers=8, sppt_on=sppt, seed=11)
-        c.set_option("member_ready", ready)
-        c.set_option("graphs", graphs)
+        for k, v in opts.items():
+            c.set_option(k, v)
         c.model_init(BC)
         assert c.run_steps(72) == 0
-        out[(ready, graphs)] = {n: c.get_field(n, all_members=True) for n in PROG + ("sst_om", "tau2")}
+        out[name] = {n: c.get_field(n, all_members=True) for n in PROG + ("sst_om", "tau2", "hfluxn", "precnv")}
         c.close()
-    base = out[(0, 1)]
+    base = out["plain"]
     if sppt:
         assert not np.array_equal(base["t"][0], base["t"][7])
-    for key in ((1, 1), (1, 0)):
+    for name in cases:
         for n, v in base.items():
-            assert np.array_equal(out[key][n], v), (key, n)
+            assert np.array_equal(out[name][n], v), (name, n)
