@@ -192,7 +192,10 @@ int speedy_set_graphs(speedy_ctx* ctx, int on);
  * kernels): "k2_field" (grid->spec batches through the whole-field FFT kernel), "dense_inverse" (spec->grid Fourier stage as the
  * dense FFTPACK operator), "k1_quad" / "k2_quad" (ensemble batches through the four-field FFT + DMMA kernels, default 1),
  * "member_ready" (default 1: in the main-loop step the column tiles of a member start when that member's grid fields are stored,
- * 0: when the whole spec->grid launch is complete), "graphs".  Returns <0 for an unknown name. */
+ * 0: when the whole spec->grid launch is complete), "l2_discard" (default 1: the ensemble step drops its transient grid fields
+ * from L2 after their only read), "transient_alias" (default 1: the ensemble step keeps grid fields, grid tendencies and their
+ * coefficients in one buffer per member; get_field of "gin" / "gout" / "sout" is then not meaningful after a step), "graphs".
+ * None of the last three changes a bit of the results.  Returns <0 for an unknown name. */
 int speedy_set_option(speedy_ctx* ctx, const char* name, int value);
 
 

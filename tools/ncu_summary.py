@@ -15,7 +15,13 @@ raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_outpu
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 g = lambda r, n: r[hdr.index(n)]
-names = {"k_grid_columns": "grid_columns", "g2s_stream": "grid_to_spec", "k_spec_step": "spec_step", "s2g_stream": "spec_to_grid"}
+names = {"k_grid_columns": "grid_columns", "g2s_stream": "grid_to_spec", "k_spec_step": "spec_step", "s2g_stream": "spec_to_grid",
+         "s2g_quad": "spec_to_grid", "g2s_quad": "grid_to_spec"}
+def opt(r, n):
+    try:
+        return float(g(r, n))
+    except (ValueError, IndexError):
+        return None
 mul = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out = {}
 for r in rows[2:]:
@@ -31,9 +37,14 @@ for r in rows[2:]:
                 "warps_active_pct": float(g(r, "sm__warps_active.avg.pct_of_peak_sustained_active")),
                 "issue_active_pct": float(g(r, "smsp__issue_active.avg.pct_of_peak_sustained_active")),
                 "dram_throughput_pct": float(g(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")),
+                "fp64_pipe_active_pct": opt(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                "l2_hit_rate_pct": opt(r, "lts__t_sector_hit_rate.pct"),
+                "local_store_sectors": opt(r, "l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
+                "smem_wavefronts": opt(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
                 "warp_inst": float(g(r, "smsp__inst_executed.sum")), "stalls_per_issue": st}
-json.dump({"source": "ncu --set full --clock-control none --import-source on, python bench.py --steps 3 --warmup 3 (1 member, T30); one launch of "
-                     "each kernel, mid-run (ncu serialises the kernels: no PDL overlap, cold caches)", "kernels": out},
+json.dump({"source": "ncu --set full --clock-control none --import-source on (tools/gpu_profiles.sh: bench.py --steps 3 --warmup 3 at 1 member, "
+                     "tools/run_members.py 8 1 for the *_8members tag); one launch of each kernel, mid-run (ncu serialises the kernels: no PDL "
+                     "overlap, cold caches)", "kernels": out},
           open(f"profiles/{tag}_ncu_full_summary.json", "w"), indent=1)
 for k, v in out.items():
     print(k, v["duration_us"], v["traffic_bytes"], v["registers"], v["grid"], v["block"], v["stalls_per_issue"])
