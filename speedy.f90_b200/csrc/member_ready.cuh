@@ -8,13 +8,13 @@
 //     + 1), in place of griddepcontrol.wait; the kernel is a programmatic dependent of the transform, so its CTAs start on the SMs the
 //     finished transform CTAs leave (every transform CTA is resident before the dependent launches: no SM is taken from the producer).
 //   k_spec_step (a full dependency later) zeroes the counts for the next step.
-// A poll that lasts longer than READY_TIMEOUT_NS traps instead of hanging the device.
+// A poll that lasts longer than READY_TIMEOUT_NS (5 s) traps instead of hanging the device.
 #pragma once
 #include "tma.cuh"
 
 namespace spd {
 
-constexpr unsigned long long READY_TIMEOUT_NS = 200ull * 1000 * 1000;
+constexpr unsigned long long READY_TIMEOUT_NS = 5000ull * 1000 * 1000;   // 5 s: far beyond any real wait, also under compute-sanitizer
 
 __device__ __forceinline__ void ready_signal(unsigned* cnt) {
     asm volatile("fence.proxy.async;" ::: "memory");   // the stores went through the async proxy
