@@ -113,7 +113,10 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
     }
     const LevelConsts& lc = *reinterpret_cast<const LevelConsts*>(sLc);
     const double el2 = tv.el2[q], elz_q = tv.elz[q], trf_q = tv.trfilt[q], elm2_q = tv.elm2[q];
-    const double dmp = tv.dmp[q], dmpd = tv.dmpd[q], dmps = tv.dmps[q], dmp1 = tv.dmp1[q], dmp1d = tv.dmp1d[q], dmp1s = tv.dmp1s[q];
+    // horizontal-diffusion factors: fetched ahead of the wait in the latency variant; the batch variant (128 registers for two blocks per SM)
+    // would spill them across the whole kernel and reads them where they are used (L1 / L2 hits)
+    double dmp = 0.0, dmpd = 0.0, dmps = 0.0, dmp1 = 0.0, dmp1d = 0.0, dmp1s = 0.0;
+    if (!BATCH) { dmp = tv.dmp[q]; dmpd = tv.dmpd[q]; dmps = tv.dmps[q]; dmp1 = tv.dmp1[q]; dmp1d = tv.dmp1d[q]; dmp1s = tv.dmp1s[q]; }
     pdl_wait();                 // everything above reads constant tables only; the fields below come from the previous kernel
     pdl_trigger();
     if (a.ready_reset && blockIdx.x == 0 && tid == 0) a.ready_reset[blockIdx.y] = 0u;   // every column tile of the step has passed its wait
@@ -127,13 +130,14 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
     const cd phis_q = ld(mb + a.L.phis, mx, m, n);
     // time level j1 of the prognostics for the filter (time_stepping.f90:163-166); j1 == 1 re-uses level 1
     cd vorj = zero, divj = zero, tj = zero, trj = zero, psj = zero;
-    if (a.j1 != 1) {
+    auto load_level_j = [&]() {
         vorj = ld(sfield(mb, a.L.vor, nsp, KX + k), mx, m, n);
         divj = ld(sfield(mb, a.L.div, nsp, KX + k), mx, m, n);
         tj = ld(sfield(mb, a.L.t, nsp, KX + k), mx, m, n);
         trj = ld(sfield(mb, a.L.tr, nsp, KX + k), mx, m, n);
         psj = ld(sfield(mb, a.L.ps, nsp, 1), mx, m, n);
-    }
+    };
+    if (!BATCH && a.j1 != 1) load_level_j();     // the batch variant fetches them in front of the filter (fewer values live across the solve)
 
     // ---- tendencies.f90:212-234: spectral assembly of the transformed grid-point tendencies
     cd vordt, divdt, tdt, trdt, psdt = zero;
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
         } else {
             qcorh = qcorh_old;
         }
+        if (BATCH) { dmp = tv.dmp[q]; dmpd = tv.dmpd[q]; dmps = tv.dmps[q]; dmp1 = tv.dmp1[q]; dmp1d = tv.dmp1d[q]; dmp1s = tv.dmp1s[q]; }
         vordt = dmp1 * (vordt - dmp * vor1);
         divdt = dmp1d * (divdt - dmpd * div1);
         const cd ctmp = t1 + lc.tcorv[k] * tcorh;
@@ -273,6 +278,7 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
     }
     // ---- step_field_2d  time_stepping.f90:141-167
     cd vor2n = zero, div2n = zero, t2n = zero, t1n = zero;
+    if (BATCH && a.j1 != 1) load_level_j();
     {
         const double eps = (a.j1 == 1) ? 0.0 : lc.rob;
         const double trf = trf_q;
