@@ -124,3 +124,20 @@ def test_step_plumbing_is_bitwise_neutral(pkg, sppt):
     for name in cases:
         for n, v in base.items():
             assert np.array_equal(out[name][n], v), (name, n)
+
+
+def test_step_plumbing_is_bitwise_neutral_over_a_month_boundary(pkg):
+    """the same over 35 days (1260 steps, into February: daily forcing and its gated humidity-correction transform 35 times, a new
+    climatology month), 8 SPPT members, everything on against everything off"""
+    out = {}
+    for name, v in (("plain", 0), ("all", 1)):
+        c = pkg.Speedy(trunc=30, nmembers=8, sppt_on=1, seed=5)
+        for k in ("member_ready", "l2_discard", "transient_alias"):
+            c.set_option(k, v)
+        c.model_init(BC)
+        assert c.run_steps(35 * 36) == 0
+        out[name] = {n: c.get_field(n, all_members=True) for n in PROG + ("sst_om", "stl_am", "tau2", "qcorh")}
+        c.close()
+    for n, v in out["plain"].items():
+        assert np.isfinite(v).all(), n
+        assert np.array_equal(out["all"][n], v), n
