@@ -184,6 +184,75 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         if (want_dyn) tensor_g2s_3d(&smem[(size_t)R_GIN * TC], &a.m_dyn, col0, 0, e, &bars[1]);
     }
 
+    const double cor = a.coriol[j];
+    // ---------------- tendencies.f90:109-197 for one level ----------------
+    // Needs the dynamics rows of the tile only, so any warp can run any level: level warp 1 goes straight from the prep into the
+    // convection (the head of the tile's serial chain) and the slab warp, done early, takes level 1 in its place; level warp 3 runs
+    // its level behind the downward long-wave sweep.  1.0 (one member) to 1.7 us (8 members) off the chain of every tile.
+    auto dynamics_level = [&](const int kd) {
+        if (a.mode == 0) {
+            mbar_wait(&bars[0], 0);                    // every load of the tile has landed before its first store: the K2 inputs may share the rows
+            mbar_wait(&bars[1], 0);
+            const double px = SG(GI_PX), py = SG(GI_PY);
+            double umean = 0.0, vmean = 0.0, dmean = 0.0;
+    #pragma unroll
+            for (int kk = 1; kk <= KX; kk++) {
+                umean = umean + SG(GI_U + kk - 1) * lc.dhs[kk - 1];
+                vmean = vmean + SG(GI_V + kk - 1) * lc.dhs[kk - 1];
+                dmean = dmean + SG(GI_DIV + kk - 1) * lc.dhs[kk - 1];
+            }
+            if (kd == 1) GOUT(GO_PSDT) = -umean * px - vmean * py;   // :125
+            // sigma-dot and its mean-flow part at the two interfaces of level kd (:140-143 prefix sums, re-done per level)
+            double sd_lo = 0.0, sm_lo = 0.0, sd_hi = 0.0, sm_hi = 0.0;    // interfaces kd and kd+1
+            double puvk = 0.0;
+            {
+                double sd = 0.0, sm = 0.0;
+    #pragma unroll
+                for (int kk = 1; kk <= KX; kk++) {
+                    const double puv = (SG(GI_U + kk - 1) - umean) * px + (SG(GI_V + kk - 1) - vmean) * py;
+                    if (kk == kd) { sd_lo = sd; sm_lo = sm; puvk = puv; }
+                    sd = sd - lc.dhs[kk - 1] * (puv + SG(GI_DIV + kk - 1) - dmean);
+                    sm = sm - lc.dhs[kk - 1] * puv;
+                    if (kk == kd) { sd_hi = sd; sm_hi = sm; }
+                }
+            }
+            const double ugk = SG(GI_U + kd - 1), vgk = SG(GI_V + kd - 1), tg2k = SG(GI_T + kd - 1), trgk = SG(GI_TR + kd - 1);
+            const double divgk = SG(GI_DIV + kd - 1), vorgk = SG(GI_VOR + kd - 1) + cor;   // :103-107
+            const double tggk = tg2k - lc.tref[kd - 1];
+            // neighbours (level kd-1 for the lower-index interface, kd+1 for the upper one)
+            const double ugm = (kd > 1) ? SG(GI_U + kd - 2) : 0.0, ugp = (kd < KX) ? SG(GI_U + kd) : 0.0;
+            const double vgm = (kd > 1) ? SG(GI_V + kd - 2) : 0.0, vgp = (kd < KX) ? SG(GI_V + kd) : 0.0;
+            const double tggm = (kd > 1) ? SG(GI_T + kd - 2) - lc.tref[kd - 2] : 0.0, tggp = (kd < KX) ? SG(GI_T + kd) - lc.tref[kd] : 0.0;
+            const double trgm = (kd > 1) ? SG(GI_TR + kd - 2) : 0.0, trgp = (kd < KX) ? SG(GI_TR + kd) : 0.0;
+            // temp(kd) lives on interface kd (kd = 2..kx), temp(1) = temp(kx+1) = 0
+            double t_lo, t_hi;
+            t_lo = (kd >= 2) ? sd_lo * (ugk - ugm) : 0.0;
+            t_hi = (kd < KX) ? sd_hi * (ugp - ugk) : 0.0;
+            const double utend = vgk * vorgk - tggk * lc.rgas * px - (t_hi + t_lo) * lc.dhsr[kd - 1];
+            t_lo = (kd >= 2) ? sd_lo * (vgk - vgm) : 0.0;
+            t_hi = (kd < KX) ? sd_hi * (vgp - vgk) : 0.0;
+            const double vtend = -ugk * vorgk - tggk * lc.rgas * py - (t_hi + t_lo) * lc.dhsr[kd - 1];
+            t_lo = (kd >= 2) ? sd_lo * (tggk - tggm) + sm_lo * (lc.tref[kd - 1] - lc.tref[kd - 2]) : 0.0;
+            t_hi = (kd < KX) ? sd_hi * (tggp - tggk) + sm_hi * (lc.tref[kd] - lc.tref[kd - 1]) : 0.0;
+            const double ttend = tggk * divgk - (t_hi + t_lo) * lc.dhsr[kd - 1] + lc.fsgr[kd - 1] * tggk * (sd_hi + sd_lo) +
+                                 lc.tref3[kd - 1] * (sm_hi + sm_lo) + lc.akap * (tg2k * puvk - tggk * dmean);
+            t_lo = (kd >= 4) ? sd_lo * (trgk - trgm) : 0.0;            // :192 the tracer flux is zeroed at interfaces 2 and 3
+            t_hi = (kd < KX && kd + 1 >= 4) ? sd_hi * (trgp - trgk) : 0.0;
+            const double qtend = trgk * divgk - (t_hi + t_lo) * lc.dhsr[kd - 1];
+            DYN(0, kd) = utend; DYN(1, kd) = vtend; DYN(2, kd) = ttend; DYN(3, kd) = qtend;
+            // products for the direct transforms (tendencies.f90:219-232)
+            const int f = GO_PER * (kd - 1);
+            GOUT(f + 2) = 0.5 * (ugk * ugk + vgk * vgk);
+            GOUT(f + 3) = -ugk * tggk;
+            GOUT(f + 4) = -vgk * tggk;
+            GOUT(f + 6) = -ugk * trgk;
+            GOUT(f + 7) = -vgk * trgk;
+        } else {
+            const int f = GO_PER * (kd - 1);
+            DYN(0, kd) = GOUT(f + 0); DYN(1, kd) = GOUT(f + 1); DYN(2, kd) = GOUT(f + 5); DYN(3, kd) = GOUT(f + 8);
+        }
+    };
+
     if (warp == W_SLAB) {
         // ===== main loop only: couple_sea_land of the previous step (speedy.f90:53) and set_forcing(1) (speedy.f90:29-32),
         // both column-local, in front of the physics that consumes them
@@ -199,6 +268,8 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         SURF(SF_ALBS) = G2(a.L.alb_s); SURF(SF_SNOWC) = G2(a.L.snowc); SURF(SF_FOROG) = G2(a.L.forog); SURF(SF_SSRD) = G2(a.L.ssrd);
         STAMP(11);
         named_arrive(BAR_MID, COL_THREADS);
+        dynamics_level(1);
+        named_arrive(BAR_END, COL_THREADS);
         return;
     }
 
@@ -279,7 +350,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
             for (int k = 1; k <= KX; k++) { VD(0, k) = ttenvd[k]; VD(1, k) = qtenvd[k]; }
         }
         STAMP(12);
-        named_arrive(BAR_END, 9 * 32);
+        named_arrive(BAR_END, COL_THREADS);
         return;
     }
 
@@ -288,7 +359,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
     const int k = warp + 1;
     const int nl1 = KX - 1, nlp = KX + 1;
     const int csw = (a.csw_override >= 0) ? a.csw_override : a.clk->csw;
-    const double cor = a.coriol[j], coa_j = a.coa[j];
+    const double coa_j = a.coa[j];
     mbar_wait(&bars[0], 0);
     STAMP(0);
     // ---------------- phase A (wide): thermodynamic prep, physics.f90:110-122 ----------------
@@ -342,69 +413,8 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         }
         LWS(0, k) = s1; LWS(1, k) = s2;
     }
-    // ---------------- tendencies.f90:109-197 for level k ----------------
-    if (a.mode == 0) {
-        mbar_wait(&bars[1], 0);
-        const double px = SG(GI_PX), py = SG(GI_PY);
-        double umean = 0.0, vmean = 0.0, dmean = 0.0;
-#pragma unroll
-        for (int kk = 1; kk <= KX; kk++) {
-            umean = umean + SG(GI_U + kk - 1) * lc.dhs[kk - 1];
-            vmean = vmean + SG(GI_V + kk - 1) * lc.dhs[kk - 1];
-            dmean = dmean + SG(GI_DIV + kk - 1) * lc.dhs[kk - 1];
-        }
-        if (k == 1) GOUT(GO_PSDT) = -umean * px - vmean * py;   // :125
-        // sigma-dot and its mean-flow part at the two interfaces of level k (:140-143 prefix sums, re-done per level)
-        double sd_lo = 0.0, sm_lo = 0.0, sd_hi = 0.0, sm_hi = 0.0;    // interfaces k and k+1
-        double puvk = 0.0;
-        {
-            double sd = 0.0, sm = 0.0;
-#pragma unroll
-            for (int kk = 1; kk <= KX; kk++) {
-                const double puv = (SG(GI_U + kk - 1) - umean) * px + (SG(GI_V + kk - 1) - vmean) * py;
-                if (kk == k) { sd_lo = sd; sm_lo = sm; puvk = puv; }
-                sd = sd - lc.dhs[kk - 1] * (puv + SG(GI_DIV + kk - 1) - dmean);
-                sm = sm - lc.dhs[kk - 1] * puv;
-                if (kk == k) { sd_hi = sd; sm_hi = sm; }
-            }
-        }
-        const double ugk = SG(GI_U + k - 1), vgk = SG(GI_V + k - 1), tg2k = SG(GI_T + k - 1), trgk = SG(GI_TR + k - 1);
-        const double divgk = SG(GI_DIV + k - 1), vorgk = SG(GI_VOR + k - 1) + cor;   // :103-107
-        const double tggk = tg2k - lc.tref[k - 1];
-        // neighbours (level k-1 for the lower-index interface, k+1 for the upper one)
-        const double ugm = (k > 1) ? SG(GI_U + k - 2) : 0.0, ugp = (k < KX) ? SG(GI_U + k) : 0.0;
-        const double vgm = (k > 1) ? SG(GI_V + k - 2) : 0.0, vgp = (k < KX) ? SG(GI_V + k) : 0.0;
-        const double tggm = (k > 1) ? SG(GI_T + k - 2) - lc.tref[k - 2] : 0.0, tggp = (k < KX) ? SG(GI_T + k) - lc.tref[k] : 0.0;
-        const double trgm = (k > 1) ? SG(GI_TR + k - 2) : 0.0, trgp = (k < KX) ? SG(GI_TR + k) : 0.0;
-        // temp(k) lives on interface k (k = 2..kx), temp(1) = temp(kx+1) = 0
-        double t_lo, t_hi;
-        t_lo = (k >= 2) ? sd_lo * (ugk - ugm) : 0.0;
-        t_hi = (k < KX) ? sd_hi * (ugp - ugk) : 0.0;
-        const double utend = vgk * vorgk - tggk * lc.rgas * px - (t_hi + t_lo) * lc.dhsr[k - 1];
-        t_lo = (k >= 2) ? sd_lo * (vgk - vgm) : 0.0;
-        t_hi = (k < KX) ? sd_hi * (vgp - vgk) : 0.0;
-        const double vtend = -ugk * vorgk - tggk * lc.rgas * py - (t_hi + t_lo) * lc.dhsr[k - 1];
-        t_lo = (k >= 2) ? sd_lo * (tggk - tggm) + sm_lo * (lc.tref[k - 1] - lc.tref[k - 2]) : 0.0;
-        t_hi = (k < KX) ? sd_hi * (tggp - tggk) + sm_hi * (lc.tref[k] - lc.tref[k - 1]) : 0.0;
-        const double ttend = tggk * divgk - (t_hi + t_lo) * lc.dhsr[k - 1] + lc.fsgr[k - 1] * tggk * (sd_hi + sd_lo) +
-                             lc.tref3[k - 1] * (sm_hi + sm_lo) + lc.akap * (tg2k * puvk - tggk * dmean);
-        t_lo = (k >= 4) ? sd_lo * (trgk - trgm) : 0.0;            // :192 the tracer flux is zeroed at interfaces 2 and 3
-        t_hi = (k < KX && k + 1 >= 4) ? sd_hi * (trgp - trgk) : 0.0;
-        const double qtend = trgk * divgk - (t_hi + t_lo) * lc.dhsr[k - 1];
-        DYN(0, k) = utend; DYN(1, k) = vtend; DYN(2, k) = ttend; DYN(3, k) = qtend;
-        // products for the direct transforms (tendencies.f90:219-232)
-        const int f = GO_PER * (k - 1);
-        GOUT(f + 2) = 0.5 * (ugk * ugk + vgk * vgk);
-        GOUT(f + 3) = -ugk * tggk;
-        GOUT(f + 4) = -vgk * tggk;
-        GOUT(f + 6) = -ugk * trgk;
-        GOUT(f + 7) = -vgk * trgk;
-    } else {
-        const int f = GO_PER * (k - 1);
-        DYN(0, k) = GOUT(f + 0); DYN(1, k) = GOUT(f + 1); DYN(2, k) = GOUT(f + 5); DYN(3, k) = GOUT(f + 8);
-    }
-    STAMP(1);
-    named_sync(BAR_LEV, LEV_THREADS);
+    STAMP(8);
+    named_sync(BAR_LEV, LEV_THREADS);          // the prep of every level is in shared memory: the sweeps may start
 
     const double emisfc = F32(0.98), epslw = F32(0.05);
     // level warp 3 sweeps the long wave downward while level warp 1 is busy with convection (or the short-wave sweeps):
@@ -470,6 +480,8 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         named_arrive(BAR_SEA, 96);
     };
     if (k == 3 && !csw) lw_down();
+    if (k != 1) dynamics_level(k);
+    STAMP(1);
 
     // ---------------- phase B (level warp 1): convection.f90:27-245 + the LSC reductions ----------------
     int iptop = 0, icltop = 0;
@@ -891,7 +903,7 @@ __global__ void __launch_bounds__(COL_THREADS, BATCH ? 2 : 1) k_grid_columns(con
         STAMP(6);
     }
     // ---------------- closing stage (wide): physics.f90:137-138, 182-186, 197-205, 208-222 for level k ----------------
-    named_sync(BAR_END, 9 * 32);     // serial results of level warp 1 and the vertical-diffusion fluxes are in shared memory
+    named_sync(BAR_END, COL_THREADS);     // serial results of level warp 1 and the vertical-diffusion fluxes are in shared memory
     {
         const double ut_dyn = DYN(0, k), vt_dyn = DYN(1, k), tt_dyn = DYN(2, k), qt_dyn = DYN(3, k);
         double ut = ut_dyn, vt = vt_dyn, tt = tt_dyn, qt = qt_dyn;
