@@ -91,8 +91,6 @@ struct speedy_ctx {
     bool transient_alias = true;       // ensemble main-loop step on the quad transforms: one buffer per member carries the step's transient fields — the column
                                        // kernel writes its grid tendencies over the grid fields it has staged, grid->spec writes each field's coefficients over
                                        // that field's own grid rows — so a step allocates a third of the L2 lines ("one transient buffer")
-    long long g2s_out_field_stride = 0; // set by the main-loop step around its grid->spec launch: doubles between consecutive output fields (0: packed, 2*nspec)
-    bool input_is_transient = false;   // set by the main-loop step around its grid->spec launch: the input fields are dead once read (the next step rewrites them)
     bool l2_discard = true;  // ensemble steps: transient grid fields are dropped from L2 after their only read (discard.global.L2) instead of being written back
     bool k1_quad = true;     // spec->grid ensemble batches at T30: four fields at a time (k_s2g_quad); 0: the streaming kernel
     bool k2_quad = true;     // grid->spec ensemble batches at T30: four fields at a time, FFT + DMMA Legendre (k_g2s_quad); 0: the streaming kernel with the dense operator
@@ -130,9 +128,15 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_membe
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
                          int nmembers, int mode, const CloseArgs* close = nullptr, bool quad_ok = false);   // quad_ok: derived fields (op != 0) come as aligned pairs
 // mode: 0 full grid->spec, 1 fourier_dir only (out = (2mx,il)), 2 legendre_dir only (in = (2mx,il))
+// what the main-loop step of an ensemble tells its grid->spec launch (the quad kernel honours it; the other variants ignore it,
+// and the step only sets it when the quad kernel is the one selected)
+struct G2sStepOpts {
+    bool transient_input = false;      // the input fields are dead once read (the next step rewrites them): their L2 lines may be dropped
+    long long out_field_stride = 0;    // doubles between consecutive output fields (0: packed, 2 * nspec)
+};
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_member_stride,
                          const XDesc* d_desc, int nbatch, double* d_out, long long out_member_stride,
-                         int nmembers, int mode, const int* gate = nullptr);
+                         int nmembers, int mode, const int* gate = nullptr, G2sStepOpts step = G2sStepOpts());
 void setup_transform_kernels();
 void setup_f32_kernels();          // transforms_f32.cu
 void setup_column_kernels();       // physics.cu

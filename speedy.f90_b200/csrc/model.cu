@@ -254,13 +254,12 @@ static void xform_output(speedy_ctx* ctx) {
 }
 static void xform_direct(speedy_ctx* ctx, bool with_daily_qcorh = false) {
     Model& M = *ctx->model;
-    ctx->input_is_transient = with_daily_qcorh;     // main-loop step: the column kernel's output is read here and nowhere else
     const bool alias = with_daily_qcorh && M.alias_active;
-    ctx->g2s_out_field_stride = alias ? ctx->d.ngrid() : 0;
+    G2sStepOpts step;
+    step.transient_input = with_daily_qcorh;        // main-loop step: the column kernel's output is read here and nowhere else
+    step.out_field_stride = alias ? ctx->d.ngrid() : 0;
     launch_grid_to_spec(ctx, M.mem.p + (alias ? M.L.gin : M.L.gout), M.L.stride, M.desc_dir.p, with_daily_qcorh ? GO_N : GO_QCORH,
-                        M.mem.p + (alias ? M.L.gin : M.L.sout), M.L.stride, ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr);
-    ctx->input_is_transient = false;
-    ctx->g2s_out_field_stride = 0;
+                        M.mem.p + (alias ? M.L.gin : M.L.sout), M.L.stride, ctx->nmembers, 0, with_daily_qcorh ? &M.clock.p->do_forcing : nullptr, step);
 }
 static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     Model& M = *ctx->model;

@@ -894,7 +894,8 @@ k_g2s_field(const __grid_constant__ CUtensorMap gmap, const XDesc* __restrict__ 
     if (tv.trace && tid == 0) trace_end(tv.trace, 2);
 }
 
-void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
+void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate,
+                     const G2sStepOpts& step);
 
 void setup_transform_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_to_grid<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TCfg<30>::K1_SMEM));
@@ -1017,15 +1018,19 @@ bool g2s_quad_selected(speedy_ctx* ctx, int nbatch, int nmembers) {
 
 template <int TRUNC>
 static void launch_g2s_stream(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                              double* d_out, long long out_ms, int nmembers, const int* gate) {
+                              double* d_out, long long out_ms, int nmembers, const int* gate, const G2sStepOpts& step) {
     using C = SCfg<TRUNC>;
     const int nchunk = g2s_chunks<TRUNC>(ctx, nbatch, nmembers);
     const CUtensorMap& gmap = grid_field_map(d_in, in_ms, nmembers, C::IX, C::IL);
     if constexpr (TRUNC == 30) {
         if (ctx->k2_quad && (nbatch + nchunk - 1) / nchunk >= 3) {     // four fields at a time: FFT + DMMA Legendre (transforms_quad.cu)
-            launch_g2s_quad(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+            launch_g2s_quad(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate, step);
             return;
         }
+    }
+    // several CTAs share a field in the other variants: an output over the field's own grid rows would race with their reads
+    if (step.out_field_stride) throw std::runtime_error("grid->spec: an in-place output needs the quad kernel");
+    if constexpr (TRUNC == 30) {
         // experimental whole-field kernel (see k_g2s_field): opt-in, ensemble batches only
         if (ctx->k2_field == 2 || (ctx->k2_field && (nbatch + nchunk - 1) / nchunk >= 3)) {
             using F = FieldCfg<TRUNC>;
@@ -1067,13 +1072,13 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, c
 }
 
 void launch_grid_to_spec(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                         double* d_out, long long out_ms, int nmembers, int mode, const int* gate) {
+                         double* d_out, long long out_ms, int nmembers, int mode, const int* gate, G2sStepOpts step) {
     if (nbatch <= 0) return;
     if (mode == 0 && ctx->precision == 1) {
         launch_grid_to_spec_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
     } else if (mode == 0) {
-        if (ctx->d.trunc == 30) launch_g2s_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
-        else launch_g2s_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate);
+        if (ctx->d.trunc == 30) launch_g2s_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate, step);
+        else launch_g2s_stream<47>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, gate, step);
     } else if (ctx->d.trunc == 30) {
         dim3 grid(nbatch * TCfg<30>::CG, nmembers);
         k_grid_to_spec<30><<<grid, TCfg<30>::K2_THREADS, TCfg<30>::K2_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, mode, gate);

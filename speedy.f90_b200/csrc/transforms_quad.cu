@@ -773,7 +773,8 @@ static const CUtensorMap& grid_band_map(const double* d_in, long long in_ms, int
     return cache.emplace(key, m).first->second;
 }
 
-void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate) {
+void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate,
+                     const G2sStepOpts& step) {
     using C = QCfg;
     const CUtensorMap& gmap = grid_band_map(d_in, in_ms, nmembers);
     const int nf = nbatch * nmembers, per = C::LCAP * ctx->num_sms;      // fields per launch: at most LCAP per CTA
@@ -784,8 +785,8 @@ void launch_g2s_quad(speedy_ctx* ctx, const double* d_in, long long in_ms, const
         const int nunit = (end - base + unit - 1) / unit;
         const int ncta = nunit < ctx->num_sms ? nunit : ctx->num_sms;
         CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_g2s_quad, dim3(ncta), dim3(C::THREADS), C::SMEM_G2S, ctx->stream, gmap, d_desc, nbatch, base, end, unit,
-                              d_out, out_ms, ctx->dv, gate, (ctx->input_is_transient && ctx->l2_discard) ? d_in : (const double*)nullptr, in_ms,
-                              ctx->g2s_out_field_stride ? ctx->g2s_out_field_stride : (long long)C::NSPEC2));
+                              d_out, out_ms, ctx->dv, gate, (step.transient_input && ctx->l2_discard) ? d_in : (const double*)nullptr, in_ms,
+                              step.out_field_stride ? step.out_field_stride : (long long)C::NSPEC2));
     }
 }
 
