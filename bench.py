@@ -289,8 +289,9 @@ def run_b200(args):
         legendre_batched = {"spec_to_grid": _transform_batch(c, torch, stream, flush, True, 5824, hbm),
                             "grid_to_spec": _transform_batch(c, torch, stream, flush, False, 4672, hbm),
                             "note": "BASELINE metric (2): algorithmic bytes per transform over the measured HBM copy bandwidth, device-resident random fields, L2 flushed "
-                                    "between repetitions; grid->spec runs the quad kernel (FFTPACK FFT + DMMA Legendre tiles, P fragments in tensor memory), spec->grid "
-                                    "the streaming kernel (FFT + scalar Legendre sums); both are bound by shared-memory wavefronts and the FP64 pipe before HBM (profiles/README.md r2)"}
+                                    "between repetitions; both directions run the quad kernels (four fields at a time: FFTPACK FFT, Legendre sums as FP64 tensor-core "
+                                    "tiles with the P fragments in tensor memory, tensor-map loads and stores); both are bound by shared-memory wavefronts and the "
+                                    "FP64 pipe before HBM (profiles/README.md r2)"}
     except Exception as ex:
         legendre_batched = {"error": str(ex)}
     dom = max(alg, key=lambda k: timeline["us"][k])     # the longest kernel of the step on the GPU's own timer
