@@ -166,6 +166,7 @@ int speedy_create(const speedy_cfg* cfg, speedy_ctx** out) {
         if (const char* v = getenv("SPEEDY_MEMBER_READY")) ctx->member_ready = atoi(v) != 0;
         if (const char* v = getenv("SPEEDY_L2_DISCARD")) ctx->l2_discard = atoi(v) != 0;
         if (const char* v = getenv("SPEEDY_TRANSIENT_ALIAS")) ctx->transient_alias = atoi(v) != 0;
+        if (const char* v = getenv("SPEEDY_SPPT_FOLD")) ctx->sppt_fold = atoi(v) != 0;
         if (cfg->precision != 0 && cfg->precision != 1) throw std::runtime_error("precision must be 0 (fp64) or 1 (real32 transforms)");
         if (cfg->member_offset < 0 || cfg->member_offset + cfg->nmembers > 65536) throw std::runtime_error("member_offset + nmembers must stay within 65536");
         CUDA_CHECK(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, cfg->device));

@@ -88,6 +88,7 @@ struct speedy_ctx {
     bool trace_pdl = false;  // SPEEDY_TRACE_PDL=1: keep programmatic dependent launch on while tracing (stamps under production overlap; the kernel timeline is then not meaningful)
     bool fft_inverse = true; // spec->grid Fourier stage: regrouped FFTPACK FFT (fft96.cuh / fft144.cuh); SPEEDY_DENSE_INVERSE=1 selects the dense DMMA operator
     bool member_ready = true; // main-loop step on the quad transforms: the column tiles of a member start when that member's grid fields are stored (member_ready.cuh); 0: when the whole transform is
+    bool sppt_fold = true;             // SPPT with device-drawn noise: the spectral step prepares the next step's pattern in its prologue (no separate kernel in the step)
     bool transient_alias = true;       // ensemble main-loop step on the quad transforms: one buffer per member carries the step's transient fields — the column
                                        // kernel writes its grid tendencies over the grid fields it has staged, grid->spec writes each field's coefficients over
                                        // that field's own grid rows — so a step allocates a third of the L2 lines ("one transient buffer")

@@ -19,6 +19,12 @@ namespace spd {
 
 #define KX 8
 
+// SPPT pattern update (see sppt_point below)
+struct SpptParams {
+    unsigned long long seed; int* state; int member0; int draw;     // state[0] = updates done so far, state[1] = block ticket; state == nullptr: off
+    double phi, f0;          // sppt.f90:32 and :76-80, evaluated once on the host (thirty exp() per thread otherwise)
+};
+
 struct SpecArgs {
     double* base; long long stride;
     Layout L;
@@ -29,6 +35,7 @@ struct SpecArgs {
     double dt;
     int flag;
     double* partial;
+    SpptParams sppt;         // state != nullptr: this launch also prepares the SPPT pattern of the next get_tendencies call (prologue)
     long long sout_off, sout_fs;   // the grid->spec output of the step: offset in the member block and doubles between fields (packed, or in place over the grid rows)
     unsigned* ready_reset;   // main-loop step: the per-member completion counts of this step's spec->grid kernel, zeroed here for the next step
 };
@@ -75,6 +82,61 @@ constexpr int SPEC_LC_DOUBLES = sizeof(LevelConsts) / sizeof(double);
 static size_t spec_step_smem(int mx, int nx) { return sizeof(double) * (SPEC_LC_DOUBLES + 2 * KX * KX + (size_t)KX * KX * (mx + nx + 1)) + sizeof(uint64_t); }
 // BATCH = false (single-member step): no register cap, every operand load of a thread is in flight at once;
 // BATCH = true (ensemble batches): two CTAs per SM
+// ---- SPPT AR(1) update in spectral space (sppt.f90:74-91) -------------------------------------------------
+// eta is supplied (caller noise) or drawn with a counter-based generator keyed by (update count, global member, level, coefficient).
+// One point = one (level, coefficient) of one member.  Two callers: the stand-alone kernel (first update of a run, supplied noise,
+// the physics-only entry point) and the prologue of k_spec_step, which prepares the pattern of the NEXT get_tendencies call while it
+// waits for its own inputs: a separate kernel between the spectral step and the next spec->grid launch holds every SM until the
+// spectral step has drained (its blocks end in griddepcontrol.wait to keep the dependency chain transitive), so that the 216 KB
+// transform CTAs cannot start their prologue underneath it.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long h) { return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+// t = level * nspec + coefficient (the stand-alone kernel's thread index: the noise of a point does not depend on who computes it)
+__device__ __forceinline__ void sppt_point(double* mb, const Layout& L, const DevTables& tv, const SpptParams& p, int counter, int e, int t, bool live) {
+    const int mx = tv.mx, nx = tv.nx, nsp = mx * nx;
+    const int k = live ? t / nsp : 0, r = live ? t - k * nsp : 0;
+    const int n = r / mx, m = r - n * mx;
+    const bool first = counter == 0;
+    const double len_decorr = 500000.0;
+    const double phi = p.phi, f0 = p.f0;
+    const double sigma = f0 * exp(-0.25 * (len_decorr * len_decorr) * tv.el2[r]);
+    cd eta;
+    if (p.draw) {
+        // counter-based Box-Muller (sppt.f90:103-117 shape: u = sqrt(-2 ln r1), v = 2*2pi*r2, sin only), clipped to +-10
+        const unsigned long long id = ((unsigned long long)counter * 65536ull + (unsigned long long)(p.member0 + e)) * (unsigned long long)(KX * nsp) + (unsigned long long)t;
+        const unsigned long long h = splitmix64(p.seed ^ splitmix64(id));
+        const double r1 = u01(splitmix64(h + 1)), r2 = u01(splitmix64(h + 2)), r3 = u01(splitmix64(h + 3)), r4 = u01(splitmix64(h + 4));
+        const double c = (double)(2.0f * 6.28318530718f);
+        double gr = sqrt(-2.0 * log(r1)) * sin(c * r2), gi = sqrt(-2.0 * log(r3)) * sin(c * r4);
+        gr = fmin(10.0, fabs(gr)) * copysign(1.0, gr);
+        gi = fmin(10.0, fabs(gi)) * copysign(1.0, gi);
+        eta = cd{gr, gi};
+        if (live) st(sfield(mb, L.sppt_eta, nsp, k), mx, m, n, eta);
+    } else {
+        eta = ld(sfield(mb, L.sppt_eta, nsp, k), mx, m, n);
+    }
+    double* sp = sfield(mb, L.sppt_spec, nsp, k);
+    cd v;
+    if (first) {
+        const double c = pow(1 - phi * phi, -0.5);
+        v = (c * sigma) * eta;
+    } else {
+        v = phi * ld(sp, mx, m, n) + sigma * eta;
+    }
+    if (live) st(sp, mx, m, n, v);
+}
+// the update counter lives on the device so that a replayed CUDA graph draws fresh noise every step; the last block to finish
+// advances it (every block has read it by then).  One thread per block, after the block's points are stored.
+__device__ __forceinline__ void sppt_ticket(int* state, int counter, int nblk) {
+    __threadfence();
+    if (atomicAdd(&state[1], 1) == nblk - 1) { state[0] = counter + 1; state[1] = 0; __threadfence(); }
+}
+
 template <bool BATCH>
 __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a) {
     const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
@@ -110,6 +172,14 @@ __global__ void __launch_bounds__(SC * KX, BATCH ? 2 : 1) k_spec_step(SpecArgs a
         bulk_g2s(sXd, tv.xd, mb64, bar);
         bulk_g2s(sXc, tv.xc, mb64, bar);
         bulk_g2s(sXj, tv.xjt, mb64 * nl, bar);
+    }
+    // SPPT pattern of the next get_tendencies call: independent of this step's data, so it runs while the grid->spec kernel drains
+    // (and first of all: nothing of the step proper is live in registers yet)
+    if (a.sppt.state) {
+        const int sppt_counter = a.sppt.state[0];
+        sppt_point(mb, a.L, tv, a.sppt, sppt_counter, blockIdx.y, k * nsp + rr, valid);
+        __syncthreads();
+        if (tid == 0) sppt_ticket(a.sppt.state, sppt_counter, gridDim.x * gridDim.y);    // here, not at the end: two of the paths below return early
     }
     const LevelConsts& lc = *reinterpret_cast<const LevelConsts*>(sLc);
     const double el2 = tv.el2[q], elz_q = tv.elz[q], trf_q = tv.trfilt[q], elm2_q = tv.elm2[q];
@@ -418,68 +488,17 @@ __global__ void k_ensemble_sums(const double* __restrict__ base, long long strid
     sum[q] = s; sumsq[q] = s2;
 }
 
-// SPPT AR(1) update in spectral space (sppt.f90:74-91); eta is supplied (caller noise) or
-// drawn with a counter-based generator: flag bit0 = first step, bit1 = draw eta on device
-struct SpptArgs {
-    double* base; long long stride; Layout L; DevTables tv;
-    unsigned long long seed; int* state; int member0; int draw; int nsteps; double rearth;   // state[0] = updates done so far, state[1] = block ticket
-    double phi, f0;          // sppt.f90:32 and :76-80, evaluated once on the host (thirty exp() per thread otherwise)
-};
-__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ double u01(unsigned long long h) { return ((double)(h >> 11) + 0.5) * (1.0 / 9007199254740992.0); }
+struct SpptArgs { double* base; long long stride; Layout L; DevTables tv; SpptParams p; };
 __global__ void k_sppt_update(SpptArgs a) {
-    // nothing here reads what the previous kernel (the spectral step) writes: dependents may launch at once and the work runs under
-    // the spectral step's tail; the wait at the END keeps the chain transitive (spec->grid's wait on this kernel implies the step)
+    // nothing here reads what the previous kernel writes: dependents may launch at once; the wait at the END keeps the chain
+    // transitive (the next kernel's wait on this one implies everything before it)
     pdl_trigger();
-    const int mx = a.tv.mx, nx = a.tv.nx, nsp = mx * nx;
+    const int nsp = a.tv.mx * a.tv.nx;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t < KX * nsp;
-    const int k = live ? t / nsp : 0, r = live ? t - k * nsp : 0;
-    const int n = r / mx, m = r - n * mx;
-    const int e = blockIdx.y;
-    // the update counter lives on the device so that a replayed CUDA graph draws fresh noise every
-    // step; the last block to finish advances it (every block has read it by then)
-    const int counter = a.state[0];
-    const bool first = counter == 0;
-    double* mb = a.base + (size_t)e * a.stride;
-    const double len_decorr = 500000.0;
-    const double phi = a.phi, f0 = a.f0;
-    const double sigma = f0 * exp(-0.25 * (len_decorr * len_decorr) * a.tv.el2[r]);
-    cd eta;
-    if (a.draw) {
-        // counter-based Box-Muller (sppt.f90:103-117 shape: u = sqrt(-2 ln r1), v = 2*2pi*r2, sin only), clipped to +-10
-        const unsigned long long id = ((unsigned long long)counter * 65536ull + (unsigned long long)(a.member0 + e)) * (unsigned long long)(KX * nsp) + (unsigned long long)t;
-        const unsigned long long h = splitmix64(a.seed ^ splitmix64(id));
-        const double r1 = u01(splitmix64(h + 1)), r2 = u01(splitmix64(h + 2)), r3 = u01(splitmix64(h + 3)), r4 = u01(splitmix64(h + 4));
-        const double c = (double)(2.0f * 6.28318530718f);
-        double gr = sqrt(-2.0 * log(r1)) * sin(c * r2), gi = sqrt(-2.0 * log(r3)) * sin(c * r4);
-        gr = fmin(10.0, fabs(gr)) * copysign(1.0, gr);
-        gi = fmin(10.0, fabs(gi)) * copysign(1.0, gi);
-        eta = cd{gr, gi};
-        if (live) st(sfield(mb, a.L.sppt_eta, nsp, k), mx, m, n, eta);
-    } else {
-        eta = ld(sfield(mb, a.L.sppt_eta, nsp, k), mx, m, n);
-    }
-    double* sp = sfield(mb, a.L.sppt_spec, nsp, k);
-    cd v;
-    if (first) {
-        const double c = pow(1 - phi * phi, -0.5);
-        v = (c * sigma) * eta;
-    } else {
-        v = phi * ld(sp, mx, m, n) + sigma * eta;
-    }
-    if (live) st(sp, mx, m, n, v);
+    const int counter = a.p.state[0];
+    sppt_point(a.base + (size_t)blockIdx.y * a.stride, a.L, a.tv, a.p, counter, blockIdx.y, t, t < KX * nsp);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const int nblk = gridDim.x * gridDim.y;
-        if (atomicAdd(&a.state[1], 1) == nblk - 1) { a.state[0] = counter + 1; a.state[1] = 0; __threadfence(); }
-    }
+    if (threadIdx.x == 0) sppt_ticket(a.p.state, counter, gridDim.x * gridDim.y);
     pdl_wait();
 }
 
@@ -488,7 +507,7 @@ static SpecArgs spec_args(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpecArgs a;
     a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv; a.lc = M.lc.p; a.clk = M.clock.p;
-    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p; a.ready_reset = nullptr;
+    a.j1 = 1; a.j2 = 1; a.dt = 0.0; a.flag = 0; a.partial = M.diag_partial.p; a.ready_reset = nullptr; a.sppt.state = nullptr;
     a.sout_off = M.L.sout; a.sout_fs = 2LL * ctx->d.nspec();
     return a;
 }
@@ -502,11 +521,14 @@ void launch_geopotential(speedy_ctx* ctx, int which) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+static SpptParams sppt_params(speedy_ctx* ctx);
 void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step) {
     Model& M = *ctx->model;
     SpecArgs a = spec_args(ctx);
     a.j1 = j1; a.j2 = j2; a.dt = dt; a.flag = (store_tend_only ? 1 : 0) | (close_step ? 2 : 0);
     if (close_step && M.ready_target) a.ready_reset = M.ready.p;
+    // SPPT with device-drawn noise: the pattern of the next get_tendencies call is prepared here (model.cu sppt_next consumes it)
+    if (ctx->sppt_on && M.sppt_draw && ctx->sppt_fold) { a.sppt = sppt_params(ctx); M.sppt_prepared = true; }
     if (close_step && M.alias_active) { a.sout_off = M.L.gin; a.sout_fs = ctx->d.ngrid(); }
     dim3 grid((ctx->d.nspec() + SC - 1) / SC, ctx->nmembers);
     const size_t need = (size_t)grid.x * grid.y * 2 * KX + (size_t)grid.y * KX;
@@ -549,19 +571,25 @@ void launch_output_convert(speedy_ctx* ctx, int member, float* d_out) {
     CUDA_CHECK(cudaGetLastError());
 }
 
+static SpptParams sppt_params(speedy_ctx* ctx) {
+    Model& M = *ctx->model;
+    SpptParams p;
+    p.seed = ctx->seed; p.state = M.sppt_state.p; p.member0 = ctx->member_offset; p.draw = M.sppt_draw ? 1 : 0;
+    {   // sppt.f90:32,76-80 in the reference's order of operations
+        const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
+        p.phi = exp(-(24 / (double)ctx->tab.c.nsteps) / time_decorr);
+        double f0 = 0.0;
+        const double rr = len_decorr / ctx->tab.c.rearth;
+        for (int nn = 1; nn <= ctx->d.trunc; nn++) f0 = f0 + (2 * nn + 1) * exp(-0.5 * (rr * rr) * nn * (nn + 1));
+        p.f0 = sqrt(((stddev * stddev) * (1 - p.phi * p.phi)) / (2 * f0));
+    }
+    return p;
+}
+
 void launch_sppt_update(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     SpptArgs a;
-    a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv;
-    a.seed = ctx->seed; a.state = M.sppt_state.p; a.member0 = ctx->member_offset; a.draw = M.sppt_draw ? 1 : 0; a.nsteps = ctx->tab.c.nsteps; a.rearth = ctx->tab.c.rearth;
-    {   // sppt.f90:32,76-80 in the reference's order of operations
-        const double time_decorr = 6.0, len_decorr = 500000.0, stddev = (double)0.33f;
-        a.phi = exp(-(24 / (double)a.nsteps) / time_decorr);
-        double f0 = 0.0;
-        const double rr = len_decorr / a.rearth;
-        for (int nn = 1; nn <= ctx->d.trunc; nn++) f0 = f0 + (2 * nn + 1) * exp(-0.5 * (rr * rr) * nn * (nn + 1));
-        a.f0 = sqrt(((stddev * stddev) * (1 - a.phi * a.phi)) / (2 * f0));
-    }
+    a.base = M.mem.p; a.stride = M.L.stride; a.L = M.L; a.tv = ctx->dv; a.p = sppt_params(ctx);
     const int total = KX * ctx->d.nspec();
     dim3 grid((total + 127) / 128, ctx->nmembers);
     CUDA_CHECK(launch_pdl(ctx->dv.trace == nullptr || ctx->trace_pdl, k_sppt_update, grid, dim3(128), 0, ctx->stream, a));

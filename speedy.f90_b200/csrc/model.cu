@@ -267,10 +267,18 @@ static void xform_qcorh(speedy_ctx* ctx, bool gated) {
     launch_grid_to_spec(ctx, M.mem.p + M.L.gout, M.L.stride, M.desc_one_dir.p, 1, M.mem.p + M.L.qcorh, M.L.stride, ctx->nmembers, 0, nullptr);
 }
 
+// gen_sppt of a get_tendencies call (sppt.f90:45): the pattern is already there when the last spectral step prepared it in its
+// prologue (dynamics.cu), else the stand-alone kernel draws it now.  The host flag follows the order of the enqueued work.
+static void sppt_next(speedy_ctx* ctx) {
+    if (!ctx->sppt_on) return;
+    Model& M = *ctx->model;
+    if (M.sppt_prepared) M.sppt_prepared = false;
+    else launch_sppt_update(ctx);
+}
 // get_tendencies up to (and including) the direct transforms
 static void enqueue_tendency_front(speedy_ctx* ctx, int j2, int csw_override) {
     launch_geopotential(ctx, 3);
-    if (ctx->sppt_on) launch_sppt_update(ctx);
+    sppt_next(ctx);
     xform_step(ctx, j2);
     launch_grid_columns(ctx, 0, csw_override);
     xform_direct(ctx);
@@ -290,7 +298,7 @@ static void enqueue_main_loop_step(speedy_ctx* ctx) {
     // trace mode (exact timeline) and the real32-transform mode (its spec->grid kernel has no closing CTA) close each step
     // with the stand-alone kernel
     const bool tracing = ctx->dv.trace != nullptr || ctx->precision != 0;
-    if (ctx->sppt_on) launch_sppt_update(ctx);
+    sppt_next(ctx);
     ctx->model->alias_active = ctx->transient_alias && ctx->l2_discard && g2s_quad_selected(ctx, GO_N, ctx->nmembers) &&
                                s2g_quad_selected(ctx, ctx->model->nstep_fields, ctx->nmembers, true);
     xform_step(ctx, 2, !tracing);
@@ -439,7 +447,7 @@ int speedy_get_physical_tendencies(speedy_ctx* ctx, const double* vor, const dou
         memcpy(&g[(size_t)(GO_PER * k + 8) * NG], qtend + k * NG, NG * sizeof(double));
     }
     up(L.gout, g.data(), g.size());
-    if (ctx->sppt_on) { launch_sppt_update(ctx); xform_inverse(ctx, 1, GI_SPPT, 8); }
+    if (ctx->sppt_on) { sppt_next(ctx); xform_inverse(ctx, 1, GI_SPPT, 8); }
     xform_inverse(ctx, 1, GI_U1, 41);
     launch_grid_columns(ctx, 1, compute_shortwave ? 1 : 0);
     CUDA_CHECK(cudaMemcpyAsync(g.data(), M.mem.p + L.gout, g.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -649,6 +657,7 @@ int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month,
     launch_geopotential(ctx, 3);
     if (M.sppt_state.n != 2) M.sppt_state.alloc(2);
     CUDA_CHECK(cudaMemsetAsync(M.sppt_state.p, 0, 2 * sizeof(int), ctx->stream));   // gen_sppt's `first` (sppt.f90:52)
+    M.sppt_prepared = false;
     // ---- first_step (time_stepping.f90:12-24)
     if (speedy_first_step(ctx)) throw std::runtime_error(speedy_last_error());
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -666,6 +675,10 @@ static void run_steps_core(speedy_ctx* ctx, int nsteps) {
     // phi_next of the current level-1 T: every main-loop step leaves it up to date; it is recomputed only after another
     // entry point of the library ran in between (which may have changed the state)
     if (nsteps > 0 && !M.phi_next_valid) launch_geopotential(ctx, 2);
+    // SPPT with device-drawn noise: every spectral step prepares the next step's pattern, so a captured day holds no stand-alone update —
+    // which is right only if the day starts with a prepared pattern: the first step after start-up runs outside the graph
+    const bool folding = ctx->sppt_on && M.sppt_draw && ctx->sppt_fold;
+    if (folding && !M.sppt_prepared && left > 0) { enqueue_main_loop_step(ctx); left--; }
     if (ctx->use_graphs && left >= G) {
         if (!M.day_graph) {
             cudaGraph_t graph;
@@ -682,7 +695,7 @@ static void run_steps_core(speedy_ctx* ctx, int nsteps) {
         }
         while (left >= G) {
             CUDA_CHECK(cudaGraphLaunch(M.day_graph, ctx->stream));
-            ctx->launches += (long long)G * (kLaunchesPerStep + (ctx->sppt_on ? 1 : 0));
+            ctx->launches += (long long)G * (kLaunchesPerStep + ((ctx->sppt_on && !folding) ? 1 : 0));
             left -= G;
         }
     }
@@ -869,6 +882,7 @@ struct RestartHeader {
     double implicit_dt;
     DevClock clock;
     int precision, sppt_draw;    // version 2: the arithmetic mode and the noise source continue as they were
+    int sppt_prepared, reserved; // version 3: the SPPT pattern of the next step is already drawn (the update count in the file includes it)
 };
 const char kRestartMagic[8] = {'S', 'P', 'D', 'B', '2', '0', '0', 'R'};
 }  // namespace
@@ -883,7 +897,7 @@ int speedy_save_restart(speedy_ctx* ctx, const char* path) {
     RestartHeader h;
     memset(&h, 0, sizeof h);
     memcpy(h.magic, kRestartMagic, 8);
-    h.version = 2; h.precision = ctx->precision; h.sppt_draw = M.sppt_draw ? 1 : 0; h.trunc = ctx->d.trunc; h.nmembers = ctx->nmembers; h.nsteps = ctx->tab.c.nsteps; h.sppt_on = ctx->sppt_on;
+    h.version = 3; h.precision = ctx->precision; h.sppt_draw = M.sppt_draw ? 1 : 0; h.sppt_prepared = M.sppt_prepared ? 1 : 0; h.trunc = ctx->d.trunc; h.nmembers = ctx->nmembers; h.nsteps = ctx->tab.c.nsteps; h.sppt_on = ctx->sppt_on;
     h.member_offset = ctx->member_offset; h.stride = (long long)M.L.stride; h.istride = (long long)M.L.istride; h.seed = ctx->seed;
     memcpy(h.start, M.start, sizeof h.start);
     h.phi_next_valid = M.phi_next_valid ? 1 : 0;
@@ -918,7 +932,7 @@ int speedy_load_restart(speedy_ctx* ctx, const char* path) {
     std::vector<double> mem;
     std::vector<int> imem, sppt;
     std::string err;
-    if (fread(&h, sizeof h, 1, f) != 1 || fread(cnt, sizeof cnt, 1, f) != 1 || memcmp(h.magic, kRestartMagic, 8) != 0 || h.version != 2) err = "not a restart file of this library (version 2)";
+    if (fread(&h, sizeof h, 1, f) != 1 || fread(cnt, sizeof cnt, 1, f) != 1 || memcmp(h.magic, kRestartMagic, 8) != 0 || h.version != 3) err = "not a restart file of this library (version 3)";
     else if (h.trunc != ctx->d.trunc || h.nmembers != ctx->nmembers || h.nsteps != ctx->tab.c.nsteps || h.sppt_on != ctx->sppt_on ||
              h.stride != (long long)M.L.stride || h.istride != (long long)M.L.istride || cnt[0] != M.mem.n || cnt[1] != M.imem.n || cnt[2] != M.sppt_state.n)
         err = "restart file was written by a context of another configuration (trunc / nmembers / nsteps / sppt_on)";
@@ -946,6 +960,7 @@ int speedy_load_restart(speedy_ctx* ctx, const char* path) {
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (h.implicit_dt != M.implicit_dt && h.implicit_dt > 0.0 && speedy_initialize_implicit(ctx, h.implicit_dt)) throw std::runtime_error(speedy_last_error());
     M.phi_next_valid = h.phi_next_valid != 0;
+    M.sppt_prepared = h.sppt_prepared != 0;
     API_END
 }
 
@@ -954,7 +969,7 @@ int speedy_load_restart(speedy_ctx* ctx, const char* path) {
 int speedy_set_sppt_draw(speedy_ctx* ctx, int on) {
     API_BEGIN
     check_ready(ctx);
-    ctx->model->sppt_draw = on != 0;
+    ctx->model->sppt_draw = on != 0;      // a pattern the last spectral step has already drawn is still used by the next step
     drop_graph(*ctx->model);   // the flag is a captured kernel argument
     API_END
 }
@@ -975,6 +990,7 @@ int speedy_set_option(speedy_ctx* ctx, const char* name, int value) {
     else if (n == "member_ready") ctx->member_ready = value != 0;
     else if (n == "l2_discard") ctx->l2_discard = value != 0;
     else if (n == "transient_alias") ctx->transient_alias = value != 0;
+    else if (n == "sppt_fold") ctx->sppt_fold = value != 0;
     else if (n == "dense_inverse") ctx->fft_inverse = value == 0;
     else if (n == "graphs") ctx->use_graphs = value != 0;
     else throw std::runtime_error("unknown option " + n);

@@ -102,6 +102,7 @@ struct Model {
     double implicit_dt = 0.0;
     // SPPT (sppt.f90): AR(1) state is device-resident; eta drawn on device unless supplied
     bool sppt_draw = true;
+    bool sppt_prepared = false;    // the SPPT pattern of the next get_tendencies call is already on the device (the last spectral step drew it)
     void* colmaps = nullptr;       // tensor maps of the column kernel's tiles (physics.cu)
     DevBuf<int> sppt_state;   // [0] AR(1) updates done so far (device-resident: CUDA-graph replays advance it), [1] block ticket
 };

@@ -102,14 +102,15 @@ def test_48h_run_variant(pkg, oracle, variant):
 def test_step_plumbing_is_bitwise_neutral(pkg, sppt):
     """what only changes WHEN or WHERE the ensemble step moves its data must not change a bit: the per-member hand-off between the quad
     spec->grid kernel and the column kernel (member_ready.cuh), the L2 discards of the transient grid fields, the shared transient buffer
-    (grid tendencies over the staged grid fields, coefficients over their own grid rows), CUDA graphs vs plain launches.
+    (grid tendencies over the staged grid fields, coefficients over their own grid rows), the SPPT pattern drawn in the spectral step's prologue
+    instead of a kernel of its own, CUDA graphs vs plain launches.
     72 steps of 8 members (SPPT members differ from each other)."""
     out = {}
-    cases = {"plain": dict(member_ready=0, l2_discard=0, transient_alias=0, graphs=1),
-             "all": dict(member_ready=1, l2_discard=1, transient_alias=1, graphs=1),
-             "all, no graphs": dict(member_ready=1, l2_discard=1, transient_alias=1, graphs=0),
-             "no alias": dict(member_ready=1, l2_discard=1, transient_alias=0, graphs=1),
-             "no hand-off": dict(member_ready=0, l2_discard=1, transient_alias=1, graphs=1)}
+    cases = {"plain": dict(member_ready=0, l2_discard=0, transient_alias=0, sppt_fold=0, graphs=1),
+             "all": dict(member_ready=1, l2_discard=1, transient_alias=1, sppt_fold=1, graphs=1),
+             "all, no graphs": dict(member_ready=1, l2_discard=1, transient_alias=1, sppt_fold=1, graphs=0),
+             "no alias": dict(member_ready=1, l2_discard=1, transient_alias=0, sppt_fold=1, graphs=1),
+             "no hand-off, no fold": dict(member_ready=0, l2_discard=1, transient_alias=1, sppt_fold=0, graphs=1)}
     for name, opts in cases.items():
         c = pkg.Speedy(trunc=30, nmembers=8, sppt_on=sppt, seed=11)
         for k, v in opts.items():
@@ -132,7 +133,7 @@ def test_step_plumbing_is_bitwise_neutral_over_a_month_boundary(pkg):
     out = {}
     for name, v in (("plain", 0), ("all", 1)):
         c = pkg.Speedy(trunc=30, nmembers=8, sppt_on=1, seed=5)
-        for k in ("member_ready", "l2_discard", "transient_alias"):
+        for k in ("member_ready", "l2_discard", "transient_alias", "sppt_fold"):
             c.set_option(k, v)
         c.model_init(BC)
         assert c.run_steps(35 * 36) == 0
