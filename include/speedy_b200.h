@@ -194,8 +194,9 @@ int speedy_set_graphs(speedy_ctx* ctx, int on);
  * "member_ready" (default 1: in the main-loop step the column tiles of a member start when that member's grid fields are stored,
  * 0: when the whole spec->grid launch is complete), "l2_discard" (default 1: the ensemble step drops its transient grid fields
  * from L2 after their only read), "transient_alias" (default 1: the ensemble step keeps grid fields, grid tendencies and their
- * coefficients in one buffer per member; get_field of "gin" / "gout" / "sout" is then not meaningful after a step), "graphs".
- * None of the last three changes a bit of the results.  Returns <0 for an unknown name. */
+ * coefficients in one buffer per member; get_field of "gin" / "gout" / "sout" is then not meaningful after a step), "graphs",
+ * "sppt_fold" (default 1: with device-drawn SPPT noise the spectral step prepares the next step's pattern itself instead of a
+ * separate kernel per step).  None of the last four changes a bit of the results.  Returns <0 for an unknown name. */
 int speedy_set_option(speedy_ctx* ctx, const char* name, int value);
 
 
