@@ -14,6 +14,12 @@ module speedy_b200_c
         integer(c_int) :: member_offset, nsteps, precision
     end type
 
+    !> namelist.nml as the reference reads it (params.f90:46-70, date.f90:54-71); datetimes = (year, month, day, hour, minute)
+    type, bind(C) :: speedy_namelist
+        integer(c_int) :: nsteps_out, nstdia
+        integer(c_int) :: start_datetime(5), end_datetime(5)
+    end type
+
     interface
         integer(c_int) function speedy_create(cfg, ctx) bind(C, name="speedy_create")
             import; type(speedy_cfg), intent(in) :: cfg; type(c_ptr), intent(out) :: ctx
@@ -243,6 +249,26 @@ module speedy_b200_c
         integer(c_int) function speedy_host_calendar(ymdhm, nsteps, tmonth, tyear, imont1) bind(C, name="speedy_host_calendar")
             import; integer(c_int), intent(inout) :: ymdhm(5); integer(c_int), value :: nsteps
             real(c_double), intent(out) :: tmonth, tyear; integer(c_int), intent(out) :: imont1
+        end function
+        ! ---- program speedy (speedy.f90:1-54) on the library: namelist.nml, trip count, main loop -------------------------
+        integer(c_int) function speedy_namelist_defaults(nml) bind(C, name="speedy_namelist_defaults")
+            import; type(speedy_namelist), intent(out) :: nml
+        end function
+        integer(c_int) function speedy_read_namelist(path, nml) bind(C, name="speedy_read_namelist")
+            import; character(kind=c_char), intent(in) :: path(*); type(speedy_namelist), intent(out) :: nml
+        end function
+        integer(c_long_long) function speedy_steps_between(start_ymdhm, end_ymdhm, nsteps) bind(C, name="speedy_steps_between")
+            import; integer(c_int), intent(in) :: start_ymdhm(5), end_ymdhm(5); integer(c_int), value :: nsteps
+        end function
+        integer(c_int) function speedy_run_info(ctx, info) bind(C, name="speedy_run_info")
+            import; type(c_ptr), value :: ctx; integer(c_int), intent(out) :: info(4)
+        end function
+        integer(c_int) function speedy_range_failure(ctx, step, diag) bind(C, name="speedy_range_failure")
+            import; type(c_ptr), value :: ctx; integer(c_long_long), intent(out) :: step; real(c_double), intent(out) :: diag(24)
+        end function
+        integer(c_int) function speedy_main_loop(ctx, nml, out_dir, member, verbose, steps_done) bind(C, name="speedy_main_loop")
+            import; type(c_ptr), value :: ctx; type(speedy_namelist), intent(in) :: nml; character(kind=c_char), intent(in) :: out_dir(*)
+            integer(c_int), value :: member, verbose; integer(c_long_long), intent(out) :: steps_done
         end function
     end interface
 

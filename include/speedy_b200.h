@@ -211,6 +211,38 @@ int speedy_trace_read(speedy_ctx* ctx, double* out9);
 /* host-only: date.f90:109-157 newdate applied nsteps times to ymdhm[5] (no GPU needed) */
 int speedy_host_calendar(int* ymdhm, int nsteps, double* tmonth, double* tyear, int* imont1);
 
+/* ---- the caller of the path: program speedy (speedy.f90:1-54) ------------------------- */
+/* The two namelist groups the reference reads from namelist.nml: &params (params.f90:46-70) and &date
+ * (date.f90:54-71); datetimes are (year, month, day, hour, minute) as type(datetime), date.f90:14-20. */
+typedef struct speedy_namelist {
+    int nsteps_out;          /* params.f90:50  time steps between outputs, default 1 */
+    int nstdia;              /* params.f90:49  period of the diagnostic print-out, default 36*5 */
+    int start_datetime[5];   /* date.f90:62    default 1982-01-01 00:00 */
+    int end_datetime[5];     /* date.f90:63    default 1982-02-01 00:00 */
+} speedy_namelist;
+/* the reference's defaults (host-only) */
+int speedy_namelist_defaults(speedy_namelist* nml);
+/* initialize_params + the namelist part of initialize_date (host-only): a missing file keeps the defaults, as the
+ * reference's `inquire(exist=)` does; a file that exists must hold both groups.  Accepts `name = v`,
+ * `start_datetime%year = v` and `start_datetime = y, m, d, h, mi`, `!` comments, any letter case. */
+int speedy_read_namelist(const char* path, speedy_namelist* nml);
+/* trips of `do while (.not. datetime_equal(model_datetime, end_datetime))` (speedy.f90:27) under newdate's calendar
+ * (date.f90:109-157) at nsteps steps per day; -1 if the end date is never met (the reference would not terminate) */
+long long speedy_steps_between(const int* start_ymdhm, const int* end_ymdhm, int nsteps);
+/* info[4] = nmembers, time steps per day (params.f90:30), sppt_on, precision of the context */
+int speedy_run_info(const speedy_ctx* ctx, int* info);
+/* 0, or 1 once check_diagnostics has stopped the run (sticky): *step = the main-loop step that left the accepted range
+ * (the reference's istep, diagnostics.f90:60-69) and diag = the diag(kx,3) of member 0 at that step; nothing is recomputed */
+int speedy_range_failure(speedy_ctx* ctx, long long* step, double* diag);
+/* The main program from after `call initialize` to `end` (speedy.f90:24-54) plus the step-0 print and file of
+ * initialize_prognostics (prognostics.f90:120-126), on a context whose speedy_model_init ran with nml->start_datetime:
+ * the state stays on the device; every nsteps_out steps member `member` (every member into out_dir/member<e>/ when
+ * member < 0) is written as yyyymmddhhmm.nc into out_dir (NULL: no files); every nstdia steps the reference's
+ * ' step = ... reke = / deke = / temp =' lines go to stdout when verbose != 0.  Returns 0 at the end date, 1 for
+ * 'Model variables out of accepted range' (the lines of the failing step are printed, diagnostics.f90:60-69),
+ * <0 on errors; *steps_done = main-loop steps completed. */
+int speedy_main_loop(speedy_ctx* ctx, const speedy_namelist* nml, const char* out_dir, int member, int verbose, long long* steps_done);
+
 #ifdef __cplusplus
 }
 #endif

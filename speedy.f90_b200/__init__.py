@@ -28,6 +28,16 @@ class Cfg(ctypes.Structure):
                 ("seed", ctypes.c_ulonglong), ("member_offset", ctypes.c_int), ("nsteps", ctypes.c_int), ("precision", ctypes.c_int)]
 
 
+class Namelist(ctypes.Structure):
+    """speedy_namelist: the &params / &date groups of namelist.nml (params.f90:46-70, date.f90:54-71)"""
+    _fields_ = [("nsteps_out", ctypes.c_int), ("nstdia", ctypes.c_int),
+                ("start_datetime", ctypes.c_int * 5), ("end_datetime", ctypes.c_int * 5)]
+
+    def as_dict(self):
+        return {"nsteps_out": self.nsteps_out, "nstdia": self.nstdia,
+                "start_datetime": tuple(self.start_datetime), "end_datetime": tuple(self.end_datetime)}
+
+
 def lib():
     """Load libspeedy_b200.so (built in-tree by `make -C speedy.f90_b200`)."""
     global _lib
@@ -38,7 +48,7 @@ def lib():
         for name, rt in (("speedy_last_error", ctypes.c_char_p), ("speedy_launch_count", ctypes.c_longlong),
                          ("speedy_stream", ctypes.c_void_p), ("speedy_host_table_len", ctypes.c_longlong),
                          ("speedy_output_len", ctypes.c_size_t), ("speedy_state_len", ctypes.c_size_t),
-                         ("speedy_field_names", ctypes.c_char_p)):
+                         ("speedy_field_names", ctypes.c_char_p), ("speedy_steps_between", ctypes.c_longlong)):
             getattr(_lib, name).restype = rt
         _lib.speedy_set_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
         _lib.speedy_get_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -53,6 +63,10 @@ def lib():
         _lib.speedy_save_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_load_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        _lib.speedy_read_namelist.argtypes = [ctypes.c_char_p, ctypes.POINTER(Namelist)]
+        _lib.speedy_namelist_defaults.argtypes = [ctypes.POINTER(Namelist)]
+        _lib.speedy_steps_between.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _lib.speedy_main_loop.argtypes = [ctypes.c_void_p, ctypes.POINTER(Namelist), ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
     return _lib
 
 
@@ -75,6 +89,23 @@ def host_table(trunc, name):
     out = np.zeros(n)
     _chk(L.speedy_host_table(trunc, name.encode(), _p(out), ctypes.c_size_t(n)))
     return out
+
+
+def read_namelist(path=None):
+    """initialize_params + the namelist part of initialize_date (host-only): `path` None or missing -> the reference's defaults."""
+    nml = Namelist()
+    _chk(lib().speedy_read_namelist(None if path is None else str(path).encode(), ctypes.byref(nml)))
+    return nml
+
+
+def steps_between(start, end, nsteps=36):
+    """trips of the reference's main loop from `start` to `end` ((y, m, d, h, mi)); raises if the end date is never met."""
+    a = np.ascontiguousarray(start, dtype=np.int32)
+    b = np.ascontiguousarray(end, dtype=np.int32)
+    n = lib().speedy_steps_between(_p(a), _p(b), int(nsteps))
+    if n < 0:
+        raise SpeedyError(lib().speedy_last_error().decode())
+    return n
 
 
 def write_output_file(path, u, v, t, q, phi, ps, trunc=30, nsteps=36, start=(1982, 1, 1, 0, 0), timestep=0):
@@ -338,6 +369,18 @@ class Speedy:
         buf = ctypes.create_string_buffer(4096)
         _chk(self.L.speedy_write_output(self.h, int(member), str(directory).encode(), buf, ctypes.c_size_t(len(buf))))
         return buf.value.decode()
+
+    def main_loop(self, nml, out_dir=None, member=0, verbose=False):
+        """program speedy (speedy.f90:24-54) after model_init(start date of `nml`): output every nsteps_out steps into `out_dir`
+        (None: no files), diagnostics every nstdia steps to stdout when verbose.  Returns (rc, main-loop steps done); rc 1 = range error."""
+        done = ctypes.c_longlong()
+        rc = _chk(self.L.speedy_main_loop(self.h, ctypes.byref(nml), None if out_dir is None else str(out_dir).encode(), int(member), int(bool(verbose)), ctypes.byref(done)))
+        return rc, done.value
+
+    def run_info(self):
+        d = (ctypes.c_int * 4)()
+        _chk(self.L.speedy_run_info(self.h, d))
+        return {"nmembers": d[0], "nsteps": d[1], "sppt_on": d[2], "precision": d[3]}
 
     def save_restart(self, path):
         _chk(self.L.speedy_save_restart(self.h, str(path).encode()))

@@ -211,6 +211,13 @@ int speedy_dims(const speedy_ctx* ctx, int* dims) {
     API_END
 }
 
+int speedy_run_info(const speedy_ctx* ctx, int* info) {
+    API_BEGIN
+    if (!ctx || !info) throw std::runtime_error("null argument");
+    info[0] = ctx->nmembers; info[1] = ctx->tab.c.nsteps; info[2] = ctx->sppt_on; info[3] = ctx->precision;
+    API_END
+}
+
 int speedy_get_table(const speedy_ctx* ctx, const char* name, double* out, size_t n) {
     API_BEGIN
     auto m = const_cast<speedy_ctx*>(ctx)->tab.named();

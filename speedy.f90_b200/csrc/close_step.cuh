@@ -51,7 +51,9 @@ __device__ __forceinline__ void close_step_cta(const CloseArgs& a, int tid) {
                 const int e = e0 + u;
                 if (e >= ne) break;
                 const double t3 = (double)sqrtf(0.5f) * d3[u];
-                if (e == 0) { a.clk->diag[kk] = d1[u]; a.clk->diag[KXL + kk] = d2[u]; a.clk->diag[2 * KXL + kk] = t3; }
+                // after a range failure the numbers of the failing step stay (the reference prints them and stops, diagnostics.f90:60-69)
+                const int failed = a.clk->diag_fail;
+                if (e == 0 && (failed == 0 || failed == a.clk->model_step)) { a.clk->diag[kk] = d1[u]; a.clk->diag[KXL + kk] = d2[u]; a.clk->diag[2 * KXL + kk] = t3; }
                 const bool bad = !(d1[u] <= 500.0) || !(d2[u] <= 500.0) || !(t3 >= 180.0) || !(t3 <= 320.0);
                 if (bad) atomicCAS(&a.clk->diag_fail, 0, a.clk->model_step);
             }

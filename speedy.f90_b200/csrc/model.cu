@@ -527,6 +527,17 @@ int speedy_check_diagnostics(speedy_ctx* ctx, int time_level, double* diag) {
     API_END
 }
 
+int speedy_range_failure(speedy_ctx* ctx, long long* step, double* diag) {
+    API_BEGIN
+    check_ready(ctx, true);
+    pull_clock(ctx);
+    const DevClock& c = ctx->model->hclock;
+    if (step) *step = c.diag_fail;
+    if (diag) memcpy(diag, c.diag, sizeof(double) * 24);
+    if (c.diag_fail) return 1;
+    API_END
+}
+
 int speedy_model_date(const speedy_ctx* cctx, int* ymdhm, long long* model_step) {
     API_BEGIN
     speedy_ctx* ctx = const_cast<speedy_ctx*>(cctx);
