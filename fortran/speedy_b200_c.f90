@@ -111,6 +111,14 @@ module speedy_b200_c
             import; type(c_ptr), value :: ctx; integer(c_int), value :: member
             character(kind=c_char), intent(in) :: dir(*); type(c_ptr), value :: path_out; integer(c_size_t), value :: path_cap
         end function
+        ! asynchronous form: conversions enqueued, files written by host threads; ymdhm / timestep = date and step of the enqueued state
+        integer(c_int) function speedy_write_output_async(ctx, member, dir, ymdhm, timestep) bind(C, name="speedy_write_output_async")
+            import; type(c_ptr), value :: ctx; integer(c_int), value :: member; character(kind=c_char), intent(in) :: dir(*)
+            integer(c_int), intent(in) :: ymdhm(5); integer(c_long_long), value :: timestep
+        end function
+        integer(c_int) function speedy_output_drain(ctx) bind(C, name="speedy_output_drain")
+            import; type(c_ptr), value :: ctx
+        end function
         integer(c_int) function speedy_save_restart(ctx, path) bind(C, name="speedy_save_restart")
             import; type(c_ptr), value :: ctx; character(kind=c_char), intent(in) :: path(*)
         end function

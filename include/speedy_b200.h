@@ -157,6 +157,13 @@ int speedy_output_fields(speedy_ctx* ctx, int member, float* u, float* v, float*
  * resident state on the device and writes the file into `dir` (path returned in path_out when non-NULL);
  * speedy_write_output_file is the host-only writer underneath (timestep = model_step - 1, speedy.f90:50). */
 int speedy_write_output(speedy_ctx* ctx, int member, const char* dir, char* path_out, size_t path_cap);
+/* the same without waiting for the device or the file system: the conversions are enqueued on the context's stream, the fields
+ * land in a ring of pinned host buffers and host threads write the files while the device runs on (the reference's default
+ * writes a file after EVERY step).  ymdhm / timestep: the model date and `model_step - 1` the enqueued state will have (the host knows
+ * the calendar: speedy_host_calendar; no device round trip).  speedy_output_drain returns when every file is on disk (<0: a write
+ * failed); speedy_destroy drains too. */
+int speedy_write_output_async(speedy_ctx* ctx, int member, const char* dir, const int* ymdhm, long long timestep);
+int speedy_output_drain(speedy_ctx* ctx);
 int speedy_write_output_file(const char* path, int trunc, int nsteps, const int* start_ymdhm, int timestep,
                              const float* u, const float* v, const float* t, const float* q, const float* phi, const float* ps);
 /* restart files (absent in the reference, which always starts from rest, prognostics.f90:29-31): the complete

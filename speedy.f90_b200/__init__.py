@@ -63,6 +63,7 @@ def lib():
         _lib.speedy_save_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_load_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
+        _lib.speedy_write_output_async.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_longlong]
         _lib.speedy_read_namelist.argtypes = [ctypes.c_char_p, ctypes.POINTER(Namelist)]
         _lib.speedy_namelist_defaults.argtypes = [ctypes.POINTER(Namelist)]
         _lib.speedy_steps_between.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -369,6 +370,15 @@ class Speedy:
         buf = ctypes.create_string_buffer(4096)
         _chk(self.L.speedy_write_output(self.h, int(member), str(directory).encode(), buf, ctypes.c_size_t(len(buf))))
         return buf.value.decode()
+
+    def write_output_async(self, directory, ymdhm, timestep, member=0):
+        """output() without waiting: conversions enqueued on the stream, the file written by the library's host threads.  `ymdhm`,
+        `timestep`: date and step counter - 1 of the enqueued state (the caller knows the calendar).  output_drain() waits for the files."""
+        d = (ctypes.c_int * 5)(*[int(x) for x in ymdhm])
+        _chk(self.L.speedy_write_output_async(self.h, int(member), str(directory).encode(), d, ctypes.c_longlong(int(timestep))))
+
+    def output_drain(self):
+        _chk(self.L.speedy_output_drain(self.h))
 
     def main_loop(self, nml, out_dir=None, member=0, verbose=False):
         """program speedy (speedy.f90:24-54) after model_init(start date of `nml`): output every nsteps_out steps into `out_dir`

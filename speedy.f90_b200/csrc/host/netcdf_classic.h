@@ -24,6 +24,13 @@ public:
     void put_var(int var, const float* data, size_t n) {
         if (n != var_len(vars_[var])) throw std::runtime_error("netcdf writer: size mismatch for variable " + vars_[var].name);
         vars_[var].data.assign(data, data + n);
+        vars_[var].ref = nullptr;
+    }
+    // the same without a copy: `data` must stay valid until write() has returned (the large fields of an output file)
+    void put_var_ref(int var, const float* data, size_t n) {
+        if (n != var_len(vars_[var])) throw std::runtime_error("netcdf writer: size mismatch for variable " + vars_[var].name);
+        vars_[var].data.clear();
+        vars_[var].ref = data;
     }
     void write(const std::string& path) const {
         // header size first (offsets of the data sections depend on it)
@@ -64,28 +71,36 @@ public:
         };
         build(0);
         build((uint32_t)h.size());
-        FILE* f = fopen(path.c_str(), "wb");
-        if (!f) throw std::runtime_error("netcdf writer: cannot create " + path);
-        bool ok = fwrite(h.data(), 1, h.size(), f) == h.size();
-        std::vector<uint8_t> be;
-        for (int pass = 0; pass < 2 && ok; pass++)
+        // one buffer, one write: header, then every variable byte-swapped straight into its place
+        size_t total = h.size();
+        for (const Var& v : vars_) total += 4 * var_len(v);
+        std::vector<uint8_t> file(total);
+        memcpy(file.data(), h.data(), h.size());
+        size_t off = h.size();
+        for (int pass = 0; pass < 2; pass++)
             for (const Var& v : vars_) {
                 if (is_record(v) != (pass == 1)) continue;
-                if (v.data.size() != var_len(v)) { fclose(f); throw std::runtime_error("netcdf writer: variable " + v.name + " was never written"); }
-                be.resize(4 * v.data.size());
-                for (size_t i = 0; i < v.data.size(); i++) {
-                    uint32_t w; memcpy(&w, &v.data[i], 4);
-                    be[4 * i] = (uint8_t)(w >> 24); be[4 * i + 1] = (uint8_t)(w >> 16); be[4 * i + 2] = (uint8_t)(w >> 8); be[4 * i + 3] = (uint8_t)w;
+                const size_t n = var_len(v);
+                const float* src = v.ref ? v.ref : v.data.data();
+                if (!v.ref && v.data.size() != n) throw std::runtime_error("netcdf writer: variable " + v.name + " was never written");
+                uint8_t* dst = file.data() + off;
+                for (size_t i = 0; i < n; i++) {
+                    uint32_t w; memcpy(&w, &src[i], 4);
+                    w = __builtin_bswap32(w);
+                    memcpy(dst + 4 * i, &w, 4);
                 }
-                ok = ok && fwrite(be.data(), 1, be.size(), f) == be.size();
+                off += 4 * n;
             }
+        FILE* f = fopen(path.c_str(), "wb");
+        if (!f) throw std::runtime_error("netcdf writer: cannot create " + path);
+        bool ok = fwrite(file.data(), 1, file.size(), f) == file.size();
         ok = (fclose(f) == 0) && ok;
         if (!ok) throw std::runtime_error("netcdf writer: short write to " + path);
     }
 
 private:
     struct Dim { std::string name; uint32_t len; };
-    struct Var { std::string name; std::vector<int> dimids; std::vector<std::pair<std::string, std::string>> atts; std::vector<float> data; };
+    struct Var { std::string name; std::vector<int> dimids; std::vector<std::pair<std::string, std::string>> atts; std::vector<float> data; const float* ref = nullptr; };
     std::vector<Dim> dims_;
     std::vector<Var> vars_;
     bool is_record(const Var& v) const { return !v.dimids.empty() && dims_[v.dimids[0]].len == 0; }

@@ -208,53 +208,76 @@ int speedy_main_loop(speedy_ctx* ctx, const speedy_namelist* nml, const char* ou
         if (total < 0) throw std::runtime_error(speedy_last_error());
         std::vector<double> diag(3 * (size_t)kx);
         const bool write = out_dir != nullptr;
-        // ---- step 0 (prognostics.f90:120-126): level-1 diagnostics, phi = get_geopotential(t(:,:,:,1)), output(0, ...)
+        // the host's own copy of the calendar (date.f90:109-157): names the files without asking the device
+        spd::DevClock hc;
+        spd::calendar_init(hc, nml->start_datetime[0], nml->start_datetime[1], nml->start_datetime[2], nml->start_datetime[3], nml->start_datetime[4], 1 << 30, nsteps_day);
+        std::vector<std::pair<long long, std::string>> files;          // (timestep, path) of every file of this run
+        const int lo = member < 0 ? 0 : member, hi = member < 0 ? nmem : member + 1;
+        auto member_dir = [&](int e) { return member < 0 ? std::string(out_dir) + "/member" + std::to_string(e) : std::string(out_dir); };
+        // output(timestep, ...) of the state now at the end of the stream: conversions enqueued, files written by the library's host threads
+        auto emit = [&](long long timestep) {
+            const int ymdhm[5] = {hc.year, hc.month, hc.day, hc.hour, hc.minute};
+            char name[40];
+            snprintf(name, sizeof name, "%04d%02d%02d%02d%02d.nc", ymdhm[0], ymdhm[1], ymdhm[2], ymdhm[3], ymdhm[4]);
+            for (int e = lo; e < hi; e++) {
+                const std::string dir = member_dir(e);
+                if (speedy_write_output_async(ctx, e, dir.c_str(), ymdhm, timestep)) throw std::runtime_error(speedy_last_error());
+                files.push_back({timestep, dir.empty() ? std::string(name) : dir + "/" + name});
+            }
+        };
+        // 'Model variables out of accepted range' (diagnostics.f90:60-69): the failing step's numbers, then stop.  The reference stops
+        // inside check_diagnostics of step `bad`, before that step's output: files from there on (enqueued before the guard was polled) go
+        auto range_failure = [&]() {
+            long long bad = 0;
+            if (speedy_range_failure(ctx, &bad, diag.data()) < 0) throw std::runtime_error(speedy_last_error());
+            speedy_output_drain(ctx);
+            for (const auto& f : files)
+                if (f.first >= bad) remove(f.second.c_str());
+            done = bad;
+            print_diagnostics(done, diag.data(), kx);
+            return finish(1);
+        };
+        // ---- step 0 (prognostics.f90:120-126): level-1 diagnostics and output(0, ...).  first_step leaves time level 1 and its
+        // geopotential as they were (eps = 0, time_stepping.f90:31-32): the state initialize_prognostics wrote is still the resident one
         {
             const int rc = speedy_check_diagnostics(ctx, 1, diag.data());
             if (rc < 0) throw std::runtime_error(speedy_last_error());
-            if (verbose) print_diagnostics(0, diag.data(), kx);       // mod(0, nstdia) == 0
-            if (rc > 0) { if (!verbose) print_diagnostics(0, diag.data(), kx); return finish(1); }
+            if (verbose || rc > 0) print_diagnostics(0, diag.data(), kx);     // mod(0, nstdia) == 0
+            if (rc > 0) return finish(1);
             if (write) {
-                // the resident phi is get_geopotential(t(:,:,:,1)) (tendencies.f90:203) and first_step leaves time level 1 as it was (eps = 0,
-                // time_stepping.f90:31-32): the state output(0, ...) wrote in initialize_prognostics is still the resident one
-                const int lo = member < 0 ? 0 : member, hi = member < 0 ? nmem : member + 1;
-                for (int e = lo; e < hi; e++) {
-                    const std::string dir = member < 0 ? std::string(out_dir) + "/member" + std::to_string(e) : std::string(out_dir);
-                    if (member < 0 && mkdir(dir.c_str(), 0777) && errno != EEXIST) throw std::runtime_error("cannot create " + dir);
-                    if (speedy_write_output(ctx, e, dir.c_str(), nullptr, 0)) throw std::runtime_error(speedy_last_error());
-                }
+                if (member < 0)
+                    for (int e = lo; e < hi; e++)
+                        if (mkdir(member_dir(e).c_str(), 0777) && errno != EEXIST) throw std::runtime_error("cannot create " + member_dir(e));
+                emit(0);
             }
         }
-        // ---- main loop (speedy.f90:27-54): advance to the next event
+        // ---- main loop (speedy.f90:27-54): enqueue up to the next event; the range guard is polled at every print, every 30 simulated
+        // days and at the end (it is sticky and remembers the failing step)
+        long long since_poll = 0;
         while (done < total) {
             const long long to_out = write ? nml->nsteps_out - done % nml->nsteps_out : total - done;
-            const long long to_dia = nml->nstdia - done % nml->nstdia;
+            const long long to_dia = verbose ? nml->nstdia - done % nml->nstdia : total - done;
             long long chunk = std::min(std::min(to_out, to_dia), total - done);
             if (chunk > (1 << 20)) chunk = 1 << 20;
-            const int rc = speedy_run_steps(ctx, (int)chunk);
-            if (rc < 0) throw std::runtime_error(speedy_last_error());
-            if (rc > 0) {
-                // 'Model variables out of accepted range' (diagnostics.f90:60-69): the failing step's numbers, then stop
-                long long bad = 0;
-                if (speedy_range_failure(ctx, &bad, diag.data()) < 0) throw std::runtime_error(speedy_last_error());
-                done = bad;
-                print_diagnostics(done, diag.data(), kx);
-                return finish(1);
-            }
+            if (speedy_enqueue_steps(ctx, (int)chunk)) throw std::runtime_error(speedy_last_error());
+            for (long long k = 0; k < chunk; k++) spd::cal_advance(hc);
             done += chunk;
-            if (done % nml->nstdia == 0 && verbose) {
+            since_poll += chunk;
+            const bool print = verbose && done % nml->nstdia == 0;
+            if (print || done == total || since_poll >= 30LL * nsteps_day) {
+                const int rc = speedy_finish(ctx);
+                if (rc < 0) throw std::runtime_error(speedy_last_error());
+                if (rc > 0) return range_failure();
+                since_poll = 0;
+            }
+            if (print) {
                 // the numbers check_diagnostics(vor(:,:,:,2), ...) of this step left on the device (speedy.f90:41): nothing is recomputed
                 if (speedy_range_failure(ctx, nullptr, diag.data()) < 0) throw std::runtime_error(speedy_last_error());
                 print_diagnostics(done, diag.data(), kx);
             }
-            if (write && done % nml->nsteps_out == 0) {
-                const int lo = member < 0 ? 0 : member, hi = member < 0 ? nmem : member + 1;
-                for (int e = lo; e < hi; e++) {
-                    const std::string dir = member < 0 ? std::string(out_dir) + "/member" + std::to_string(e) : std::string(out_dir);
-                    if (speedy_write_output(ctx, e, dir.c_str(), nullptr, 0)) throw std::runtime_error(speedy_last_error());
-                }
-            }
+            if (write && done % nml->nsteps_out == 0) emit(done);
         }
+        if (speedy_output_drain(ctx)) throw std::runtime_error(speedy_last_error());
         if (speedy_model_date(ctx, now, &model_step)) throw std::runtime_error(speedy_last_error());
         if (!same_date(now, nml->end_datetime)) throw std::runtime_error("speedy_main_loop: the device calendar did not arrive at the end date");
     } catch (const std::exception& e_) { spd::last_error() = e_.what(); return finish(-1); }

@@ -104,6 +104,7 @@ struct Model {
     bool sppt_draw = true;
     bool sppt_prepared = false;    // the SPPT pattern of the next get_tendencies call is already on the device (the last spectral step drew it)
     void* colmaps = nullptr;       // tensor maps of the column kernel's tiles (physics.cu)
+    void* outpipe = nullptr;       // asynchronous output: pinned slots + writer threads (model.cu, speedy_write_output_async)
     DevBuf<int> sppt_state;   // [0] AR(1) updates done so far (device-resident: CUDA-graph replays advance it), [1] block ticket
 };
 

@@ -1,5 +1,6 @@
 """The caller of the path on the GPU: `program speedy` (speedy.f90:1-54) as the speedy_b200 executable and as speedy_main_loop —
 BASELINE configs[0]: the reference's namelist, a 2-day run, NetCDF output compared field by field."""
+import ctypes
 import os
 import re
 import subprocess
@@ -105,9 +106,45 @@ def test_main_loop_events_do_not_touch_the_trajectory(pkg, tmp_path, capfd):
 def test_executable_reports_a_range_failure(tmp_path):
     """T47 at the reference's 36 steps per day leaves the accepted range on day 33: exit code 1, the reference's message, the failing step's lines"""
     from conftest import bc_t47
-    (tmp_path / "namelist.nml").write_text("&params\nnsteps_out = 100000\nnstdia = 100000\n/\n&date\nend_datetime%month = 3\n/\n")
+    (tmp_path / "namelist.nml").write_text("&params\nnsteps_out = 360\nnstdia = 100000\n/\n&date\nend_datetime%month = 3\n/\n")
     r = subprocess.run([EXE, "--bc", bc_t47(), "--trunc", "47"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1, (r.stdout, r.stderr)
     assert "Model variables out of accepted range" in r.stderr
     steps = [int(x) for x in re.findall(r"^ step =\s*(\d+) reke", r.stdout, re.M)]
     assert len(steps) == 2 and steps[0] == 0 and 36 * 25 < steps[1] < 36 * 45
+    # the reference stops inside check_diagnostics of the failing step: no file from that step on (the loop enqueues ahead of the guard)
+    hours = sorted(_read(p)[1] for p in tmp_path.glob("*.nc"))
+    assert hours[0] == 0.0 and len(hours) >= 3 and all(h * 36 / 24 < steps[1] for h in hours)
+    assert hours == [240.0 * k for k in range(len(hours))]
+
+
+def test_async_output_equals_the_synchronous_writer(pkg, tmp_path):
+    """speedy_write_output_async (conversions enqueued, pinned ring, host writer threads) while the device runs on: 40 files, more than the
+    ring holds, byte-identical to speedy_write_output of the same steps"""
+    a = pkg.Speedy(trunc=30, nmembers=2)
+    a.model_init(BC)
+    b = pkg.Speedy(trunc=30, nmembers=2)
+    b.model_init(BC)
+    da, db = tmp_path / "async", tmp_path / "sync"
+    da.mkdir(); db.mkdir()
+    ymdhm = [1982, 1, 1, 0, 0]
+    for k in range(1, 41):
+        a.enqueue_steps(1)
+        d = (ctypes.c_int * 5)(*ymdhm)
+        assert pkg.lib().speedy_host_calendar(d, 1, None, None, None) == 0      # newdate on the host: no device round trip
+        ymdhm = list(d)
+        a.write_output_async(da, ymdhm, k, member=k % 2)
+        assert b.run_steps(1) == 0
+        b.write_output(db, member=k % 2)
+    assert a.finish() == 0
+    a.output_drain()
+    names = sorted(p.name for p in db.glob("*.nc"))
+    assert len(names) == 40 and names == sorted(p.name for p in da.glob("*.nc"))
+    for n in names:
+        assert (da / n).read_bytes() == (db / n).read_bytes(), n
+    for n in PROG:
+        assert np.array_equal(a.get_field(n, all_members=True), b.get_field(n, all_members=True)), n
+    with pytest.raises(pkg.SpeedyError):                       # a write that fails is reported by the drain
+        a.write_output_async(tmp_path / "no" / "such" / "dir", ymdhm, 41)
+        a.output_drain()
+    a.close(); b.close()
