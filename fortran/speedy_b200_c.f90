@@ -271,6 +271,10 @@ module speedy_b200_c
         integer(c_int) function speedy_run_info(ctx, info) bind(C, name="speedy_run_info")
             import; type(c_ptr), value :: ctx; integer(c_int), intent(out) :: info(4)
         end function
+        integer(c_long_long) function speedy_host_boundary(bc_path, trunc, name, out, n) bind(C, name="speedy_host_boundary")
+            import; character(kind=c_char), intent(in) :: bc_path(*), name(*); integer(c_int), value :: trunc
+            real(c_double), intent(out) :: out(*); integer(c_size_t), value :: n
+        end function
         integer(c_int) function speedy_range_failure(ctx, step, diag) bind(C, name="speedy_range_failure")
             import; type(c_ptr), value :: ctx; integer(c_long_long), intent(out) :: step; real(c_double), intent(out) :: diag(24)
         end function

@@ -141,12 +141,19 @@ int speedy_enqueue_steps(speedy_ctx* ctx, int nsteps);
 int speedy_finish(speedy_ctx* ctx);
 
 /* ---- model environment: boundaries.f90, forcing.f90, date.f90, land/sea init -------- */
-/* initialize (initialization.f90:12-82) from a boundary-condition source: `bc_path` is the packed
- * .bin that tools/pack_boundary.py makes from the reference's data/bc/t30 tree (the float32 variables of the
- * NetCDF-4 files copied verbatim; the flip / missing-value / forchk logic runs in the loader).  The pack holds a
- * window of the SST-anomaly record (72 months from 1979-01 as shipped; `--months` of the packer widens it): a run
- * that leaves it fails with an error instead of reading past it.  Start date as in namelist.nml. */
+/* initialize (initialization.f90:12-82) from a boundary-condition source.  `bc_path` is either
+ *  - a DIRECTORY holding the reference's own NetCDF-4 files — side by side, as run.sh links them into the run directory, or as the
+ *    data/bc/t30 tree with clim/ and anom/ — read without an HDF5 library (contiguous float32 variables located through their HDF5
+ *    link / object-header messages, csrc/host/env.cpp; all 420 months of the SST anomaly are resident then), or
+ *  - the packed .bin that tools/pack_boundary.py makes from those files (what travels with this repo: float32 variables copied
+ *    verbatim, a window of the SST-anomaly record — 72 months from 1979-01 as shipped, `--months` widens it; a run that leaves the
+ *    window fails with an error instead of reading past it).
+ * The flip / missing-value / forchk logic (input_output.f90:36-41, boundaries.f90:47-72) runs in the loader for both.  Start date as in namelist.nml. */
 int speedy_model_init(speedy_ctx* ctx, const char* bc_path, int year, int month, int day, int hour, int minute);
+/* host-only (no GPU): the start-up boundary field `name` as boundaries.f90:28-68 / land_model.f90:50-181 / sea_model.f90:80-250 leave it,
+ * from either source ("phi0", "fmask", "alb0", "stl12", "snowd12", "soilw12", "sst12", "sice12", "ssta", "fmask_l", ...).  Returns the
+ * field's length (out == NULL: just that) or -1; copies its first n values. */
+long long speedy_host_boundary(const char* bc_path, int trunc, const char* name, double* out, size_t n);
 /* current model date (date.f90:20) and step counter */
 int speedy_model_date(const speedy_ctx* ctx, int* ymdhm, long long* model_step);
 /* output() conversions input_output.f90:184-214: float32 u,v,t,q,phi (ix,il,kx) and ps (ix,il) */

@@ -48,7 +48,8 @@ def lib():
         for name, rt in (("speedy_last_error", ctypes.c_char_p), ("speedy_launch_count", ctypes.c_longlong),
                          ("speedy_stream", ctypes.c_void_p), ("speedy_host_table_len", ctypes.c_longlong),
                          ("speedy_output_len", ctypes.c_size_t), ("speedy_state_len", ctypes.c_size_t),
-                         ("speedy_field_names", ctypes.c_char_p), ("speedy_steps_between", ctypes.c_longlong)):
+                         ("speedy_field_names", ctypes.c_char_p), ("speedy_steps_between", ctypes.c_longlong),
+                         ("speedy_host_boundary", ctypes.c_longlong)):
             getattr(_lib, name).restype = rt
         _lib.speedy_set_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
         _lib.speedy_get_field.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -64,6 +65,7 @@ def lib():
         _lib.speedy_load_restart.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
         _lib.speedy_set_option.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int]
         _lib.speedy_write_output_async.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_longlong]
+        _lib.speedy_host_boundary.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_size_t]
         _lib.speedy_read_namelist.argtypes = [ctypes.c_char_p, ctypes.POINTER(Namelist)]
         _lib.speedy_namelist_defaults.argtypes = [ctypes.POINTER(Namelist)]
         _lib.speedy_steps_between.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
@@ -89,6 +91,18 @@ def host_table(trunc, name):
         raise SpeedyError(f"unknown table {name}")
     out = np.zeros(n)
     _chk(L.speedy_host_table(trunc, name.encode(), _p(out), ctypes.c_size_t(n)))
+    return out
+
+
+def host_boundary(bc_path, name, trunc=30, n=None):
+    """Start-up boundary field `name` (host-only) from a packed .bin or a directory of the reference's NetCDF-4 files; `n`: leading values only."""
+    L = lib()
+    total = L.speedy_host_boundary(str(bc_path).encode(), int(trunc), name.encode(), None, 0)
+    if total < 0:
+        raise SpeedyError(L.speedy_last_error().decode())
+    out = np.zeros(total if n is None else min(int(n), total))
+    if L.speedy_host_boundary(str(bc_path).encode(), int(trunc), name.encode(), _p(out), ctypes.c_size_t(out.size)) < 0:
+        raise SpeedyError(L.speedy_last_error().decode())
     return out
 
 

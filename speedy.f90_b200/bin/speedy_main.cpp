@@ -1,6 +1,7 @@
 // speedy_b200: the reference's executable (`program speedy`, speedy.f90:1-54) on the B200 library.  Run it where the
 // reference's `speedy` would be run: it reads ./namelist.nml (params.f90:62-67, date.f90:66-71; a missing file keeps the
-// defaults), initialises the model from the packed boundary file, and writes yyyymmddhhmm.nc files into the working
+// defaults), initialises the model from the reference's boundary files in the working directory (or --bc: a directory of them / a
+// packed file), and writes yyyymmddhhmm.nc files into the working
 // directory while printing the reference's start-up lines and diagnostics.  Plain C ABI only (include/speedy_b200.h).
 //
 //   speedy_b200 [--namelist FILE] [--bc FILE] [--out DIR] [--trunc 30|47] [--steps-per-day N] [--members M] [--member E]
@@ -42,8 +43,11 @@ int main(int argc, char** argv) {
         else { fprintf(stderr, "speedy_b200: unknown option %s\n", a.c_str()); return 2; }
     }
     if (bc.empty()) {
+        // the reference's run directory holds its boundary files side by side (run.sh links them): read them where they are
         const char* env = getenv("SPEEDY_BC");
-        bc = env ? env : (cfg.trunc == 30 ? "data/bc_t30.bin" : "data/bc_t47.bin");
+        FILE* probe = env ? nullptr : fopen("surface.nc", "rb");
+        if (probe) fclose(probe);
+        bc = env ? env : probe ? "." : (cfg.trunc == 30 ? "data/bc_t30.bin" : "data/bc_t47.bin");
     }
     speedy_namelist nml;
     if (speedy_read_namelist(namelist.c_str(), &nml)) return fail("namelist");

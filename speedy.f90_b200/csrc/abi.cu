@@ -2,6 +2,7 @@
 // The model-level entry points live in model.cu.
 #include "../../include/speedy_b200.h"
 #include "ctx.h"
+#include "model.h"
 #include "abi_util.h"
 #include <cstring>
 
@@ -249,6 +250,32 @@ int speedy_host_table(int trunc, const char* name, double* out, size_t n) {
     if (it->second->size() != n) throw std::runtime_error(std::string("table ") + name + ": size mismatch, have " + std::to_string(it->second->size()));
     memcpy(out, it->second->data(), n * sizeof(double));
     API_END
+}
+
+// host-only: the start-up boundary fields (boundaries.f90:28-68, land_model.f90:50-181, sea_model.f90:80-250) from either source
+long long speedy_host_boundary(const char* bc_path, int trunc, const char* name, double* out, size_t n) {
+    try {
+        if (!bc_path || !name) throw std::runtime_error("null argument");
+        HostEnv env;
+        load_host_env(bc_path, host_tables(trunc), env);
+        const std::string s = name;
+        std::vector<double> ssta_d;
+        const std::vector<double>* v = nullptr;
+        if (s == "phi0") v = &env.phi0; else if (s == "fmask") v = &env.fmask; else if (s == "alb0") v = &env.alb0;
+        else if (s == "fmask_l") v = &env.fmask_l; else if (s == "bmask_l") v = &env.bmask_l; else if (s == "stl12") v = &env.stl12;
+        else if (s == "snowd12") v = &env.snowd12; else if (s == "soilw12") v = &env.soilw12; else if (s == "rhcapl") v = &env.rhcapl;
+        else if (s == "cdland") v = &env.cdland; else if (s == "fmask_s") v = &env.fmask_s; else if (s == "bmask_s") v = &env.bmask_s;
+        else if (s == "sst12") v = &env.sst12; else if (s == "sice12") v = &env.sice12; else if (s == "rhcaps") v = &env.rhcaps;
+        else if (s == "rhcapi") v = &env.rhcapi; else if (s == "cdsea") v = &env.cdsea; else if (s == "cdice") v = &env.cdice;
+        else if (s == "solar") v = &env.solar;
+        else if (s == "ssta") { ssta_d.assign(env.ssta.begin(), env.ssta.end()); v = &ssta_d; }
+        else throw std::runtime_error("unknown boundary field " + s);
+        if (out) {
+            if (n > v->size()) throw std::runtime_error("boundary field " + s + " holds " + std::to_string(v->size()) + " values");
+            memcpy(out, v->data(), n * sizeof(double));       // the first n values (ssta: the leading months)
+        }
+        return (long long)v->size();
+    } catch (const std::exception& e_) { spd::last_error() = e_.what(); return -1; }
 }
 
 int speedy_set_table(speedy_ctx* ctx, const char* name, const double* in, size_t n) {

@@ -8,15 +8,145 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <stdexcept>
+#include <sys/stat.h>
 
 namespace spd {
 
 namespace {
+// ---- the reference's own boundary files (data/bc/t30/{clim,anom}/*.nc: NetCDF-4 = HDF5) read without an HDF5 library -------------
+// What load_boundary_file (input_output.f90:23-92) asks of NetCDF — a named float32 variable of a file — is, in these files, one
+// CONTIGUOUS little-endian dataset.  The reader finds the variable's hard link (1-byte name length, name, 8-byte object-header address:
+// the encoding of a link message whether it sits in the group's header or in its fractal heap), checks that the address holds a
+// version-2 object header ('OHDR'), and reads its dataspace (dimensions), datatype (4-byte IEEE little-endian float) and data-layout
+// (version 3, contiguous: address + size) messages, following continuation blocks ('OCHK').  Anything else — chunked or compressed
+// storage, another type — is refused with a pointer to tools/pack_boundary.py.
+struct Hdf5Var { std::vector<unsigned long long> dims; unsigned long long addr = 0, size = 0; };
+
+unsigned long long le(const std::vector<unsigned char>& b, size_t o, int n) {
+    if (o + n > b.size()) throw std::runtime_error("boundary file: truncated HDF5 structure");
+    unsigned long long v = 0;
+    for (int k = n - 1; k >= 0; k--) v = (v << 8) | b[o + k];
+    return v;
+}
+
+bool parse_dataset_header(const std::vector<unsigned char>& b, size_t a, Hdf5Var& out, std::string& why) {
+    if (a + 8 > b.size() || memcmp(&b[a], "OHDR", 4) != 0 || b[a + 4] != 2) return false;
+    const unsigned flags = b[a + 5];
+    size_t p = a + 6;
+    if (flags & 0x20) p += 16;                 // access / modification / change / birth times
+    if (flags & 0x10) p += 4;                  // attribute storage phase-change values
+    const int szn = 1 << (flags & 3);
+    const unsigned long long c0 = le(b, p, szn);
+    p += szn;
+    const int co = (flags & 0x04) ? 2 : 0;     // creation-order field of every message
+    std::vector<std::pair<size_t, size_t>> chunks{{p, p + (size_t)c0}};
+    bool have_space = false, have_type = false, have_layout = false;
+    for (size_t i = 0; i < chunks.size() && i < 64; i++) {
+        size_t q = chunks[i].first;
+        const size_t end = std::min(chunks[i].second, b.size());
+        while (q + 4 + co <= end) {
+            const unsigned type = b[q];
+            const size_t sz = (size_t)le(b, q + 1, 2);
+            q += 4 + co;
+            const size_t d = q;
+            q += sz;
+            if (q > end) break;
+            if (type == 0x10) {                // continuation: offset, length of an 'OCHK' block (signature first, checksum last)
+                const size_t off = (size_t)le(b, d, 8), len = (size_t)le(b, d + 8, 8);
+                if (off + len <= b.size() && len >= 8 && memcmp(&b[off], "OCHK", 4) == 0) chunks.push_back({off + 4, off + len - 4});
+            } else if (type == 0x01) {         // dataspace
+                const unsigned ver = b[d], rank = b[d + 1];
+                const size_t dp = d + (ver == 2 ? 4 : 8);
+                out.dims.clear();
+                for (unsigned k = 0; k < rank; k++) out.dims.push_back(le(b, dp + 8 * k, 8));
+                have_space = true;
+            } else if (type == 0x03) {         // datatype: class in the low nibble, bit 0 of the first flag byte = byte order
+                const unsigned cls = b[d] & 0x0f, big_endian = b[d + 1] & 1;
+                const unsigned long long size = le(b, d + 4, 4);
+                if (cls != 1 || size != 4 || big_endian) { why = "the variable is not a 4-byte little-endian float"; return false; }
+                have_type = true;
+            } else if (type == 0x08) {         // data layout
+                if (b[d] != 3 || b[d + 1] != 1) { why = "the variable is not stored contiguously (chunked / compressed)"; return false; }
+                out.addr = le(b, d + 2, 8);
+                out.size = le(b, d + 10, 8);
+                have_layout = true;
+            }
+        }
+    }
+    if (!(have_space && have_type && have_layout)) { why = "dataspace / datatype / layout message missing"; return false; }
+    return true;
+}
+
+Hdf5Var find_variable(const std::vector<unsigned char>& b, const std::string& file, const std::string& name) {
+    static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+    if (b.size() < 64 || memcmp(b.data(), sig, 8) != 0)
+        throw std::runtime_error(file + ": not a NetCDF-4 / HDF5 file (the reference's data/bc/t30 files are)");
+    std::string why = "no link to a dataset of that name";
+    const size_t n = name.size();
+    for (size_t k = 1; k + n + 8 <= b.size(); k++) {
+        if (b[k - 1] != n || memcmp(&b[k], name.data(), n) != 0) continue;
+        const size_t addr = (size_t)le(b, k + n, 8);
+        Hdf5Var v;
+        if (addr + 8 <= b.size() && parse_dataset_header(b, addr, v, why)) {
+            unsigned long long cnt = 1;
+            for (auto d : v.dims) cnt *= d;
+            if (v.size != 4 * cnt || v.addr + v.size > b.size()) { why = "layout size does not match the dimensions"; continue; }
+            return v;
+        }
+    }
+    throw std::runtime_error(file + ": variable " + name + ": " + why + " — pack the files with tools/pack_boundary.py instead");
+}
+
+std::vector<unsigned char> read_whole(const std::string& path) {
+    FILE* fp = fopen(path.c_str(), "rb");
+    if (!fp) throw std::runtime_error("cannot open " + path);
+    std::vector<unsigned char> b;
+    unsigned char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, fp)) > 0) b.insert(b.end(), buf, buf + n);
+    fclose(fp);
+    return b;
+}
+
+bool is_directory(const char* path) {
+    struct stat st;
+    return stat(path, &st) == 0 && S_ISDIR(st.st_mode);
+}
+bool file_exists(const std::string& path) {
+    struct stat st;
+    return stat(path.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+
 struct Packed {
     int ix = 0, il = 0;
     std::map<std::string, std::vector<float>> f;
+    // `dir` holds the reference's files, either side by side (the run directory run.sh links them into) or as the data/bc/t30 tree
+    void load_reference_tree(const std::string& dir) {
+        struct Src { const char *file, *sub; std::vector<const char*> vars; };
+        const Src srcs[] = {{"surface.nc", "clim", {"orog", "lsm", "alb", "vegh", "vegl"}}, {"land.nc", "clim", {"stl"}},
+                            {"sea_surface_temperature.nc", "clim", {"sst"}}, {"sea_ice.nc", "clim", {"icec"}}, {"snow.nc", "clim", {"snowd"}},
+                            {"soil.nc", "clim", {"swl1", "swl2"}}, {"sea_surface_temperature_anomaly.nc", "anom", {"ssta"}}};
+        for (const Src& s : srcs) {
+            std::string path = dir + "/" + s.file;
+            if (!file_exists(path)) path = dir + "/" + s.sub + "/" + s.file;
+            if (!file_exists(path)) throw std::runtime_error("boundary directory " + dir + ": " + s.file + " not found (nor under " + s.sub + "/)");
+            const std::vector<unsigned char> b = read_whole(path);
+            for (const char* name : s.vars) {
+                const Hdf5Var v = find_variable(b, path, name);
+                if (v.dims.size() < 2 || v.dims.size() > 3) throw std::runtime_error(path + ": variable " + name + " is not (lat, lon) or (time, lat, lon)");
+                const int vil = (int)v.dims[v.dims.size() - 2], vix = (int)v.dims[v.dims.size() - 1];
+                if (ix == 0) { ix = vix; il = vil; }
+                if (vix != ix || vil != il) throw std::runtime_error(path + ": variable " + name + " has another grid than the other boundary fields");
+                std::vector<float> data((size_t)(v.size / 4));
+                memcpy(data.data(), b.data() + v.addr, (size_t)v.size);      // little-endian float32, as the host
+                f[name] = std::move(data);
+            }
+        }
+    }
     void load(const char* path) {
+        if (is_directory(path)) { load_reference_tree(path); return; }
         FILE* fp = fopen(path, "rb");
         if (!fp) throw std::runtime_error(std::string("cannot open boundary file ") + path);
         char magic[8];

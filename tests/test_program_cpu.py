@@ -115,3 +115,34 @@ def test_executable_fails_loudly_without_a_gpu(tmp_path):
     assert r.returncode == 2 and "no CUDA device" in r.stderr
     assert "nsteps_out (frequency of output)  =    36" in r.stdout and "  End date: 1982/01/03 00:00" in r.stdout      # params.f90:69, date.f90:79-81
     assert not list(tmp_path.glob("*.nc"))
+
+
+REF_BC = "/root/reference/data/bc/t30"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_BC), reason="the reference's boundary files are not on this machine (GPU box)")
+def test_reference_netcdf4_tree_read_directly(tmp_path):
+    """speedy_model_init's other boundary source: a directory of the reference's own NetCDF-4 files, read without an HDF5 library.  Every
+    start-up field equals the one from the packed file bit for bit; the anomaly record is complete (420 months, the pack carries 72); the
+    flat layout of a run directory (run.sh links the files side by side) works like the clim/ + anom/ tree"""
+    import numpy as np
+    pkg = load_pkg()
+    pack = os.path.join(ROOT, "data", "bc_t30.bin")
+    for name in ("phi0", "fmask", "alb0", "stl12", "snowd12", "soilw12", "sst12", "sice12", "fmask_l", "bmask_l", "fmask_s", "rhcapl", "cdland", "cdsea", "cdice", "solar"):
+        a, b = pkg.host_boundary(REF_BC, name), pkg.host_boundary(pack, name)
+        assert a.size == b.size and np.array_equal(a, b), name
+    a, b = pkg.host_boundary(REF_BC, "ssta"), pkg.host_boundary(pack, "ssta")
+    assert a.size == 420 * 96 * 48 and b.size == 72 * 96 * 48 and np.array_equal(a[:b.size], b)
+    flat = tmp_path / "rundir"
+    flat.mkdir()
+    for sub in ("clim", "anom"):
+        for f in os.listdir(os.path.join(REF_BC, sub)):
+            os.symlink(os.path.join(REF_BC, sub, f), flat / f)
+    assert np.array_equal(pkg.host_boundary(flat, "sst12"), pkg.host_boundary(pack, "sst12"))
+    # errors are loud: a file missing from the directory, a file that is not HDF5
+    os.remove(flat / "soil.nc")
+    with pytest.raises(pkg.SpeedyError, match="soil.nc not found"):
+        pkg.host_boundary(flat, "phi0")
+    (flat / "soil.nc").write_bytes(b"CDF\x01" + b"\0" * 4096)
+    with pytest.raises(pkg.SpeedyError, match="not a NetCDF-4 / HDF5 file"):
+        pkg.host_boundary(flat, "phi0")
