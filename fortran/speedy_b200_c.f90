@@ -516,3 +516,28 @@ contains
                                                        merge(1_c_int, 0_c_int, compute_shortwave)), 'get_physical_tendencies')
     end subroutine
 end module
+
+!> Drop-in for `program speedy` (speedy.f90:1-54) when nothing of the reference but its namelist.nml and boundary files is kept: the
+!> five calls `speedy.f90_b200/bin/speedy_b200` makes from C++.  Build this unit with -DSPEEDY_B200_PROGRAM (it is the only `program`
+!> of the file; the modules above are for a host that keeps the reference's own main program).
+#ifdef SPEEDY_B200_PROGRAM
+program speedy_b200_main
+    use speedy_b200_c
+    implicit none
+    type(speedy_cfg) :: cfg
+    type(speedy_namelist) :: nml
+    integer(c_long_long) :: steps
+    integer(c_int) :: rc
+
+    call b200_check(speedy_read_namelist('namelist.nml'//c_null_char, nml), 'namelist')            ! params.f90:54-70, date.f90:54-71
+    cfg = speedy_cfg(30_c_int, 8_c_int, 1_c_int, 1_c_int, 0_c_int, 0_c_int, 0_c_long_long, 0_c_int, 0_c_int, 0_c_int)
+    call b200_check(speedy_create(cfg, b200_ctx), 'create')
+    ! initialize (initialization.f90:12-82) from the boundary files of the run directory, start date of the namelist
+    call b200_check(speedy_model_init(b200_ctx, '.'//c_null_char, nml%start_datetime(1), nml%start_datetime(2), nml%start_datetime(3), &
+                                      nml%start_datetime(4), nml%start_datetime(5)), 'initialize')
+    ! speedy.f90:24-54: files every nsteps_out steps into the working directory, diagnostics every nstdia steps
+    rc = speedy_main_loop(b200_ctx, nml, '.'//c_null_char, 0_c_int, 1_c_int, steps)
+    call b200_check(rc, 'main loop')                                                               ! rc = 1: stop 'Model variables out of accepted range'
+    call b200_check(speedy_destroy(b200_ctx), 'destroy')
+end program
+#endif

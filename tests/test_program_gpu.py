@@ -148,3 +148,24 @@ def test_async_output_equals_the_synchronous_writer(pkg, tmp_path):
         a.write_output_async(tmp_path / "no" / "such" / "dir", ymdhm, 41)
         a.output_drain()
     a.close(); b.close()
+
+
+def test_executable_ensemble_members_into_their_own_directories(pkg, tmp_path):
+    """--members 3 --sppt --member -1: every member's files under member<e>/, equal to speedy_write_output of the same members"""
+    (tmp_path / "namelist.nml").write_text("&params\nnsteps_out = 18\nnstdia = 36\n/\n&date\nend_datetime%month = 1\nend_datetime%day = 2\n/\n")
+    r = subprocess.run([EXE, "--bc", BC, "--members", "3", "--sppt", "--seed", "11", "--member", "-1"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    c = pkg.Speedy(trunc=30, nmembers=3, sppt_on=1, seed=11)
+    c.model_init(BC)
+    assert c.run_steps(36) == 0
+    last = []
+    for e in range(3):
+        names = sorted(p.name for p in (tmp_path / f"member{e}").glob("*.nc"))
+        assert names == ["198201010000.nc", "198201011200.nc", "198201020000.nc"]
+        f, hours = _read(tmp_path / f"member{e}" / names[-1])
+        want = c.output_fields(member=e)
+        for n in FIELDS:
+            assert np.array_equal(f[n], want[n]), (e, n)
+        last.append(f["t"])
+    assert not np.array_equal(last[0], last[1])                 # SPPT: the members differ
+    c.close()
