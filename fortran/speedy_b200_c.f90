@@ -518,7 +518,7 @@ contains
 end module
 
 !> Drop-in for `program speedy` (speedy.f90:1-54) when nothing of the reference but its namelist.nml and boundary files is kept: the
-!> five calls `speedy.f90_b200/bin/speedy_b200` makes from C++.  Build this unit with -DSPEEDY_B200_PROGRAM (it is the only `program`
+!> five calls `speedy.f90_b200/bin/speedy_b200` makes from C++.  Build this unit with -cpp -DSPEEDY_B200_PROGRAM (it is the only `program`
 !> of the file; the modules above are for a host that keeps the reference's own main program).
 #ifdef SPEEDY_B200_PROGRAM
 program speedy_b200_main

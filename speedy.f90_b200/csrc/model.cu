@@ -967,6 +967,10 @@ struct OutPipe {
         free_slots.pop_back();
         return s;
     }
+    void release(int s) {                   // a slot that was acquired but never submitted
+        { std::lock_guard<std::mutex> lk(mu); free_slots.push_back(s); }
+        cv_done.notify_all();
+    }
     void submit(Job j) {
         { std::lock_guard<std::mutex> lk(mu); jobs.push_back(std::move(j)); in_flight++; }
         cv_job.notify_one();
@@ -1000,9 +1004,11 @@ int speedy_write_output_async(speedy_ctx* ctx, int member, const char* dir, cons
     if (!M.outpipe) { auto* p = new OutPipe; M.outpipe = p; p->start(ctx->device, n); }
     OutPipe& P = *static_cast<OutPipe*>(M.outpipe);
     const int s = P.acquire();
-    float* d = enqueue_output(ctx, member);
-    CUDA_CHECK(cudaMemcpyAsync(P.slot[s], d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaEventRecord(P.ev[s], ctx->stream));
+    try {
+        float* d = enqueue_output(ctx, member);
+        CUDA_CHECK(cudaMemcpyAsync(P.slot[s], d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_CHECK(cudaEventRecord(P.ev[s], ctx->stream));
+    } catch (...) { P.release(s); throw; }
     char name[40];
     snprintf(name, sizeof name, "%04d%02d%02d%02d%02d.nc", ymdhm[0], ymdhm[1], ymdhm[2], ymdhm[3], ymdhm[4]);
     OutPipe::Job j;
