@@ -19,6 +19,13 @@ FIELDS = ("u", "v", "t", "q", "phi", "ps")
 PROG = ("vor", "div", "t", "tr", "ps")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _executable():
+    """the executable is built in-tree by __graft_entry__.build(); a checkout without built artefacts builds it here (g++, C ABI only)"""
+    if not os.path.exists(EXE):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "speedy.f90_b200"), "bin/speedy_b200"])
+
+
 def _read(path):
     nc = netcdf_file(str(path), "r", mmap=False)
     out = {n: np.array(nc.variables[n][0]) for n in FIELDS}
