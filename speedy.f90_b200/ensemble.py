@@ -65,13 +65,13 @@ class Ensemble:
     """`total_members` members over the ranks of the default process group; this rank's block
     is one speedy context on `device`."""
 
-    def __init__(self, pkg, total_members, device=0, trunc=30, sppt_on=1, seed=0, rank=0, world=1):
+    def __init__(self, pkg, total_members, device=0, trunc=30, sppt_on=1, seed=0, rank=0, world=1, precision=0, nsteps=0):
         self.rank, self.world, self.total = rank, world, total_members
         self.lo, self.hi = block_partition(total_members, world, rank)
         if self.hi == self.lo:
             raise ValueError("more ranks than members")
         self.ctx = pkg.Speedy(trunc=trunc, nmembers=self.hi - self.lo, device=device, sppt_on=sppt_on, seed=seed,
-                              member_offset=self.lo)
+                              member_offset=self.lo, precision=precision, nsteps=nsteps)
         self.device = device
 
     def model_init(self, bc_path, *date):
