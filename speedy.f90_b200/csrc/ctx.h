@@ -109,6 +109,7 @@ struct speedy_ctx {
     // device tables
     std::map<std::string, spd::DevBuf<double>> dtab;
     spd::DevBuf<int> d_qtile, d_qtile_inv;
+    spd::DevBuf<float> f32tab;          // real32 copies of the transform tables (precision = 1, transforms_f32.cu)
     spd::DevTables dv{};
     // scratch for host-pointer API calls
     spd::DevBuf<double> scratch_a, scratch_b, scratch_c, scratch_d;
