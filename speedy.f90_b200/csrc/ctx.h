@@ -151,7 +151,7 @@ unsigned s2g_quad_ready_counts(int nbatch);                                     
 void build_quad_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyq);
 void build_quad_inverse_tables(const Tables& t, std::vector<int>& tiles, std::vector<double>& polyi);
 // transforms_f32.cu (precision = 1)
-void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers);
+void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const CloseArgs& cl);
 void launch_grid_to_spec_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch, double* d_out, long long out_ms, int nmembers, const int* gate);
 int polyd_groups(int trunc);
 int polyd_mg(int trunc);

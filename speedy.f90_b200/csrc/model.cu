@@ -302,9 +302,8 @@ static void enqueue_step(speedy_ctx* ctx, int j1, int j2, double dt, int csw_ove
 static const int kLaunchesPerStep = 4;
 static void enqueue_main_loop_step(speedy_ctx* ctx) {
     const double delt = ctx->tab.c.delt;
-    // trace mode (exact timeline) and the real32-transform mode (its spec->grid kernel has no closing CTA) close each step
-    // with the stand-alone kernel
-    const bool tracing = ctx->dv.trace != nullptr || ctx->precision != 0;
+    // trace mode (exact timeline) closes each step with the stand-alone kernel
+    const bool tracing = ctx->dv.trace != nullptr;
     sppt_next(ctx);
     ctx->model->alias_active = ctx->transient_alias && ctx->l2_discard && g2s_quad_selected(ctx, GO_N, ctx->nmembers) &&
                                s2g_quad_selected(ctx, ctx->model->nstep_fields, ctx->nmembers, true);

@@ -1055,7 +1055,8 @@ void launch_spec_to_grid(speedy_ctx* ctx, const double* d_in, long long in_ms, c
                          double* d_out, long long out_ms, int nmembers, int mode, const CloseArgs* close, bool quad_ok) {
     if (nbatch <= 0) return;
     if (mode == 0 && ctx->precision == 1) {
-        launch_spec_to_grid_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers);   // the caller closes the step separately
+        const CloseArgs cl = close ? *close : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
+        launch_spec_to_grid_f32(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl);
     } else if (mode == 0) {
         const CloseArgs cl = close ? *close : CloseArgs{nullptr, nullptr, 0, 0, nullptr};
         if (ctx->d.trunc == 30) launch_s2g_stream<30>(ctx, d_in, in_ms, d_desc, nbatch, d_out, out_ms, nmembers, cl, quad_ok);

@@ -12,6 +12,8 @@
 //   k_g2s_f32 = fourier_dir (fourier.f90:56-82) + legendre_dir (legendre.f90:114-155)
 #include "ctx.h"
 #include "spectral_ops.cuh"
+#include "tma.cuh"
+#include "close_step.cuh"
 
 namespace spd {
 
@@ -38,8 +40,12 @@ struct FCfg {
 template <int TRUNC>
 __global__ void __launch_bounds__(FCfg<TRUNC>::THREADS)
 k_s2g_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __restrict__ desc,
-          double* __restrict__ out_base, long long out_ms, DevTables tv, const float* __restrict__ ftab) {
+          double* __restrict__ out_base, long long out_ms, DevTables tv, const float* __restrict__ ftab, CloseArgs cl, int nwork) {
     using C = FCfg<TRUNC>;
+    if (blockIdx.x == (unsigned)nwork) {                         // the extra CTAs: member 0's closes the previous main-loop step, off the critical path (close_step.cuh)
+        if (blockIdx.y == 0 && cl.clk) { pdl_wait(); pdl_trigger(); close_step_cta(cl, threadIdx.x); }
+        return;
+    }
     extern __shared__ __align__(16) unsigned char raw[];
     double* sA = reinterpret_cast<double*>(raw);                 // source fields of a derived input (fp64 state)
     double* sB = sA + C::NSPEC2;
@@ -54,6 +60,8 @@ k_s2g_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __re
         const float4* gf = reinterpret_cast<const float4*>(ftab + C::T_FINV);
         for (int t = tid; t < C::K2 * C::IX / 4; t += nthr) reinterpret_cast<float4*>(sF)[t] = gf[t];
     }
+    pdl_wait();                                                  // the spectral fields of the previous kernel are complete
+    pdl_trigger();
     const XDesc dsc = desc[b];
     const double* mbase = in_base + (size_t)e * in_ms;
     const double* in = mbase + dsc.off;
@@ -145,7 +153,6 @@ k_g2s_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __re
     float* sP = sA + C::RG * C::IX;                  // [IY][NX][MG] P of this group's wavenumbers
     const int b = blockIdx.x / C::CG, grp = blockIdx.x - b * C::CG, e = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     const XDesc dsc = desc[b];
-    if (gate && (dsc.flags & 4) && !*gate) return;
     const double* in = in_base + (size_t)e * in_ms + dsc.off;
     const int c0row = grp * C::RG;
     {
@@ -154,6 +161,9 @@ k_g2s_f32(const double* __restrict__ in_base, long long in_ms, const XDesc* __re
         const float4* gp = reinterpret_cast<const float4*>(ftab + C::T_POLYD + (size_t)grp * C::IY * C::NX * C::MG);
         for (int t = tid; t < C::IY * C::NX * C::MG / 4; t += nthr) reinterpret_cast<float4*>(sP)[t] = gp[t];
     }
+    pdl_wait();                                                  // the grid fields (and the clock flag behind `gate`) of the previous kernels are complete
+    pdl_trigger();
+    if (gate && (dsc.flags & 4) && !*gate) return;
     const double* scl = (dsc.flags & 1) ? tv.cosgr : ((dsc.flags & 2) ? tv.cosgr2 : nullptr);
     for (int t = tid; t < C::IL * C::IX; t += nthr) {
         const int j = t / C::IX, i = t - j * C::IX;
@@ -229,17 +239,28 @@ static const float* f32_tables(speedy_ctx* ctx) {
 }
 
 void launch_spec_to_grid_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
-                             double* d_out, long long out_ms, int nmembers) {
-    if (ctx->d.trunc == 30) k_s2g_f32<30><<<dim3(nbatch * FCfg<30>::LG, nmembers), FCfg<30>::THREADS, FCfg<30>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, f32_tables<30>(ctx));
-    else k_s2g_f32<47><<<dim3(nbatch * FCfg<47>::LG, nmembers), FCfg<47>::THREADS, FCfg<47>::S2G_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, f32_tables<47>(ctx));
-    CUDA_CHECK(cudaGetLastError());
+                             double* d_out, long long out_ms, int nmembers, const CloseArgs& cl) {
+    const bool pdl = ctx->dv.trace == nullptr || ctx->trace_pdl;
+    if (ctx->d.trunc == 30) {
+        const int nwork = nbatch * FCfg<30>::LG;
+        CUDA_CHECK(launch_pdl(pdl, k_s2g_f32<30>, dim3(nwork + (cl.clk ? 1 : 0), nmembers), dim3(FCfg<30>::THREADS), FCfg<30>::S2G_SMEM, ctx->stream,
+                              d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, f32_tables<30>(ctx), cl, nwork));
+    } else {
+        const int nwork = nbatch * FCfg<47>::LG;
+        CUDA_CHECK(launch_pdl(pdl, k_s2g_f32<47>, dim3(nwork + (cl.clk ? 1 : 0), nmembers), dim3(FCfg<47>::THREADS), FCfg<47>::S2G_SMEM, ctx->stream,
+                              d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, f32_tables<47>(ctx), cl, nwork));
+    }
 }
 
 void launch_grid_to_spec_f32(speedy_ctx* ctx, const double* d_in, long long in_ms, const XDesc* d_desc, int nbatch,
                              double* d_out, long long out_ms, int nmembers, const int* gate) {
-    if (ctx->d.trunc == 30) k_g2s_f32<30><<<dim3(nbatch * FCfg<30>::CG, nmembers), FCfg<30>::THREADS, FCfg<30>::G2S_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate, f32_tables<30>(ctx));
-    else k_g2s_f32<47><<<dim3(nbatch * FCfg<47>::CG, nmembers), FCfg<47>::THREADS, FCfg<47>::G2S_SMEM, ctx->stream>>>(d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate, f32_tables<47>(ctx));
-    CUDA_CHECK(cudaGetLastError());
+    const bool pdl = ctx->dv.trace == nullptr || ctx->trace_pdl;
+    if (ctx->d.trunc == 30)
+        CUDA_CHECK(launch_pdl(pdl, k_g2s_f32<30>, dim3(nbatch * FCfg<30>::CG, nmembers), dim3(FCfg<30>::THREADS), FCfg<30>::G2S_SMEM, ctx->stream,
+                              d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate, f32_tables<30>(ctx)));
+    else
+        CUDA_CHECK(launch_pdl(pdl, k_g2s_f32<47>, dim3(nbatch * FCfg<47>::CG, nmembers), dim3(FCfg<47>::THREADS), FCfg<47>::G2S_SMEM, ctx->stream,
+                              d_in, in_ms, d_desc, d_out, out_ms, ctx->dv, gate, f32_tables<47>(ctx)));
 }
 
 }  // namespace spd
