@@ -193,6 +193,14 @@ module speedy_b200_c
             import; type(c_ptr), value :: ctx; character(kind=c_char), intent(in) :: name(*)
             integer(c_int), intent(out) :: host(*); integer(c_size_t), value :: n
         end function
+        ! implicit.f90:168-217 and horizontal_diffusion.f90:86-105 as stand-alone operators on host arrays (in place)
+        integer(c_int) function speedy_implicit_terms(ctx, divdt, tdt, psdt) bind(C, name="speedy_implicit_terms")
+            import; type(c_ptr), value :: ctx; complex(c_double_complex), intent(inout) :: divdt(*), tdt(*), psdt(*)
+        end function
+        integer(c_int) function speedy_do_horizontal_diffusion(ctx, field, fdt, dmp, dmp1, nlev) bind(C, name="speedy_do_horizontal_diffusion")
+            import; type(c_ptr), value :: ctx; complex(c_double_complex), intent(in) :: field(*); complex(c_double_complex), intent(inout) :: fdt(*)
+            real(c_double), intent(in) :: dmp(*), dmp1(*); integer(c_int), value :: nlev
+        end function
         integer(c_int) function speedy_get_geopotential(ctx, j) bind(C, name="speedy_get_geopotential")
             import; type(c_ptr), value :: ctx; integer(c_int), value :: j
         end function
@@ -499,6 +507,50 @@ contains
         call b200_check(speedy_get_field(b200_ctx, 'psdt'//c_null_char, buf(1:2*mx*nx), int(2*mx*nx, c_size_t)), 'get psdt')
         psdt = reshape(transfer(buf(1:2*mx*nx), psdt), shape(psdt))
     end subroutine
+end module
+
+!> Drop-in for the procedures of module `implicit` (implicit.f90:11-12): initialize_implicit(dt), implicit_terms(divdt, tdt, psdt).
+module implicit_b200
+    use types, only: p
+    use params
+    use speedy_b200_c
+    implicit none
+contains
+    subroutine initialize_implicit(dt)
+        real(p), intent(in) :: dt
+        call b200_check(speedy_initialize_implicit(b200_ctx, real(dt, c_double)), 'initialize_implicit')
+    end subroutine
+    subroutine implicit_terms(divdt, tdt, psdt)
+        complex(p), intent(inout) :: divdt(mx,nx,kx), tdt(mx,nx,kx), psdt(mx,nx)
+        call b200_check(speedy_implicit_terms(b200_ctx, divdt, tdt, psdt), 'implicit_terms')
+    end subroutine
+end module
+
+!> Drop-in for the generic `do_horizontal_diffusion` of module `horizontal_diffusion` (horizontal_diffusion.f90:13-17,86-105).
+module horizontal_diffusion_b200
+    use types, only: p
+    use params
+    use speedy_b200_c
+    implicit none
+    interface do_horizontal_diffusion
+        module procedure do_horizontal_diffusion_2d
+        module procedure do_horizontal_diffusion_3d
+    end interface
+contains
+    function do_horizontal_diffusion_2d(field, fdt_in, dmp, dmp1) result(fdt_out)
+        complex(p), intent(in) :: field(mx,nx), fdt_in(mx,nx)
+        real(p), intent(in) :: dmp(mx,nx), dmp1(mx,nx)
+        complex(p) :: fdt_out(mx,nx)
+        fdt_out = fdt_in
+        call b200_check(speedy_do_horizontal_diffusion(b200_ctx, field, fdt_out, dmp, dmp1, 1_c_int), 'do_horizontal_diffusion')
+    end function
+    function do_horizontal_diffusion_3d(field, fdt_in, dmp, dmp1) result(fdt_out)
+        complex(p), intent(in) :: field(mx,nx,kx), fdt_in(mx,nx,kx)
+        real(p), intent(in) :: dmp(mx,nx), dmp1(mx,nx)
+        complex(p) :: fdt_out(mx,nx,kx)
+        fdt_out = fdt_in
+        call b200_check(speedy_do_horizontal_diffusion(b200_ctx, field, fdt_out, dmp, dmp1, int(kx, c_int)), 'do_horizontal_diffusion')
+    end function
 end module
 
 !> Drop-in for module `physics` (physics.f90:8,43): get_physical_tendencies on host arrays.

@@ -107,6 +107,14 @@ const char* speedy_field_names(void);
 
 /* initialize_implicit(dt)  implicit.f90:36-165 (host LU, uploads xj,xc,xd,elz,dmp1*,tref*) */
 int speedy_initialize_implicit(speedy_ctx* ctx, double dt);
+/* implicit_terms(divdt, tdt, psdt)  implicit.f90:168-217 on the caller's tendencies (complex(mx,nx,kx) x 2, complex(mx,nx); host
+ * arrays, in place) with the matrices of the last speedy_initialize_implicit: the operator-level drop-in (the main loop runs it fused
+ * inside the spectral step) */
+int speedy_implicit_terms(speedy_ctx* ctx, double* divdt, double* tdt, double* psdt);
+/* do_horizontal_diffusion(field, fdt_in, dmp, dmp1)  horizontal_diffusion.f90:86-105, the generic of both forms: nlev = 1 for
+ * complex(mx,nx), kx for complex(mx,nx,kx); fdt = (fdt - dmp*field)*dmp1 in place; dmp / dmp1 are real(mx,nx) (the module's
+ * coefficient arrays are the tables "dmp", "dmpd", "dmps", "dmp1", "dmp1d", "dmp1s" of speedy_get_table) */
+int speedy_do_horizontal_diffusion(speedy_ctx* ctx, const double* field, double* fdt, const double* dmp, const double* dmp1, int nlev);
 /* get_geopotential  geopotential.f90:33-57 on the resident state: phi <- T(time level j) */
 int speedy_get_geopotential(speedy_ctx* ctx, int j);
 /* get_tendencies    tendencies.f90:11-37 (grid-point + spectral + implicit) into the

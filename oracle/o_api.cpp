@@ -176,6 +176,20 @@ int orc_model_date(int* ymdhm, long long* step) {
 }
 int orc_set_date_fractions(double tmonth_, double tyear_, int imont1_) { tmonth = tmonth_; tyear = tyear_; imont1 = imont1_; return 0; }
 int orc_initialize_implicit(double dt) { initialize_implicit(dt); return 0; }
+/* implicit.f90:168-217 and horizontal_diffusion.f90:86-105 on caller-supplied arrays (in place) */
+int orc_implicit_terms(double* divdt, double* tdt, double* psdt) {
+    static Spec3 a, b; static Spec2 c;
+    memcpy((void*)a.p(), divdt, sizeof(cplx) * a.size()); memcpy((void*)b.p(), tdt, sizeof(cplx) * b.size()); memcpy((void*)c.p(), psdt, sizeof(cplx) * c.size());
+    implicit_terms(a, b, c);
+    memcpy(divdt, a.p(), sizeof(cplx) * a.size()); memcpy(tdt, b.p(), sizeof(cplx) * b.size()); memcpy(psdt, c.p(), sizeof(cplx) * c.size());
+    return 0;
+}
+int orc_do_horizontal_diffusion(const double* field, double* fdt, const double* d, const double* d1, int nlev) {
+    const cplx* f = (const cplx*)field; cplx* t = (cplx*)fdt;
+    for (int k = 0; k < nlev; k++)
+        for (int q = 0; q < mx * nx; q++) t[(size_t)k * mx * nx + q] = (t[(size_t)k * mx * nx + q] - d[q] * f[(size_t)k * mx * nx + q]) * d1[q];
+    return 0;
+}
 int orc_step(int j1, int j2, double dt, int csw) { compute_shortwave = csw != 0; step(j1, j2, dt); return 0; }
 int orc_set_sppt(int on) { sppt_on = on != 0; if (on) sppt_reset(); return 0; }
 int orc_get_geopotential(const double* tt, const double* phis_, double* phi_) {

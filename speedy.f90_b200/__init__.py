@@ -321,6 +321,23 @@ class Speedy:
         """initialization.f90:12 — boundary data, rest state, coupler, forcing, first_step."""
         _chk(self.L.speedy_model_init(self.h, str(bc_path).encode(), year, month, day, hour, minute))
 
+    def implicit_terms(self, divdt, tdt, psdt):
+        """implicit.f90:168-217 — returns the corrected (divdt, tdt, psdt); complex (kx, nx, mx) x 2 and (nx, mx)."""
+        a, b, c = (np.array(x, dtype=np.complex128, order="C") for x in (divdt, tdt, psdt))
+        assert a.shape == (self.kx, self.nx, self.mx) and b.shape == a.shape and c.shape == (self.nx, self.mx)
+        _chk(self.L.speedy_implicit_terms(self.h, _p(a), _p(b), _p(c)))
+        return a, b, c
+
+    def do_horizontal_diffusion(self, field, fdt, dmp, dmp1):
+        """horizontal_diffusion.f90:86-105 — (fdt - dmp*field)*dmp1 for a complex (nx, mx) or (nlev, nx, mx) field."""
+        f = _c(field, np.complex128)
+        t = np.array(fdt, dtype=np.complex128, order="C")
+        d, d1 = _c(dmp, np.float64), _c(dmp1, np.float64)
+        assert f.shape == t.shape and d.shape == (self.nx, self.mx) and d1.shape == d.shape
+        nlev = 1 if f.ndim == 2 else f.shape[0]
+        _chk(self.L.speedy_do_horizontal_diffusion(self.h, _p(f), _p(t), _p(d), _p(d1), int(nlev)))
+        return t
+
     def initialize_implicit(self, dt):
         _chk(self.L.speedy_initialize_implicit(self.h, ctypes.c_double(dt)))
 

@@ -546,6 +546,70 @@ void setup_spec_step_kernels() {
     CUDA_CHECK(cudaFuncSetAttribute(k_spec_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 }
 
+// Stand-alone forms of two operators that the main loop only runs fused inside k_spec_step, for the operator-level drop-ins of the
+// C ABI (implicit.f90:168-217 implicit_terms, horizontal_diffusion.f90:86-105 do_horizontal_diffusion): one thread per (m,n),
+// the sums in the reference's order.
+__global__ void k_implicit_terms(double* __restrict__ divdt_, double* __restrict__ tdt_, double* __restrict__ psdt_, DevTables tv, const LevelConsts* __restrict__ lcp) {
+    const int mx = tv.mx, nx = tv.nx, nsp = mx * nx;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nsp) return;
+    const int n = r / mx, m = r - n * mx;
+    const LevelConsts& lc = *lcp;
+    const cd zero{0.0, 0.0};
+    cd tdt[KX], divdt[KX], ye[KX], yf[KX];
+#pragma unroll
+    for (int k = 0; k < KX; k++) { tdt[k] = ld(tdt_ + (size_t)2 * nsp * k, mx, m, n); divdt[k] = ld(divdt_ + (size_t)2 * nsp * k, mx, m, n); ye[k] = zero; }
+    cd psdt = ld(psdt_, mx, m, n);
+#pragma unroll
+    for (int k1 = 0; k1 < KX; k1++)
+#pragma unroll
+        for (int k = 0; k < KX; k++) ye[k] = ye[k] + tv.xd[k + KX * k1] * tdt[k1];
+    const double elz = tv.elz[m + (size_t)mx * n];
+#pragma unroll
+    for (int k = 0; k < KX; k++) { ye[k] = ye[k] + lc.tref1[k] * psdt; yf[k] = divdt[k] + elz * ye[k]; divdt[k] = zero; }
+    if (m + n != 0) {
+        const double* xj = tv.xj + (size_t)KX * KX * (m + n - 1);      // xj(:,:,l), l = m + n - 2 in the reference's 1-based indices
+#pragma unroll
+        for (int k1 = 0; k1 < KX; k1++)
+#pragma unroll
+            for (int k = 0; k < KX; k++) divdt[k] = divdt[k] + xj[k + KX * k1] * yf[k1];
+    }
+#pragma unroll
+    for (int k = 0; k < KX; k++) psdt = psdt - lc.dhsx[k] * divdt[k];
+#pragma unroll
+    for (int k = 0; k < KX; k++) {
+        cd t = tdt[k];
+#pragma unroll
+        for (int k1 = 0; k1 < KX; k1++) t = t + tv.xc[k + KX * k1] * divdt[k1];
+        st(tdt_ + (size_t)2 * nsp * k, mx, m, n, t);
+        st(divdt_ + (size_t)2 * nsp * k, mx, m, n, divdt[k]);
+    }
+    st(psdt_, mx, m, n, psdt);
+}
+
+__global__ void k_horizontal_diffusion(const double* __restrict__ field, double* __restrict__ fdt, const double* __restrict__ dmp, const double* __restrict__ dmp1,
+                                       int nsp, int nlev) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nsp * nlev) return;
+    const int q = t % nsp;
+    const cd f{field[2 * (size_t)t], field[2 * (size_t)t + 1]}, d{fdt[2 * (size_t)t], fdt[2 * (size_t)t + 1]};
+    const cd o = dmp1[q] * (d - dmp[q] * f);      // (fdt_in - dmp*field)*dmp1
+    fdt[2 * (size_t)t] = o.re; fdt[2 * (size_t)t + 1] = o.im;
+}
+
+void launch_implicit_terms(speedy_ctx* ctx, double* d_divdt, double* d_tdt, double* d_psdt) {
+    k_implicit_terms<<<(ctx->d.nspec() + 63) / 64, 64, 0, ctx->stream>>>(d_divdt, d_tdt, d_psdt, ctx->dv, ctx->model->lc.p);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_horizontal_diffusion(speedy_ctx* ctx, const double* d_field, double* d_fdt, const double* d_dmp, const double* d_dmp1, int nlev) {
+    const int total = ctx->d.nspec() * nlev;
+    k_horizontal_diffusion<<<(total + 127) / 128, 128, 0, ctx->stream>>>(d_field, d_fdt, d_dmp, d_dmp1, ctx->d.nspec(), nlev);
+    ctx->launches++;
+    CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_close_step(speedy_ctx* ctx) {
     Model& M = *ctx->model;
     CloseArgs cl{M.clock.p, M.diag_partial.p, (int)((ctx->d.nspec() + SC - 1) / SC), ctx->nmembers, ctx->dv.trace};

@@ -414,6 +414,47 @@ int speedy_initialize_implicit(speedy_ctx* ctx, double dt) {
     API_END
 }
 
+// implicit.f90:168-217 on the caller's tendencies (host arrays, in place), with the matrices of the last speedy_initialize_implicit
+int speedy_implicit_terms(speedy_ctx* ctx, double* divdt, double* tdt, double* psdt) {
+    API_BEGIN
+    check_ready(ctx);
+    if (!divdt || !tdt || !psdt) throw std::runtime_error("speedy_implicit_terms: null argument");
+    if (ctx->model->implicit_dt == 0.0) throw std::runtime_error("speedy_implicit_terms: call speedy_initialize_implicit(dt) first (implicit.f90:36)");
+    const size_t n2 = (size_t)2 * ctx->d.nspec(), n3 = n2 * KXc;
+    ctx->ensure_scratch(ctx->scratch_a, n3);
+    ctx->ensure_scratch(ctx->scratch_b, n3);
+    ctx->ensure_scratch(ctx->scratch_c, n2);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_a.p, divdt, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_b.p, tdt, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_c.p, psdt, n2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_implicit_terms(ctx, ctx->scratch_a.p, ctx->scratch_b.p, ctx->scratch_c.p);
+    CUDA_CHECK(cudaMemcpyAsync(divdt, ctx->scratch_a.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(tdt, ctx->scratch_b.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(psdt, ctx->scratch_c.p, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+
+// horizontal_diffusion.f90:86-105: fdt = (fdt - dmp*field)*dmp1 on nlev levels (1: the 2-D form, kx: the 3-D form), host arrays
+int speedy_do_horizontal_diffusion(speedy_ctx* ctx, const double* field, double* fdt, const double* dmp, const double* dmp1, int nlev) {
+    API_BEGIN
+    check_ready(ctx);
+    if (!field || !fdt || !dmp || !dmp1) throw std::runtime_error("speedy_do_horizontal_diffusion: null argument");
+    if (nlev < 1) throw std::runtime_error("speedy_do_horizontal_diffusion: nlev must be positive");
+    const size_t ns = (size_t)ctx->d.nspec(), n3 = 2 * ns * nlev;
+    ctx->ensure_scratch(ctx->scratch_a, n3);
+    ctx->ensure_scratch(ctx->scratch_b, n3);
+    ctx->ensure_scratch(ctx->scratch_c, 2 * ns);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_a.p, field, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_b.p, fdt, n3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_c.p, dmp, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->scratch_c.p + ns, dmp1, ns * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    launch_horizontal_diffusion(ctx, ctx->scratch_a.p, ctx->scratch_b.p, ctx->scratch_c.p, ctx->scratch_c.p + ns, nlev);
+    CUDA_CHECK(cudaMemcpyAsync(fdt, ctx->scratch_b.p, n3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END
+}
+
 int speedy_get_geopotential(speedy_ctx* ctx, int j) {
     API_BEGIN
     check_ready(ctx);

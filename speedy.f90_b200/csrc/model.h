@@ -113,6 +113,8 @@ void launch_geopotential(speedy_ctx* ctx, int which);   // which: bit0 module ph
 void launch_grid_columns(speedy_ctx* ctx, int mode, int csw_override, int merged = 0);   // mode 0 dyn+phys, 1 physics only on resident tendencies
 void launch_spec_step(speedy_ctx* ctx, int j1, int j2, double dt, int store_tend_only, int close_step = 0);
 void launch_close_step(speedy_ctx* ctx);
+void launch_implicit_terms(speedy_ctx* ctx, double* d_divdt, double* d_tdt, double* d_psdt);   // stand-alone implicit.f90:168-217 on device arrays
+void launch_horizontal_diffusion(speedy_ctx* ctx, const double* d_field, double* d_fdt, const double* d_dmp, const double* d_dmp1, int nlev);
 void free_column_maps(Model& M);   // stand-alone closing of a pending step
 void launch_diagnostics(speedy_ctx* ctx, int level);
 void launch_slab(speedy_ctx* ctx, int day0);

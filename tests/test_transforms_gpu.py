@@ -114,3 +114,34 @@ def test_vdspec(ctx, oracle):
             rv = np.empty((o.nx, o.mx), complex); rd = np.empty_like(rv)
             o.L.orc_vdspec(o.p(np.ascontiguousarray(ug[i])), o.p(np.ascontiguousarray(vg[i])), o.p(rv), o.p(rd), kcos)
             assert rel_rms(vo[i], rv) < TOL and rel_rms(di[i], rd) < TOL
+
+
+def test_implicit_terms_and_horizontal_diffusion(ctx, oracle):
+    """the operator-level drop-ins of implicit.f90:168-217 and horizontal_diffusion.f90:86-105 (the main loop runs both fused inside the
+    spectral step): random tendencies on the triangle, matrices of initialize_implicit(dt) for the three time steps first_step uses"""
+    import ctypes
+    o = oracle
+    rng = np.random.default_rng(21)
+    kx = 8
+    for dt in (0.5 * 2400.0, 2400.0, 2 * 2400.0):
+        o.L.orc_initialize_implicit(ctypes.c_double(dt))
+        ctx.initialize_implicit(dt)
+        divdt = 1e-9 * random_spec(rng, (kx,), o.nx, o.mx, o.trunc)
+        tdt = 1e-4 * random_spec(rng, (kx,), o.nx, o.mx, o.trunc)
+        psdt = 1e-8 * random_spec(rng, (), o.nx, o.mx, o.trunc)
+        a, b, c = ctx.implicit_terms(divdt, tdt, psdt)
+        ra, rb, rc = divdt.copy(), tdt.copy(), psdt.copy()
+        assert o.L.orc_implicit_terms(o.p(ra), o.p(rb), o.p(rc)) == 0
+        assert rel_rms(a, ra) < 1e-14 and rel_rms(b, rb) < 1e-14 and rel_rms(c, rc) < 1e-14
+        assert not np.array_equal(a, divdt)
+        assert np.all(a[:, 0, 0] == 0)                          # l = 0: divdt(1,1,:) stays zero (implicit.f90:199)
+    for name, name1, nlev in (("dmp", "dmp1", kx), ("dmpd", "dmp1d", kx), ("dmps", "dmp1s", 1)):
+        d = ctx.table(name, o.nx * o.mx).reshape(o.nx, o.mx)
+        d1 = ctx.table(name1, o.nx * o.mx).reshape(o.nx, o.mx)
+        lead = (nlev,) if nlev > 1 else ()
+        field = random_spec(rng, lead, o.nx, o.mx, o.trunc)
+        fdt = 1e-5 * random_spec(rng, lead, o.nx, o.mx, o.trunc)
+        got = ctx.do_horizontal_diffusion(field, fdt, d, d1)
+        ref = fdt.copy()
+        assert o.L.orc_do_horizontal_diffusion(o.p(np.ascontiguousarray(field)), o.p(ref), o.p(np.ascontiguousarray(d)), o.p(np.ascontiguousarray(d1)), nlev) == 0
+        assert np.array_equal(got, ref), name                   # one multiply-subtract-multiply per coefficient: bit for bit
