@@ -53,6 +53,7 @@ bool parse_dataset_header(const std::vector<unsigned char>& b, size_t a, Hdf5Var
             const size_t d = q;
             q += sz;
             if (q > end) break;
+            if (sz < 2 && type != 0) continue;        // too short to be one of the messages read below
             if (type == 0x10) {                // continuation: offset, length of an 'OCHK' block (signature first, checksum last)
                 const size_t off = (size_t)le(b, d, 8), len = (size_t)le(b, d + 8, 8);
                 if (off + len <= b.size() && len >= 8 && memcmp(&b[off], "OCHK", 4) == 0) chunks.push_back({off + 4, off + len - 4});

@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <cmath>
@@ -1041,7 +1042,11 @@ int speedy_write_output_async(speedy_ctx* ctx, int member, const char* dir, cons
     if (!ymdhm) throw std::runtime_error("speedy_write_output_async: the date of the enqueued state is required");
     Model& M = *ctx->model;
     const size_t n = speedy_output_len(ctx);
-    if (!M.outpipe) { auto* p = new OutPipe; M.outpipe = p; p->start(ctx->device, n); }
+    if (!M.outpipe) {                       // published only when complete: a start that throws (pinned memory) leaves no half-built pipe behind
+        std::unique_ptr<OutPipe> p(new OutPipe);
+        p->start(ctx->device, n);
+        M.outpipe = p.release();
+    }
     OutPipe& P = *static_cast<OutPipe*>(M.outpipe);
     const int s = P.acquire();
     try {
